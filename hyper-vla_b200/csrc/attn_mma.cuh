@@ -1,0 +1,170 @@
+// DINOv2 self-attention (257 tokens, 12 heads x 64) on bf16 tensor cores, flash style.
+// One CTA per (head, image, query half); K and V of that head live in shared memory, each warp
+// owns one 16-query tile and streams the 257 keys in chunks of 64 with an online softmax.
+// Warp-level mma.sync m16n8k16 is used on purpose: per (image, head) the problem is 257x257x64 --
+// far below a tcgen05 tile -- and attention is 5% of the step's FLOPs.
+// q arrives pre-divided by sqrt(64) (folded into the QKV GEMM epilogue).
+#pragma once
+#include "common.cuh"
+
+namespace hvla {
+namespace attn {
+
+constexpr int S = DTOK;          // 257
+constexpr int SP = 272;          // keys padded to 17 tiles of 16
+constexpr int ROW = DHD + 8;     // padded smem row (bf16 elements) -> 144 B, conflict-free ldmatrix
+constexpr int WARPS = 9;
+constexpr int QSPLIT = 2;
+constexpr int SMEM = 2 * SP * ROW * 2;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// one chunk of NT*8 keys starting at key0
+template <int NT>
+__device__ __forceinline__ void chunk(const uint32_t (&qf)[4][4], uint32_t sK, uint32_t sV, int key0, int lane,
+                                      float (&o)[8][4], float& m0, float& m1, float& l0, float& l1) {
+  float s[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+    for (int kp = 0; kp < 2; ++kp) {   // pairs of 16-wide d steps
+      uint32_t b0, b1, b2, b3;
+      const uint32_t addr = sK + (uint32_t)(((key0 + nt * 8 + (lane & 7)) * ROW + kp * 32 + (lane >> 3) * 8) * 2);
+      ldsm_x4(addr, b0, b1, b2, b3);
+      mma_bf16(s[nt], qf[2 * kp], b0, b1);
+      mma_bf16(s[nt], qf[2 * kp + 1], b2, b3);
+    }
+  }
+  // mask padded keys (only in the tail chunk), running max
+  float mx0 = m0, mx1 = m1;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int kbase = key0 + nt * 8 + (lane & 3) * 2;
+    if (kbase >= S) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+    if (kbase + 1 >= S) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+    mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+    mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  constexpr float LOG2E = 1.4426950408889634f;
+  const float c0 = exp2f((m0 - mx0) * LOG2E), c1 = exp2f((m1 - mx1) * LOG2E);   // m = -inf on the first chunk -> 0
+  m0 = mx0; m1 = mx1;
+  l0 *= c0; l1 *= c1;
+#pragma unroll
+  for (int dn = 0; dn < 8; ++dn) { o[dn][0] *= c0; o[dn][1] *= c0; o[dn][2] *= c1; o[dn][3] *= c1; }
+  float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    s[nt][0] = exp2f((s[nt][0] - mx0) * LOG2E);
+    s[nt][1] = exp2f((s[nt][1] - mx0) * LOG2E);
+    s[nt][2] = exp2f((s[nt][2] - mx1) * LOG2E);
+    s[nt][3] = exp2f((s[nt][3] - mx1) * LOG2E);
+    r0 += s[nt][0] + s[nt][1];
+    r1 += s[nt][2] + s[nt][3];
+  }
+  l0 += r0; l1 += r1;   // per-thread partial sums; reduced across the quad at the end
+  // O += P * V
+#pragma unroll
+  for (int t = 0; t < NT / 2; ++t) {
+    uint32_t pa[4];
+    pa[0] = pack2(s[2 * t][0], s[2 * t][1]);
+    pa[1] = pack2(s[2 * t][2], s[2 * t][3]);
+    pa[2] = pack2(s[2 * t + 1][0], s[2 * t + 1][1]);
+    pa[3] = pack2(s[2 * t + 1][2], s[2 * t + 1][3]);
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {   // pairs of 8-wide d tiles
+      uint32_t b0, b1, b2, b3;
+      const int i = lane >> 3;
+      const uint32_t addr = sV + (uint32_t)(((key0 + 16 * t + (i & 1) * 8 + (lane & 7)) * ROW + (dp * 2 + (i >> 1)) * 8) * 2);
+      ldsm_x4_t(addr, b0, b1, b2, b3);
+      mma_bf16(o[2 * dp], pa, b0, b1);
+      mma_bf16(o[2 * dp + 1], pa, b2, b3);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WARPS * 32) dino_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  bf16* Ks = reinterpret_cast<bf16*>(smem);
+  bf16* Vs = Ks + SP * ROW;
+  const int h = blockIdx.x, b = blockIdx.y, qs = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bf16* base = qkv + (int64_t)b * S * (3 * DD) + h * DHD;
+  // stage K and V (rows >= 257 are zero so they contribute nothing to P*V)
+  for (int i = threadIdx.x; i < SP * 8; i += WARPS * 32) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    if (r < S) {
+      kv = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)r * (3 * DD) + DD + c));
+      vv = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)r * (3 * DD) + 2 * DD + c));
+    }
+    *reinterpret_cast<uint4*>(Ks + r * ROW + c) = kv;
+    *reinterpret_cast<uint4*>(Vs + r * ROW + c) = vv;
+  }
+  __syncthreads();
+  const int tile = qs * WARPS + warp;      // 17 query tiles of 16 rows: tiles 0..8 | 9..16
+  if (tile * 16 >= S) return;
+  const int row0 = tile * 16 + (lane >> 2), row1 = row0 + 8;
+  uint32_t qf[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int c = ks * 16 + (lane & 3) * 2;
+    qf[ks][0] = row0 < S ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row0 * (3 * DD) + c)) : 0u;
+    qf[ks][1] = row1 < S ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row1 * (3 * DD) + c)) : 0u;
+    qf[ks][2] = row0 < S ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row0 * (3 * DD) + c + 8)) : 0u;
+    qf[ks][3] = row1 < S ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row1 * (3 * DD) + c + 8)) : 0u;
+  }
+  float o[8][4];
+#pragma unroll
+  for (int dn = 0; dn < 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const uint32_t sK = (uint32_t)__cvta_generic_to_shared(Ks), sV = (uint32_t)__cvta_generic_to_shared(Vs);
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) chunk<8>(qf, sK, sV, c * 64, lane, o, m0, m1, l0, l1);
+  chunk<2>(qf, sK, sV, 256, lane, o, m0, m1, l0, l1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  bf16* ob = out + (int64_t)b * S * DD + h * DHD;
+#pragma unroll
+  for (int dn = 0; dn < 8; ++dn) {
+    const int c = dn * 8 + (lane & 3) * 2;
+    if (row0 < S) *reinterpret_cast<uint32_t*>(ob + (int64_t)row0 * DD + c) = pack2(o[dn][0] * i0, o[dn][1] * i0);
+    if (row1 < S) *reinterpret_cast<uint32_t*>(ob + (int64_t)row1 * DD + c) = pack2(o[dn][2] * i1, o[dn][3] * i1);
+  }
+}
+
+inline int dino_attention(cudaStream_t st, const bf16* qkv, bf16* out, int B) {
+  static bool attr = false;
+  if (!attr) {
+    HVLA_CUDA(cudaFuncSetAttribute(dino_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr = true;
+  }
+  dim3 grid(DH, B, QSPLIT);
+  dino_attention_kernel<<<grid, WARPS * 32, SMEM, st>>>(qkv, out);
+  HVLA_LAUNCH_CHECK("dino_attention");
+  return HVLA_OK;
+}
+
+}  // namespace attn
+}  // namespace hvla

@@ -1,0 +1,130 @@
+// Shared constants, blob layouts and small helpers for libhvla (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <atomic>
+
+#include "../../include/hvla.h"
+
+namespace hvla {
+
+// ---- model constants (README configuration of the reference) ----------
+constexpr int IMG = 224, PATCH = 14, GRID = 16, NPATCH = 256;
+constexpr int DTOK = 257, DD = 768, DL = 12, DH = 12, DHD = 64, DF = 3072;
+constexpr int PATCH_K = 588, PATCH_KP = 640;
+constexpr int CD = 128, CL = 6, CH = 4, CHD = 32, CF = 512, LANG = 32, LANGD = 768, CTOK = 34;
+constexpr int BD = 64, BL = 4, BH = 4, BHD = 16, BF = 128, BTOK = 257;
+constexpr int AH = 4, AD = 7, NCONT = 24;
+constexpr int64_t NG = 201500, NGP = 201504;
+
+// ---- HN blob layout (fp32 elements) ----------------------------------------------------
+struct HnLayout {
+  static constexpr int64_t tok_w = 0;
+  static constexpr int64_t tok_b = tok_w + (int64_t)LANGD * CD;
+  static constexpr int64_t img_w = tok_b + CD;
+  static constexpr int64_t img_b = img_w + (int64_t)DD * CD;
+  static constexpr int64_t task_pos = img_b + CD;
+  static constexpr int64_t img_pos = task_pos + LANG * CD;
+  static constexpr int64_t layer_pos = img_pos + CD;
+  static constexpr int64_t layers = layer_pos + CD;
+  // per layer
+  static constexpr int64_t ln0_s = 0, ln0_b = ln0_s + CD, wqkv = ln0_b + CD, bqkv = wqkv + CD * 3 * CD,
+                           wo = bqkv + 3 * CD, bo = wo + CD * CD, ln1_s = bo + CD, ln1_b = ln1_s + CD,
+                           w0 = ln1_b + CD, b0 = w0 + CD * CF, w1 = b0 + CF, b1 = w1 + CF * CD,
+                           layer_size = b1 + CD;
+  static constexpr int64_t encn_s = layers + CL * layer_size;
+  static constexpr int64_t encn_b = encn_s + CD;
+  static constexpr int64_t total = encn_b + CD;
+};
+
+// ---- generated (per-task) row layout ----------------------------------------------------
+struct GenLayout {
+  static constexpr int64_t proj_w = 0;
+  static constexpr int64_t proj_b = proj_w + (int64_t)DD * BD;
+  static constexpr int64_t pos = proj_b + BD;
+  static constexpr int64_t layers = pos + BTOK * BD;
+  static constexpr int64_t ln0_s = 0, ln0_b = 64, wq = 128, bq = wq + 4096, wk = bq + 64, bk = wk + 4096,
+                           wv = bk + 64, bv = wv + 4096, wo = bv + 64, bo = wo + 4096, ln1_s = bo + 64,
+                           ln1_b = ln1_s + 64, w0 = ln1_b + 64, b0 = w0 + 8192, w1 = b0 + 128, b1 = w1 + 8192,
+                           layer_size = b1 + 64;
+  static constexpr int64_t encn_s = layers + BL * layer_size;
+  static constexpr int64_t encn_b = encn_s + 64;
+  static constexpr int64_t wc = encn_b + 64;
+  static constexpr int64_t bc = wc + 64 * NCONT;
+  static constexpr int64_t wd = bc + NCONT;
+  static constexpr int64_t bd = wd + 64 * AH;
+  static constexpr int64_t total = bd + AH;
+};
+static_assert(GenLayout::layer_size == 33472, "base block size");
+static_assert(GenLayout::total == NG, "generated row size");
+
+// ---- DINO vector blob (fp32) -----------------------------------------------------------------
+struct DvecLayout {
+  static constexpr int64_t patch_b = 0, cls = DD, pos = 2 * DD, layers = pos + (int64_t)DTOK * DD;
+  static constexpr int64_t ln1_s = 0, ln1_b = DD, bqkv = 2 * DD, bo = bqkv + 3 * DD, ls1 = bo + DD, ln2_s = ls1 + DD,
+                           ln2_b = ln2_s + DD, b1 = ln2_b + DD, b2 = b1 + DF, ls2 = b2 + DD, layer_size = ls2 + DD;
+  static constexpr int64_t lnf_s = layers + DL * layer_size, lnf_b = lnf_s + DD, total = lnf_b + DD;
+};
+
+// ---- DINO matrix blob (fp32 [K,N] or bf16 [N,K]; same element offsets) ------------------------
+struct DmatLayout {
+  static constexpr int64_t patch_w = 0, layers = (int64_t)PATCH_KP * DD;
+  static constexpr int64_t wqkv = 0, wo = wqkv + (int64_t)DD * 3 * DD, w1 = wo + (int64_t)DD * DD,
+                           w2 = w1 + (int64_t)DD * DF, layer_size = w2 + (int64_t)DF * DD;
+  static constexpr int64_t total = layers + DL * layer_size;
+};
+
+// ---- error plumbing -------------------------------------------------------------------------
+extern thread_local std::string g_last_error;
+extern std::atomic<int64_t> g_launches;
+
+inline int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+  char buf[512];
+  snprintf(buf, sizeof buf, fmt, a, b);
+  g_last_error = buf;
+  return code;
+}
+
+#define HVLA_CUDA(expr)                                                                     \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess) return ::hvla::fail(HVLA_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define HVLA_LAUNCH_CHECK(name)                                                             \
+  do {                                                                                      \
+    ::hvla::g_launches.fetch_add(1, std::memory_order_relaxed);                             \
+    cudaError_t e__ = cudaPeekAtLastError();                                                \
+    if (e__ != cudaSuccess) return ::hvla::fail(HVLA_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define HVLA_TRY(expr)        \
+  do {                        \
+    int r__ = (expr);         \
+    if (r__ != HVLA_OK) return r__; \
+  } while (0)
+
+// ---- dtype helpers -------------------------------------------------------------------------
+typedef __nv_bfloat16 bf16;
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ void from_f(float& d, float v) { d = v; }
+__device__ __forceinline__ void from_f(bf16& d, float v) { d = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  // flax.linen.gelu(approximate=True): 0.5x(1+tanh(sqrt(2/pi)(x+0.044715x^3)))  (transformer.py:66)
+  const float c = 0.7978845608028654f;
+  return 0.5f * x * (1.0f + tanhf(c * (x + 0.044715f * (x * x * x))));
+}
+__device__ __forceinline__ float gelu_erf_f(float x) {
+  // exact GELU used by DINOv2 (HF ACT2FN["gelu"])
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace hvla

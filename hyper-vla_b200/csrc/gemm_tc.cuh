@@ -1,0 +1,371 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = epi(A[M,K] * Wt[N,K]^T)
+//   A, Wt bf16 K-major; fp32 accumulation in tensor memory.
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
+// warps 2..9 = epilogue (TMEM -> registers -> global).  128x256x64 tiles, 4-stage smem ring,
+// two 256-column TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Used for the DINOv2 patch-embed / QKV / out-proj / fc1 / fc2 GEMMs (99% of the FLOPs of one
+// control step).
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace hvla {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+
+enum Epi { EPI_BIAS_BF16 = 0, EPI_BIAS_GELU_BF16 = 1, EPI_RESIDUAL_F32 = 2, EPI_PATCH_F32 = 3 };
+
+struct EpiP {
+  const float* bias;   // [N]
+  void* out;           // bf16 [M,ldo] (EPI 0/1) | fp32 residual stream X (EPI 2/3)
+  int ldo;
+  const float* ls;     // [N] layer scale (EPI 2)
+  const float* pos;    // [257,768] position table (EPI 3)
+  float qscale;        // EPI 0: columns < qcols are multiplied by qscale (query pre-scaling)
+  int qcols;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor: K-major operand, SWIZZLE_128B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address  [0,14)
+  d |= (uint64_t)1 << 16;                    // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256
+constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiP ep, int M, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
+  const uint32_t bars = sB + STAGES * B_STAGE_BYTES;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
+  const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
+  const uint32_t tmem_slot = tempty_bar + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles_n = N / BN;
+  const int n_tiles_m = (M + BM - 1) / BM;
+  const int n_tiles = n_tiles_m * n_tiles_n;
+  const int n_kb = K / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar + 8 * s, 1);
+      mbar_init(tempty_bar + 8 * s, NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          mbar_expect_tx(full_bar + 8 * s, A_STAGE_BYTES + B_STAGE_BYTES);
+          tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, full_bar + 8 * s, kb * BK, m0);
+          tma_load_2d(sB + s * B_STAGE_BYTES, &tmB, full_bar + 8 * s, kb * BK, n0);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(tempty_bar + 8 * as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(full_bar + 8 * s, ph);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(sA + s * A_STAGE_BYTES);
+          const uint64_t db = make_smem_desc(sB + s * B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 B (16 bf16) inside the 128 B swizzle atom: +2 in the (addr>>4) field
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar + 8 * s);     // frees the smem stage when these MMAs retire
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(tfull_bar + 8 * as);      // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = ew >> 2;              // which 128-column half of the tile
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+      mbar_wait(tfull_bar + 8 * as, aph);
+      tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < M;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col = n0 + half * 128 + c * 32;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * 128 + c * 32), r);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
+          v[j] = __uint_as_float(r[j]) + b4.x;
+          v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+          v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
+          v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+        }
+        if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+          if (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+          } else if (col < ep.qcols) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= ep.qscale;
+          }
+          if (row_ok) {
+            bf16* o = reinterpret_cast<bf16*>(ep.out) + (int64_t)row * ep.ldo + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 q;
+              q.x = pack_bf16(v[j], v[j + 1]);
+              q.y = pack_bf16(v[j + 2], v[j + 3]);
+              q.z = pack_bf16(v[j + 4], v[j + 5]);
+              q.w = pack_bf16(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = q;
+            }
+          }
+        } else if (EPI == EPI_RESIDUAL_F32) {
+          if (row_ok) {
+            float* x = reinterpret_cast<float*>(ep.out) + (int64_t)row * ep.ldo + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 l4 = __ldg(reinterpret_cast<const float4*>(ep.ls + col + j));
+              float4 x4 = *reinterpret_cast<const float4*>(x + j);
+              x4.x = x4.x + v[j] * l4.x;
+              x4.y = x4.y + v[j + 1] * l4.y;
+              x4.z = x4.z + v[j + 2] * l4.z;
+              x4.w = x4.w + v[j + 3] * l4.w;
+              *reinterpret_cast<float4*>(x + j) = x4;
+            }
+          }
+        } else {  // EPI_PATCH_F32: row = b*256+p -> token b*257+1+p, add position table
+          if (row_ok) {
+            const int b = row >> 8, pidx = row & 255;
+            float* x = reinterpret_cast<float*>(ep.out) + ((int64_t)b * DTOK + 1 + pidx) * ep.ldo + col;
+            const float* pz = ep.pos + (int64_t)(1 + pidx) * DD + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 p4 = __ldg(reinterpret_cast<const float4*>(pz + j));
+              *reinterpret_cast<float4*>(x + j) = make_float4(v[j] + p4.x, v[j + 1] + p4.y, v[j + 2] + p4.z, v[j + 3] + p4.w);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-byte swizzle
+inline int make_map_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(HVLA_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(HVLA_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return HVLA_OK;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int EPI>
+inline int launch_one(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const EpiP& ep, int M, int N, int K) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    HVLA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * (N / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tc_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, ep, M, N, K);
+  HVLA_LAUNCH_CHECK("gemm_tc");
+  return HVLA_OK;
+}
+
+// C = epi(A[M,K] * Wt[N,K]^T);  N % 256 == 0, K % 64 == 0
+inline int gemm_tc(cudaStream_t st, const void* A, const void* Wt, int M, int N, int K, int epi, const EpiP& ep) {
+  if (N % BN != 0 || K % BK != 0 || M <= 0) return fail(HVLA_ERR_ARG, "gemm_tc: N %% 256 or K %% 64 != 0");
+  CUtensorMap ma, mb;
+  HVLA_TRY(make_map_bf16(&ma, A, M, K, BM));
+  HVLA_TRY(make_map_bf16(&mb, Wt, N, K, BN));
+  switch (epi) {
+    case EPI_BIAS_BF16: return launch_one<EPI_BIAS_BF16>(st, ma, mb, ep, M, N, K);
+    case EPI_BIAS_GELU_BF16: return launch_one<EPI_BIAS_GELU_BF16>(st, ma, mb, ep, M, N, K);
+    case EPI_RESIDUAL_F32: return launch_one<EPI_RESIDUAL_F32>(st, ma, mb, ep, M, N, K);
+    case EPI_PATCH_F32: return launch_one<EPI_PATCH_F32>(st, ma, mb, ep, M, N, K);
+  }
+  return fail(HVLA_ERR_ARG, "gemm_tc: unknown epilogue");
+}
+
+}  // namespace tc
+}  // namespace hvla

@@ -1,0 +1,582 @@
+// libhvla.so -- C ABI + host orchestration of the HyperVLA hot path on sm_100a.
+// See include/hvla.h for the contract and the reference code each entry point replaces.
+#include "common.cuh"
+#include "simt_kernels.cuh"
+#include "gemm_tc.cuh"
+#include "attn_mma.cuh"
+
+#include <stdlib.h>
+#include <type_traits>
+
+namespace hvla {
+
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+
+static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// ---- workspace plan ---------------------------------------------------------------------------------
+struct Plan {
+  // generate region (fp32)
+  size_t tp, ip, xc, yc, qkvc, cc, hc, e;
+  // DINO region
+  size_t x, y, qkv, att, hid, emb;
+  // base region (fp32)
+  size_t pt, xb, yb, qkvb, cb, hb;
+  // host staging (hvla_act_host)
+  size_t img, act, logit, tidx;
+  size_t total;
+};
+
+static Plan make_plan(int B, int T, int dtype) {
+  Plan p;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+  const size_t es = dtype == HVLA_BF16 ? 2 : 4;
+  const size_t Tt = (size_t)(T > 0 ? T : 1), Bb = (size_t)(B > 0 ? B : 1);
+  p.tp = take(Tt * LANG * CD * 4);
+  p.ip = take(Tt * CD * 4);
+  p.xc = take(Tt * CTOK * CD * 4);
+  p.yc = take(Tt * CTOK * CD * 4);
+  p.qkvc = take(Tt * CTOK * 3 * CD * 4);
+  p.cc = take(Tt * CTOK * CD * 4);
+  p.hc = take(Tt * CTOK * CF * 4);
+  p.e = take(Tt * CD * 4);
+  const size_t M = Bb * DTOK;
+  p.x = take(M * DD * 4);
+  p.y = take(M * DD * es);
+  p.qkv = take(M * 3 * DD * es);
+  p.att = take(M * DD * es);
+  p.hid = take(M * DF * es);
+  p.emb = take(M * DD * es);
+  p.pt = take(Bb * NPATCH * BD * 4);
+  p.xb = take(Bb * BTOK * BD * 4);
+  p.yb = take(Bb * BTOK * BD * 4);
+  p.qkvb = take(Bb * BTOK * 3 * BD * 4);
+  p.cb = take(Bb * BTOK * BD * 4);
+  p.hb = take(Bb * BTOK * BF * 4);
+  p.img = take(Bb * IMG * IMG * 3);
+  p.act = take(Bb * AH * AD * 4);
+  p.logit = take(Bb * AH * 4);
+  p.tidx = take(Bb * 4);
+  p.total = off;
+  return p;
+}
+
+// debugging aid: the tensor-core GEMM's math on CUDA cores (same bf16 operands, W transposed)
+static int gemm_simt_debug(cudaStream_t st, const bf16* A, const bf16* Wt, int M, int N, int K, int epi, const tc::EpiP& ep) {
+  if (epi == tc::EPI_BIAS_BF16) {
+    bf16* C = reinterpret_cast<bf16*>(ep.out);
+    const int nq = ep.qcols;
+    if (nq > 0) {
+      GemmP g = gemm_params(A, K, Wt, K, ep.bias, C, ep.ldo, M, nq, K);
+      g.wt = 1; g.out_scale = ep.qscale;
+      HVLA_TRY((gemm_simt<bf16, bf16, float, bf16>(st, g, 1)));
+    }
+    if (N > nq) {
+      GemmP g = gemm_params(A, K, Wt + (int64_t)nq * K, K, ep.bias + nq, C + nq, ep.ldo, M, N - nq, K);
+      g.wt = 1;
+      HVLA_TRY((gemm_simt<bf16, bf16, float, bf16>(st, g, 1)));
+    }
+    return HVLA_OK;
+  }
+  if (epi == tc::EPI_BIAS_GELU_BF16) {
+    GemmP g = gemm_params(A, K, Wt, K, ep.bias, ep.out, ep.ldo, M, N, K);
+    g.wt = 1; g.act = 2;
+    return gemm_simt<bf16, bf16, float, bf16>(st, g, 1);
+  }
+  if (epi == tc::EPI_RESIDUAL_F32) {
+    GemmP g = gemm_params(A, K, Wt, K, ep.bias, ep.out, ep.ldo, M, N, K);
+    g.wt = 1; g.R = reinterpret_cast<const float*>(ep.out); g.ldr = ep.ldo; g.ls = ep.ls;
+    return gemm_simt<bf16, bf16, float, float>(st, g, 1);
+  }
+  return fail(HVLA_ERR_ARG, "gemm_simt_debug: unsupported epilogue");
+}
+
+static bool env_flag(const char* name) {
+  const char* v = getenv(name);
+  return v && v[0] && v[0] != '0';
+}
+
+// ---- generate (K1-K3) ---------------------------------------------------------------------------------
+template <typename TW>
+static int generate_impl(cudaStream_t st, const float* hn, const void* heads_w, const float* heads_b, const float* tok_emb,
+                         const int32_t* tok_mask, const uint8_t* lang_pad, const float* init_cls, int T, void* out_w,
+                         float* out_ctx, uint8_t* ws, const Plan& pl) {
+  float* TPj = reinterpret_cast<float*>(ws + pl.tp);
+  float* IPj = reinterpret_cast<float*>(ws + pl.ip);
+  float* X = reinterpret_cast<float*>(ws + pl.xc);
+  float* Y = reinterpret_cast<float*>(ws + pl.yc);
+  float* QKV = reinterpret_cast<float*>(ws + pl.qkvc);
+  float* CC = reinterpret_cast<float*>(ws + pl.cc);
+  float* HC = reinterpret_cast<float*>(ws + pl.hc);
+  float* E = out_ctx ? out_ctx : reinterpret_cast<float*>(ws + pl.e);
+  const int M = T * CTOK;
+  typedef HnLayout L;
+  // K1: projections (hypernetwork.py:112, 126)
+  HVLA_TRY((gemm_simt<float, float, float, float>(
+      st, gemm_params(tok_emb, LANGD, hn + L::tok_w, CD, hn + L::tok_b, TPj, CD, T * LANG, CD, LANGD), 1)));
+  HVLA_TRY((gemm_simt<float, float, float, float>(
+      st, gemm_params(init_cls, DD, hn + L::img_w, CD, hn + L::img_b, IPj, CD, T, CD, DD), 1)));
+  {
+    const int64_t total = (int64_t)M * CD;
+    ctx_assemble_kernel<<<cdiv(total, 256), 256, 0, st>>>(TPj, IPj, hn + L::task_pos, hn + L::img_pos, hn + L::layer_pos, X, T);
+    HVLA_LAUNCH_CHECK("ctx_assemble");
+  }
+  // K2: context encoder (transformer.py:247-260)
+  for (int l = 0; l < CL; ++l) {
+    const float* lw = hn + L::layers + (int64_t)l * L::layer_size;
+    LnP ln; memset(&ln, 0, sizeof ln);
+    ln.x = X; ln.ldx = CD; ln.y = Y; ln.ldy = CD; ln.scale = lw + L::ln0_s; ln.bias = lw + L::ln0_b; ln.rows = M; ln.rows_per_batch = 1;
+    HVLA_TRY((layernorm<float, float>(st, ln, CD)));
+    HVLA_TRY((gemm_simt<float, float, float, float>(st, gemm_params(Y, CD, lw + L::wqkv, 3 * CD, lw + L::bqkv, QKV, 3 * CD, M, 3 * CD, CD), 1)));
+    AttnP ap; memset(&ap, 0, sizeof ap);
+    ap.qkv = QKV; ap.out = CC; ap.S = CTOK; ap.H = CH; ap.nbatch = T; ap.mask = 2; ap.tok_mask = tok_mask; ap.lang_pad = lang_pad;
+    HVLA_TRY((attention_simt<float, float>(st, ap, CHD)));
+    GemmP g = gemm_params(CC, CD, lw + L::wo, CD, lw + L::bo, X, CD, M, CD, CD);
+    g.R = X; g.ldr = CD;
+    HVLA_TRY((gemm_simt<float, float, float, float>(st, g, 1)));
+    ln.scale = lw + L::ln1_s; ln.bias = lw + L::ln1_b;
+    HVLA_TRY((layernorm<float, float>(st, ln, CD)));
+    GemmP g0 = gemm_params(Y, CD, lw + L::w0, CF, lw + L::b0, HC, CF, M, CF, CD);
+    g0.act = 1;
+    HVLA_TRY((gemm_simt<float, float, float, float>(st, g0, 1)));
+    GemmP g1 = gemm_params(HC, CF, lw + L::w1, CD, lw + L::b1, X, CD, M, CD, CF);
+    g1.R = X; g1.ldr = CD;
+    HVLA_TRY((gemm_simt<float, float, float, float>(st, g1, 1)));
+  }
+  {  // encoder_norm on the layer token only, then / sqrt(128)  (hypernetwork.py:188-192)
+    LnP ln; memset(&ln, 0, sizeof ln);
+    ln.x = X + (int64_t)(CTOK - 1) * CD; ln.ldx = (int64_t)CTOK * CD; ln.y = E; ln.ldy = CD;
+    ln.scale = hn + L::encn_s; ln.bias = hn + L::encn_b; ln.rows = T; ln.rows_per_batch = 1;
+    ln.post_div = sqrtf((float)CD);
+    HVLA_TRY((layernorm<float, float>(st, ln, CD)));
+  }
+  // K3: all 73 output heads as one skinny GEMM (hypernetwork.py:205-217, 227)
+  heads_gemm_kernel<TW, TW><<<cdiv(NGP, 1024), 256, 0, st>>>(E, reinterpret_cast<const TW*>(heads_w), heads_b,
+                                                             reinterpret_cast<TW*>(out_w), T);
+  HVLA_LAUNCH_CHECK("heads_gemm");
+  return HVLA_OK;
+}
+
+// ---- DINOv2 (K4-K7) -----------------------------------------------------------------------------------
+static int dino_f32(cudaStream_t st, const float* dv, const float* dm, const uint8_t* images, int B, float* out_emb,
+                    uint8_t* ws, const Plan& pl) {
+  typedef DvecLayout V;
+  typedef DmatLayout Mx;
+  const int M = B * DTOK;
+  float* X = reinterpret_cast<float*>(ws + pl.x);
+  float* Y = reinterpret_cast<float*>(ws + pl.y);
+  float* QKV = reinterpret_cast<float*>(ws + pl.qkv);
+  float* ATT = reinterpret_cast<float*>(ws + pl.att);
+  float* HID = reinterpret_cast<float*>(ws + pl.hid);
+  float* A0 = HID;   // im2col matrix aliases the MLP hidden buffer
+  float* P = QKV;    // patch projections alias the qkv buffer
+  {
+    const int64_t total = (int64_t)B * NPATCH * PATCH_KP;
+    im2col_norm_kernel<float><<<cdiv(total, 256), 256, 0, st>>>(images, A0, B);
+    HVLA_LAUNCH_CHECK("im2col");
+  }
+  HVLA_TRY((gemm_simt<float, float, float, float>(
+      st, gemm_params(A0, PATCH_KP, dm + Mx::patch_w, DD, dv + V::patch_b, P, DD, B * NPATCH, DD, PATCH_KP), 1)));
+  {
+    const int64_t total = (int64_t)M * DD;
+    dino_assemble_kernel<float><<<cdiv(total, 256), 256, 0, st>>>(P, dv + V::cls, dv + V::pos, X, B);
+    HVLA_LAUNCH_CHECK("dino_assemble");
+  }
+  for (int l = 0; l < DL; ++l) {
+    const float* v = dv + V::layers + (int64_t)l * V::layer_size;
+    const float* m = dm + Mx::layers + (int64_t)l * Mx::layer_size;
+    LnP ln; memset(&ln, 0, sizeof ln);
+    ln.x = X; ln.ldx = DD; ln.y = Y; ln.ldy = DD; ln.scale = v + V::ln1_s; ln.bias = v + V::ln1_b; ln.rows = M; ln.rows_per_batch = 1;
+    HVLA_TRY((layernorm<float, float>(st, ln, DD)));
+    HVLA_TRY((gemm_simt<float, float, float, float>(st, gemm_params(Y, DD, m + Mx::wqkv, 3 * DD, v + V::bqkv, QKV, 3 * DD, M, 3 * DD, DD), 1)));
+    AttnP ap; memset(&ap, 0, sizeof ap);
+    ap.qkv = QKV; ap.out = ATT; ap.S = DTOK; ap.H = DH; ap.nbatch = B; ap.mask = 0;
+    HVLA_TRY((attention_simt<float, float>(st, ap, DHD)));
+    GemmP g = gemm_params(ATT, DD, m + Mx::wo, DD, v + V::bo, X, DD, M, DD, DD);
+    g.R = X; g.ldr = DD; g.ls = v + V::ls1;
+    HVLA_TRY((gemm_simt<float, float, float, float>(st, g, 1)));
+    ln.scale = v + V::ln2_s; ln.bias = v + V::ln2_b;
+    HVLA_TRY((layernorm<float, float>(st, ln, DD)));
+    GemmP g1 = gemm_params(Y, DD, m + Mx::w1, DF, v + V::b1, HID, DF, M, DF, DD);
+    g1.act = 2;
+    HVLA_TRY((gemm_simt<float, float, float, float>(st, g1, 1)));
+    GemmP g2 = gemm_params(HID, DF, m + Mx::w2, DD, v + V::b2, X, DD, M, DD, DF);
+    g2.R = X; g2.ldr = DD; g2.ls = v + V::ls2;
+    HVLA_TRY((gemm_simt<float, float, float, float>(st, g2, 1)));
+  }
+  LnP ln; memset(&ln, 0, sizeof ln);
+  ln.x = X; ln.ldx = DD; ln.y = out_emb; ln.ldy = DD; ln.scale = dv + V::lnf_s; ln.bias = dv + V::lnf_b; ln.rows = M; ln.rows_per_batch = 1;
+  HVLA_TRY((layernorm<float, float>(st, ln, DD)));
+  return HVLA_OK;
+}
+
+// cls rows of the residual stream: X[b,0,:] = cls + pos[0]
+__global__ void dino_cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ X, int B) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * DD) return;
+  const int c = idx % DD, b = idx / DD;
+  X[(int64_t)b * DTOK * DD + c] = cls[c] + pos[c];
+}
+
+static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uint8_t* images, int B, bf16* out_emb,
+                     uint8_t* ws, const Plan& pl) {
+  typedef DvecLayout V;
+  typedef DmatLayout Mx;
+  const int M = B * DTOK;
+  float* X = reinterpret_cast<float*>(ws + pl.x);
+  bf16* Y = reinterpret_cast<bf16*>(ws + pl.y);
+  bf16* QKV = reinterpret_cast<bf16*>(ws + pl.qkv);
+  bf16* ATT = reinterpret_cast<bf16*>(ws + pl.att);
+  bf16* HID = reinterpret_cast<bf16*>(ws + pl.hid);
+  bf16* A0 = HID;
+  const bool simt_gemm = env_flag("HVLA_DEBUG_SIMT_GEMM");   // debugging aid: CUDA-core GEMMs on the bf16 data
+  const bool simt_attn = env_flag("HVLA_DEBUG_SIMT_ATTN");
+  {
+    const int64_t total = (int64_t)B * NPATCH * PATCH_KP;
+    im2col_norm_kernel<bf16><<<cdiv(total, 256), 256, 0, st>>>(images, A0, B);
+    HVLA_LAUNCH_CHECK("im2col");
+    dino_cls_rows_kernel<<<cdiv(B * DD, 256), 256, 0, st>>>(dv + V::cls, dv + V::pos, X, B);
+    HVLA_LAUNCH_CHECK("dino_cls_rows");
+  }
+  auto gemm = [&](const bf16* A, const bf16* Wt, int m, int n, int k, int epi, const tc::EpiP& ep) -> int {
+    if (!simt_gemm) return tc::gemm_tc(st, A, Wt, m, n, k, epi, ep);
+    // debug path: same math on CUDA cores (W given transposed)
+    return gemm_simt_debug(st, A, Wt, m, n, k, epi, ep);
+  };
+  if (simt_gemm) {   // debug: patch projections to a bf16 temp (aliases QKV), then assemble tokens
+    GemmP g = gemm_params(A0, PATCH_KP, dm + Mx::patch_w, PATCH_KP, dv + V::patch_b, QKV, DD, B * NPATCH, DD, PATCH_KP);
+    g.wt = 1;
+    HVLA_TRY((gemm_simt<bf16, bf16, float, bf16>(st, g, 1)));
+    const int64_t total = (int64_t)M * DD;
+    dino_assemble_kernel<bf16><<<cdiv(total, 256), 256, 0, st>>>(QKV, dv + V::cls, dv + V::pos, X, B);
+    HVLA_LAUNCH_CHECK("dino_assemble");
+  } else {
+    tc::EpiP ep; memset(&ep, 0, sizeof ep);
+    ep.bias = dv + V::patch_b; ep.out = X; ep.ldo = DD; ep.pos = dv + V::pos;
+    HVLA_TRY(gemm(A0, dm + Mx::patch_w, B * NPATCH, DD, PATCH_KP, tc::EPI_PATCH_F32, ep));
+  }
+  for (int l = 0; l < DL; ++l) {
+    const float* v = dv + V::layers + (int64_t)l * V::layer_size;
+    const bf16* m = dm + Mx::layers + (int64_t)l * Mx::layer_size;
+    LnP ln; memset(&ln, 0, sizeof ln);
+    ln.x = X; ln.ldx = DD; ln.y = Y; ln.ldy = DD; ln.scale = v + V::ln1_s; ln.bias = v + V::ln1_b; ln.rows = M; ln.rows_per_batch = 1;
+    HVLA_TRY((layernorm<float, bf16>(st, ln, DD)));
+    {
+      tc::EpiP ep; memset(&ep, 0, sizeof ep);
+      ep.bias = v + V::bqkv; ep.out = QKV; ep.ldo = 3 * DD; ep.qscale = 0.125f; ep.qcols = DD;   // q / sqrt(64)
+      HVLA_TRY(gemm(Y, m + Mx::wqkv, M, 3 * DD, DD, tc::EPI_BIAS_BF16, ep));
+    }
+    if (simt_attn) {
+      AttnP ap; memset(&ap, 0, sizeof ap);
+      ap.qkv = QKV; ap.out = ATT; ap.S = DTOK; ap.H = DH; ap.nbatch = B; ap.mask = 0; ap.prescaled = 1;
+      HVLA_TRY((attention_simt<bf16, bf16>(st, ap, DHD)));
+    } else {
+      HVLA_TRY(attn::dino_attention(st, QKV, ATT, B));
+    }
+    {
+      tc::EpiP ep; memset(&ep, 0, sizeof ep);
+      ep.bias = v + V::bo; ep.out = X; ep.ldo = DD; ep.ls = v + V::ls1;
+      HVLA_TRY(gemm(ATT, m + Mx::wo, M, DD, DD, tc::EPI_RESIDUAL_F32, ep));
+    }
+    ln.scale = v + V::ln2_s; ln.bias = v + V::ln2_b;
+    HVLA_TRY((layernorm<float, bf16>(st, ln, DD)));
+    {
+      tc::EpiP ep; memset(&ep, 0, sizeof ep);
+      ep.bias = v + V::b1; ep.out = HID; ep.ldo = DF;
+      HVLA_TRY(gemm(Y, m + Mx::w1, M, DF, DD, tc::EPI_BIAS_GELU_BF16, ep));
+    }
+    {
+      tc::EpiP ep; memset(&ep, 0, sizeof ep);
+      ep.bias = v + V::b2; ep.out = X; ep.ldo = DD; ep.ls = v + V::ls2;
+      HVLA_TRY(gemm(HID, m + Mx::w2, M, DD, DF, tc::EPI_RESIDUAL_F32, ep));
+    }
+  }
+  LnP ln; memset(&ln, 0, sizeof ln);
+  ln.x = X; ln.ldx = DD; ln.y = out_emb; ln.ldy = DD; ln.scale = dv + V::lnf_s; ln.bias = dv + V::lnf_b; ln.rows = M; ln.rows_per_batch = 1;
+  HVLA_TRY((layernorm<float, bf16>(st, ln, DD)));
+  return HVLA_OK;
+}
+
+// ---- base ViT + head, generic path (K8, K9) --------------------------------------------------------------
+// TE: embedding storage type; TW: generated-weight storage type.  All math fp32.
+template <typename TE, typename TW>
+static int base_generic(cudaStream_t st, const TE* emb, const TW* weights, const int32_t* tidx, int B, int T,
+                        float* out_action, float* out_logit, uint8_t* ws, const Plan& pl) {
+  typedef GenLayout G;
+  float* PT = reinterpret_cast<float*>(ws + pl.pt);
+  float* X = reinterpret_cast<float*>(ws + pl.xb);
+  float* Y = reinterpret_cast<float*>(ws + pl.yb);
+  float* QKV = reinterpret_cast<float*>(ws + pl.qkvb);
+  float* CB = reinterpret_cast<float*>(ws + pl.cb);
+  float* HB = reinterpret_cast<float*>(ws + pl.hb);
+  const int64_t sW = T == 1 ? NGP : NGP;   // weight-batch stride; T==1 is handled by an all-zero index below
+  // image_embedding_projection on patch tokens (skip CLS row): base_vit.py:122, 130-133
+  {
+    GemmP g = gemm_params(emb + DD, DD, weights + G::proj_w, BD, weights + G::proj_b, PT, BD, NPATCH, BD, DD);
+    g.sA = (int64_t)DTOK * DD; g.sW = sW; g.sBias = sW; g.sC = (int64_t)NPATCH * BD; g.widx = tidx;
+    HVLA_TRY((gemm_simt<TE, TW, TW, float>(st, g, B)));
+  }
+  {
+    const int64_t total = (int64_t)B * BTOK * BD;
+    base_assemble_kernel<TW><<<cdiv(total, 256), 256, 0, st>>>(PT, weights, tidx, X, B);
+    HVLA_LAUNCH_CHECK("base_assemble");
+  }
+  for (int l = 0; l < BL; ++l) {
+    const TW* lw = weights + G::layers + (int64_t)l * G::layer_size;
+    LnP ln; memset(&ln, 0, sizeof ln);
+    ln.x = X; ln.ldx = BD; ln.y = Y; ln.ldy = BD; ln.scale = lw + G::ln0_s; ln.bias = lw + G::ln0_b; ln.sS = sW; ln.widx = tidx;
+    ln.rows = B * BTOK; ln.rows_per_batch = BTOK;
+    HVLA_TRY((layernorm<TW, float>(st, ln, BD)));
+    const int64_t wofs[3] = {G::wq, G::wk, G::wv}, bofs[3] = {G::bq, G::bk, G::bv};
+    for (int j = 0; j < 3; ++j) {
+      GemmP g = gemm_params(Y, BD, lw + wofs[j], BD, lw + bofs[j], QKV + j * BD, 3 * BD, BTOK, BD, BD);
+      g.sA = (int64_t)BTOK * BD; g.sW = sW; g.sBias = sW; g.sC = (int64_t)BTOK * 3 * BD; g.widx = tidx;
+      HVLA_TRY((gemm_simt<float, TW, TW, float>(st, g, B)));
+    }
+    AttnP ap; memset(&ap, 0, sizeof ap);
+    ap.qkv = QKV; ap.out = CB; ap.S = BTOK; ap.H = BH; ap.nbatch = B; ap.mask = 1;
+    HVLA_TRY((attention_simt<float, float>(st, ap, BHD)));
+    {
+      GemmP g = gemm_params(CB, BD, lw + G::wo, BD, lw + G::bo, X, BD, BTOK, BD, BD);
+      g.sA = (int64_t)BTOK * BD; g.sW = sW; g.sBias = sW; g.sC = (int64_t)BTOK * BD; g.widx = tidx;
+      g.R = X; g.ldr = BD; g.sR = (int64_t)BTOK * BD;
+      HVLA_TRY((gemm_simt<float, TW, TW, float>(st, g, B)));
+    }
+    ln.scale = lw + G::ln1_s; ln.bias = lw + G::ln1_b;
+    HVLA_TRY((layernorm<TW, float>(st, ln, BD)));
+    {
+      GemmP g = gemm_params(Y, BD, lw + G::w0, BF, lw + G::b0, HB, BF, BTOK, BF, BD);
+      g.sA = (int64_t)BTOK * BD; g.sW = sW; g.sBias = sW; g.sC = (int64_t)BTOK * BF; g.widx = tidx; g.act = 1;
+      HVLA_TRY((gemm_simt<float, TW, TW, float>(st, g, B)));
+    }
+    {
+      GemmP g = gemm_params(HB, BF, lw + G::w1, BD, lw + G::b1, X, BD, BTOK, BD, BF);
+      g.sA = (int64_t)BTOK * BF; g.sW = sW; g.sBias = sW; g.sC = (int64_t)BTOK * BD; g.widx = tidx;
+      g.R = X; g.ldr = BD; g.sR = (int64_t)BTOK * BD;
+      HVLA_TRY((gemm_simt<float, TW, TW, float>(st, g, B)));
+    }
+  }
+  mix_head_kernel<TW><<<cdiv(B, 4), 128, 0, st>>>(X, weights, tidx, out_action, out_logit, B);
+  HVLA_LAUNCH_CHECK("mix_head");
+  return HVLA_OK;
+}
+
+// task index handling: NULL means identity (T==B) or all-zero (T==1)
+__global__ void fill_index_kernel(int* idx, int B, int identity) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) idx[i] = identity ? i : 0;
+}
+
+static int check_common(int B, int T, int dtype, const void* ws, size_t ws_bytes) {
+  if (dtype != HVLA_F32 && dtype != HVLA_BF16) return fail(HVLA_ERR_ARG, "dtype must be HVLA_F32 or HVLA_BF16");
+  if (B < 0 || T < 0) return fail(HVLA_ERR_ARG, "negative batch");
+  if (!ws) return fail(HVLA_ERR_WORKSPACE, "workspace is NULL");
+  if (ws_bytes < make_plan(B, T, dtype).total) return fail(HVLA_ERR_WORKSPACE, "workspace too small (see hvla_workspace_bytes)");
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(HVLA_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  return HVLA_OK;
+}
+
+static int base_act_impl(cudaStream_t st, const void* emb, const void* weights, const int32_t* task_index, int B, int T,
+                         float* out_action, float* out_logit, uint8_t* ws, const Plan& pl, int dtype) {
+  if (!task_index && !(T == B || T == 1)) return fail(HVLA_ERR_ARG, "task_index is NULL but T != B and T != 1");
+  const int32_t* tidx = task_index;
+  if (!tidx && T == 1) {   // shared weights: materialise an all-zero index
+    int* z = reinterpret_cast<int*>(ws + pl.tidx);
+    fill_index_kernel<<<cdiv(B, 256), 256, 0, st>>>(z, B, 0);
+    HVLA_LAUNCH_CHECK("fill_index");
+    tidx = z;
+  }
+  if (dtype == HVLA_F32)
+    return base_generic<float, float>(st, reinterpret_cast<const float*>(emb), reinterpret_cast<const float*>(weights), tidx, B,
+                                      T, out_action, out_logit, ws, pl);
+  return base_generic<bf16, bf16>(st, reinterpret_cast<const bf16*>(emb), reinterpret_cast<const bf16*>(weights), tidx, B, T,
+                                  out_action, out_logit, ws, pl);
+}
+
+}  // namespace hvla
+
+// =====================================================================================================
+// extern "C"
+// =====================================================================================================
+using namespace hvla;
+
+extern "C" {
+
+int hvla_version(void) { return 1; }
+const char* hvla_last_error(void) { return g_last_error.c_str(); }
+int64_t hvla_hn_blob_elems(void) { return HnLayout::total; }
+int64_t hvla_generated_elems(void) { return NG; }
+int64_t hvla_generated_row_stride(void) { return NGP; }
+int64_t hvla_dino_vec_elems(void) { return DvecLayout::total; }
+int64_t hvla_dino_mat_elems(void) { return DmatLayout::total; }
+int64_t hvla_launch_count(void) { return g_launches.load(); }
+
+int64_t hvla_layout_offset(const char* name) {
+  if (!name) return -1;
+  std::string s(name);
+  int layer = 0;
+  auto split_layer = [&](std::string& rest) -> bool {   // "l<k>.<field>" -> layer, field
+    if (rest.size() > 2 && rest[0] == 'l' && isdigit((unsigned char)rest[1])) {
+      size_t dot = rest.find('.');
+      if (dot == std::string::npos) return false;
+      layer = atoi(rest.substr(1, dot - 1).c_str());
+      rest = rest.substr(dot + 1);
+      return true;
+    }
+    return false;
+  };
+#define F(tbl, nm) if (f == #nm) return tbl::nm;
+#define FL(tbl, nm) if (f == #nm) return tbl::layers + (int64_t)layer * tbl::layer_size + tbl::nm;
+  if (s.rfind("hn.", 0) == 0) {
+    std::string f = s.substr(3);
+    if (split_layer(f)) {
+      if (layer < 0 || layer >= CL) return -1;
+      FL(HnLayout, ln0_s) FL(HnLayout, ln0_b) FL(HnLayout, wqkv) FL(HnLayout, bqkv) FL(HnLayout, wo) FL(HnLayout, bo)
+      FL(HnLayout, ln1_s) FL(HnLayout, ln1_b) FL(HnLayout, w0) FL(HnLayout, b0) FL(HnLayout, w1) FL(HnLayout, b1)
+      return -1;
+    }
+    F(HnLayout, tok_w) F(HnLayout, tok_b) F(HnLayout, img_w) F(HnLayout, img_b) F(HnLayout, task_pos) F(HnLayout, img_pos)
+    F(HnLayout, layer_pos) F(HnLayout, encn_s) F(HnLayout, encn_b) F(HnLayout, total)
+    return -1;
+  }
+  if (s.rfind("gen.", 0) == 0) {
+    std::string f = s.substr(4);
+    if (split_layer(f)) {
+      if (layer < 0 || layer >= BL) return -1;
+      FL(GenLayout, ln0_s) FL(GenLayout, ln0_b) FL(GenLayout, wq) FL(GenLayout, bq) FL(GenLayout, wk) FL(GenLayout, bk)
+      FL(GenLayout, wv) FL(GenLayout, bv) FL(GenLayout, wo) FL(GenLayout, bo) FL(GenLayout, ln1_s) FL(GenLayout, ln1_b)
+      FL(GenLayout, w0) FL(GenLayout, b0) FL(GenLayout, w1) FL(GenLayout, b1)
+      return -1;
+    }
+    F(GenLayout, proj_w) F(GenLayout, proj_b) F(GenLayout, pos) F(GenLayout, encn_s) F(GenLayout, encn_b) F(GenLayout, wc)
+    F(GenLayout, bc) F(GenLayout, wd) F(GenLayout, bd) F(GenLayout, total)
+    return -1;
+  }
+  if (s.rfind("dvec.", 0) == 0) {
+    std::string f = s.substr(5);
+    if (split_layer(f)) {
+      if (layer < 0 || layer >= DL) return -1;
+      FL(DvecLayout, ln1_s) FL(DvecLayout, ln1_b) FL(DvecLayout, bqkv) FL(DvecLayout, bo) FL(DvecLayout, ls1)
+      FL(DvecLayout, ln2_s) FL(DvecLayout, ln2_b) FL(DvecLayout, b1) FL(DvecLayout, b2) FL(DvecLayout, ls2)
+      return -1;
+    }
+    F(DvecLayout, patch_b) F(DvecLayout, cls) F(DvecLayout, pos) F(DvecLayout, lnf_s) F(DvecLayout, lnf_b) F(DvecLayout, total)
+    return -1;
+  }
+  if (s.rfind("dmat.", 0) == 0) {
+    std::string f = s.substr(5);
+    if (split_layer(f)) {
+      if (layer < 0 || layer >= DL) return -1;
+      FL(DmatLayout, wqkv) FL(DmatLayout, wo) FL(DmatLayout, w1) FL(DmatLayout, w2)
+      return -1;
+    }
+    F(DmatLayout, patch_w) F(DmatLayout, total)
+    return -1;
+  }
+#undef F
+#undef FL
+  return -1;
+}
+
+size_t hvla_workspace_bytes(int B, int T, int dtype) { return make_plan(B, T, dtype).total; }
+
+int hvla_generate(hvla_stream_t stream, const float* hn_blob, const void* heads_w, const float* heads_b, const float* tok_emb,
+                  const int32_t* tok_mask, const uint8_t* lang_pad, const float* init_cls, int T, void* out_weights,
+                  float* out_ctx, void* workspace, size_t workspace_bytes, int dtype) {
+  if (!hn_blob || !heads_w || !heads_b || !tok_emb || !tok_mask || !init_cls || !out_weights)
+    return fail(HVLA_ERR_ARG, "hvla_generate: NULL argument");
+  HVLA_TRY(check_common(0, T, dtype, workspace, workspace_bytes));
+  if (T == 0) return HVLA_OK;
+  const Plan pl = make_plan(0, T, dtype);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  if (dtype == HVLA_F32)
+    return generate_impl<float>(st, hn_blob, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, out_weights, out_ctx, ws, pl);
+  return generate_impl<bf16>(st, hn_blob, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, out_weights, out_ctx, ws, pl);
+}
+
+int hvla_dino_forward(hvla_stream_t stream, const float* dino_vec, const void* dino_mat, const uint8_t* images, int B,
+                      void* out_emb, void* workspace, size_t workspace_bytes, int dtype) {
+  if (!dino_vec || !dino_mat || !images || !out_emb) return fail(HVLA_ERR_ARG, "hvla_dino_forward: NULL argument");
+  HVLA_TRY(check_common(B, 0, dtype, workspace, workspace_bytes));
+  if (B == 0) return HVLA_OK;
+  const Plan pl = make_plan(B, 0, dtype);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  if (dtype == HVLA_F32)
+    return dino_f32(st, dino_vec, reinterpret_cast<const float*>(dino_mat), images, B, reinterpret_cast<float*>(out_emb), ws, pl);
+  return dino_bf16(st, dino_vec, reinterpret_cast<const bf16*>(dino_mat), images, B, reinterpret_cast<bf16*>(out_emb), ws, pl);
+}
+
+int hvla_base_act(hvla_stream_t stream, const void* emb, const void* weights, const int32_t* task_index, int B, int T,
+                  float* out_action, float* out_logit, void* workspace, size_t workspace_bytes, int dtype) {
+  if (!emb || !weights || !out_action) return fail(HVLA_ERR_ARG, "hvla_base_act: NULL argument");
+  if (T <= 0 && B > 0) return fail(HVLA_ERR_ARG, "hvla_base_act: T must be >= 1");
+  HVLA_TRY(check_common(B, 0, dtype, workspace, workspace_bytes));
+  if (B == 0) return HVLA_OK;
+  const Plan pl = make_plan(B, 0, dtype);
+  return base_act_impl(reinterpret_cast<cudaStream_t>(stream), emb, weights, task_index, B, T, out_action, out_logit,
+                       reinterpret_cast<uint8_t*>(workspace), pl, dtype);
+}
+
+int hvla_act(hvla_stream_t stream, const float* dino_vec, const void* dino_mat, const uint8_t* images, const void* weights,
+             const int32_t* task_index, int B, int T, float* out_action, float* out_logit, void* workspace,
+             size_t workspace_bytes, int dtype) {
+  if (!dino_vec || !dino_mat || !images || !weights || !out_action) return fail(HVLA_ERR_ARG, "hvla_act: NULL argument");
+  if (T <= 0 && B > 0) return fail(HVLA_ERR_ARG, "hvla_act: T must be >= 1");
+  HVLA_TRY(check_common(B, 0, dtype, workspace, workspace_bytes));
+  if (B == 0) return HVLA_OK;
+  const Plan pl = make_plan(B, 0, dtype);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  void* emb = ws + pl.emb;
+  HVLA_TRY(hvla_dino_forward(stream, dino_vec, dino_mat, images, B, emb, workspace, workspace_bytes, dtype));
+  return base_act_impl(reinterpret_cast<cudaStream_t>(stream), emb, weights, task_index, B, T, out_action, out_logit, ws, pl, dtype);
+}
+
+int hvla_act_host(hvla_stream_t stream, const float* dino_vec, const void* dino_mat, const uint8_t* images_host,
+                  const void* weights, const int32_t* task_index, int B, int T, float* out_action_host, float* out_logit_host,
+                  void* workspace, size_t workspace_bytes, int dtype) {
+  if (!images_host || !out_action_host) return fail(HVLA_ERR_ARG, "hvla_act_host: NULL host buffer");
+  HVLA_TRY(check_common(B, 0, dtype, workspace, workspace_bytes));
+  if (B == 0) return HVLA_OK;
+  const Plan pl = make_plan(B, 0, dtype);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  uint8_t* d_img = ws + pl.img;
+  float* d_act = reinterpret_cast<float*>(ws + pl.act);
+  float* d_logit = reinterpret_cast<float*>(ws + pl.logit);
+  HVLA_CUDA(cudaMemcpyAsync(d_img, images_host, (size_t)B * IMG * IMG * 3, cudaMemcpyHostToDevice, st));
+  HVLA_TRY(hvla_act(stream, dino_vec, dino_mat, d_img, weights, task_index, B, T, d_act, d_logit, workspace, workspace_bytes, dtype));
+  HVLA_CUDA(cudaMemcpyAsync(out_action_host, d_act, (size_t)B * AH * AD * 4, cudaMemcpyDeviceToHost, st));
+  if (out_logit_host)
+    HVLA_CUDA(cudaMemcpyAsync(out_logit_host, d_logit, (size_t)B * AH * 4, cudaMemcpyDeviceToHost, st));
+  HVLA_CUDA(cudaStreamSynchronize(st));
+  return HVLA_OK;
+}
+
+int hvla_gemm_bf16(hvla_stream_t stream, const void* A, const void* Wt, const float* bias, void* C, int M, int N, int K, int act) {
+  if (!A || !Wt || !bias || !C) return fail(HVLA_ERR_ARG, "hvla_gemm_bf16: NULL argument");
+  tc::EpiP ep; memset(&ep, 0, sizeof ep);
+  ep.bias = bias; ep.out = C; ep.ldo = N;
+  return tc::gemm_tc(reinterpret_cast<cudaStream_t>(stream), A, Wt, M, N, K, act == 2 ? tc::EPI_BIAS_GELU_BF16 : tc::EPI_BIAS_BF16, ep);
+}
+
+// ---- legacy XLA custom-call wrappers (no status channel in this ABI revision: errors are logged) ---------
+void hvla_xla_generate(void* stream, void** b, const char* opaque, size_t opaque_len) {
+  if (opaque_len < sizeof(hvla_xla_opaque)) return;
+  hvla_xla_opaque o; memcpy(&o, opaque, sizeof o);
+  int r = hvla_generate(stream, (const float*)b[0], b[1], (const float*)b[2], (const float*)b[3], (const int32_t*)b[4],
+                        (const uint8_t*)b[5], (const float*)b[6], o.T, b[7], (float*)b[8], b[9], (size_t)o.workspace_bytes, o.dtype);
+  if (r != HVLA_OK) fprintf(stderr, "hvla_xla_generate: %s\n", hvla_last_error());
+}
+void hvla_xla_act(void* stream, void** b, const char* opaque, size_t opaque_len) {
+  if (opaque_len < sizeof(hvla_xla_opaque)) return;
+  hvla_xla_opaque o; memcpy(&o, opaque, sizeof o);
+  int r = hvla_act(stream, (const float*)b[0], b[1], (const uint8_t*)b[2], b[3], (const int32_t*)b[4], o.B, o.T, (float*)b[5],
+                   (float*)b[6], b[7], (size_t)o.workspace_bytes, o.dtype);
+  if (r != HVLA_OK) fprintf(stderr, "hvla_xla_act: %s\n", hvla_last_error());
+}
+
+}  // extern "C"

@@ -1,0 +1,463 @@
+// CUDA-core (fp32 math) kernels: the exact HVLA_F32 path and the glue of the bf16 path.
+// Storage types are templated (float or bf16); all arithmetic is fp32 in the reference's
+// op order, so this path matches the fp32 oracle to ~1e-6.
+#pragma once
+#include "common.cuh"
+#include <float.h>
+
+namespace hvla {
+
+// =============================================================================================
+// Batched GEMM  C[b] = epi( A[b][M,K] * W[w(b)][K,N] + bias[w(b)][N] )
+//   epi: out_scale * (.) -> activation -> optional  R + ls * (.)
+// 64x64x16 tiles, 256 threads, 4x4 micro-tile.  K % 16 == 0.
+// =============================================================================================
+struct GemmP {
+  const void* A; int lda; int64_t sA;
+  const void* W; int ldw; int64_t sW;
+  const void* bias; int64_t sBias;
+  void* C; int ldc; int64_t sC;
+  const float* R; int ldr; int64_t sR;
+  const float* ls;
+  const int* widx;
+  int M, N, K;
+  float out_scale;
+  int act;  // 0 none, 1 tanh-GELU, 2 erf-GELU
+  int wt;   // W is stored transposed: element (k,n) at W[n*ldw + k]
+};
+
+template <typename TA, typename TW, typename TB, typename TC>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmP p) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Ws[16][64 + 4];
+  const int b = blockIdx.z;
+  const int wb = p.sW == 0 ? 0 : (p.widx ? p.widx[b] : b);
+  const TA* A = reinterpret_cast<const TA*>(p.A) + (int64_t)b * p.sA;
+  const TW* W = reinterpret_cast<const TW*>(p.W) + (int64_t)wb * p.sW;
+  const TB* bias = p.bias ? reinterpret_cast<const TB*>(p.bias) + (int64_t)wb * p.sBias : nullptr;
+  TC* C = reinterpret_cast<TC*>(p.C) + (int64_t)b * p.sC;
+  const float* R = p.R ? p.R + (int64_t)b * p.sR : nullptr;
+
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int ar = tid >> 2, ak = (tid & 3) * 4;   // A tile: 64 rows x 16 k
+  const int wk = tid >> 4, wn = (tid & 15) * 4;  // W tile: 16 k x 64 n
+  for (int k0 = 0; k0 < p.K; k0 += 16) {
+    {
+      const int m = m0 + ar;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) As[ak + j][ar] = (m < p.M) ? to_f(A[(int64_t)m * p.lda + k0 + ak + j]) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + wn + j;
+        Ws[wk][wn + j] = (n < p.N) ? to_f(p.wt ? W[(int64_t)n * p.ldw + k0 + wk] : W[(int64_t)(k0 + wk) * p.ldw + n]) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (bias) v += to_f(bias[n]);
+      if (p.out_scale != 1.0f) v *= p.out_scale;
+      if (p.act == 1) v = gelu_tanh_f(v);
+      else if (p.act == 2) v = gelu_erf_f(v);
+      if (p.ls) v *= p.ls[n];
+      if (R) v = R[(int64_t)m * p.ldr + n] + v;
+      from_f(C[(int64_t)m * p.ldc + n], v);
+    }
+  }
+}
+
+template <typename TA, typename TW, typename TB, typename TC>
+inline int gemm_simt(cudaStream_t st, const GemmP& p, int batch) {
+  if (p.K % 16 != 0 || p.M <= 0 || p.N <= 0 || batch <= 0) return fail(HVLA_ERR_ARG, "gemm_simt: bad shape");
+  dim3 grid(cdiv(p.N, 64), cdiv(p.M, 64), batch);
+  gemm_simt_kernel<TA, TW, TB, TC><<<grid, 256, 0, st>>>(p);
+  HVLA_LAUNCH_CHECK("gemm_simt");
+  return HVLA_OK;
+}
+
+inline GemmP gemm_params(const void* A, int lda, const void* W, int ldw, const void* bias, void* C, int ldc,
+                         int M, int N, int K) {
+  GemmP p;
+  memset(&p, 0, sizeof p);
+  p.A = A; p.lda = lda; p.W = W; p.ldw = ldw; p.bias = bias; p.C = C; p.ldc = ldc;
+  p.M = M; p.N = N; p.K = K; p.out_scale = 1.0f;
+  return p;
+}
+
+// =============================================================================================
+// LayerNorm (flax: eps 1e-6, fast variance E[x^2]-E[x]^2 clipped at 0), one warp per row.
+// scale/bias may be per-batch (per-sample generated weights).  D in {64,128,768}.
+// =============================================================================================
+struct LnP {
+  const float* x; int64_t ldx;      // row stride (elements)
+  void* y; int64_t ldy;
+  const void* scale; const void* bias; int64_t sS;   // per weight-batch stride (0 = shared)
+  const int* widx; int rows_per_batch;
+  int rows; float post_div;          // y /= post_div when != 0
+};
+
+template <typename TS, typename TO, int D>
+__global__ void __launch_bounds__(128) layernorm_kernel(LnP p) {
+  constexpr int PER = D / 32;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.rows) return;
+  const float* x = p.x + (int64_t)row * p.ldx;
+  float v[PER];
+  float s = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    v[i] = x[lane + 32 * i];
+    s += v[i];
+    s2 = fmaf(v[i], v[i], s2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const float mean = s / (float)D;
+  const float mean2 = s2 / (float)D;
+  const float var = fmaxf(0.f, mean2 - mean * mean);
+  const float rstd = 1.0f / sqrtf(var + 1e-6f);
+  int wb = 0;
+  if (p.sS != 0) {
+    const int b = row / p.rows_per_batch;
+    wb = p.widx ? p.widx[b] : b;
+  }
+  const TS* sc = reinterpret_cast<const TS*>(p.scale) + (int64_t)wb * p.sS;
+  const TS* bi = reinterpret_cast<const TS*>(p.bias) + (int64_t)wb * p.sS;
+  TO* y = reinterpret_cast<TO*>(p.y) + (int64_t)row * p.ldy;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = lane + 32 * i;
+    float o = (v[i] - mean) * (rstd * to_f(sc[c])) + to_f(bi[c]);
+    if (p.post_div != 0.f) o = o / p.post_div;
+    from_f(y[c], o);
+  }
+}
+
+template <typename TS, typename TO>
+inline int layernorm(cudaStream_t st, const LnP& p, int D) {
+  dim3 grid(cdiv(p.rows, 4));
+  if (D == 64) layernorm_kernel<TS, TO, 64><<<grid, 128, 0, st>>>(p);
+  else if (D == 128) layernorm_kernel<TS, TO, 128><<<grid, 128, 0, st>>>(p);
+  else if (D == 768) layernorm_kernel<TS, TO, 768><<<grid, 128, 0, st>>>(p);
+  else return fail(HVLA_ERR_ARG, "layernorm: unsupported width");
+  HVLA_LAUNCH_CHECK("layernorm");
+  return HVLA_OK;
+}
+
+// =============================================================================================
+// Attention over a packed qkv buffer [rows, 3*H*DH] (q | k | v), one warp per query row.
+// q is divided by sqrt(DH) first (flax dot_product_attention_weights), masked scores are
+// finfo(f32).min (-FLT_MAX), softmax fp32.
+//   mask 0: none (DINOv2)
+//   mask 1: base ViT   -- key S-1 (action token) visible only to query S-1 (base_vit.py:209-214)
+//   mask 2: context    -- keys 0..31: tok_mask & lang_pad; key 32: 1; key 33: only query 33
+//                         (hypernetwork.py:151-181)
+// =============================================================================================
+struct AttnP {
+  const void* qkv; void* out;      // out [rows, H*DH]
+  int S, H, nbatch, mask;
+  const int32_t* tok_mask;         // [nbatch, 32] (mask 2)
+  const uint8_t* lang_pad;         // [nbatch] or null
+  int prescaled;                   // q already divided by sqrt(DH)
+};
+
+template <typename T, typename TO, int DH_>
+__global__ void __launch_bounds__(128) attention_simt_kernel(AttnP p) {
+  constexpr int MAXK = 9;  // keys per lane: S <= 288
+  __shared__ float qs[4][DH_];
+  __shared__ float ps[4][288];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 4 + w;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int D = p.H * DH_, ld = 3 * D;
+  if (q >= p.S) return;  // whole warp exits together (q is warp-uniform); no block-level sync below
+  const T* base = reinterpret_cast<const T*>(p.qkv) + (int64_t)b * p.S * ld;
+  const T* qp = base + (int64_t)q * ld + h * DH_;
+  const float inv = sqrtf((float)DH_);
+  for (int d = lane; d < DH_; d += 32) qs[w][d] = p.prescaled ? to_f(qp[d]) : to_f(qp[d]) / inv;
+  __syncwarp();
+  float sc[MAXK];
+  float m = -FLT_MAX;
+#pragma unroll
+  for (int i = 0; i < MAXK; ++i) {
+    const int key = lane + 32 * i;
+    float s = -FLT_MAX;
+    if (key < p.S) {
+      const T* kp = base + (int64_t)key * ld + D + h * DH_;
+      float a = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < DH_; ++d) a = fmaf(qs[w][d], to_f(kp[d]), a);
+      bool ok = true;
+      if (p.mask == 1) ok = (key != p.S - 1) || (q == p.S - 1);
+      else if (p.mask == 2) {
+        if (key < 32) ok = (p.tok_mask[b * 32 + key] != 0) && (p.lang_pad ? p.lang_pad[b] != 0 : true);
+        else if (key == 33) ok = (q == 33);
+      }
+      s = ok ? a : -FLT_MAX;
+      m = fmaxf(m, s);
+    }
+    sc[i] = s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXK; ++i) {
+    const int key = lane + 32 * i;
+    if (key < p.S) {
+      const float e = expf(sc[i] - m);
+      sc[i] = e;
+      sum += e;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+  for (int i = 0; i < MAXK; ++i) {
+    const int key = lane + 32 * i;
+    if (key < p.S) ps[w][key] = sc[i] / sum;
+  }
+  __syncwarp();
+  TO* op = reinterpret_cast<TO*>(p.out) + ((int64_t)b * p.S + q) * D + h * DH_;
+  for (int d = lane; d < DH_; d += 32) {
+    float a = 0.f;
+    const T* vp = base + 2 * D + h * DH_ + d;
+    for (int key = 0; key < p.S; ++key) a = fmaf(ps[w][key], to_f(vp[(int64_t)key * ld]), a);
+    from_f(op[d], a);
+  }
+}
+
+template <typename T, typename TO>
+inline int attention_simt(cudaStream_t st, const AttnP& p, int dh) {
+  if (p.S > 288) return fail(HVLA_ERR_ARG, "attention_simt: S too large");
+  dim3 grid(cdiv(p.S, 4), p.H, p.nbatch);
+  if (dh == 16) attention_simt_kernel<T, TO, 16><<<grid, 128, 0, st>>>(p);
+  else if (dh == 32) attention_simt_kernel<T, TO, 32><<<grid, 128, 0, st>>>(p);
+  else if (dh == 64) attention_simt_kernel<T, TO, 64><<<grid, 128, 0, st>>>(p);
+  else return fail(HVLA_ERR_ARG, "attention_simt: unsupported head dim");
+  HVLA_LAUNCH_CHECK("attention_simt");
+  return HVLA_OK;
+}
+
+// =============================================================================================
+// Small data-movement kernels
+// =============================================================================================
+// (u8/255 - mean)/std, im2col of the VALID 14x14/14 conv: A0[b*256+p, k], k = (kh,kw,c), K padded to 640.
+template <typename TO>
+__global__ void im2col_norm_kernel(const uint8_t* __restrict__ img, TO* __restrict__ out, int B) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * NPATCH * PATCH_KP;
+  if (idx >= total) return;
+  const int k = (int)(idx % PATCH_KP);
+  const int64_t row = idx / PATCH_KP;
+  const int pidx = (int)(row % NPATCH), b = (int)(row / NPATCH);
+  float v = 0.f;
+  if (k < PATCH_K) {
+    const int kh = k / 42, rem = k % 42, kw = rem / 3, c = rem % 3;
+    const int py = pidx / GRID, px = pidx % GRID;
+    const uint8_t pix = img[(((int64_t)b * IMG + py * PATCH + kh) * IMG + px * PATCH + kw) * 3 + c];
+    const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+    const float sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+    v = ((float)pix / 255.0f - mean) / sd;   // base_vit.py:111-114
+  }
+  from_f(out[idx], v);
+}
+
+// X[b,0,:] = cls + pos[0];  X[b,1+p,:] = P[b*256+p,:] + pos[1+p]   (fp32 residual stream)
+template <typename TP>
+__global__ void dino_assemble_kernel(const TP* __restrict__ P, const float* __restrict__ cls,
+                                     const float* __restrict__ pos, float* __restrict__ X, int B) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * DTOK * DD;
+  if (idx >= total) return;
+  const int c = (int)(idx % DD);
+  const int64_t row = idx / DD;
+  const int t = (int)(row % DTOK), b = (int)(row / DTOK);
+  const float base = t == 0 ? cls[c] : to_f(P[((int64_t)b * NPATCH + (t - 1)) * DD + c]);
+  X[idx] = base + pos[t * DD + c];
+}
+
+// context tokens (hypernetwork.py:112-147): [T,34,128]
+__global__ void ctx_assemble_kernel(const float* __restrict__ TPj, const float* __restrict__ IPj,
+                                    const float* __restrict__ task_pos, const float* __restrict__ img_pos,
+                                    const float* __restrict__ layer_pos, float* __restrict__ X, int T) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)T * CTOK * CD;
+  if (idx >= total) return;
+  const int c = (int)(idx % CD);
+  const int64_t row = idx / CD;
+  const int j = (int)(row % CTOK), t = (int)(row / CTOK);
+  float v;
+  if (j < LANG) v = TPj[((int64_t)t * LANG + j) * CD + c] + task_pos[j * CD + c];
+  else if (j == LANG) v = IPj[(int64_t)t * CD + c] + img_pos[c];
+  else v = 0.f + layer_pos[c];
+  X[idx] = v;
+}
+
+// base-ViT tokens (base_vit.py:182-204): X[b,p,:] = patches + pos;  X[b,256,:] = 0 + pos[256]
+template <typename TW>
+__global__ void base_assemble_kernel(const float* __restrict__ Pt, const TW* __restrict__ weights,
+                                     const int* __restrict__ tidx, float* __restrict__ X, int B) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * BTOK * BD;
+  if (idx >= total) return;
+  const int c = (int)(idx % BD);
+  const int64_t row = idx / BD;
+  const int t = (int)(row % BTOK), b = (int)(row / BTOK);
+  const TW* pos = weights + (int64_t)(tidx ? tidx[b] : b) * NGP + GenLayout::pos;
+  const float base = t < NPATCH ? Pt[((int64_t)b * NPATCH + t) * BD + c] : 0.f;
+  X[idx] = base + to_f(pos[t * BD + c]);
+}
+
+// =============================================================================================
+// Final encoder_norm on the action token + mix action head (action_heads.py:455-470, 536-537)
+// one warp per environment.
+// =============================================================================================
+template <typename TW>
+__global__ void __launch_bounds__(128) mix_head_kernel(const float* __restrict__ X /*[B,257,64]*/,
+                                                       const TW* __restrict__ weights, const int* __restrict__ tidx,
+                                                       float* __restrict__ action, float* __restrict__ logit_out, int B) {
+  __shared__ float hs[4][BD];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + w;
+  if (b >= B) return;
+  const TW* wr = weights + (int64_t)(tidx ? tidx[b] : b) * NGP;
+  const float* x = X + ((int64_t)b * BTOK + (BTOK - 1)) * BD;
+  float v0 = x[lane], v1 = x[lane + 32];
+  float s = v0 + v1, s2 = fmaf(v0, v0, v1 * v1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const float mean = s / 64.f, var = fmaxf(0.f, s2 / 64.f - mean * mean);
+  const float rstd = 1.0f / sqrtf(var + 1e-6f);
+  hs[w][lane] = (v0 - mean) * (rstd * to_f(wr[GenLayout::encn_s + lane])) + to_f(wr[GenLayout::encn_b + lane]);
+  hs[w][lane + 32] = (v1 - mean) * (rstd * to_f(wr[GenLayout::encn_s + lane + 32])) + to_f(wr[GenLayout::encn_b + lane + 32]);
+  __syncwarp();
+  if (lane < NCONT) {
+    float a = 0.f;
+    for (int k = 0; k < BD; ++k) a = fmaf(hs[w][k], to_f(wr[GenLayout::wc + k * NCONT + lane]), a);
+    a += to_f(wr[GenLayout::bc + lane]);
+    a = tanhf(a / 5.0f) * 5.0f;
+    action[(int64_t)b * (AH * AD) + (lane / 6) * AD + (lane % 6)] = a;
+  } else if (lane < NCONT + AH) {
+    const int j = lane - NCONT;
+    float a = 0.f;
+    for (int k = 0; k < BD; ++k) a = fmaf(hs[w][k], to_f(wr[GenLayout::wd + k * AH + j]), a);
+    a += to_f(wr[GenLayout::bd + j]);
+    action[(int64_t)b * (AH * AD) + j * AD + 6] = a >= 0.f ? 1.0f : 0.0f;
+    if (logit_out) logit_out[(int64_t)b * AH + j] = a;
+  }
+}
+
+// =============================================================================================
+// Generation heads: out[T, NGP] = E[T,128] * W[128, NGP] + b   (the 73 Dense heads of
+// hypernetwork.py:205-217 as one skinny GEMM).  HBM-bound on W for small T.
+// Each thread owns 4 adjacent columns; tasks are processed 8 at a time from smem.
+// =============================================================================================
+template <typename TW> struct Vec4;
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec4<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[4]) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t;
+    t.x = *reinterpret_cast<uint32_t*>(&a);
+    t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+
+constexpr int HEADS_TT = 8;
+template <typename TW, typename TO>
+__global__ void __launch_bounds__(256) heads_gemm_kernel(const float* __restrict__ E, const TW* __restrict__ W,
+                                                         const float* __restrict__ bias, TO* __restrict__ out, int T) {
+  __shared__ float es[HEADS_TT][CD];
+  const int64_t col = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  const bool active = col < NGP;
+  float bv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active) Vec4<float>::load(bias + col, bv);
+  for (int t0 = 0; t0 < T; t0 += HEADS_TT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < HEADS_TT * CD; i += 256) {
+      const int tt = i / CD, k = i % CD;
+      es[tt][k] = (t0 + tt < T) ? E[(int64_t)(t0 + tt) * CD + k] : 0.f;
+    }
+    __syncthreads();
+    if (!active) continue;
+    float acc[HEADS_TT][4];
+#pragma unroll
+    for (int tt = 0; tt < HEADS_TT; ++tt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[tt][j] = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < CD; ++k) {
+      float w[4];
+      Vec4<TW>::load(W + (int64_t)k * NGP + col, w);
+#pragma unroll
+      for (int tt = 0; tt < HEADS_TT; ++tt) {
+        const float e = es[tt][k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[tt][j] = fmaf(e, w[j], acc[tt][j]);
+      }
+    }
+#pragma unroll
+    for (int tt = 0; tt < HEADS_TT; ++tt) {
+      if (t0 + tt < T) {
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = acc[tt][j] + bv[j];
+        Vec4<TO>::store(out + (int64_t)(t0 + tt) * NGP + col, o);
+      }
+    }
+  }
+}
+
+}  // namespace hvla

@@ -1,0 +1,184 @@
+"""Device-side state of one HyperVLA model on one B200: packed parameter blobs, workspace,
+pinned staging buffers, and the calls into libhvla.so.  PyTorch is used only for device
+memory, streams and pinned host memory (plumbing); all compute is in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _native as N
+from . import config as Cfg
+from . import metadata as M
+from . import params as P
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Runtime:
+    def __init__(self, params: dict, precision: str = "bf16", device: Optional[object] = None):
+        torch = _torch()
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if not torch.cuda.is_available():
+            raise N.HvlaError("no CUDA device: the hvla hot path is CUDA-only (there is no CPU fallback)")
+        self.lib = N.lib()
+        self.precision = precision
+        self.dtype = N.HVLA_BF16 if precision == "bf16" else N.HVLA_F32
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.tdtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self._ws = None
+        self._ws_key = (0, 0)
+        self._pinned = {}
+        self.upload(params)
+
+    # ---- parameters -------------------------------------------------------------------------------
+    def upload(self, params: dict) -> None:
+        torch = _torch()
+        dev = self.device
+        hn = P.pack_hn_blob(params)
+        assert hn.size == self.lib.hvla_hn_blob_elems()
+        self.hn_blob = torch.from_numpy(hn).to(dev)
+        W, b = P.pack_heads(params)
+        self.heads_w = torch.from_numpy(W).to(self.tdtype).to(dev)
+        self.heads_b = torch.from_numpy(b).to(dev)
+        del W
+        vec, mat = P.pack_dino(params, transposed=(self.precision == "bf16"))
+        assert vec.size == self.lib.hvla_dino_vec_elems() and mat.size == self.lib.hvla_dino_mat_elems()
+        self.dino_vec = torch.from_numpy(vec).to(dev)
+        self.dino_mat = torch.from_numpy(mat).to(self.tdtype).to(dev)
+        del mat
+        self._params_id = id(params)
+
+    # ---- scratch ------------------------------------------------------------------------------------
+    def workspace(self, B: int, T: int):
+        torch = _torch()
+        kb, kt = self._ws_key
+        if self._ws is None or B > kb or T > kt:
+            nb, nt = max(B, kb), max(T, kt)
+            nbytes = int(self.lib.hvla_workspace_bytes(nb, nt, self.dtype))
+            self._ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            self._ws_key = (nb, nt)
+        ptr = (self._ws.data_ptr() + 255) & ~255
+        return ptr, self._ws.numel() - (ptr - self._ws.data_ptr())
+
+    def pinned(self, name: str, shape, dtype):
+        torch = _torch()
+        t = self._pinned.get(name)
+        n = int(np.prod(shape))
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(n, dtype=dtype).pin_memory()
+            self._pinned[name] = t
+        return t[:n].view(*shape)
+
+    def stream(self) -> int:
+        return int(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    # ---- generate -------------------------------------------------------------------------------------
+    def generate(self, token_embedding, attention_mask, init_cls, lang_pad=None):
+        """-> (weights [T, NGP] device tensor, ctx_emb [T,128] device tensor)"""
+        torch = _torch()
+        dev = self.device
+        tok = torch.as_tensor(np.ascontiguousarray(token_embedding, dtype=np.float32) if not torch.is_tensor(token_embedding)
+                              else token_embedding).to(dev, torch.float32).contiguous()
+        T = int(tok.shape[0])
+        if tuple(tok.shape[1:]) != (Cfg.LANG_TOKENS, Cfg.LANG_DIM):
+            raise ValueError(f"token_embedding must be (T,{Cfg.LANG_TOKENS},{Cfg.LANG_DIM}), got {tuple(tok.shape)}")
+        am = torch.as_tensor(np.asarray(attention_mask) if not torch.is_tensor(attention_mask) else attention_mask)
+        am = am.to(dev).to(torch.int32).contiguous()
+        cls = torch.as_tensor(np.ascontiguousarray(init_cls, dtype=np.float32) if not torch.is_tensor(init_cls) else init_cls)
+        cls = cls.to(dev, torch.float32).contiguous()
+        if tuple(am.shape) != (T, Cfg.LANG_TOKENS) or tuple(cls.shape) != (T, Cfg.DINO_DIM):
+            raise ValueError("attention_mask must be (T,32) and the initial-image CLS embedding (T,768)")
+        pad_ptr = None
+        if lang_pad is not None:
+            pad = torch.as_tensor(np.asarray(lang_pad)).to(dev).to(torch.uint8).contiguous()
+            pad_ptr = pad.data_ptr()
+        out = torch.empty((T, M.N_GENERATED_PADDED), dtype=self.tdtype, device=dev)
+        ctx = torch.empty((T, Cfg.CTX_DIM), dtype=torch.float32, device=dev)
+        ws, ws_bytes = self.workspace(0, T)
+        st = self.lib.hvla_generate(self.stream(), self.hn_blob.data_ptr(), self.heads_w.data_ptr(), self.heads_b.data_ptr(),
+                                    tok.data_ptr(), am.data_ptr(), pad_ptr, cls.data_ptr(), T, out.data_ptr(), ctx.data_ptr(),
+                                    ws, ws_bytes, self.dtype)
+        N.check(st, "hvla_generate")
+        return out, ctx
+
+    # ---- act --------------------------------------------------------------------------------------------
+    def _tidx(self, task_index, B, T):
+        torch = _torch()
+        if task_index is None:
+            if T not in (1, B):
+                raise ValueError(f"task_index is required when T ({T}) is neither 1 nor B ({B})")
+            return None, None
+        ti = torch.as_tensor(np.asarray(task_index) if not torch.is_tensor(task_index) else task_index)
+        ti = ti.to(self.device).to(torch.int32).contiguous()
+        if tuple(ti.shape) != (B,):
+            raise ValueError("task_index must have shape (B,)")
+        return ti, ti.data_ptr()
+
+    def act_device(self, images, weights, task_index=None):
+        """images: uint8 CUDA tensor (B,224,224,3); returns (action, logit) CUDA tensors (async)."""
+        torch = _torch()
+        B, T = int(images.shape[0]), int(weights.shape[0])
+        if tuple(images.shape[1:]) != (Cfg.IMAGE_SIZE, Cfg.IMAGE_SIZE, 3) or images.dtype != torch.uint8:
+            raise ValueError("Input image size must be 224x224 (uint8, NHWC)")   # base_vit.py:87-89
+        images = images.contiguous()
+        keep, tptr = self._tidx(task_index, B, T)
+        act = torch.empty((B, Cfg.ACTION_HORIZON, Cfg.ACTION_DIM), dtype=torch.float32, device=self.device)
+        logit = torch.empty((B, Cfg.ACTION_HORIZON), dtype=torch.float32, device=self.device)
+        ws, ws_bytes = self.workspace(B, 0)
+        st = self.lib.hvla_act(self.stream(), self.dino_vec.data_ptr(), self.dino_mat.data_ptr(), images.data_ptr(),
+                               weights.data_ptr(), tptr, B, T, act.data_ptr(), logit.data_ptr(), ws, ws_bytes, self.dtype)
+        N.check(st, "hvla_act")
+        return act, logit
+
+    def act_host(self, images, weights, task_index=None):
+        """images: host uint8 (numpy or pinned torch CPU tensor) (B,224,224,3); returns numpy
+        (action (B,4,7), logit (B,4)).  Includes H2D + D2H + one stream sync."""
+        torch = _torch()
+        if torch.is_tensor(images):
+            if images.dtype != torch.uint8 or tuple(images.shape[1:]) != (Cfg.IMAGE_SIZE, Cfg.IMAGE_SIZE, 3):
+                raise ValueError("Input image size must be 224x224 (uint8, NHWC)")
+            src = images.contiguous()
+        else:
+            arr = np.ascontiguousarray(images)
+            if arr.dtype != np.uint8 or arr.shape[1:] != (Cfg.IMAGE_SIZE, Cfg.IMAGE_SIZE, 3):
+                raise ValueError("Input image size must be 224x224 (uint8, NHWC)")
+            src = self.pinned("img", arr.shape, torch.uint8)
+            src.numpy()[...] = arr
+        B, T = int(src.shape[0]), int(weights.shape[0])
+        keep, tptr = self._tidx(task_index, B, T)
+        act = self.pinned("act", (B, Cfg.ACTION_HORIZON, Cfg.ACTION_DIM), torch.float32)
+        logit = self.pinned("logit", (B, Cfg.ACTION_HORIZON), torch.float32)
+        ws, ws_bytes = self.workspace(B, 0)
+        st = self.lib.hvla_act_host(self.stream(), self.dino_vec.data_ptr(), self.dino_mat.data_ptr(), src.data_ptr(),
+                                    weights.data_ptr(), tptr, B, T, act.data_ptr(), logit.data_ptr(), ws, ws_bytes, self.dtype)
+        N.check(st, "hvla_act_host")
+        return act.numpy().copy(), logit.numpy().copy()
+
+    def dino_forward(self, images):
+        torch = _torch()
+        B = int(images.shape[0])
+        out = torch.empty((B, Cfg.DINO_TOKENS, Cfg.DINO_DIM), dtype=self.tdtype, device=self.device)
+        ws, ws_bytes = self.workspace(B, 0)
+        st = self.lib.hvla_dino_forward(self.stream(), self.dino_vec.data_ptr(), self.dino_mat.data_ptr(),
+                                        images.contiguous().data_ptr(), B, out.data_ptr(), ws, ws_bytes, self.dtype)
+        N.check(st, "hvla_dino_forward")
+        return out
+
+    def base_act(self, emb, weights, task_index=None):
+        torch = _torch()
+        B, T = int(emb.shape[0]), int(weights.shape[0])
+        keep, tptr = self._tidx(task_index, B, T)
+        act = torch.empty((B, Cfg.ACTION_HORIZON, Cfg.ACTION_DIM), dtype=torch.float32, device=self.device)
+        logit = torch.empty((B, Cfg.ACTION_HORIZON), dtype=torch.float32, device=self.device)
+        ws, ws_bytes = self.workspace(B, 0)
+        st = self.lib.hvla_base_act(self.stream(), emb.contiguous().data_ptr(), weights.data_ptr(), tptr, B, T,
+                                    act.data_ptr(), logit.data_ptr(), ws, ws_bytes, self.dtype)
+        N.check(st, "hvla_base_act")
+        return act, logit

@@ -1,0 +1,126 @@
+/*
+ * hvla.h -- C ABI of the B200-native HyperVLA inference hot path (libhvla.so).
+ *
+ * The reference (MasterXiong/Hyper-VLA) has no FFI or plugin interface: its boundary is
+ * the Python object API of `HyperVLA` (hypervla/model.py:24-137).  These entry points are
+ * what a `jax.ffi` / XLA custom-call binding for that path would bind instead of the
+ * Flax `apply` calls; each one cites the reference code it replaces.  INTEGRATION.md
+ * shows the reference-side stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every buffer is owned by the caller;
+ *   - every function returns 0 (HVLA_OK) or a negative HVLA_ERR_* code and never
+ *     throws or aborts; `hvla_last_error()` returns a thread-local message;
+ *   - all launches are asynchronous on `stream`; no host synchronisation inside
+ *     (except the *_host entry points, which say so);
+ *   - `dtype` selects the arithmetic: HVLA_F32 = exact fp32 CUDA-core path (parity
+ *     <= 1e-5 against the fp32 oracle); HVLA_BF16 = tensor-core path (bf16 operands,
+ *     fp32 accumulation; parity <= 2e-2);
+ *   - there is no CPU fallback: without a CUDA device every compute entry point
+ *     returns HVLA_ERR_CUDA.
+ *
+ * Blob layouts (element offsets can be queried with hvla_layout_offset()):
+ *   HN blob (fp32):   tok_proj_w[768,128] tok_proj_b[128] img_proj_w[768,128] img_proj_b[128]
+ *                     task_pos[32,128] img_pos[128] layer_pos[128]
+ *                     6 x { ln0_s ln0_b wqkv[128,384] bqkv[384] wo[128,128] bo ln1_s ln1_b
+ *                           w0[128,512] b0[512] w1[512,128] b1[128] }  encn_s encn_b
+ *   heads:            W[128, NGP] (dtype) and b[NGP] (fp32); NGP = 201504 (201500 used).
+ *                     Column order = packed per-task weight row (below).
+ *   generated row:    [NGP] (dtype): proj_w[768,64] proj_b[64] pos[257,64]
+ *                     4 x { ln0_s ln0_b wq[64,64] bq wk bk wv bv wo[64,64] bo ln1_s ln1_b
+ *                           w0[64,128] b0[128] w1[128,64] b1[64] }
+ *                     encn_s encn_b wc[64,24] bc[24] wd[64,4] bd[4]
+ *   DINO vec (fp32):  patch_b[768] cls[768] pos[257,768]
+ *                     12 x { ln1_s ln1_b bqkv[2304] bo ls1 ln2_s ln2_b b1[3072] b2 ls2 } lnf_s lnf_b
+ *   DINO mat:         patch_w, 12 x { wqkv wo w1 w2 }.  HVLA_F32: fp32, Flax [K,N] layout,
+ *                     patch K padded 588->640.  HVLA_BF16: bf16, transposed [N,K] (K contiguous).
+ */
+#ifndef HVLA_H_
+#define HVLA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* hvla_stream_t; /* cudaStream_t */
+
+enum { HVLA_OK = 0, HVLA_ERR_ARG = -1, HVLA_ERR_CUDA = -2, HVLA_ERR_UNSUPPORTED = -3, HVLA_ERR_WORKSPACE = -4 };
+enum { HVLA_F32 = 0, HVLA_BF16 = 1 };
+
+/* ---- host-only queries (usable without a GPU) -------------------------------------- */
+int hvla_version(void);
+const char* hvla_last_error(void);
+int64_t hvla_hn_blob_elems(void);
+int64_t hvla_generated_elems(void);        /* 201500 */
+int64_t hvla_generated_row_stride(void);   /* NGP = 201504 */
+int64_t hvla_dino_vec_elems(void);
+int64_t hvla_dino_mat_elems(void);
+/* element offset of a named field: "hn.<field>", "gen.<field>", "dvec.<field>", "dmat.<field>";
+ * per-layer fields are "l<k>.<field>".  Returns -1 for an unknown name. */
+int64_t hvla_layout_offset(const char* name);
+/* bytes of scratch the compute entry points need for B environments and T tasks */
+size_t hvla_workspace_bytes(int B, int T, int dtype);
+
+/* ---- generate: replaces HyperNetwork.apply inside HyperVLA.create_tasks -----------------
+ * (hypervla/model.py:73-80 -> hypervla/components/hypernetwork.py:99-233).
+ *   tok_emb   [T,32,768] f32  instruction_dict.language_instruction.token_embedding
+ *   tok_mask  [T,32]     i32  ...attention_mask
+ *   lang_pad  [T]        u8   tasks.pad_mask_dict.language_instruction (model.py:69: all ones); NULL = ones
+ *   init_cls  [T,768]    f32  initial_state.patch_embeddings[:, 0]   (hypernetwork.py:126)
+ *   out_weights [T,NGP] (dtype)  packed generated base-net weights, one row per task
+ *   out_ctx   [T,128] f32 or NULL  context embedding (second return of HyperNetwork.__call__) */
+int hvla_generate(hvla_stream_t stream, const float* hn_blob, const void* heads_w, const float* heads_b,
+                  const float* tok_emb, const int32_t* tok_mask, const uint8_t* lang_pad, const float* init_cls,
+                  int T, void* out_weights, float* out_ctx, void* workspace, size_t workspace_bytes, int dtype);
+
+/* ---- DINOv2 image encoder: replaces self.image_encoder(raw_images) + normalisation ------
+ * (hypervla/components/base_vit.py:111-122; FlaxDinov2Module of transformers==4.50.0).
+ *   images  [B,224,224,3] u8 (NHWC)      out_emb [B,257,768] (dtype) = last_hidden_state */
+int hvla_dino_forward(hvla_stream_t stream, const float* dino_vec, const void* dino_mat, const uint8_t* images,
+                      int B, void* out_emb, void* workspace, size_t workspace_bytes, int dtype);
+
+/* ---- base ViT with per-task generated weights + mix action head -------------------------
+ * (hypervla/components/base_vit.py:130-226, transformer.py:127-262, action_heads.py:455-470,
+ *  524-538; batching semantics of scripts/train.py:559-579).
+ *   emb [B,257,768] (dtype) DINOv2 last_hidden_state (row 0 = CLS is skipped, base_vit.py:122)
+ *   weights [T,NGP] (dtype); task_index [B] i32 or NULL (NULL: env b uses row b, needs T==B,
+ *   or T==1 shared)   out_action [B,4,7] f32   out_logit [B,4] f32 (gripper logits) or NULL */
+int hvla_base_act(hvla_stream_t stream, const void* emb, const void* weights, const int32_t* task_index,
+                  int B, int T, float* out_action, float* out_logit, void* workspace, size_t workspace_bytes, int dtype);
+
+/* ---- act = dino_forward + base_act: replaces base_net.apply(method=predict_action) -------
+ * inside HyperVLA.sample_actions (hypervla/model.py:125-136). */
+int hvla_act(hvla_stream_t stream, const float* dino_vec, const void* dino_mat, const uint8_t* images,
+             const void* weights, const int32_t* task_index, int B, int T,
+             float* out_action, float* out_logit, void* workspace, size_t workspace_bytes, int dtype);
+
+/* ---- same, HOST image/action buffers (pinned or pageable): H2D copy, act, D2H copy on
+ * `stream`, then ONE cudaStreamSynchronize.  The call InferenceWrapper.step makes
+ * (data/utils/hypervla_interface.py:197-207: model call followed by the host read). */
+int hvla_act_host(hvla_stream_t stream, const float* dino_vec, const void* dino_mat, const uint8_t* images_host,
+                  const void* weights, const int32_t* task_index, int B, int T,
+                  float* out_action_host, float* out_logit_host, void* workspace, size_t workspace_bytes, int dtype);
+
+/* ---- building blocks exported for tests / profiling -----------------------------------
+ * C[M,N] (bf16) = act(A[M,K] (bf16, row-major) * Wt[N,K]^T (bf16) + bias[N] (f32));
+ * act: 0 none, 2 erf-GELU.  The tcgen05/TMEM/TMA GEMM used by the DINOv2 blocks. */
+int hvla_gemm_bf16(hvla_stream_t stream, const void* A, const void* Wt, const float* bias, void* C,
+                   int M, int N, int K, int act);
+/* number of kernels launched by this library since load (for bench.py's gpu_launches) */
+int64_t hvla_launch_count(void);
+
+/* ---- legacy XLA GPU custom-call wrappers (jax<=0.4.30: xla_client.register_custom_call_target;
+ * signature void(cudaStream_t, void** buffers, const char* opaque, size_t opaque_len)).
+ * `opaque` = struct hvla_xla_opaque.  Buffer order = the argument order above (inputs, then
+ * outputs, then workspace).  Untestable in this image (no jax); see INTEGRATION.md. */
+struct hvla_xla_opaque { int32_t B, T, dtype, reserved; uint64_t workspace_bytes; };
+void hvla_xla_generate(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+void hvla_xla_act(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HVLA_H_ */

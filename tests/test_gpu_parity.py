@@ -1,0 +1,164 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every test calls through the C ABI
+(libhvla.so via ctypes) and checks against the CPU oracle / committed golden vectors.
+
+Tolerances (BASELINE.json north_star):
+  * fp32 path: max|x - ref| / max|ref| <= 1e-5 for generated weights and continuous actions;
+  * bf16 path: <= 2e-2;
+  * gripper bits identical wherever the reference logit magnitude exceeds 1e-3.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-5, "bf16": 2e-2}
+CASES = {"c1_b1_t1": (1, 1, 1), "c2_b3_t3": (2, 3, 3), "c5_b6_t2": (5, 6, 2)}
+
+
+def rel_err(x, ref):
+    x, ref = np.asarray(x, np.float64), np.asarray(ref, np.float64)
+    return float(np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device visible: -m gpu tests must run on the GPU box")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def models(params_p1, torch_cuda):
+    from hvla import config as C
+    from hvla.model import HyperVLA
+    out = {}
+    for prec in ("fp32", "bf16"):
+        out[prec] = HyperVLA.from_config(C.default_config(), precision=prec, params=params_p1)
+        out[prec].runtime  # upload now
+    return out
+
+
+def run_case(model, ci, B, T):
+    from hvla import synthetic as S
+    inp = S.make_inputs(ci, B, T)
+    base_params, tasks, _ = model.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"])
+    ti = None if T in (1, B) else inp["task_index"]
+    action, inter = model.sample_actions(inp["images"], inp["instruction_dict"], tasks, inp["timestep_pad_mask"], base_params,
+                                         task_index=ti)
+    return inp, base_params, action, inter["gripper_logits"]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", list(CASES))
+def test_generate_and_act_match_golden(models, golden, prec, case):
+    ci, B, T = CASES[case]
+    g = golden[case]
+    inp, bp, action, logit = run_case(models[prec], ci, B, T)
+    assert action.shape == (B, 4, 7) and action.dtype == np.float32
+    rows = bp.packed_numpy()
+    tol = TOL[prec]
+    e_ctx = rel_err(bp.context_embedding.cpu().numpy(), g["ctx"])
+    e_rows = rel_err(rows[:, ::97], g["rows_sample"])
+    e_sum = float(np.abs(np.abs(rows.astype(np.float64)).sum(1) - g["rows_abs"]).max() / g["rows_abs"].max())
+    e_act = rel_err(action[..., :6], g["action"][..., :6])
+    e_logit = rel_err(logit, g["logit"])
+    print(f"[{prec} {case}] ctx {e_ctx:.2e} rows {e_rows:.2e} abs-sum {e_sum:.2e} action {e_act:.2e} logit {e_logit:.2e}")
+    assert e_ctx <= (1e-5 if prec == "fp32" else 1e-5)       # the context encoder is fp32 in both modes
+    assert e_rows <= tol
+    assert e_sum <= tol
+    assert e_act <= tol
+    sure = np.abs(g["logit"]) > (1e-3 if prec == "fp32" else 2e-2 * np.abs(g["logit"]).max())
+    assert np.array_equal(action[..., 6][sure], g["action"][..., 6][sure])
+    assert set(np.unique(action[..., 6])) <= {0.0, 1.0}
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_dino_hidden_matches_golden(models, golden, torch_cuda, prec):
+    from hvla import synthetic as S
+    g = golden["c2_b3_t3"]
+    inp = S.make_inputs(2, 3, 3)
+    rt = models[prec].runtime
+    img = torch_cuda.from_numpy(inp["images"][:, 0]).to(rt.device)
+    hid = rt.dino_forward(img).float().cpu().numpy()
+    e = rel_err(hid[:, ::16, ::48], g["hidden_sample"])
+    em = rel_err(np.abs(hid).mean((1, 2)), g["hidden_abs_mean"])
+    print(f"[{prec}] dino hidden sample err {e:.2e}, abs-mean err {em:.2e}")
+    assert e <= TOL[prec] * (1 if prec == "bf16" else 2)
+    assert np.isfinite(hid).all()
+
+
+@pytest.mark.parametrize("shape", [(300, 256, 64, 0), (1285, 768, 768, 0), (1285, 3072, 768, 2), (771, 768, 3072, 0), (128, 2304, 640, 0)])
+def test_tcgen05_gemm_against_torch(torch_cuda, shape):
+    """The tcgen05/TMEM/TMA GEMM alone, against a float32 matmul of the same bf16 operands."""
+    torch = torch_cuda
+    from hvla import _native as N
+    M_, N_, K_, act = shape
+    gen = torch.Generator(device="cuda").manual_seed(M_ + N_ + K_)
+    A = (torch.randn(M_, K_, device="cuda", generator=gen)).to(torch.bfloat16)
+    Wt = (torch.randn(N_, K_, device="cuda", generator=gen) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N_, device="cuda", generator=gen)
+    Cout = torch.full((M_, N_), float("nan"), device="cuda", dtype=torch.bfloat16)
+    st = N.lib().hvla_gemm_bf16(int(torch.cuda.current_stream().cuda_stream), A.data_ptr(), Wt.data_ptr(), bias.data_ptr(),
+                                Cout.data_ptr(), M_, N_, K_, act)
+    N.check(st, "hvla_gemm_bf16")
+    torch.cuda.synchronize()
+    ref = A.float() @ Wt.float().t() + bias
+    if act == 2:
+        ref = torch.nn.functional.gelu(ref)
+    err = (Cout.float() - ref).abs().max().item() / ref.abs().max().item()
+    print(f"tc gemm {shape}: rel err {err:.3e}")
+    assert torch.isfinite(Cout.float()).all()
+    assert err < 1e-2
+
+
+def test_debug_cuda_core_paths_agree_with_tensor_core_paths(models, torch_cuda):
+    """bf16 mode: tcgen05 GEMM + mma.sync attention vs the same math on CUDA cores."""
+    from hvla import synthetic as S
+    inp = S.make_inputs(2, 3, 3)
+    rt = models["bf16"].runtime
+    img = torch_cuda.from_numpy(inp["images"][:, 0]).to(rt.device)
+    fast = rt.dino_forward(img).float().cpu().numpy()
+    os.environ["HVLA_DEBUG_SIMT_GEMM"] = "1"
+    os.environ["HVLA_DEBUG_SIMT_ATTN"] = "1"
+    try:
+        slow = rt.dino_forward(img).float().cpu().numpy()
+    finally:
+        os.environ.pop("HVLA_DEBUG_SIMT_GEMM"), os.environ.pop("HVLA_DEBUG_SIMT_ATTN")
+    e = rel_err(fast, slow)
+    print(f"tensor-core vs CUDA-core bf16 DINOv2: {e:.2e}")
+    assert e < 2e-2
+
+
+def test_edge_cases(models, torch_cuda):
+    from hvla import _native as N
+    from hvla import synthetic as S
+    m = models["fp32"]
+    inp = S.make_inputs(7, 4, 1)
+    bp, tasks, _ = m.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"])
+    # T == 1 weights shared by all envs == same env evaluated alone
+    a_all, _ = m.sample_actions(inp["images"], None, tasks, None, bp)
+    a_one, _ = m.sample_actions(inp["images"][2:3], None, tasks, None, bp)
+    assert np.array_equal(a_all[2:3], a_one)
+    # pytree view has Flax names and reference shapes (model.py:81 squeeze for T == 1)
+    t = bp["encoder"]["Transformer_0"]["encoderblock_2"]["MultiHeadDotProductAttention_0"]["query"]["kernel"]
+    assert t.shape == (64, 4, 16)
+    assert bp["encoder"]["image_encoder"]["embeddings"]["position_embeddings"].shape == (1, 1370, 768)
+    # empty batch
+    a0, _ = m.sample_actions(np.zeros((0, 1, 224, 224, 3), np.uint8), None, tasks, None, bp)
+    assert a0.shape == (0, 4, 7)
+    # wrong image size -> ValueError before any launch (base_vit.py:87-89)
+    with pytest.raises(ValueError):
+        m.sample_actions(np.zeros((1, 1, 256, 256, 3), np.uint8), None, tasks, None, bp)
+    # undersized workspace -> error code, not a crash
+    rt = m.runtime
+    st = N.lib().hvla_dino_forward(rt.stream(), rt.dino_vec.data_ptr(), rt.dino_mat.data_ptr(), rt.dino_vec.data_ptr(), 1,
+                                   rt.dino_vec.data_ptr(), rt.dino_vec.data_ptr(), 1024, rt.dtype)
+    assert st == -4
+    # device in -> device out
+    img = torch_cuda.from_numpy(inp["images"]).to(rt.device)
+    a_dev, inter = m.sample_actions(img, None, tasks, None, bp)
+    assert a_dev.is_cuda and np.array_equal(a_dev.cpu().numpy(), a_all)
