@@ -161,6 +161,7 @@ inline int dino_attention(cudaStream_t st, const bf16* qkv, bf16* out, int B) {
     attr = true;
   }
   dim3 grid(DH, B, QSPLIT);
+  ProfScope ps(st, "dino_attention");
   dino_attention_kernel<<<grid, WARPS * 32, SMEM, st>>>(qkv, out);
   HVLA_LAUNCH_CHECK("dino_attention");
   return HVLA_OK;

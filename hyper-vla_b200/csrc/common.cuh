@@ -7,6 +7,7 @@
 #include <string.h>
 #include <string>
 #include <atomic>
+#include <vector>
 
 #include "../../include/hvla.h"
 
@@ -101,6 +102,23 @@ inline int fail(int code, const char* fmt, const char* a = "", const char* b = "
     cudaError_t e__ = cudaPeekAtLastError();                                                \
     if (e__ != cudaSuccess) return ::hvla::fail(HVLA_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(e__)); \
   } while (0)
+
+// ---- optional per-kernel-class event timing (bench.py's live roofline measurement) --------------
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+struct ProfState { bool on = false; std::vector<ProfRec> recs; };
+extern ProfState g_prof;
+struct ProfScope {
+  cudaStream_t st; cudaEvent_t b = nullptr;
+  ProfScope(cudaStream_t s, const char* name) : st(s) {
+    if (!g_prof.on) return;
+    ProfRec r; r.name = name;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    b = r.b;
+    g_prof.recs.push_back(r);
+  }
+  ~ProfScope() { if (b) cudaEventRecord(b, st); }
+};
 
 #define HVLA_TRY(expr)        \
   do {                        \

@@ -347,6 +347,7 @@ inline int launch_one(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap&
   }
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  ProfScope ps(st, "gemm_tc");
   gemm_tc_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, ep, M, N, K);
   HVLA_LAUNCH_CHECK("gemm_tc");
   return HVLA_OK;

@@ -12,6 +12,7 @@ namespace hvla {
 
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
+ProfState g_prof;
 
 static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -561,6 +562,35 @@ int hvla_gemm_bf16(hvla_stream_t stream, const void* A, const void* Wt, const fl
   tc::EpiP ep; memset(&ep, 0, sizeof ep);
   ep.bias = bias; ep.out = C; ep.ldo = N;
   return tc::gemm_tc(reinterpret_cast<cudaStream_t>(stream), A, Wt, M, N, K, act == 2 ? tc::EPI_BIAS_GELU_BF16 : tc::EPI_BIAS_BF16, ep);
+}
+
+int hvla_profile_enable(int on) {
+  for (auto& r : g_prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.recs.clear();
+  g_prof.on = on != 0;
+  return HVLA_OK;
+}
+
+int hvla_profile_report(char* buf, size_t cap) {
+  if (!buf || cap == 0) return fail(HVLA_ERR_ARG, "hvla_profile_report: NULL buffer");
+  HVLA_CUDA(cudaDeviceSynchronize());
+  struct Agg { const char* name; int n; double ms; };
+  std::vector<Agg> agg;
+  for (auto& r : g_prof.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+    bool found = false;
+    for (auto& a : agg) if (!strcmp(a.name, r.name)) { a.n++; a.ms += ms; found = true; break; }
+    if (!found) agg.push_back({r.name, 1, (double)ms});
+  }
+  size_t off = 0;
+  buf[0] = 0;
+  for (auto& a : agg) {
+    int w = snprintf(buf + off, cap - off, "%s %d %.6f\n", a.name, a.n, a.ms);
+    if (w < 0 || (size_t)w >= cap - off) break;
+    off += (size_t)w;
+  }
+  return HVLA_OK;
 }
 
 // ---- legacy XLA custom-call wrappers (no status channel in this ABI revision: errors are logged) ---------

@@ -98,6 +98,7 @@ template <typename TA, typename TW, typename TB, typename TC>
 inline int gemm_simt(cudaStream_t st, const GemmP& p, int batch) {
   if (p.K % 16 != 0 || p.M <= 0 || p.N <= 0 || batch <= 0) return fail(HVLA_ERR_ARG, "gemm_simt: bad shape");
   dim3 grid(cdiv(p.N, 64), cdiv(p.M, 64), batch);
+  ProfScope ps(st, "gemm_simt");
   gemm_simt_kernel<TA, TW, TB, TC><<<grid, 256, 0, st>>>(p);
   HVLA_LAUNCH_CHECK("gemm_simt");
   return HVLA_OK;
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(128) layernorm_kernel(LnP p) {
 template <typename TS, typename TO>
 inline int layernorm(cudaStream_t st, const LnP& p, int D) {
   dim3 grid(cdiv(p.rows, 4));
+  ProfScope ps(st, "layernorm");
   if (D == 64) layernorm_kernel<TS, TO, 64><<<grid, 128, 0, st>>>(p);
   else if (D == 128) layernorm_kernel<TS, TO, 128><<<grid, 128, 0, st>>>(p);
   else if (D == 768) layernorm_kernel<TS, TO, 768><<<grid, 128, 0, st>>>(p);
@@ -263,6 +265,7 @@ template <typename T, typename TO>
 inline int attention_simt(cudaStream_t st, const AttnP& p, int dh) {
   if (p.S > 288) return fail(HVLA_ERR_ARG, "attention_simt: S too large");
   dim3 grid(cdiv(p.S, 4), p.H, p.nbatch);
+  ProfScope ps(st, "attention_simt");
   if (dh == 16) attention_simt_kernel<T, TO, 16><<<grid, 128, 0, st>>>(p);
   else if (dh == 32) attention_simt_kernel<T, TO, 32><<<grid, 128, 0, st>>>(p);
   else if (dh == 64) attention_simt_kernel<T, TO, 64><<<grid, 128, 0, st>>>(p);

@@ -131,6 +131,8 @@ class Runtime:
         keep, tptr = self._tidx(task_index, B, T)
         act = torch.empty((B, Cfg.ACTION_HORIZON, Cfg.ACTION_DIM), dtype=torch.float32, device=self.device)
         logit = torch.empty((B, Cfg.ACTION_HORIZON), dtype=torch.float32, device=self.device)
+        if B == 0:
+            return act, logit
         ws, ws_bytes = self.workspace(B, 0)
         st = self.lib.hvla_act(self.stream(), self.dino_vec.data_ptr(), self.dino_mat.data_ptr(), images.data_ptr(),
                                weights.data_ptr(), tptr, B, T, act.data_ptr(), logit.data_ptr(), ws, ws_bytes, self.dtype)
@@ -150,8 +152,11 @@ class Runtime:
             if arr.dtype != np.uint8 or arr.shape[1:] != (Cfg.IMAGE_SIZE, Cfg.IMAGE_SIZE, 3):
                 raise ValueError("Input image size must be 224x224 (uint8, NHWC)")
             src = self.pinned("img", arr.shape, torch.uint8)
-            src.numpy()[...] = arr
+            if arr.size:
+                src.numpy()[...] = arr
         B, T = int(src.shape[0]), int(weights.shape[0])
+        if B == 0:
+            return (np.zeros((0, Cfg.ACTION_HORIZON, Cfg.ACTION_DIM), np.float32), np.zeros((0, Cfg.ACTION_HORIZON), np.float32))
         keep, tptr = self._tidx(task_index, B, T)
         act = self.pinned("act", (B, Cfg.ACTION_HORIZON, Cfg.ACTION_DIM), torch.float32)
         logit = self.pinned("logit", (B, Cfg.ACTION_HORIZON), torch.float32)
@@ -160,6 +165,22 @@ class Runtime:
                                     weights.data_ptr(), tptr, B, T, act.data_ptr(), logit.data_ptr(), ws, ws_bytes, self.dtype)
         N.check(st, "hvla_act_host")
         return act.numpy().copy(), logit.numpy().copy()
+
+    def profile(self, fn, repeats: int = 1) -> dict:
+        """Run ``fn`` with per-kernel-class event timing on; -> {class: (launches, total_ms)} per repeat."""
+        self.lib.hvla_profile_enable(1)
+        try:
+            for _ in range(repeats):
+                fn()
+            buf = C.create_string_buffer(4096)
+            N.check(self.lib.hvla_profile_report(buf, 4096), "hvla_profile_report")
+        finally:
+            self.lib.hvla_profile_enable(0)
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split()
+            out[name] = (int(n) / repeats, float(ms) / repeats)
+        return out
 
     def dino_forward(self, images):
         torch = _torch()

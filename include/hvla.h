@@ -111,6 +111,11 @@ int hvla_gemm_bf16(hvla_stream_t stream, const void* A, const void* Wt, const fl
                    int M, int N, int K, int act);
 /* number of kernels launched by this library since load (for bench.py's gpu_launches) */
 int64_t hvla_launch_count(void);
+/* per-kernel-class CUDA-event timing on the launching stream (bench.py's live roofline numbers).
+ * enable(1) clears and starts recording an event pair around every launch; report() synchronises
+ * and writes one "name launches total_ms" line per kernel class. */
+int hvla_profile_enable(int on);
+int hvla_profile_report(char* buf, size_t cap);
 
 /* ---- legacy XLA GPU custom-call wrappers (jax<=0.4.30: xla_client.register_custom_call_target;
  * signature void(cudaStream_t, void** buffers, const char* opaque, size_t opaque_len)).

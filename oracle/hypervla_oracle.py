@@ -62,12 +62,8 @@ def gelu_tanh(x):
 def gelu_erf(x):
     """Exact GELU (HF ACT2FN['gelu']) used inside DINOv2."""
     dt = x.dtype
-    try:
-        from scipy.special import erf
-        e = erf(x.astype(np.float64) / math.sqrt(2.0))
-    except Exception:  # pragma: no cover
-        e = np.vectorize(math.erf)(x.astype(np.float64) / math.sqrt(2.0))
-    return (dt.type(0.5) * x * (dt.type(1) + e.astype(dt))).astype(dt)
+    from scipy.special import erf
+    return dt.type(0.5) * x * (dt.type(1) + erf(x * dt.type(1.0 / math.sqrt(2.0))))
 
 
 def softmax(x):
@@ -76,37 +72,50 @@ def softmax(x):
     return e / e.sum(axis=-1, keepdims=True)
 
 
+def _attend(q, k, v, mask):
+    """q,k,v (N,S,H,e) -> (N,S,H*e): q/sqrt(e), masked softmax(qk^T) v (batched matmuls, BLAS)."""
+    dt = q.dtype
+    q = q / dt.type(math.sqrt(q.shape[-1]))
+    s = np.matmul(q.transpose(0, 2, 1, 3), k.transpose(0, 2, 3, 1))          # (N,H,S,S)
+    if mask is not None:
+        s = np.where(mask, s, np.finfo(dt).min)
+    w = softmax(s)
+    o = np.matmul(w, v.transpose(0, 2, 1, 3))                                 # (N,H,S,e)
+    N, H, S, e = o.shape
+    return o.transpose(0, 2, 1, 3).reshape(N, S, H * e)
+
+
 def mha(x, p, mask):
     """flax.linen.MultiHeadDotProductAttention as called at transformer.py:183-190:
     q,k,v DenseGeneral -> q / sqrt(head_dim) -> where(mask, s, finfo.min) -> softmax ->
     weighted sum -> DenseGeneral over (heads, head_dim).  x: (N,S,d); mask: (N,1,S,S) bool."""
     dt = x.dtype
-    q = np.einsum("nsd,dhe->nshe", x, p["query"]["kernel"].astype(dt)) + p["query"]["bias"].astype(dt)
-    k = np.einsum("nsd,dhe->nshe", x, p["key"]["kernel"].astype(dt)) + p["key"]["bias"].astype(dt)
-    v = np.einsum("nsd,dhe->nshe", x, p["value"]["kernel"].astype(dt)) + p["value"]["bias"].astype(dt)
-    q = q / dt.type(math.sqrt(q.shape[-1]))
-    s = np.einsum("nqhe,nkhe->nhqk", q, k)
-    if mask is not None:
-        s = np.where(mask, s, np.finfo(dt).min)
-    w = softmax(s)
-    o = np.einsum("nhqk,nkhe->nqhe", w, v)
-    return np.einsum("nqhe,hed->nqd", o, p["out"]["kernel"].astype(dt)) + p["out"]["bias"].astype(dt)
+    N, S, d = x.shape
+
+    def proj(name):
+        w = p[name]["kernel"].astype(dt)
+        H, e = w.shape[1], w.shape[2]
+        return (x @ w.reshape(d, H * e) + p[name]["bias"].astype(dt).reshape(H * e)).reshape(N, S, H, e)
+
+    o = _attend(proj("query"), proj("key"), proj("value"), mask)
+    wo = p["out"]["kernel"].astype(dt)
+    return o @ wo.reshape(-1, wo.shape[-1]) + p["out"]["bias"].astype(dt)
 
 
 def mha_per_sample(x, p, mask):
     """Same as `mha` but every sample has its own weights (leaves carry a leading N):
     the jax.vmap of scripts/train.py:559-579."""
     dt = x.dtype
-    q = np.einsum("nsd,ndhe->nshe", x, p["query"]["kernel"].astype(dt)) + p["query"]["bias"].astype(dt)[:, None]
-    k = np.einsum("nsd,ndhe->nshe", x, p["key"]["kernel"].astype(dt)) + p["key"]["bias"].astype(dt)[:, None]
-    v = np.einsum("nsd,ndhe->nshe", x, p["value"]["kernel"].astype(dt)) + p["value"]["bias"].astype(dt)[:, None]
-    q = q / dt.type(math.sqrt(q.shape[-1]))
-    s = np.einsum("nqhe,nkhe->nhqk", q, k)
-    if mask is not None:
-        s = np.where(mask, s, np.finfo(dt).min)
-    w = softmax(s)
-    o = np.einsum("nhqk,nkhe->nqhe", w, v)
-    return np.einsum("nqhe,nhed->nqd", o, p["out"]["kernel"].astype(dt)) + p["out"]["bias"].astype(dt)[:, None]
+    N, S, d = x.shape
+
+    def proj(name):
+        w = p[name]["kernel"].astype(dt)
+        H, e = w.shape[2], w.shape[3]
+        return (np.matmul(x, w.reshape(N, d, H * e)) + p[name]["bias"].astype(dt).reshape(N, 1, H * e)).reshape(N, S, H, e)
+
+    o = _attend(proj("query"), proj("key"), proj("value"), mask)
+    wo = p["out"]["kernel"].astype(dt)
+    return np.matmul(o, wo.reshape(N, -1, wo.shape[-1])) + p["out"]["bias"].astype(dt)[:, None]
 
 
 # =====================================================================================
@@ -122,9 +131,9 @@ def encoder_block(x, p, mask, per_sample=False):
         x = x + mha_per_sample(y, p["MultiHeadDotProductAttention_0"], mask)
         y = _ln_ps(x, p["LayerNorm_1"]["scale"], p["LayerNorm_1"]["bias"])
         m = p["MlpBlock_0"]
-        h = np.einsum("nsd,ndf->nsf", y, m["Dense_0"]["kernel"].astype(dt)) + vec(m["Dense_0"]["bias"])
+        h = np.matmul(y, m["Dense_0"]["kernel"].astype(dt)) + vec(m["Dense_0"]["bias"])
         h = gelu_tanh(h)
-        h = np.einsum("nsf,nfd->nsd", h, m["Dense_1"]["kernel"].astype(dt)) + vec(m["Dense_1"]["bias"])
+        h = np.matmul(h, m["Dense_1"]["kernel"].astype(dt)) + vec(m["Dense_1"]["bias"])
         return x + h
     y = layer_norm(x, p["LayerNorm_0"]["scale"], p["LayerNorm_0"]["bias"])
     x = x + mha(y, p["MultiHeadDotProductAttention_0"], mask)
@@ -279,9 +288,7 @@ def dinov2_layer(x, L):
     q = (y @ a["query"]["kernel"].astype(dt) + a["query"]["bias"].astype(dt)).reshape(B, S, DINO_HEADS, hd)
     k = (y @ a["key"]["kernel"].astype(dt) + a["key"]["bias"].astype(dt)).reshape(B, S, DINO_HEADS, hd)
     v = (y @ a["value"]["kernel"].astype(dt) + a["value"]["bias"].astype(dt)).reshape(B, S, DINO_HEADS, hd)
-    q = q / dt.type(math.sqrt(hd))
-    w = softmax(np.einsum("bqhd,bkhd->bhqk", q, k))
-    o = np.einsum("bhqk,bkhd->bqhd", w, v).reshape(B, S, D)
+    o = _attend(q, k, v, None)
     o = o @ L["attention"]["output"]["dense"]["kernel"].astype(dt) + L["attention"]["output"]["dense"]["bias"].astype(dt)
     x = x + o * L["layer_scale1"]["lambda1"].astype(dt)
     y = layer_norm(x, L["norm2"]["scale"], L["norm2"]["bias"])
@@ -319,7 +326,7 @@ def base_vit_forward(gen, image_embeddings, dtype=np.float32):
     x = image_embeddings.astype(dt)
     B = x.shape[0]
     pk = enc["image_embedding_projection"]
-    patches = np.einsum("bsk,bkd->bsd", x, pk["kernel"].astype(dt)) + pk["bias"].astype(dt)[:, None, :]   # :130-133
+    patches = np.matmul(x, pk["kernel"].astype(dt)) + pk["bias"].astype(dt)[:, None, :]                  # :130-133
     tok = np.concatenate([patches, np.zeros((B, 1, BASE_DIM), dt)], axis=1)           # :182-183
     tok = tok + enc["pos_embedding"].astype(dt).reshape(B, N_PATCH + 1, BASE_DIM)      # :204
     out = transformer(tok, enc["Transformer_0"], base_mask(B, N_PATCH + 1), BASE_LAYERS, per_sample=True)
