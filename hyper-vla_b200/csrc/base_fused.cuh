@@ -1,0 +1,534 @@
+// Per-sample base network in ONE kernel: image_embedding_projection (768->64) + pos-emb, 4 pre-LN
+// encoder blocks (4 heads x 16, mlp 128, tanh-GELU), encoder_norm and the mix action head, with the
+// sample's own GENERATED weights (one packed row of 201,500 bf16 per task).
+//   reference: hypervla/components/base_vit.py:130-226, transformer.py:127-262,
+//              action_heads.py:455-470, 536-537; batching = jax.vmap of scripts/train.py:559-579.
+//
+// One CTA per environment, 9 warps.  Everything stays on chip between the embedding read and the
+// 28 output floats: the fp32 residual stream (256 patch tokens) and the layer's K/V live in shared
+// memory, the layer's weights are staged there once, GEMMs are warp-level mma.sync m16n8k16 (bf16
+// operands, fp32 accumulation) -- the problem is 64-wide and per-sample, far below a tcgen05 tile.
+//
+// Structure exploited (base_vit.py:209-214): patch tokens cannot attend to the action token, so the
+// 256 patch rows form an unmasked 256-token transformer (16 m-tiles, warps 0..7 own two each); the
+// action token is a single query row over 256 patch keys + itself, handled by warp 8 in fp32 on CUDA
+// cores.  Only the action token is needed from the last block, so patch rows stop after writing that
+// block's K/V.
+#pragma once
+#include "common.cuh"
+#include "attn_mma.cuh"
+
+namespace hvla {
+namespace basefused {
+
+using attn::ldsm_x4;
+using attn::ldsm_x4_t;
+using attn::mma_bf16;
+using attn::pack2;
+
+constexpr int NW = 9, NT = NW * 32;
+constexpr int XLD = 72;                 // fp32 residual row stride (floats): conflict-free float2 C-fragment access
+constexpr int KLD = 72;                 // bf16 row stride for 64-wide matrices (144 B)
+constexpr int W0LD = 136;               // bf16 row stride for the 64x128 Dense_0 kernel
+constexpr int PLD = 72;                 // staged projection kernel [768][72]
+
+// shared memory map (bytes)
+constexpr int OFF_X = 0;
+constexpr int OFF_K = OFF_X + 256 * XLD * 4;            // 73728
+constexpr int OFF_V = OFF_K + 256 * KLD * 2;            // +36864
+constexpr int OFF_W = OFF_V + 256 * KLD * 2;            // weights region (also: tail of the staged projection kernel)
+constexpr int OFF_WQ = OFF_W, OFF_WK = OFF_WQ + 64 * KLD * 2, OFF_WV = OFF_WK + 64 * KLD * 2, OFF_WO = OFF_WV + 64 * KLD * 2;
+constexpr int OFF_W0 = OFF_WO + 64 * KLD * 2;
+constexpr int OFF_W1 = OFF_W0 + 64 * W0LD * 2;
+constexpr int OFF_VEC = OFF_W1 + 128 * KLD * 2;         // fp32 vectors
+constexpr int V_LN0S = 0, V_LN0B = 64, V_BQ = 128, V_BK = 192, V_BV = 256, V_BO = 320, V_LN1S = 384, V_LN1B = 448, V_B0 = 512,
+              V_B1 = 640, V_COUNT = 704;
+constexpr int OFF_ACT = OFF_VEC + V_COUNT * 4;          // action-token scratch (fp32)
+constexpr int A_X = 0, A_XN = 64, A_Q = 128, A_K = 192, A_V = 256, A_O = 320, A_H = 384, A_P = 512, A_COUNT = 512 + 264;
+constexpr int SMEM = OFF_ACT + A_COUNT * 4;
+static_assert(768 * PLD * 2 <= OFF_VEC - OFF_K, "projection kernel staging must fit in the K/V/W region");
+static_assert(SMEM <= 232448, "shared memory budget");
+
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float c = 0.7978845608028654f;
+  return 0.5f * x * (1.0f + tanhf(c * (x + 0.044715f * (x * x * x))));
+}
+
+// C[16 x NTL*8] += A[16 x KS*16] * W[k0.., n0..]   (W row-major bf16 in smem, row stride ld elements)
+template <int NTL, int KS>
+__device__ __forceinline__ void gemm_tile(float (&c)[NTL][4], const uint32_t (&a)[KS][4], uint32_t sW, int ld, int k0, int n0, int lane) {
+  const int i = lane >> 3;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+    for (int np = 0; np < NTL / 2; ++np) {
+      uint32_t b0, b1, b2, b3;
+      const uint32_t addr = sW + (uint32_t)(((k0 + ks * 16 + (i & 1) * 8 + (lane & 7)) * ld + n0 + (np * 2 + (i >> 1)) * 8) * 2);
+      ldsm_x4_t(addr, b0, b1, b2, b3);
+      mma_bf16(c[2 * np], a[ks], b0, b1);
+      mma_bf16(c[2 * np + 1], a[ks], b2, b3);
+    }
+  }
+}
+
+// C-layout fp32 [16 x 64] -> bf16 A fragments for 4 k-steps
+__device__ __forceinline__ void c_to_a(const float (&c)[8][4], uint32_t (&a)[4][4]) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    a[ks][0] = pack2(c[2 * ks][0], c[2 * ks][1]);
+    a[ks][1] = pack2(c[2 * ks][2], c[2 * ks][3]);
+    a[ks][2] = pack2(c[2 * ks + 1][0], c[2 * ks + 1][1]);
+    a[ks][3] = pack2(c[2 * ks + 1][2], c[2 * ks + 1][3]);
+  }
+}
+
+__device__ __forceinline__ void load_x(const float* X, int row0, int lane, float (&c)[8][4]) {
+  const float* p0 = X + (row0 + (lane >> 2)) * XLD + (lane & 3) * 2;
+  const float* p1 = p0 + 8 * XLD;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 u = *reinterpret_cast<const float2*>(p0 + j * 8);
+    const float2 w = *reinterpret_cast<const float2*>(p1 + j * 8);
+    c[j][0] = u.x; c[j][1] = u.y; c[j][2] = w.x; c[j][3] = w.y;
+  }
+}
+__device__ __forceinline__ void store_x(float* X, int row0, int lane, const float (&c)[8][4]) {
+  float* p0 = X + (row0 + (lane >> 2)) * XLD + (lane & 3) * 2;
+  float* p1 = p0 + 8 * XLD;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    *reinterpret_cast<float2*>(p0 + j * 8) = make_float2(c[j][0], c[j][1]);
+    *reinterpret_cast<float2*>(p1 + j * 8) = make_float2(c[j][2], c[j][3]);
+  }
+}
+
+// flax LayerNorm (eps 1e-6, fast variance) of a C-layout tile, result as bf16 A fragments
+__device__ __forceinline__ void ln_tile(const float (&c)[8][4], const float* sc, const float* bi, int lane, uint32_t (&a)[4][4]) {
+  float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s0 += c[j][0] + c[j][1]; q0 = fmaf(c[j][0], c[j][0], fmaf(c[j][1], c[j][1], q0));
+    s1 += c[j][2] + c[j][3]; q1 = fmaf(c[j][2], c[j][2], fmaf(c[j][3], c[j][3], q1));
+  }
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+  }
+  const float m0 = s0 * (1.f / 64.f), m1 = s1 * (1.f / 64.f);
+  const float r0 = rsqrtf(fmaxf(0.f, q0 * (1.f / 64.f) - m0 * m0) + 1e-6f);
+  const float r1 = rsqrtf(fmaxf(0.f, q1 * (1.f / 64.f) - m1 * m1) + 1e-6f);
+  float n[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = j * 8 + (lane & 3) * 2;
+    const float2 g = *reinterpret_cast<const float2*>(sc + col);
+    const float2 b = *reinterpret_cast<const float2*>(bi + col);
+    n[j][0] = (c[j][0] - m0) * (r0 * g.x) + b.x;
+    n[j][1] = (c[j][1] - m0) * (r0 * g.y) + b.y;
+    n[j][2] = (c[j][2] - m1) * (r1 * g.x) + b.x;
+    n[j][3] = (c[j][3] - m1) * (r1 * g.y) + b.y;
+  }
+  c_to_a(n, a);
+}
+
+__device__ __forceinline__ void add_bias(float (&c)[8][4], const float* b, int lane) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 v = *reinterpret_cast<const float2*>(b + j * 8 + (lane & 3) * 2);
+    c[j][0] += v.x; c[j][1] += v.y; c[j][2] += v.x; c[j][3] += v.y;
+  }
+}
+__device__ __forceinline__ void zero8(float (&c)[8][4]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+}
+
+// copy a [rows x cols] bf16 matrix from global (dense) to padded smem (row stride ld); cols % 8 == 0
+__device__ __forceinline__ void stage_matrix(uint8_t* smem, int off, const bf16* g, int rows, int cols, int ld) {
+  const int per_row = cols / 8;
+  for (int i = threadIdx.x; i < rows * per_row; i += NT) {
+    const int r = i / per_row, c = (i % per_row) * 8;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(g + (int64_t)r * cols + c));
+    *reinterpret_cast<uint4*>(smem + off + (r * ld + c) * 2) = v;
+  }
+}
+__device__ __forceinline__ void stage_vec(float* dst, const bf16* g, int n) {
+  for (int i = threadIdx.x; i < n; i += NT) dst[i] = __bfloat162float(g[i]);
+}
+
+// fp32 GEMV helper for the action-token warp: out[n] = sum_k x[k] * W[k][n] (W bf16 smem, row stride ld)
+template <int K>
+__device__ __forceinline__ float gemv_col(const float* x, const bf16* W, int ld, int n) {
+  float a = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < K; ++k) a = fmaf(x[k], __bfloat162float(W[k * ld + n]), a);
+  return a;
+}
+
+__device__ __forceinline__ void warp_ln64(const float* x, const float* sc, const float* bi, float* out, int lane) {
+  const float v0 = x[lane], v1 = x[lane + 32];
+  float s = v0 + v1, q = fmaf(v0, v0, v1 * v1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const float m = s / 64.f, var = fmaxf(0.f, q / 64.f - m * m);
+  const float r = 1.0f / sqrtf(var + 1e-6f);
+  out[lane] = (v0 - m) * (r * sc[lane]) + bi[lane];
+  out[lane + 32] = (v1 - m) * (r * sc[lane + 32]) + bi[lane + 32];
+}
+
+__global__ void __launch_bounds__(NT, 1)
+base_fused_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ weights, const int* __restrict__ tidx,
+                  float* __restrict__ action, float* __restrict__ logit_out) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  typedef GenLayout G;
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bf16* wrow = weights + (int64_t)(tidx ? tidx[b] : b) * NGP;
+  const bf16* erow = emb + ((int64_t)b * DTOK + 1) * DD;     // skip the CLS row (base_vit.py:122)
+  float* X = reinterpret_cast<float*>(smem + OFF_X);
+  float* VEC = reinterpret_cast<float*>(smem + OFF_VEC);
+  float* ACT = reinterpret_cast<float*>(smem + OFF_ACT);
+  bf16* Ks = reinterpret_cast<bf16*>(smem + OFF_K);
+  bf16* Vs = reinterpret_cast<bf16*>(smem + OFF_V);
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t sK = sbase + OFF_K, sV = sbase + OFF_V;
+
+  // ------------------------------------------------------------------ P0: projection + pos-emb
+  stage_matrix(smem, OFF_K, wrow + G::proj_w, DD, BD, PLD);
+  stage_vec(VEC, wrow + G::proj_b, BD);
+  __syncthreads();
+  if (warp < 8) {
+    float acc[2][8][4];
+    zero8(acc[0]); zero8(acc[1]);
+    const int r0 = warp * 32 + (lane >> 2);
+    const bf16* e0 = erow + (int64_t)r0 * DD + (lane & 3) * 2;
+#pragma unroll 2
+    for (int ks = 0; ks < DD / 16; ++ks) {
+      uint32_t a[2][1][4];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const bf16* p = e0 + (int64_t)t * 16 * DD + ks * 16;
+        a[t][0][0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+        a[t][0][1] = __ldg(reinterpret_cast<const uint32_t*>(p + 8 * DD));
+        a[t][0][2] = __ldg(reinterpret_cast<const uint32_t*>(p + 8));
+        a[t][0][3] = __ldg(reinterpret_cast<const uint32_t*>(p + 8 * DD + 8));
+      }
+      const int i = lane >> 3;
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b0, b1, b2, b3;
+        const uint32_t addr = sK + (uint32_t)(((ks * 16 + (i & 1) * 8 + (lane & 7)) * PLD + (np * 2 + (i >> 1)) * 8) * 2);
+        ldsm_x4_t(addr, b0, b1, b2, b3);
+        mma_bf16(acc[0][2 * np], a[0][0], b0, b1);
+        mma_bf16(acc[0][2 * np + 1], a[0][0], b2, b3);
+        mma_bf16(acc[1][2 * np], a[1][0], b0, b1);
+        mma_bf16(acc[1][2 * np + 1], a[1][0], b2, b3);
+      }
+    }
+    const bf16* pos = wrow + G::pos;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int row0 = warp * 32 + t * 16;
+      add_bias(acc[t], VEC, lane);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = j * 8 + (lane & 3) * 2;
+        const __nv_bfloat162 pa = *reinterpret_cast<const __nv_bfloat162*>(pos + (row0 + (lane >> 2)) * BD + col);
+        const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(pos + (row0 + 8 + (lane >> 2)) * BD + col);
+        acc[t][j][0] += __low2float(pa); acc[t][j][1] += __high2float(pa);
+        acc[t][j][2] += __low2float(pb); acc[t][j][3] += __high2float(pb);
+      }
+      store_x(X, row0, lane, acc[t]);
+    }
+  } else {
+    // action token: zeros + pos_embedding[256]  (base_vit.py:182-204)
+    const bf16* pos = wrow + G::pos + 256 * BD;
+    ACT[A_X + lane] = __bfloat162float(pos[lane]);
+    ACT[A_X + lane + 32] = __bfloat162float(pos[lane + 32]);
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ encoder blocks
+  for (int l = 0; l < BL; ++l) {
+    const bf16* lw = wrow + G::layers + (int64_t)l * G::layer_size;
+    stage_matrix(smem, OFF_WQ, lw + G::wq, 64, 64, KLD);
+    stage_matrix(smem, OFF_WK, lw + G::wk, 64, 64, KLD);
+    stage_matrix(smem, OFF_WV, lw + G::wv, 64, 64, KLD);
+    stage_matrix(smem, OFF_WO, lw + G::wo, 64, 64, KLD);
+    stage_matrix(smem, OFF_W0, lw + G::w0, 64, 128, W0LD);
+    stage_matrix(smem, OFF_W1, lw + G::w1, 128, 64, KLD);
+    stage_vec(VEC + V_LN0S, lw + G::ln0_s, 64); stage_vec(VEC + V_LN0B, lw + G::ln0_b, 64);
+    stage_vec(VEC + V_BQ, lw + G::bq, 64); stage_vec(VEC + V_BK, lw + G::bk, 64);
+    stage_vec(VEC + V_BV, lw + G::bv, 64); stage_vec(VEC + V_BO, lw + G::bo, 64);
+    stage_vec(VEC + V_LN1S, lw + G::ln1_s, 64); stage_vec(VEC + V_LN1B, lw + G::ln1_b, 64);
+    stage_vec(VEC + V_B0, lw + G::b0, 128); stage_vec(VEC + V_B1, lw + G::b1, 64);
+    __syncthreads();
+
+    // ---- phase A: K and V of every token -------------------------------------------------------
+    if (warp < 8) {
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const int row0 = warp * 32 + t * 16;
+        float c[8][4];
+        load_x(X, row0, lane, c);
+        uint32_t a[4][4];
+        ln_tile(c, VEC + V_LN0S, VEC + V_LN0B, lane, a);
+#pragma unroll
+        for (int kv = 0; kv < 2; ++kv) {
+          zero8(c);
+          gemm_tile<8, 4>(c, a, sbase + (kv ? OFF_WV : OFF_WK), KLD, 0, 0, lane);
+          add_bias(c, VEC + (kv ? V_BV : V_BK), lane);
+          bf16* dst = (kv ? Vs : Ks) + (row0 + (lane >> 2)) * KLD + (lane & 3) * 2;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            *reinterpret_cast<uint32_t*>(dst + j * 8) = pack2(c[j][0], c[j][1]);
+            *reinterpret_cast<uint32_t*>(dst + 8 * KLD + j * 8) = pack2(c[j][2], c[j][3]);
+          }
+        }
+      }
+    } else {
+      warp_ln64(ACT + A_X, VEC + V_LN0S, VEC + V_LN0B, ACT + A_XN, lane);
+      __syncwarp();
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int n = lane + 32 * h2;
+        ACT[A_Q + n] = (gemv_col<64>(ACT + A_XN, reinterpret_cast<const bf16*>(smem + OFF_WQ), KLD, n) + VEC[V_BQ + n]) * 0.25f;
+        ACT[A_K + n] = gemv_col<64>(ACT + A_XN, reinterpret_cast<const bf16*>(smem + OFF_WK), KLD, n) + VEC[V_BK + n];
+        ACT[A_V + n] = gemv_col<64>(ACT + A_XN, reinterpret_cast<const bf16*>(smem + OFF_WV), KLD, n) + VEC[V_BV + n];
+      }
+    }
+    __syncthreads();
+
+    // ---- phase B ------------------------------------------------------------------------------------
+    if (warp < 8) {
+      if (l < BL - 1) {
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          const int row0 = warp * 32 + t * 16;
+          float c[8][4];
+          load_x(X, row0, lane, c);
+          uint32_t a[4][4];
+          ln_tile(c, VEC + V_LN0S, VEC + V_LN0B, lane, a);
+          float q[8][4];
+          zero8(q);
+          gemm_tile<8, 4>(q, a, sbase + OFF_WQ, KLD, 0, 0, lane);
+          add_bias(q, VEC + V_BQ, lane);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { q[j][0] *= 0.25f; q[j][1] *= 0.25f; q[j][2] *= 0.25f; q[j][3] *= 0.25f; }   // / sqrt(16)
+          uint32_t qa[4][4];
+          c_to_a(q, qa);
+          float o[8][4];
+          zero8(o);
+          constexpr float LOG2E = 1.4426950408889634f;
+#pragma unroll
+          for (int h = 0; h < BH; ++h) {
+            float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+            float oh[2][4];
+            oh[0][0] = oh[0][1] = oh[0][2] = oh[0][3] = 0.f;
+            oh[1][0] = oh[1][1] = oh[1][2] = oh[1][3] = 0.f;
+#pragma unroll 1
+            for (int kc = 0; kc < 4; ++kc) {
+              const int key0 = kc * 64;
+              float s[8][4];
+              const int i = lane >> 3;
+#pragma unroll
+              for (int np = 0; np < 4; ++np) {
+                s[2 * np][0] = s[2 * np][1] = s[2 * np][2] = s[2 * np][3] = 0.f;
+                s[2 * np + 1][0] = s[2 * np + 1][1] = s[2 * np + 1][2] = s[2 * np + 1][3] = 0.f;
+                uint32_t b0, b1, b2, b3;
+                const uint32_t addr = sK + (uint32_t)(((key0 + (np * 2 + (i >> 1)) * 8 + (lane & 7)) * KLD + h * 16 + (i & 1) * 8) * 2);
+                ldsm_x4(addr, b0, b1, b2, b3);
+                mma_bf16(s[2 * np], qa[h], b0, b1);
+                mma_bf16(s[2 * np + 1], qa[h], b2, b3);
+              }
+              float mx0 = m0, mx1 = m1;
+#pragma unroll
+              for (int nt = 0; nt < 8; ++nt) {
+                mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+                mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+              }
+              mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+              mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+              const float c0 = exp2f((m0 - mx0) * LOG2E), c1 = exp2f((m1 - mx1) * LOG2E);
+              m0 = mx0; m1 = mx1;
+              l0 *= c0; l1 *= c1;
+              oh[0][0] *= c0; oh[0][1] *= c0; oh[0][2] *= c1; oh[0][3] *= c1;
+              oh[1][0] *= c0; oh[1][1] *= c0; oh[1][2] *= c1; oh[1][3] *= c1;
+              const float ms0 = mx0 * LOG2E, ms1 = mx1 * LOG2E;
+#pragma unroll
+              for (int nt = 0; nt < 8; ++nt) {
+                s[nt][0] = exp2f(fmaf(s[nt][0], LOG2E, -ms0)); s[nt][1] = exp2f(fmaf(s[nt][1], LOG2E, -ms0));
+                s[nt][2] = exp2f(fmaf(s[nt][2], LOG2E, -ms1)); s[nt][3] = exp2f(fmaf(s[nt][3], LOG2E, -ms1));
+                l0 += s[nt][0] + s[nt][1];
+                l1 += s[nt][2] + s[nt][3];
+              }
+#pragma unroll
+              for (int kt = 0; kt < 4; ++kt) {
+                uint32_t pa[4];
+                pa[0] = pack2(s[2 * kt][0], s[2 * kt][1]); pa[1] = pack2(s[2 * kt][2], s[2 * kt][3]);
+                pa[2] = pack2(s[2 * kt + 1][0], s[2 * kt + 1][1]); pa[3] = pack2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+                uint32_t b0, b1, b2, b3;
+                const uint32_t addr = sV + (uint32_t)(((key0 + 16 * kt + (i & 1) * 8 + (lane & 7)) * KLD + h * 16 + (i >> 1) * 8) * 2);
+                ldsm_x4_t(addr, b0, b1, b2, b3);
+                mma_bf16(oh[0], pa, b0, b1);
+                mma_bf16(oh[1], pa, b2, b3);
+              }
+            }
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+            const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+            o[2 * h][0] = oh[0][0] * i0; o[2 * h][1] = oh[0][1] * i0; o[2 * h][2] = oh[0][2] * i1; o[2 * h][3] = oh[0][3] * i1;
+            o[2 * h + 1][0] = oh[1][0] * i0; o[2 * h + 1][1] = oh[1][1] * i0; o[2 * h + 1][2] = oh[1][2] * i1; o[2 * h + 1][3] = oh[1][3] * i1;
+          }
+          // out-projection + residual
+          c_to_a(o, a);
+          zero8(o);
+          gemm_tile<8, 4>(o, a, sbase + OFF_WO, KLD, 0, 0, lane);
+          add_bias(o, VEC + V_BO, lane);
+          load_x(X, row0, lane, c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { c[j][0] += o[j][0]; c[j][1] += o[j][1]; c[j][2] += o[j][2]; c[j][3] += o[j][3]; }
+          // MLP (two halves of the 128 hidden units)
+          ln_tile(c, VEC + V_LN1S, VEC + V_LN1B, lane, a);
+          float y[8][4];
+          zero8(y);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            float hdn[8][4];
+            zero8(hdn);
+            gemm_tile<8, 4>(hdn, a, sbase + OFF_W0, W0LD, 0, hf * 64, lane);
+            add_bias(hdn, VEC + V_B0 + hf * 64, lane);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              hdn[j][0] = gelu_tanh_fast(hdn[j][0]); hdn[j][1] = gelu_tanh_fast(hdn[j][1]);
+              hdn[j][2] = gelu_tanh_fast(hdn[j][2]); hdn[j][3] = gelu_tanh_fast(hdn[j][3]);
+            }
+            uint32_t ah[4][4];
+            c_to_a(hdn, ah);
+            gemm_tile<8, 4>(y, ah, sbase + OFF_W1, KLD, hf * 64, 0, lane);
+          }
+          add_bias(y, VEC + V_B1, lane);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { c[j][0] += y[j][0]; c[j][1] += y[j][1]; c[j][2] += y[j][2]; c[j][3] += y[j][3]; }
+          store_x(X, row0, lane, c);
+        }
+      }
+    } else {
+      // ---- action token (fp32, CUDA cores): attends to 256 patch keys + itself ----------------------------
+      float* P = ACT + A_P;
+#pragma unroll 1
+      for (int h = 0; h < BH; ++h) {
+        float sc[9];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bf16* kp = Ks + (lane + 32 * i) * KLD + h * 16;
+          float a = 0.f;
+#pragma unroll
+          for (int d = 0; d < 16; ++d) a = fmaf(ACT[A_Q + h * 16 + d], __bfloat162float(kp[d]), a);
+          sc[i] = a;
+          mx = fmaxf(mx, a);
+        }
+        {
+          float a = 0.f;
+#pragma unroll
+          for (int d = 0; d < 16; ++d) a = fmaf(ACT[A_Q + h * 16 + d], ACT[A_K + h * 16 + d], a);
+          sc[8] = a;
+          mx = fmaxf(mx, a);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sc[i] = expf(sc[i] - mx); sum += sc[i]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float pself = expf(sc[8] - mx);
+        sum += pself;
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) P[lane + 32 * i] = sc[i] * inv;
+        __syncwarp();
+        const int d = lane & 15, half = lane >> 4;
+        float acc = 0.f;
+        const bf16* vp = Vs + h * 16 + d;
+#pragma unroll 4
+        for (int j = half * 128; j < half * 128 + 128; ++j) acc = fmaf(P[j], __bfloat162float(vp[j * KLD]), acc);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        if (half == 0) ACT[A_O + h * 16 + d] = acc + pself * inv * ACT[A_V + h * 16 + d];
+        __syncwarp();
+      }
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int n = lane + 32 * h2;
+        const float v = gemv_col<64>(ACT + A_O, reinterpret_cast<const bf16*>(smem + OFF_WO), KLD, n) + VEC[V_BO + n];
+        ACT[A_X + n] += v;
+      }
+      __syncwarp();
+      warp_ln64(ACT + A_X, VEC + V_LN1S, VEC + V_LN1B, ACT + A_XN, lane);
+      __syncwarp();
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int n = lane + 32 * q4;
+        ACT[A_H + n] = gelu_tanh_f(gemv_col<64>(ACT + A_XN, reinterpret_cast<const bf16*>(smem + OFF_W0), W0LD, n) + VEC[V_B0 + n]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int n = lane + 32 * h2;
+        const float v = gemv_col<128>(ACT + A_H, reinterpret_cast<const bf16*>(smem + OFF_W1), KLD, n) + VEC[V_B1 + n];
+        ACT[A_X + n] += v;
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------------ encoder_norm + mix head (warp 8)
+  if (warp == 8) {
+    const float v0 = ACT[A_X + lane], v1 = ACT[A_X + lane + 32];
+    float s = v0 + v1, q = fmaf(v0, v0, v1 * v1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    const float m = s / 64.f, var = fmaxf(0.f, q / 64.f - m * m);
+    const float r = 1.0f / sqrtf(var + 1e-6f);
+    ACT[A_XN + lane] = (v0 - m) * (r * __bfloat162float(wrow[G::encn_s + lane])) + __bfloat162float(wrow[G::encn_b + lane]);
+    ACT[A_XN + lane + 32] = (v1 - m) * (r * __bfloat162float(wrow[G::encn_s + lane + 32])) + __bfloat162float(wrow[G::encn_b + lane + 32]);
+    __syncwarp();
+    if (lane < NCONT) {
+      float a = 0.f;
+      for (int k = 0; k < BD; ++k) a = fmaf(ACT[A_XN + k], __bfloat162float(wrow[G::wc + k * NCONT + lane]), a);
+      a += __bfloat162float(wrow[G::bc + lane]);
+      action[(int64_t)b * (AH * AD) + (lane / 6) * AD + (lane % 6)] = tanhf(a / 5.0f) * 5.0f;
+    } else if (lane < NCONT + AH) {
+      const int j = lane - NCONT;
+      float a = 0.f;
+      for (int k = 0; k < BD; ++k) a = fmaf(ACT[A_XN + k], __bfloat162float(wrow[G::wd + k * AH + j]), a);
+      a += __bfloat162float(wrow[G::bd + j]);
+      action[(int64_t)b * (AH * AD) + j * AD + 6] = a >= 0.f ? 1.0f : 0.0f;
+      if (logit_out) logit_out[(int64_t)b * AH + j] = a;
+    }
+  }
+}
+
+inline int base_act_bf16(cudaStream_t st, const bf16* emb, const bf16* weights, const int* tidx, int B, float* action, float* logit) {
+  static bool attr = false;
+  if (!attr) {
+    HVLA_CUDA(cudaFuncSetAttribute(base_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr = true;
+  }
+  ProfScope ps(st, "base_fused");
+  base_fused_kernel<<<B, NT, SMEM, st>>>(emb, weights, tidx, action, logit);
+  HVLA_LAUNCH_CHECK("base_fused");
+  return HVLA_OK;
+}
+
+}  // namespace basefused
+}  // namespace hvla

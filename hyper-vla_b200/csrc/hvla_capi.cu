@@ -4,6 +4,7 @@
 #include "simt_kernels.cuh"
 #include "gemm_tc.cuh"
 #include "attn_mma.cuh"
+#include "base_fused.cuh"
 
 #include <stdlib.h>
 #include <type_traits>
@@ -392,8 +393,11 @@ static int base_act_impl(cudaStream_t st, const void* emb, const void* weights, 
   if (dtype == HVLA_F32)
     return base_generic<float, float>(st, reinterpret_cast<const float*>(emb), reinterpret_cast<const float*>(weights), tidx, B,
                                       T, out_action, out_logit, ws, pl);
-  return base_generic<bf16, bf16>(st, reinterpret_cast<const bf16*>(emb), reinterpret_cast<const bf16*>(weights), tidx, B, T,
-                                  out_action, out_logit, ws, pl);
+  if (env_flag("HVLA_DEBUG_GENERIC_BASE"))   // debugging aid: the same math through the generic CUDA-core kernels
+    return base_generic<bf16, bf16>(st, reinterpret_cast<const bf16*>(emb), reinterpret_cast<const bf16*>(weights), tidx, B, T,
+                                    out_action, out_logit, ws, pl);
+  return basefused::base_act_bf16(st, reinterpret_cast<const bf16*>(emb), reinterpret_cast<const bf16*>(weights), tidx, B,
+                                  out_action, out_logit);
 }
 
 }  // namespace hvla

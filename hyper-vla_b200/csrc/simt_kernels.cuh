@@ -4,6 +4,7 @@
 #pragma once
 #include "common.cuh"
 #include <float.h>
+#include <type_traits>
 
 namespace hvla {
 
@@ -113,6 +114,34 @@ inline GemmP gemm_params(const void* A, int lda, const void* W, int ldw, const v
   return p;
 }
 
+template <typename TW> struct Vec4;
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec4<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[4]) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t;
+    t.x = *reinterpret_cast<uint32_t*>(&a);
+    t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+
+
 // =============================================================================================
 // LayerNorm (flax: eps 1e-6, fast variance E[x^2]-E[x]^2 clipped at 0), one warp per row.
 // scale/bias may be per-batch (per-sample generated weights).  D in {64,128,768}.
@@ -166,8 +195,55 @@ __global__ void __launch_bounds__(128) layernorm_kernel(LnP p) {
   }
 }
 
+// DINOv2 LayerNorm: 768-wide fp32 rows (contiguous, shared scale/bias), vectorised; one warp per row.
+template <typename TO>
+__global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restrict__ x, TO* __restrict__ y,
+                                                           const float* __restrict__ scale, const float* __restrict__ bias, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * 768);
+  float4 v[6];
+  float s = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) v[i] = xr[lane + 32 * i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    s2 = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, fmaf(v[i].w, v[i].w, s2))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const float mean = s / 768.f;
+  const float var = fmaxf(0.f, s2 / 768.f - mean * mean);
+  const float rstd = 1.0f / sqrtf(var + 1e-6f);
+  TO* yr = y + (int64_t)row * 768;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(scale + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c));
+    float o[4];
+    o[0] = (v[i].x - mean) * (rstd * g.x) + b.x;
+    o[1] = (v[i].y - mean) * (rstd * g.y) + b.y;
+    o[2] = (v[i].z - mean) * (rstd * g.z) + b.z;
+    o[3] = (v[i].w - mean) * (rstd * g.w) + b.w;
+    Vec4<TO>::store(yr + c, o);
+  }
+}
+
 template <typename TS, typename TO>
 inline int layernorm(cudaStream_t st, const LnP& p, int D) {
+  if (D == 768 && std::is_same<TS, float>::value && p.sS == 0 && p.ldx == 768 && p.ldy == 768 && p.post_div == 0.f) {
+    ProfScope ps(st, "layernorm");
+    layernorm768_kernel<TO><<<cdiv(p.rows, 8), 256, 0, st>>>(p.x, reinterpret_cast<TO*>(p.y), reinterpret_cast<const float*>(p.scale),
+                                                             reinterpret_cast<const float*>(p.bias), p.rows);
+    HVLA_LAUNCH_CHECK("layernorm768");
+    return HVLA_OK;
+  }
   dim3 grid(cdiv(p.rows, 4));
   ProfScope ps(st, "layernorm");
   if (D == 64) layernorm_kernel<TS, TO, 64><<<grid, 128, 0, st>>>(p);
@@ -391,33 +467,6 @@ __global__ void __launch_bounds__(128) mix_head_kernel(const float* __restrict__
 // hypernetwork.py:205-217 as one skinny GEMM).  HBM-bound on W for small T.
 // Each thread owns 4 adjacent columns; tasks are processed 8 at a time from smem.
 // =============================================================================================
-template <typename TW> struct Vec4;
-template <> struct Vec4<float> {
-  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-  }
-  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  }
-};
-template <> struct Vec4<bf16> {
-  static __device__ __forceinline__ void load(const bf16* p, float (&v)[4]) {
-    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
-    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
-    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
-    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
-  }
-  static __device__ __forceinline__ void store(bf16* p, const float (&v)[4]) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
-    __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
-    uint2 t;
-    t.x = *reinterpret_cast<uint32_t*>(&a);
-    t.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(p) = t;
-  }
-};
-
 constexpr int HEADS_TT = 8;
 template <typename TW, typename TO>
 __global__ void __launch_bounds__(256) heads_gemm_kernel(const float* __restrict__ E, const TW* __restrict__ W,

@@ -133,6 +133,62 @@ def test_debug_cuda_core_paths_agree_with_tensor_core_paths(models, torch_cuda):
     assert e < 2e-2
 
 
+def test_fused_base_kernel_matches_generic_path_and_oracle(models, params_p1, torch_cuda):
+    """K8/K9: the one-kernel-per-sample bf16 base network vs (a) the generic CUDA-core kernels on the same
+    bf16 weights and (b) the fp64 oracle on the same (bf16-rounded) embeddings and weights.  Mixed task
+    weights per batch (LIBERO-shaped grouping: 5 tasks, 37 envs)."""
+    import torch
+    from hvla import metadata as M, params as P, synthetic as S
+    from oracle import hypervla_oracle as O
+    m = models["bf16"]
+    rt = m.runtime
+    B, T = 37, 5
+    inp = S.make_inputs(5, B, T)
+    bp, tasks, _ = m.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"])
+    rng = np.random.default_rng(11)
+    emb = torch.from_numpy(rng.standard_normal((B, 257, 768)).astype(np.float32)).to(rt.device).to(torch.bfloat16)
+    ti = inp["task_index"]
+    a_fused, l_fused = rt.base_act(emb, bp.weights, ti)
+    os.environ["HVLA_DEBUG_GENERIC_BASE"] = "1"
+    try:
+        a_gen, l_gen = rt.base_act(emb, bp.weights, ti)
+    finally:
+        os.environ.pop("HVLA_DEBUG_GENERIC_BASE")
+    a_fused, l_fused, a_gen, l_gen = (t.cpu().numpy() for t in (a_fused, l_fused, a_gen, l_gen))
+    e1 = rel_err(a_fused[..., :6], a_gen[..., :6])
+    # oracle on the very same rounded inputs (isolates the kernel's own arithmetic error)
+    rows = bp.packed_numpy().astype(np.float64)
+    gen = {p: rows[:, off:off + int(np.prod(shape))].reshape((T,) + tuple(shape)) for p, (off, shape) in M.packed_offsets().items()}
+    tree = O.to_tree(O.take_tasks(gen, ti))
+    h = O.base_vit_forward(tree, emb.float().cpu().numpy()[:, 1:].astype(np.float64), np.float64)
+    a_ref, l_ref = O.mix_head(tree, h)
+    e2 = rel_err(a_fused[..., :6], a_ref[..., :6])
+    e3 = rel_err(l_fused, l_ref)
+    print(f"fused base vs generic {e1:.2e}; vs fp64 oracle: action {e2:.2e}, logit {e3:.2e}")
+    assert e1 < 2e-2 and e2 < 2e-2 and e3 < 2e-2
+    sure = np.abs(l_ref) > 2e-2 * np.abs(l_ref).max()
+    assert np.array_equal(a_fused[..., 6][sure], a_ref[..., 6][sure])
+
+
+def test_grouped_equals_per_sample_and_is_deterministic(models, torch_cuda):
+    """Full-size property test (B=64): a batch with mixed task weights gives bit-identical actions to
+    evaluating every env alone with its own task's weights; and the step is deterministic."""
+    from hvla import synthetic as S
+    m = models["bf16"]
+    rt = m.runtime
+    B, T = 64, 10
+    inp = S.make_inputs(5, B, T)
+    bp, tasks, _ = m.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"])
+    ti = inp["task_index"]
+    a1, i1 = m.sample_actions(inp["images"], None, tasks, None, bp, task_index=ti)
+    a2, i2 = m.sample_actions(inp["images"], None, tasks, None, bp, task_index=ti)
+    assert np.array_equal(a1, a2) and np.array_equal(i1["gripper_logits"], i2["gripper_logits"])
+    for b in (0, 17, 63):
+        ab, _ = m.sample_actions(inp["images"][b:b + 1], None, tasks, None, bp, task_index=ti[b:b + 1])
+        assert np.array_equal(ab[0], a1[b]), b
+    assert np.isfinite(a1).all() and np.abs(a1[..., :6]).max() <= 5.0
+
+
 def test_edge_cases(models, torch_cuda):
     from hvla import _native as N
     from hvla import synthetic as S
