@@ -1,0 +1,128 @@
+"""CPU tests of the host-side mirror: config envelope, metadata rule, packing, API errors, sharding."""
+import copy
+
+import numpy as np
+import pytest
+
+from hvla import config as C, metadata as M, params as P, parallel as PL
+
+
+def test_metadata_counts_and_rule():
+    meta = M.build_base_net_metadata(C.default_config())
+    gen = M.generated_leaves_canonical()
+    assert len(gen) == 73 and len(M.shared_leaves()) == 223
+    assert sum(int(np.prod(s)) for _, s in gen) == 201_500
+    assert sum(int(np.prod(s)) for _, s in M.shared_leaves()) == 86_580_480
+    assert meta["total_param_num"] == 201_500 + 86_580_480 and meta["block_num"] == 1
+    name = "encoder_Transformer_0_encoderblock_0_MultiHeadDotProductAttention_0_query_kernel"
+    assert meta["output_head_info"][name] == dict(output_dim=4096, generation_flag=True, init_strategy=0, init_variance=0.0)
+    assert not meta["output_head_info"]["encoder_image_encoder_layernorm_scale"]["generation_flag"]
+
+
+def test_canonical_flatten_order_matches_survey_appendix_a3():
+    off, table = 0, {}
+    for path, shape in M.generated_leaves_canonical():
+        table["/".join(path)] = off
+        off += int(np.prod(shape))
+    assert table["action_head/continuous_head/bias"] == 0
+    assert table["action_head/discrete_head/kernel"] == 1564
+    assert table["encoder/Transformer_0/encoder_norm/bias"] == 1820
+    assert table["encoder/Transformer_0/encoderblock_0/MlpBlock_0/Dense_0/bias"] == 2204
+    assert table["encoder/Transformer_0/encoderblock_0/MultiHeadDotProductAttention_0/key/bias"] == 18780
+    assert table["encoder/Transformer_0/encoderblock_1/LayerNorm_0/bias"] == 35420
+    assert table["encoder/image_embedding_projection/bias"] == 135836
+    assert table["encoder/pos_embedding"] == 185052 and off == 201_500
+
+
+def test_pack_unpack_roundtrip(params_p1):
+    W, b = P.pack_heads(params_p1)
+    assert W.shape == (128, M.N_GENERATED_PADDED) and not W[:, M.N_GENERATED:].any()
+    tree = P.unpack_generated(b[:M.N_GENERATED])
+    k = tree["encoder"]["Transformer_0"]["encoderblock_3"]["MlpBlock_0"]["Dense_1"]["kernel"]
+    name = "output_head_encoder_Transformer_0_encoderblock_3_MlpBlock_0_Dense_1_kernel"
+    assert k.shape == (128, 64) and np.array_equal(k.ravel(), params_p1[name]["bias"])
+    assert P.pack_hn_blob(params_p1).size == P.hn_blob_size()
+    dino = P.dino_tree_from_params(params_p1)
+    assert dino["encoder"]["layer"]["11"]["mlp"]["fc2"]["kernel"].shape == (3072, 768)
+
+
+def test_dino_packing_layouts(params_p1):
+    vec, mat_t = P.pack_dino(params_p1, transposed=True)
+    _, mat = P.pack_dino(params_p1, transposed=False)
+    lt, ln = P.dino_mat_layout(True), P.dino_mat_layout(False)
+    o, (r, c) = lt["l3.w1"]
+    o2, (r2, c2) = ln["l3.w1"]
+    assert (r, c) == (3072, 768) and (r2, c2) == (768, 3072) and o == o2
+    assert np.array_equal(mat_t[o:o + r * c].reshape(r, c).T, mat[o2:o2 + r2 * c2].reshape(r2, c2))
+    o, (r, c) = ln["patch_w"]
+    assert not mat[o:o + r * c].reshape(r, c)[588:].any()          # K padding rows are zero
+    vo, vn = P.dino_vec_layout()["pos"]
+    pos = vec[vo:vo + vn].reshape(257, 768)
+    dino = P.dino_tree_from_params(params_p1)
+    assert np.array_equal(pos[0], dino["embeddings"]["position_embeddings"][0, 0])   # CLS position is copied
+
+
+def test_pos_table_interpolation_agrees_with_oracle_and_is_a_partition_of_unity(params_p1):
+    from oracle import hypervla_oracle as O
+    pe = P.dino_tree_from_params(params_p1)["embeddings"]["position_embeddings"]
+    assert np.array_equal(P.interpolate_pos_table(pe), O.interpolate_pos_table(pe))
+    ones = np.ones_like(pe)
+    assert np.allclose(P.interpolate_pos_table(ones), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("path,value", [
+    (("hypernet_kwargs", "context_embedding_dim"), 256), (("hypernet_kwargs", "generation_strategy"), "full"),
+    (("hypernet_kwargs", "shared_modules"), ()), (("base_net_kwargs", "action_head_type"), "diffusion"),
+    (("base_net_kwargs", "vit_kwargs", "encoder_type"), "SmallStem"), (("base_net_kwargs", "vit_kwargs", "num_layers"), 6),
+    (("base_net_kwargs", "vit_kwargs", "use_language_token"), True), (("base_net_kwargs", "action_head_kwargs", "token_per_horizon"), True),
+])
+def test_unsupported_config_raises_before_any_launch(path, value):
+    cfg = copy.deepcopy(C.default_config())
+    d = cfg
+    for k in path[:-1]:
+        d = d[k]
+    d[path[-1]] = value
+    with pytest.raises(ValueError):
+        C.validate_config(cfg)
+    C.validate_config(C.default_config())
+
+
+def test_model_api_errors_without_gpu(params_p1):
+    """Constructing the model and validating arguments needs no GPU; compute fails loudly (no CPU fallback)."""
+    import torch
+    from hvla import _native as N
+    from hvla.model import HyperVLA
+    m = HyperVLA.from_config(C.default_config(), precision="bf16", params=params_p1)
+    assert m.base_net.action_horizon == 4 and m.hypernet.layer_token_num == 1
+    with pytest.raises(ValueError):
+        m.create_tasks(instruction_dict=None)
+    with pytest.raises(TypeError):
+        m.sample_actions(np.zeros((1, 1, 224, 224, 3), np.uint8), None, None, None, base_params={"not": "ours"})
+    if not torch.cuda.is_available():
+        from hvla import synthetic as S
+        inp = S.make_inputs(1, 1, 1)
+        with pytest.raises(N.HvlaError):
+            m.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"])
+
+
+def test_save_and_load_pretrained_roundtrip(tmp_path, params_p0):
+    from hvla.model import HyperVLA
+    small = {k: v for k, v in params_p0.items()}
+    m = HyperVLA.from_config(C.default_config(), params=small, dataset_statistics={"bridge": {"action": {"mean": [0.0] * 7}}})
+    m.save_pretrained(100, str(tmp_path))
+    m2 = HyperVLA.load_pretrained(str(tmp_path), 100)
+    assert m2.config["hypernet_kwargs"]["shared_modules"] == ("image_encoder",)
+    a = m.params["context_encoder"]["encoderblock_2"]["MlpBlock_0"]["Dense_0"]["kernel"]
+    b = m2.params["context_encoder"]["encoderblock_2"]["MlpBlock_0"]["Dense_0"]["kernel"]
+    assert np.array_equal(a, b) and m2.dataset_statistics["bridge"]["action"]["mean"] == [0.0] * 7
+
+
+def test_shard_range_covers_every_env_once():
+    for n, w in ((1024, 8), (1000, 8), (7, 4), (3, 8), (0, 2)):
+        spans = [PL.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+    ti = np.repeat(np.arange(10), 100)
+    uniq, local = PL.local_task_table(ti, 250, 375)
+    assert uniq.tolist() == [2, 3] and np.array_equal(uniq[local], ti[250:375])

@@ -1,0 +1,116 @@
+"""CPU tests of the oracle: fp32 restatement vs the committed fp64 golden vectors, and the
+size-independent properties the GPU tests rely on."""
+import numpy as np
+import pytest
+
+from hvla import metadata as M, params as P, synthetic as S
+from oracle import hypervla_oracle as O
+
+CASES = {"c1_b1_t1": (1, 1, 1), "c2_b3_t3": (2, 3, 3)}
+
+
+def rel(x, ref):
+    return float(np.abs(np.asarray(x, np.float64) - ref).max() / np.abs(ref).max())
+
+
+def _run(params, ci, B, T, dtype=np.float32):
+    inp = S.make_inputs(ci, B, T)
+    lang = inp["instruction_dict"]["language_instruction"]
+    gen, emb = O.generate(params, lang["token_embedding"], lang["attention_mask"], inp["initial_state"]["patch_embeddings"][:, 0],
+                          dtype=dtype, generated_paths=M.generated_leaves_canonical())
+    tree = O.to_tree(O.take_tasks(gen, inp["task_index"]))
+    act, logit, hidden, h = O.sample_actions(P.dino_tree_from_params(params), tree, inp["images"][:, 0], dtype=dtype, return_all=True)
+    return inp, gen, emb, act, logit, hidden
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_fp32_oracle_matches_fp64_golden(params_p1, golden, case):
+    ci, B, T = CASES[case]
+    g = golden[case]
+    inp, gen, emb, act, logit, hidden = _run(params_p1, ci, B, T)
+    assert rel(emb[:, 0], g["ctx"]) < 1e-5
+    rows = np.zeros((T, M.N_GENERATED))
+    for path, (off, shape) in M.packed_offsets().items():
+        rows[:, off:off + int(np.prod(shape))] = gen[path].reshape(T, -1)
+    assert rel(rows[:, ::97], g["rows_sample"]) < 1e-5
+    assert rel(hidden[:, ::16, ::48], g["hidden_sample"]) < 1e-5
+    assert rel(act[..., :6], g["action"][..., :6].astype(np.float64)) < 1e-5
+    sure = np.abs(g["logit"]) > 1e-3
+    assert np.array_equal(act[..., 6][sure], g["action"][..., 6][sure])
+
+
+def test_p0_degenerate_init_reproduces_head_biases(params_p0):
+    """with BIAS_INIT the head kernels are zero, so generated weights == head biases whatever
+    the context is (hypernetwork.py:72-77, model.py:328-346)."""
+    inp = S.make_inputs(9, 1, 2)
+    lang = inp["instruction_dict"]["language_instruction"]
+    gen, _ = O.generate(params_p0, lang["token_embedding"], lang["attention_mask"], inp["initial_state"]["patch_embeddings"][:, 0],
+                        generated_paths=M.generated_leaves_canonical())
+    for path, v in gen.items():
+        bias = params_p0["output_head_" + "_".join(path)]["bias"]
+        assert np.array_equal(v[0].ravel(), bias) and np.array_equal(v[1].ravel(), bias)
+
+
+def test_patches_do_not_see_the_action_token(params_p1):
+    """base_vit.py:209-214: changing the action token's position embedding must not change any patch row;
+    and the last block only needs the action-token query (the kernel's legal shortcut)."""
+    rng = np.random.default_rng(3)
+    inp = S.make_inputs(4, 1, 1)
+    lang = inp["instruction_dict"]["language_instruction"]
+    gen, _ = O.generate(params_p1, lang["token_embedding"], lang["attention_mask"], inp["initial_state"]["patch_embeddings"][:, 0],
+                        generated_paths=M.generated_leaves_canonical())
+    tree = O.to_tree(gen)
+    emb = rng.standard_normal((1, 256, 768)).astype(np.float32)
+
+    def tokens(t):
+        enc = t["encoder"]
+        x = np.matmul(emb, enc["image_embedding_projection"]["kernel"]) + enc["image_embedding_projection"]["bias"][:, None]
+        x = np.concatenate([x, np.zeros((1, 1, 64), np.float32)], 1) + enc["pos_embedding"].reshape(1, 257, 64)
+        return O.transformer(x, enc["Transformer_0"], O.base_mask(1, 257), 4, per_sample=True)
+
+    a = tokens(tree)
+    gen2 = dict(gen)
+    pe = gen[("encoder", "pos_embedding")].copy()
+    pe[:, :, 256] += 1.0
+    gen2[("encoder", "pos_embedding")] = pe
+    b = tokens(O.to_tree(gen2))
+    assert np.array_equal(a[:, :256], b[:, :256])
+    assert not np.allclose(a[:, 256], b[:, 256])
+
+
+def test_grouped_by_task_equals_per_sample_loop(params_p1):
+    """Batched semantics (scripts/train.py:559-579): envs sharing a task == each env evaluated alone."""
+    inp = S.make_inputs(5, 4, 2)
+    lang = inp["instruction_dict"]["language_instruction"]
+    gen, _ = O.generate(params_p1, lang["token_embedding"], lang["attention_mask"], inp["initial_state"]["patch_embeddings"][:, 0],
+                        generated_paths=M.generated_leaves_canonical())
+    rng = np.random.default_rng(0)
+    emb = rng.standard_normal((4, 256, 768)).astype(np.float32)
+    ti = inp["task_index"]
+    h_all = O.base_vit_forward(O.to_tree(O.take_tasks(gen, ti)), emb)
+    for b in range(4):
+        h_b = O.base_vit_forward(O.to_tree(O.take_tasks(gen, ti[b:b + 1])), emb[b:b + 1])
+        assert np.allclose(h_all[b], h_b[0], rtol=0, atol=2e-6)
+
+
+def test_context_mask_blocks(params_p1):
+    am = np.zeros((2, 32), np.int32); am[0, :4] = 1; am[1, :9] = 1
+    m = O.context_mask(am, np.array([True, False]))
+    assert m.shape == (2, 1, 34, 34)
+    assert m[0, 0, :, :4].all() and not m[0, 0, :, 4:32].any()
+    assert not m[1, 0, :, :32].any()                 # lang_pad False masks every language column
+    assert m[:, 0, :, 32].all()                      # image column always visible
+    assert m[:, 0, 33, 33].all() and not m[:, 0, :33, 33].any()
+
+
+def test_mix_head_semantics():
+    """tanh(x/5)*5 for 6 continuous dims x 4 steps; gripper = logit >= 0 (action_heads.py:464-470, 536)."""
+    h = np.zeros((1, 64), np.float32); h[0, 0] = 1.0
+    wc = np.zeros((1, 64, 24), np.float32); wc[0, 0] = np.arange(24) - 10.0
+    wd = np.zeros((1, 64, 4), np.float32); wd[0, 0] = [-1.0, 0.0, 1e-4, 3.0]
+    gen = {"action_head": {"continuous_head": {"kernel": wc, "bias": np.zeros((1, 24), np.float32)},
+                           "discrete_head": {"kernel": wd, "bias": np.zeros((1, 4), np.float32)}}}
+    act, logit = O.mix_head(gen, h)
+    assert act.shape == (1, 4, 7)
+    assert np.allclose(act[0, :, :6].ravel(), np.tanh((np.arange(24) - 10.0) / 5) * 5, atol=1e-6)
+    assert act[0, :, 6].tolist() == [0.0, 1.0, 1.0, 1.0]
