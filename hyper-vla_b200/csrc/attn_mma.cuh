@@ -101,7 +101,7 @@ __device__ __forceinline__ void chunk(const uint32_t (&qf)[4][4], uint32_t sK, u
   }
 }
 
-__global__ void __launch_bounds__(WARPS * 32) dino_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out) {
+__global__ void __launch_bounds__(WARPS * 32, 2) dino_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t smem[];
   bf16* Ks = reinterpret_cast<bf16*>(smem);
   bf16* Vs = Ks + SP * ROW;
@@ -158,6 +158,7 @@ inline int dino_attention(cudaStream_t st, const bf16* qkv, bf16* out, int B) {
   static bool attr = false;
   if (!attr) {
     HVLA_CUDA(cudaFuncSetAttribute(dino_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    HVLA_CUDA(cudaFuncSetAttribute(dino_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr = true;
   }
   dim3 grid(DH, B, QSPLIT);

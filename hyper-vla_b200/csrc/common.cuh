@@ -143,6 +143,21 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
 
+// erf-GELU for bf16 epilogues: erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7) with MUFU rcp/ex2;
+// gelu(x) = x * Phi(x), Phi = 1 - q (x >= 0) or q (x < 0), q = 0.5 * poly(t) * exp(-x^2/2).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  p = fmaf(t, p, 0.5f * 1.421413741f);
+  p = fmaf(t, p, 0.5f * -0.284496736f);
+  p = fmaf(t, p, 0.5f * 0.254829592f);
+  p *= t;
+  const float e = exp2f(x * x * -0.72134752044448170f);   // exp(-x^2/2)
+  const float h = x * (p * e);
+  return x >= 0.f ? x - h : h;
+}
+
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace hvla

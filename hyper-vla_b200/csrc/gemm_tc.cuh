@@ -238,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
           if (EPI == EPI_BIAS_GELU_BF16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
           } else if (col < ep.qcols) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= ep.qscale;

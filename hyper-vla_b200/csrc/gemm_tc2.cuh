@@ -1,0 +1,277 @@
+// 2-CTA (cta_group::2) variant of the tcgen05 GEMM: a CTA pair on one TPC computes a 256x256 tile.
+// Each CTA stages its own 128 rows of A and its own 128-row half of Wt (32 KB per 64-wide K block
+// instead of 48 KB), so the L2->SM operand traffic per FLOP drops by 1/3 and 6 stages fit in smem;
+// the leader CTA issues tcgen05.mma.cta_group::2 (M256 N256 K16) for both tensor cores, every CTA
+// runs its own TMA producer and its own epilogue over its 128 TMEM lanes.
+//   full[s]   (leader)     : 1 arrival (leader producer's expect_tx of BOTH CTAs' bytes) + TMA complete_tx
+//   empty[s]  (both CTAs)  : tcgen05.commit multicast from the leader's MMA thread
+//   tfull[a]  (both CTAs)  : tcgen05.commit multicast when a tile's accumulator is complete
+//   tempty[a] (leader)     : 2 x 8 epilogue-warp arrivals (the peer's arrive remotely)
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace hvla {
+namespace tc2 {
+
+using namespace tc;   // PTX wrappers, EpiP, Epi, descriptors
+
+constexpr int BM2 = 256;                         // pair tile rows (128 per CTA)
+constexpr int STAGES2 = 6;
+constexpr int A2_BYTES = 128 * BK * 2;           // 16 KB
+constexpr int B2_BYTES = 128 * BK * 2;           // 16 KB
+constexpr int SMEM2_BYTES = STAGES2 * (A2_BYTES + B2_BYTES) + 1024 + 256;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrive on the same-offset barrier of CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 remAddr32;\n\t"
+      "mapa.shared::cluster.u32  remAddr32, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64  _, [remAddr32];\n\t"
+      "}" ::"r"(bar), "r"(cta)
+      : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiP ep, int M, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = smem_base + STAGES2 * A2_BYTES;
+  const uint32_t bars = sB + STAGES2 * B2_BYTES;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES2;
+  const uint32_t tfull_bar = bars + 16 * STAGES2, tempty_bar = tfull_bar + 16;
+  const uint32_t tmem_slot = tempty_bar + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_tiles_n = N / BN;
+  const int n_tiles_m = (M + BM2 - 1) / BM2;
+  const int n_tiles = n_tiles_m * n_tiles_n;
+  const int n_kb = K / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar + 8 * s, 1);
+      mbar_init(tempty_bar + 8 * s, 2 * NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // peer barriers are initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+        const int m0 = (tile / n_tiles_n) * BM2 + (int)rank * 128;
+        const int n0 = (tile % n_tiles_n) * BN + (int)rank * 128;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          if (rank == 0) mbar_expect_tx(full_bar + 8 * s, 2 * (A2_BYTES + B2_BYTES));
+          tma_load_2d_2sm(sA + s * A2_BYTES, &tmA, full_bar + 8 * s, kb * BK, m0);
+          tma_load_2d_2sm(sB + s * B2_BYTES, &tmB, full_bar + 8 * s, kb * BK, n0);
+          if (++s == STAGES2) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM2, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(tempty_bar + 8 * as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(full_bar + 8 * s, ph);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(sA + s * A2_BYTES);
+          const uint64_t db = make_smem_desc(sB + s * B2_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(empty_bar + 8 * s);
+          if (++s == STAGES2) { s = 0; ph ^= 1; }
+        }
+        umma_commit_2sm(tfull_bar + 8 * as);
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs, own 128 TMEM lanes) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    int it = 0;
+    for (int tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int m0 = (tile / n_tiles_n) * BM2 + (int)rank * 128, n0 = (tile % n_tiles_n) * BN;
+      mbar_wait(tfull_bar + 8 * as, aph);
+      tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < M;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col = n0 + half * 128 + c * 32;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * 128 + c * 32), r);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
+          v[j] = __uint_as_float(r[j]) + b4.x;
+          v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+          v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
+          v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+        }
+        if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+          if (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+          } else if (col < ep.qcols) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= ep.qscale;
+          }
+          if (row_ok) {
+            bf16* o = reinterpret_cast<bf16*>(ep.out) + (int64_t)row * ep.ldo + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 q;
+              q.x = pack_bf16(v[j], v[j + 1]);
+              q.y = pack_bf16(v[j + 2], v[j + 3]);
+              q.z = pack_bf16(v[j + 4], v[j + 5]);
+              q.w = pack_bf16(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = q;
+            }
+          }
+        } else if (EPI == EPI_RESIDUAL_F32) {
+          if (row_ok) {
+            float* x = reinterpret_cast<float*>(ep.out) + (int64_t)row * ep.ldo + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 l4 = __ldg(reinterpret_cast<const float4*>(ep.ls + col + j));
+              float4 x4 = *reinterpret_cast<const float4*>(x + j);
+              x4.x = x4.x + v[j] * l4.x;
+              x4.y = x4.y + v[j + 1] * l4.y;
+              x4.z = x4.z + v[j + 2] * l4.z;
+              x4.w = x4.w + v[j + 3] * l4.w;
+              *reinterpret_cast<float4*>(x + j) = x4;
+            }
+          }
+        } else {
+          if (row_ok) {
+            const int b = row >> 8, pidx = row & 255;
+            float* x = reinterpret_cast<float*>(ep.out) + ((int64_t)b * DTOK + 1 + pidx) * ep.ldo + col;
+            const float* pz = ep.pos + (int64_t)(1 + pidx) * DD + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 p4 = __ldg(reinterpret_cast<const float4*>(pz + j));
+              *reinterpret_cast<float4*>(x + j) = make_float4(v[j] + p4.x, v[j + 1] + p4.y, v[j + 2] + p4.z, v[j + 3] + p4.w);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(tempty_bar + 8 * as, 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer may still multicast into this CTA's barriers until it is done
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int EPI>
+inline int launch_one2(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const EpiP& ep, int M, int N, int K) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    HVLA_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((M + BM2 - 1) / BM2) * (N / BN);
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  ProfScope ps(st, "gemm_tc");
+  gemm_tc2_kernel<EPI><<<grid, NUM_THREADS, SMEM2_BYTES, st>>>(ma, mb, ep, M, N, K);
+  HVLA_LAUNCH_CHECK("gemm_tc2");
+  return HVLA_OK;
+}
+
+inline int gemm_tc2(cudaStream_t st, const void* A, const void* Wt, int M, int N, int K, int epi, const EpiP& ep) {
+  if (N % BN != 0 || K % BK != 0 || M <= 0) return fail(HVLA_ERR_ARG, "gemm_tc2: N %% 256 or K %% 64 != 0");
+  CUtensorMap ma, mb;
+  HVLA_TRY(make_map_bf16(&ma, A, M, K, 128));
+  HVLA_TRY(make_map_bf16(&mb, Wt, N, K, 128));
+  switch (epi) {
+    case EPI_BIAS_BF16: return launch_one2<EPI_BIAS_BF16>(st, ma, mb, ep, M, N, K);
+    case EPI_BIAS_GELU_BF16: return launch_one2<EPI_BIAS_GELU_BF16>(st, ma, mb, ep, M, N, K);
+    case EPI_RESIDUAL_F32: return launch_one2<EPI_RESIDUAL_F32>(st, ma, mb, ep, M, N, K);
+    case EPI_PATCH_F32: return launch_one2<EPI_PATCH_F32>(st, ma, mb, ep, M, N, K);
+  }
+  return fail(HVLA_ERR_ARG, "gemm_tc2: unknown epilogue");
+}
+
+}  // namespace tc2
+}  // namespace hvla

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "simt_kernels.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 #include "attn_mma.cuh"
 #include "base_fused.cuh"
 
@@ -235,6 +236,7 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
   bf16* A0 = HID;
   const bool simt_gemm = env_flag("HVLA_DEBUG_SIMT_GEMM");   // debugging aid: CUDA-core GEMMs on the bf16 data
   const bool simt_attn = env_flag("HVLA_DEBUG_SIMT_ATTN");
+  const bool one_cta = env_flag("HVLA_GEMM_1CTA");           // A/B switch: single-CTA 128x256 tiles instead of CTA pairs
   {
     const int64_t total = (int64_t)B * NPATCH * PATCH_KP;
     im2col_norm_kernel<bf16><<<cdiv(total, 256), 256, 0, st>>>(images, A0, B);
@@ -243,7 +245,7 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
     HVLA_LAUNCH_CHECK("dino_cls_rows");
   }
   auto gemm = [&](const bf16* A, const bf16* Wt, int m, int n, int k, int epi, const tc::EpiP& ep) -> int {
-    if (!simt_gemm) return tc::gemm_tc(st, A, Wt, m, n, k, epi, ep);
+    if (!simt_gemm) return one_cta ? tc::gemm_tc(st, A, Wt, m, n, k, epi, ep) : tc2::gemm_tc2(st, A, Wt, m, n, k, epi, ep);
     // debug path: same math on CUDA cores (W given transposed)
     return gemm_simt_debug(st, A, Wt, m, n, k, epi, ep);
   };
@@ -565,7 +567,9 @@ int hvla_gemm_bf16(hvla_stream_t stream, const void* A, const void* Wt, const fl
   if (!A || !Wt || !bias || !C) return fail(HVLA_ERR_ARG, "hvla_gemm_bf16: NULL argument");
   tc::EpiP ep; memset(&ep, 0, sizeof ep);
   ep.bias = bias; ep.out = C; ep.ldo = N;
-  return tc::gemm_tc(reinterpret_cast<cudaStream_t>(stream), A, Wt, M, N, K, act == 2 ? tc::EPI_BIAS_GELU_BF16 : tc::EPI_BIAS_BF16, ep);
+  const int epi = act == 2 ? tc::EPI_BIAS_GELU_BF16 : tc::EPI_BIAS_BF16;
+  if (env_flag("HVLA_GEMM_1CTA")) return tc::gemm_tc(reinterpret_cast<cudaStream_t>(stream), A, Wt, M, N, K, epi, ep);
+  return tc2::gemm_tc2(reinterpret_cast<cudaStream_t>(stream), A, Wt, M, N, K, epi, ep);
 }
 
 int hvla_profile_enable(int on) {
