@@ -101,6 +101,13 @@ __device__ __forceinline__ void chunk(const uint32_t (&qf)[4][4], uint32_t sK, u
   }
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(WARPS * 32, 2) dino_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t smem[];
   bf16* Ks = reinterpret_cast<bf16*>(smem);
@@ -108,37 +115,52 @@ __global__ void __launch_bounds__(WARPS * 32, 2) dino_attention_kernel(const bf1
   const int h = blockIdx.x, b = blockIdx.y, qs = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bf16* base = qkv + (int64_t)b * S * (3 * DD) + h * DHD;
-  // stage K and V (rows >= 257 are zero so they contribute nothing to P*V)
-  for (int i = threadIdx.x; i < SP * 8; i += WARPS * 32) {
-    const int r = i >> 3, c = (i & 7) * 8;
-    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-    if (r < S) {
-      kv = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)r * (3 * DD) + DD + c));
-      vv = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)r * (3 * DD) + 2 * DD + c));
+  const uint32_t sK = (uint32_t)__cvta_generic_to_shared(Ks), sV = (uint32_t)__cvta_generic_to_shared(Vs);
+  // stage K and V with cp.async, one commit group per 64-key chunk (5 groups: 4 x 64 rows + row 256),
+  // so the first QK^T can start while later chunks are still in flight
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    const int r0 = c * 64, nr = c < 4 ? 64 : 1;
+    for (int i = threadIdx.x; i < nr * 16; i += WARPS * 32) {
+      const int r = r0 + (i >> 4), part = i & 15;           // 16 x 16-byte pieces per row: 8 of K, 8 of V
+      const int cc = (part & 7) * 8;
+      const bf16* src = base + (int64_t)r * (3 * DD) + (part < 8 ? DD : 2 * DD) + cc;
+      cp_async16((part < 8 ? sK : sV) + (uint32_t)((r * ROW + cc) * 2), src);
     }
-    *reinterpret_cast<uint4*>(Ks + r * ROW + c) = kv;
-    *reinterpret_cast<uint4*>(Vs + r * ROW + c) = vv;
+    cp_async_commit();
   }
-  __syncthreads();
+  // rows 257..271 are zero so they contribute nothing to P*V (their scores are masked to -inf)
+  for (int i = threadIdx.x; i < (SP - S) * 16; i += WARPS * 32) {
+    const int r = S + (i >> 4), part = i & 15;
+    *reinterpret_cast<uint4*>((part < 8 ? Ks : Vs) + r * ROW + (part & 7) * 8) = make_uint4(0, 0, 0, 0);
+  }
   const int tile = qs * WARPS + warp;      // 17 query tiles of 16 rows: tiles 0..8 | 9..16
-  if (tile * 16 >= S) return;
+  const bool active = tile * 16 < S;
   const int row0 = tile * 16 + (lane >> 2), row1 = row0 + 8;
   uint32_t qf[4][4];
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
     const int c = ks * 16 + (lane & 3) * 2;
-    qf[ks][0] = row0 < S ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row0 * (3 * DD) + c)) : 0u;
-    qf[ks][1] = row1 < S ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row1 * (3 * DD) + c)) : 0u;
-    qf[ks][2] = row0 < S ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row0 * (3 * DD) + c + 8)) : 0u;
-    qf[ks][3] = row1 < S ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row1 * (3 * DD) + c + 8)) : 0u;
+    qf[ks][0] = (active && row0 < S) ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row0 * (3 * DD) + c)) : 0u;
+    qf[ks][1] = (active && row1 < S) ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row1 * (3 * DD) + c)) : 0u;
+    qf[ks][2] = (active && row0 < S) ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row0 * (3 * DD) + c + 8)) : 0u;
+    qf[ks][3] = (active && row1 < S) ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row1 * (3 * DD) + c + 8)) : 0u;
   }
   float o[8][4];
 #pragma unroll
   for (int dn = 0; dn < 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  const uint32_t sK = (uint32_t)__cvta_generic_to_shared(Ks), sV = (uint32_t)__cvta_generic_to_shared(Vs);
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) chunk<8>(qf, sK, sV, c * 64, lane, o, m0, m1, l0, l1);
+  for (int c = 0; c < 4; ++c) {
+    if (c == 0) cp_async_wait<4>();
+    else if (c == 1) cp_async_wait<3>();
+    else if (c == 2) cp_async_wait<2>();
+    else cp_async_wait<1>();
+    __syncthreads();
+    if (active) chunk<8>(qf, sK, sV, c * 64, lane, o, m0, m1, l0, l1);
+  }
+  cp_async_wait<0>(); __syncthreads();
+  if (!active) return;
   chunk<2>(qf, sK, sV, 256, lane, o, m0, m1, l0, l1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);

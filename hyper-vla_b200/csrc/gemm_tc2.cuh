@@ -9,6 +9,7 @@
 //   tempty[a] (leader)     : 2 x 8 epilogue-warp arrivals (the peer's arrive remotely)
 #pragma once
 #include "gemm_tc.cuh"
+#include <stdlib.h>
 
 namespace hvla {
 namespace tc2 {
@@ -251,7 +252,8 @@ inline int launch_one2(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap
     attr_set = true;
   }
   const int tiles = ((M + BM2 - 1) / BM2) * (N / BN);
-  const int pairs = num_sms() / 2;
+  int pairs = num_sms() / 2;
+  if (const char* e = getenv("HVLA_GEMM_MAX_PAIRS")) { const int v = atoi(e); if (v > 0 && v < pairs) pairs = v; }   // experiment knob
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
   ProfScope ps(st, "gemm_tc");
   gemm_tc2_kernel<EPI><<<grid, NUM_THREADS, SMEM2_BYTES, st>>>(ma, mb, ep, M, N, K);
