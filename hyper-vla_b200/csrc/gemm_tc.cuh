@@ -18,7 +18,7 @@ constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*epilogue bias/ls*/;
 
 enum Epi { EPI_BIAS_BF16 = 0, EPI_BIAS_GELU_BF16 = 1, EPI_RESIDUAL_F32 = 2, EPI_PATCH_F32 = 3 };
 
@@ -100,8 +100,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps only
 
 // UMMA shared-memory descriptor: K-major operand, SWIZZLE_128B, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -123,6 +124,112 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+
+// ---- epilogue of one 128x256 accumulator (per CTA), shared by the 1-CTA and 2-CTA kernels --------------
+// Called by the 8 epilogue warps.  Bias / LayerScale of the tile's 256 columns are staged in shared
+// memory while the MMAs are still running, TMEM loads are double-buffered against the math/stores,
+// and (residual epilogue) the fp32 residual values are prefetched one chunk ahead.
+constexpr int EPI_SMEM_FLOATS = 2 * 2 * 256;   // [accumulator stage][bias | ls][256]
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile(const EpiP& ep, float* sepi, uint32_t tfull_bar_addr, uint32_t aph, int as,
+                                              uint32_t tmem_base, int m0, int n0, int M, int warp, int lane) {
+  const int ew = warp - 2;
+  const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+  const int half = ew >> 2;              // which 128-column half of the tile
+  const int te = threadIdx.x - 64;       // 0..255
+  float* sb = sepi + as * 512;
+  float* sl = sb + 256;
+  sb[te] = __ldg(ep.bias + n0 + te);
+  if (EPI == EPI_RESIDUAL_F32) sl[te] = __ldg(ep.ls + n0 + te);
+  const int row = m0 + quarter * 32 + lane;
+  const bool row_ok = row < M;
+  const int colh = n0 + half * 128;
+  float4 xr[2][8];
+  float* xrow = nullptr;
+  if (EPI == EPI_RESIDUAL_F32) {
+    xrow = reinterpret_cast<float*>(ep.out) + (int64_t)(row_ok ? row : 0) * ep.ldo + colh;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xr[0][j] = *reinterpret_cast<const float4*>(xrow + 4 * j);
+  }
+  epi_bar_sync();                        // staged bias visible to all epilogue warps
+  mbar_wait(tfull_bar_addr, aph);
+  tc_fence_after();
+  const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * 128);
+  uint32_t r[2][32];
+  tmem_ld32(taddr, r[0]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    tmem_wait_ld();
+    if (c < 3) {
+      tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+      if (EPI == EPI_RESIDUAL_F32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xr[(c + 1) & 1][j] = *reinterpret_cast<const float4*>(xrow + (c + 1) * 32 + 4 * j);
+      }
+    }
+    const uint32_t(&rc)[32] = r[c & 1];
+    const int cl = half * 128 + c * 32;  // column inside the tile
+    const int col = n0 + cl;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sb + cl + j);
+      v[j] = __uint_as_float(rc[j]) + b4.x;
+      v[j + 1] = __uint_as_float(rc[j + 1]) + b4.y;
+      v[j + 2] = __uint_as_float(rc[j + 2]) + b4.z;
+      v[j + 3] = __uint_as_float(rc[j + 3]) + b4.w;
+    }
+    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+      if (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+      } else if (col < ep.qcols) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= ep.qscale;
+      }
+      if (row_ok) {
+        bf16* o = reinterpret_cast<bf16*>(ep.out) + (int64_t)row * ep.ldo + col;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 q;
+          q.x = pack_bf16(v[j], v[j + 1]);
+          q.y = pack_bf16(v[j + 2], v[j + 3]);
+          q.z = pack_bf16(v[j + 4], v[j + 5]);
+          q.w = pack_bf16(v[j + 6], v[j + 7]);
+          *reinterpret_cast<uint4*>(o + j) = q;
+        }
+      }
+    } else if (EPI == EPI_RESIDUAL_F32) {
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(sl + cl + j);
+          float4 x4 = xr[c & 1][j >> 2];
+          x4.x = x4.x + v[j] * l4.x;
+          x4.y = x4.y + v[j + 1] * l4.y;
+          x4.z = x4.z + v[j + 2] * l4.z;
+          x4.w = x4.w + v[j + 3] * l4.w;
+          *reinterpret_cast<float4*>(xrow + c * 32 + j) = x4;
+        }
+      }
+    } else {  // EPI_PATCH_F32: row = b*256+p -> token b*257+1+p, add position table
+      if (row_ok) {
+        const int b = row >> 8, pidx = row & 255;
+        float* x = reinterpret_cast<float*>(ep.out) + ((int64_t)b * DTOK + 1 + pidx) * ep.ldo + col;
+        const float* pz = ep.pos + (int64_t)(1 + pidx) * DD + col;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 p4 = __ldg(reinterpret_cast<const float4*>(pz + j));
+          *reinterpret_cast<float4*>(x + j) = make_float4(v[j] + p4.x, v[j + 1] + p4.y, v[j + 2] + p4.z, v[j + 3] + p4.w);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncwarp();
+}
+
 // ---- the kernel ---------------------------------------------------------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -136,6 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
   const uint32_t tmem_slot = tempty_bar + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  float* sepi = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles_n = N / BN;
@@ -209,81 +317,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue warps =====================
-    const int ew = warp - 2;
-    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = ew >> 2;              // which 128-column half of the tile
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
-      mbar_wait(tfull_bar + 8 * as, aph);
-      tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < M;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int col = n0 + half * 128 + c * 32;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * 128 + c * 32), r);
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
-          v[j] = __uint_as_float(r[j]) + b4.x;
-          v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-          v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
-          v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
-        }
-        if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
-          if (EPI == EPI_BIAS_GELU_BF16) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
-          } else if (col < ep.qcols) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= ep.qscale;
-          }
-          if (row_ok) {
-            bf16* o = reinterpret_cast<bf16*>(ep.out) + (int64_t)row * ep.ldo + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 q;
-              q.x = pack_bf16(v[j], v[j + 1]);
-              q.y = pack_bf16(v[j + 2], v[j + 3]);
-              q.z = pack_bf16(v[j + 4], v[j + 5]);
-              q.w = pack_bf16(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(o + j) = q;
-            }
-          }
-        } else if (EPI == EPI_RESIDUAL_F32) {
-          if (row_ok) {
-            float* x = reinterpret_cast<float*>(ep.out) + (int64_t)row * ep.ldo + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 l4 = __ldg(reinterpret_cast<const float4*>(ep.ls + col + j));
-              float4 x4 = *reinterpret_cast<const float4*>(x + j);
-              x4.x = x4.x + v[j] * l4.x;
-              x4.y = x4.y + v[j + 1] * l4.y;
-              x4.z = x4.z + v[j + 2] * l4.z;
-              x4.w = x4.w + v[j + 3] * l4.w;
-              *reinterpret_cast<float4*>(x + j) = x4;
-            }
-          }
-        } else {  // EPI_PATCH_F32: row = b*256+p -> token b*257+1+p, add position table
-          if (row_ok) {
-            const int b = row >> 8, pidx = row & 255;
-            float* x = reinterpret_cast<float*>(ep.out) + ((int64_t)b * DTOK + 1 + pidx) * ep.ldo + col;
-            const float* pz = ep.pos + (int64_t)(1 + pidx) * DD + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 p4 = __ldg(reinterpret_cast<const float4*>(pz + j));
-              *reinterpret_cast<float4*>(x + j) = make_float4(v[j] + p4.x, v[j + 1] + p4.y, v[j + 2] + p4.z, v[j + 3] + p4.w);
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
+      epilogue_tile<EPI>(ep, sepi, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, M, warp, lane);
       if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
     }
   }

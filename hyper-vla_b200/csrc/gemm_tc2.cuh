@@ -20,7 +20,7 @@ constexpr int BM2 = 256;                         // pair tile rows (128 per CTA)
 constexpr int STAGES2 = 6;
 constexpr int A2_BYTES = 128 * BK * 2;           // 16 KB
 constexpr int B2_BYTES = 128 * BK * 2;           // 16 KB
-constexpr int SMEM2_BYTES = STAGES2 * (A2_BYTES + B2_BYTES) + 1024 + 256;
+constexpr int SMEM2_BYTES = STAGES2 * (A2_BYTES + B2_BYTES) + 1024 + 256 + 4096;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -83,6 +83,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tfull_bar = bars + 16 * STAGES2, tempty_bar = tfull_bar + 16;
   const uint32_t tmem_slot = tempty_bar + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  float* sepi = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -157,81 +158,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // ===================== epilogue warps (both CTAs, own 128 TMEM lanes) =====================
-    const int ew = warp - 2;
-    const int quarter = warp & 3;
-    const int half = ew >> 2;
     int it = 0;
     for (int tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int m0 = (tile / n_tiles_n) * BM2 + (int)rank * 128, n0 = (tile % n_tiles_n) * BN;
-      mbar_wait(tfull_bar + 8 * as, aph);
-      tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < M;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int col = n0 + half * 128 + c * 32;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * 128 + c * 32), r);
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
-          v[j] = __uint_as_float(r[j]) + b4.x;
-          v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-          v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
-          v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
-        }
-        if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
-          if (EPI == EPI_BIAS_GELU_BF16) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
-          } else if (col < ep.qcols) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= ep.qscale;
-          }
-          if (row_ok) {
-            bf16* o = reinterpret_cast<bf16*>(ep.out) + (int64_t)row * ep.ldo + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 q;
-              q.x = pack_bf16(v[j], v[j + 1]);
-              q.y = pack_bf16(v[j + 2], v[j + 3]);
-              q.z = pack_bf16(v[j + 4], v[j + 5]);
-              q.w = pack_bf16(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(o + j) = q;
-            }
-          }
-        } else if (EPI == EPI_RESIDUAL_F32) {
-          if (row_ok) {
-            float* x = reinterpret_cast<float*>(ep.out) + (int64_t)row * ep.ldo + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 l4 = __ldg(reinterpret_cast<const float4*>(ep.ls + col + j));
-              float4 x4 = *reinterpret_cast<const float4*>(x + j);
-              x4.x = x4.x + v[j] * l4.x;
-              x4.y = x4.y + v[j + 1] * l4.y;
-              x4.z = x4.z + v[j + 2] * l4.z;
-              x4.w = x4.w + v[j + 3] * l4.w;
-              *reinterpret_cast<float4*>(x + j) = x4;
-            }
-          }
-        } else {
-          if (row_ok) {
-            const int b = row >> 8, pidx = row & 255;
-            float* x = reinterpret_cast<float*>(ep.out) + ((int64_t)b * DTOK + 1 + pidx) * ep.ldo + col;
-            const float* pz = ep.pos + (int64_t)(1 + pidx) * DD + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 p4 = __ldg(reinterpret_cast<const float4*>(pz + j));
-              *reinterpret_cast<float4*>(x + j) = make_float4(v[j] + p4.x, v[j + 1] + p4.y, v[j + 2] + p4.z, v[j + 3] + p4.w);
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
+      epilogue_tile<EPI>(ep, sepi, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, M, warp, lane);
       if (lane == 0) mbar_arrive_remote(tempty_bar + 8 * as, 0);
     }
   }
