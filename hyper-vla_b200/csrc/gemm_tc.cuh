@@ -18,7 +18,8 @@ constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*epilogue bias/ls*/;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*epilogue bias/ls*/ +
+                           1024 + 8 * 2048 /*TMA-store slabs*/;
 
 enum Epi { EPI_BIAS_BF16 = 0, EPI_BIAS_GELU_BF16 = 1, EPI_RESIDUAL_F32 = 2, EPI_PATCH_F32 = 3 };
 
@@ -30,6 +31,7 @@ struct EpiP {
   const float* pos;    // [257,768] position table (EPI 3)
   float qscale;        // EPI 0: columns < qcols are multiplied by qscale (query pre-scaling)
   int qcols;
+  int debug;           // experiment knob (hvla_gemm_bf16 only): 1 = handshake only, 2 = TMEM loads only, 4 = no global stores
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -66,6 +68,20 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -132,7 +148,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 constexpr int EPI_SMEM_FLOATS = 2 * 2 * 256;   // [accumulator stage][bias | ls][256]
 
 template <int EPI>
-__device__ __forceinline__ void epilogue_tile(const EpiP& ep, float* sepi, uint32_t tfull_bar_addr, uint32_t aph, int as,
+__device__ __forceinline__ void epilogue_tile_direct(const EpiP& ep, float* sepi, uint32_t tfull_bar_addr, uint32_t aph, int as,
                                               uint32_t tmem_base, int m0, int n0, int M, int warp, int lane) {
   const int ew = warp - 2;
   const int quarter = warp & 3;          // TMEM lane quarter this warp may access
@@ -155,6 +171,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiP& ep, float* sepi, uint3
   epi_bar_sync();                        // staged bias visible to all epilogue warps
   mbar_wait(tfull_bar_addr, aph);
   tc_fence_after();
+  if (ep.debug & 1) { tc_fence_before(); __syncwarp(); return; }
   const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * 128);
   uint32_t r[2][32];
   tmem_ld32(taddr, r[0]);
@@ -169,6 +186,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiP& ep, float* sepi, uint3
       }
     }
     const uint32_t(&rc)[32] = r[c & 1];
+    if (ep.debug & 2) { if (rc[0] == 0x7fc12345u && rc[7] == 0x7fc54321u) reinterpret_cast<float*>(ep.out)[0] = 1.f; continue; }
     const int cl = half * 128 + c * 32;  // column inside the tile
     const int col = n0 + cl;
     float v[32];
@@ -183,12 +201,12 @@ __device__ __forceinline__ void epilogue_tile(const EpiP& ep, float* sepi, uint3
     if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
       if (EPI == EPI_BIAS_GELU_BF16) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_tanhfit(v[j]);
       } else if (col < ep.qcols) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= ep.qscale;
       }
-      if (row_ok) {
+      if (row_ok && !((ep.debug & 4) && v[0] != 123.456f)) {
         bf16* o = reinterpret_cast<bf16*>(ep.out) + (int64_t)row * ep.ldo + col;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
@@ -230,10 +248,110 @@ __device__ __forceinline__ void epilogue_tile(const EpiP& ep, float* sepi, uint3
   __syncwarp();
 }
 
+
+// ---- epilogue through shared memory + TMA (EPI 0/1/2) -----------------------------------------------------
+// Row-per-thread global stores touch 32 different lines per warp instruction and throttled the whole
+// kernel (measured: QKV GEMM 1.03 PFLOP/s with them, 1.50 without).  Here every warp transposes 32x64-byte
+// units through a 2 KB shared-memory slab (SWIZZLE_64B, conflict-free 16-byte stores) and one lane hands
+// the slab to the TMA engine: a plain tensor store for bf16 outputs, a tensor REDUCE-ADD (fp32) for the
+// residual stream, so x += ls * (acc + bias) needs no read of x through the SM at all.
+constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 2048;
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensorMap* tmO, float* sepi, uint32_t sstage,
+                                                  uint32_t tfull_bar_addr, uint32_t aph, int as, uint32_t tmem_base, int m0,
+                                                  int n0, int warp, int lane) {
+  const int ew = warp - 2;
+  const int quarter = warp & 3;
+  const int half = ew >> 2;
+  const int te = threadIdx.x - 64;
+  float* sb = sepi + as * 512;
+  float* sl = sb + 256;
+  sb[te] = __ldg(ep.bias + n0 + te);
+  if (EPI == EPI_RESIDUAL_F32) sl[te] = __ldg(ep.ls + n0 + te);
+  const int row0 = m0 + quarter * 32;
+  const uint32_t slab = sstage + (uint32_t)ew * 2048u;
+  const uint32_t my = slab + (uint32_t)lane * 64u;
+  const uint32_t sw = (uint32_t)((lane >> 1) & 3);          // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+  epi_bar_sync();
+  mbar_wait(tfull_bar_addr, aph);
+  tc_fence_after();
+  if (ep.debug & 1) { tc_fence_before(); __syncwarp(); return; }
+  const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * 128);
+  uint32_t r[2][32];
+  tmem_ld32(taddr, r[0]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    tmem_wait_ld();
+    if (c < 3) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+    const uint32_t(&rc)[32] = r[c & 1];
+    const int cl = half * 128 + c * 32;
+    const int col = n0 + cl;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sb + cl + j);
+      v[j] = __uint_as_float(rc[j]) + b4.x;
+      v[j + 1] = __uint_as_float(rc[j + 1]) + b4.y;
+      v[j + 2] = __uint_as_float(rc[j + 2]) + b4.z;
+      v[j + 3] = __uint_as_float(rc[j + 3]) + b4.w;
+    }
+    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+      if (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_tanhfit(v[j]);
+      } else if (col < ep.qcols) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= ep.qscale;
+      }
+      if (lane == 0) bulk_wait_read0();       // the slab's previous TMA store has finished reading it
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t a = my + ((((uint32_t)j) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16(v[8 * j], v[8 * j + 1])),
+                     "r"(pack_bf16(v[8 * j + 2], v[8 * j + 3])), "r"(pack_bf16(v[8 * j + 4], v[8 * j + 5])),
+                     "r"(pack_bf16(v[8 * j + 6], v[8 * j + 7]))
+                     : "memory");
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmO, slab, col, row0);
+        bulk_commit();
+      }
+    } else {   // EPI_RESIDUAL_F32: two units of 16 fp32 columns, reduce-added into the residual stream
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int e = u * 16 + j * 4;
+          const float4 l4 = *reinterpret_cast<const float4*>(sl + cl + e);
+          const uint32_t a = my + ((((uint32_t)j) ^ sw) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[e] * l4.x), "f"(v[e + 1] * l4.y),
+                       "f"(v[e + 2] * l4.z), "f"(v[e + 3] * l4.w)
+                       : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(tmO, slab, col + u * 16, row0);
+          bulk_commit();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncwarp();
+}
+
 // ---- the kernel ---------------------------------------------------------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiP ep, int M, int N, int K) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, EpiP ep, int M, int N, int K) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
@@ -244,6 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_slot = tempty_bar + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* sepi = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
+  const uint32_t sstage = (tmem_slot + 16 + 4096 + 1023u) & ~1023u;   // per-warp 2 KB TMA-store slabs
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles_n = N / BN;
@@ -254,6 +373,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
@@ -322,9 +442,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
-      epilogue_tile<EPI>(ep, sepi, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, M, warp, lane);
+      if (EPI == EPI_PATCH_F32) epilogue_tile_direct<EPI>(ep, sepi, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, M, warp, lane);
+      else epilogue_tile_tma<EPI>(ep, &tmO, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane);
       if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
     }
+    if (lane == 0) bulk_wait0();            // all TMA stores of this warp have completed
   }
   tc_fence_before();
   __syncthreads();
@@ -366,6 +488,27 @@ inline int make_map_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int64_
   return HVLA_OK;
 }
 
+// output map for the TMA epilogue: 32-row x 64-byte boxes, SWIZZLE_64B (bf16: 32 columns, fp32: 16 columns)
+inline int make_map_out(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, bool f32) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(HVLA_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  const int es = f32 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * es};
+  cuuint32_t box[2] = {(cuuint32_t)(64 / es), 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(HVLA_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed");
+  return HVLA_OK;
+}
+// rows of the output tensor as the epilogue addresses them (patch epilogue does not use the map)
+inline int make_out_map_for(CUtensorMap* mo, int epi, const EpiP& ep, int M) {
+  if (epi == EPI_PATCH_F32) { memset(mo, 0, sizeof *mo); return HVLA_OK; }
+  return make_map_out(mo, ep.out, M, ep.ldo, epi == EPI_RESIDUAL_F32);
+}
+
 inline int num_sms() {
   static int n = 0;
   if (!n) {
@@ -378,7 +521,8 @@ inline int num_sms() {
 }
 
 template <int EPI>
-inline int launch_one(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const EpiP& ep, int M, int N, int K) {
+inline int launch_one(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const EpiP& ep, int M, int N,
+                      int K) {
   static bool attr_set = false;
   if (!attr_set) {
     HVLA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -387,7 +531,7 @@ inline int launch_one(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap&
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   ProfScope ps(st, "gemm_tc");
-  gemm_tc_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, ep, M, N, K);
+  gemm_tc_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, mo, ep, M, N, K);
   HVLA_LAUNCH_CHECK("gemm_tc");
   return HVLA_OK;
 }
@@ -395,14 +539,15 @@ inline int launch_one(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap&
 // C = epi(A[M,K] * Wt[N,K]^T);  N % 256 == 0, K % 64 == 0
 inline int gemm_tc(cudaStream_t st, const void* A, const void* Wt, int M, int N, int K, int epi, const EpiP& ep) {
   if (N % BN != 0 || K % BK != 0 || M <= 0) return fail(HVLA_ERR_ARG, "gemm_tc: N %% 256 or K %% 64 != 0");
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mo;
   HVLA_TRY(make_map_bf16(&ma, A, M, K, BM));
   HVLA_TRY(make_map_bf16(&mb, Wt, N, K, BN));
+  HVLA_TRY(make_out_map_for(&mo, epi, ep, M));
   switch (epi) {
-    case EPI_BIAS_BF16: return launch_one<EPI_BIAS_BF16>(st, ma, mb, ep, M, N, K);
-    case EPI_BIAS_GELU_BF16: return launch_one<EPI_BIAS_GELU_BF16>(st, ma, mb, ep, M, N, K);
-    case EPI_RESIDUAL_F32: return launch_one<EPI_RESIDUAL_F32>(st, ma, mb, ep, M, N, K);
-    case EPI_PATCH_F32: return launch_one<EPI_PATCH_F32>(st, ma, mb, ep, M, N, K);
+    case EPI_BIAS_BF16: return launch_one<EPI_BIAS_BF16>(st, ma, mb, mo, ep, M, N, K);
+    case EPI_BIAS_GELU_BF16: return launch_one<EPI_BIAS_GELU_BF16>(st, ma, mb, mo, ep, M, N, K);
+    case EPI_RESIDUAL_F32: return launch_one<EPI_RESIDUAL_F32>(st, ma, mb, mo, ep, M, N, K);
+    case EPI_PATCH_F32: return launch_one<EPI_PATCH_F32>(st, ma, mb, mo, ep, M, N, K);
   }
   return fail(HVLA_ERR_ARG, "gemm_tc: unknown epilogue");
 }

@@ -20,7 +20,7 @@ constexpr int BM2 = 256;                         // pair tile rows (128 per CTA)
 constexpr int STAGES2 = 6;
 constexpr int A2_BYTES = 128 * BK * 2;           // 16 KB
 constexpr int B2_BYTES = 128 * BK * 2;           // 16 KB
-constexpr int SMEM2_BYTES = STAGES2 * (A2_BYTES + B2_BYTES) + 1024 + 256 + 4096;
+constexpr int SMEM2_BYTES = STAGES2 * (A2_BYTES + B2_BYTES) + 1024 + 256 + 4096 + 1024 + 8 * 2048;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -73,7 +73,8 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiP ep, int M, int N, int K) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmO, EpiP ep, int M, int N, int K) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
@@ -84,6 +85,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_slot = tempty_bar + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* sepi = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
+  const uint32_t sstage = (tmem_slot + 16 + 4096 + 1023u) & ~1023u;   // per-warp 2 KB TMA-store slabs
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -96,6 +98,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
     for (int s = 0; s < STAGES2; ++s) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
@@ -163,9 +166,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int m0 = (tile / n_tiles_n) * BM2 + (int)rank * 128, n0 = (tile % n_tiles_n) * BN;
-      epilogue_tile<EPI>(ep, sepi, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, M, warp, lane);
+      if (EPI == EPI_PATCH_F32) epilogue_tile_direct<EPI>(ep, sepi, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, M, warp, lane);
+      else epilogue_tile_tma<EPI>(ep, &tmO, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane);
       if (lane == 0) mbar_arrive_remote(tempty_bar + 8 * as, 0);
     }
+    if (lane == 0) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -177,7 +182,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 template <int EPI>
-inline int launch_one2(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const EpiP& ep, int M, int N, int K) {
+inline int launch_one2(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const EpiP& ep, int M, int N,
+                       int K) {
   static bool attr_set = false;
   if (!attr_set) {
     HVLA_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
@@ -188,21 +194,22 @@ inline int launch_one2(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap
   if (const char* e = getenv("HVLA_GEMM_MAX_PAIRS")) { const int v = atoi(e); if (v > 0 && v < pairs) pairs = v; }   // experiment knob
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
   ProfScope ps(st, "gemm_tc");
-  gemm_tc2_kernel<EPI><<<grid, NUM_THREADS, SMEM2_BYTES, st>>>(ma, mb, ep, M, N, K);
+  gemm_tc2_kernel<EPI><<<grid, NUM_THREADS, SMEM2_BYTES, st>>>(ma, mb, mo, ep, M, N, K);
   HVLA_LAUNCH_CHECK("gemm_tc2");
   return HVLA_OK;
 }
 
 inline int gemm_tc2(cudaStream_t st, const void* A, const void* Wt, int M, int N, int K, int epi, const EpiP& ep) {
   if (N % BN != 0 || K % BK != 0 || M <= 0) return fail(HVLA_ERR_ARG, "gemm_tc2: N %% 256 or K %% 64 != 0");
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mo;
   HVLA_TRY(make_map_bf16(&ma, A, M, K, 128));
   HVLA_TRY(make_map_bf16(&mb, Wt, N, K, 128));
+  HVLA_TRY(make_out_map_for(&mo, epi, ep, M));
   switch (epi) {
-    case EPI_BIAS_BF16: return launch_one2<EPI_BIAS_BF16>(st, ma, mb, ep, M, N, K);
-    case EPI_BIAS_GELU_BF16: return launch_one2<EPI_BIAS_GELU_BF16>(st, ma, mb, ep, M, N, K);
-    case EPI_RESIDUAL_F32: return launch_one2<EPI_RESIDUAL_F32>(st, ma, mb, ep, M, N, K);
-    case EPI_PATCH_F32: return launch_one2<EPI_PATCH_F32>(st, ma, mb, ep, M, N, K);
+    case EPI_BIAS_BF16: return launch_one2<EPI_BIAS_BF16>(st, ma, mb, mo, ep, M, N, K);
+    case EPI_BIAS_GELU_BF16: return launch_one2<EPI_BIAS_GELU_BF16>(st, ma, mb, mo, ep, M, N, K);
+    case EPI_RESIDUAL_F32: return launch_one2<EPI_RESIDUAL_F32>(st, ma, mb, mo, ep, M, N, K);
+    case EPI_PATCH_F32: return launch_one2<EPI_PATCH_F32>(st, ma, mb, mo, ep, M, N, K);
   }
   return fail(HVLA_ERR_ARG, "gemm_tc2: unknown epilogue");
 }

@@ -568,6 +568,7 @@ int hvla_gemm_bf16(hvla_stream_t stream, const void* A, const void* Wt, const fl
   tc::EpiP ep; memset(&ep, 0, sizeof ep);
   ep.bias = bias; ep.out = C; ep.ldo = N;
   const int epi = act == 2 ? tc::EPI_BIAS_GELU_BF16 : tc::EPI_BIAS_BF16;
+  if (const char* e = getenv("HVLA_GEMM_DEBUG")) ep.debug = atoi(e);
   if (env_flag("HVLA_GEMM_1CTA")) return tc::gemm_tc(reinterpret_cast<cudaStream_t>(stream), A, Wt, M, N, K, epi, ep);
   return tc2::gemm_tc2(reinterpret_cast<cudaStream_t>(stream), A, Wt, M, N, K, epi, ep);
 }
