@@ -8,6 +8,16 @@
 #include "common.cuh"
 
 namespace hvla {
+inline int tc_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
 namespace attn {
 
 constexpr int S = DTOK;          // 257
@@ -108,84 +118,93 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(WARPS * 32, 2) dino_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  bf16* Ks = reinterpret_cast<bf16*>(smem);
-  bf16* Vs = Ks + SP * ROW;
-  const int h = blockIdx.x, b = blockIdx.y, qs = blockIdx.z;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// Persistent version: one CTA per SM loops over (image, head) items; 17 warps = the 17 query tiles of
+// 16 rows; K/V of the NEXT item are prefetched with cp.async into the second smem buffer while the
+// current item is computed, so the staging latency is hidden and every K/V row is read once.
+constexpr int PWARPS = 17;
+constexpr int PBUF = 2 * SP * ROW;                  // bf16 elements per buffer (K then V)
+constexpr int PSMEM = 2 * PBUF * 2;
+
+__device__ __forceinline__ void stage_item(const bf16* __restrict__ qkv, int item, uint32_t sK, uint32_t sV) {
+  const int b = item / DH, h = item % DH;
   const bf16* base = qkv + (int64_t)b * S * (3 * DD) + h * DHD;
-  const uint32_t sK = (uint32_t)__cvta_generic_to_shared(Ks), sV = (uint32_t)__cvta_generic_to_shared(Vs);
-  // stage K and V with cp.async, one commit group per 64-key chunk (5 groups: 4 x 64 rows + row 256),
-  // so the first QK^T can start while later chunks are still in flight
-#pragma unroll
-  for (int c = 0; c < 5; ++c) {
-    const int r0 = c * 64, nr = c < 4 ? 64 : 1;
-    for (int i = threadIdx.x; i < nr * 16; i += WARPS * 32) {
-      const int r = r0 + (i >> 4), part = i & 15;           // 16 x 16-byte pieces per row: 8 of K, 8 of V
-      const int cc = (part & 7) * 8;
-      const bf16* src = base + (int64_t)r * (3 * DD) + (part < 8 ? DD : 2 * DD) + cc;
-      cp_async16((part < 8 ? sK : sV) + (uint32_t)((r * ROW + cc) * 2), src);
-    }
+  for (int i = threadIdx.x; i < S * 16; i += PWARPS * 32) {
+    const int r = i >> 4, part = i & 15;            // 16 x 16-byte pieces per row: 8 of K, 8 of V
+    const int cc = (part & 7) * 8;
+    const bf16* src = base + (int64_t)r * (3 * DD) + (part < 8 ? DD : 2 * DD) + cc;
+    cp_async16((part < 8 ? sK : sV) + (uint32_t)((r * ROW + cc) * 2), src);
+  }
+}
+
+__global__ void __launch_bounds__(PWARPS * 32, 1)
+dino_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int n_items) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  bf16* buf = reinterpret_cast<bf16*>(smem);
+  const uint32_t sbuf = (uint32_t)__cvta_generic_to_shared(buf);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // rows 257..271 of K and V in both buffers stay zero (scores masked to -inf, P*V contribution zero)
+  for (int i = threadIdx.x; i < 2 * 2 * (SP - S) * 8; i += PWARPS * 32) {
+    const int which = i / ((SP - S) * 8), j = i % ((SP - S) * 8);
+    const int r = S + (j >> 3), c = (j & 7) * 8;
+    *reinterpret_cast<uint4*>(buf + which * (SP * ROW) + r * ROW + c) = make_uint4(0, 0, 0, 0);
+  }
+  int item = blockIdx.x;
+  if (item < n_items) stage_item(qkv, item, sbuf, sbuf + SP * ROW * 2);
+  cp_async_commit();
+  const int row0 = warp * 16 + (lane >> 2), row1 = row0 + 8;
+  for (int it = 0; item < n_items; item += gridDim.x, ++it) {
+    const int cur = it & 1;
+    const uint32_t sK = sbuf + (uint32_t)(cur * PBUF * 2), sV = sK + SP * ROW * 2;
+    const int nxt = item + gridDim.x;
+    if (nxt < n_items) stage_item(qkv, nxt, sbuf + (uint32_t)((cur ^ 1) * PBUF * 2), sbuf + (uint32_t)((cur ^ 1) * PBUF * 2) + SP * ROW * 2);
     cp_async_commit();
-  }
-  // rows 257..271 are zero so they contribute nothing to P*V (their scores are masked to -inf)
-  for (int i = threadIdx.x; i < (SP - S) * 16; i += WARPS * 32) {
-    const int r = S + (i >> 4), part = i & 15;
-    *reinterpret_cast<uint4*>((part < 8 ? Ks : Vs) + r * ROW + (part & 7) * 8) = make_uint4(0, 0, 0, 0);
-  }
-  const int tile = qs * WARPS + warp;      // 17 query tiles of 16 rows: tiles 0..8 | 9..16
-  const bool active = tile * 16 < S;
-  const int row0 = tile * 16 + (lane >> 2), row1 = row0 + 8;
-  uint32_t qf[4][4];
+    const int b = item / DH, h = item % DH;
+    const bf16* base = qkv + (int64_t)b * S * (3 * DD) + h * DHD;
+    uint32_t qf[4][4];
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    const int c = ks * 16 + (lane & 3) * 2;
-    qf[ks][0] = (active && row0 < S) ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row0 * (3 * DD) + c)) : 0u;
-    qf[ks][1] = (active && row1 < S) ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row1 * (3 * DD) + c)) : 0u;
-    qf[ks][2] = (active && row0 < S) ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row0 * (3 * DD) + c + 8)) : 0u;
-    qf[ks][3] = (active && row1 < S) ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row1 * (3 * DD) + c + 8)) : 0u;
-  }
-  float o[8][4];
-#pragma unroll
-  for (int dn = 0; dn < 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    if (c == 0) cp_async_wait<4>();
-    else if (c == 1) cp_async_wait<3>();
-    else if (c == 2) cp_async_wait<2>();
-    else cp_async_wait<1>();
+    for (int ks = 0; ks < 4; ++ks) {
+      const int c = ks * 16 + (lane & 3) * 2;
+      qf[ks][0] = row0 < S ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row0 * (3 * DD) + c)) : 0u;
+      qf[ks][1] = row1 < S ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row1 * (3 * DD) + c)) : 0u;
+      qf[ks][2] = row0 < S ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row0 * (3 * DD) + c + 8)) : 0u;
+      qf[ks][3] = row1 < S ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row1 * (3 * DD) + c + 8)) : 0u;
+    }
+    cp_async_wait<1>();          // everything but the prefetch just issued has landed
     __syncthreads();
-    if (active) chunk<8>(qf, sK, sV, c * 64, lane, o, m0, m1, l0, l1);
-  }
-  cp_async_wait<0>(); __syncthreads();
-  if (!active) return;
-  chunk<2>(qf, sK, sV, 256, lane, o, m0, m1, l0, l1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-  bf16* ob = out + (int64_t)b * S * DD + h * DHD;
+    float o[8][4];
 #pragma unroll
-  for (int dn = 0; dn < 8; ++dn) {
-    const int c = dn * 8 + (lane & 3) * 2;
-    if (row0 < S) *reinterpret_cast<uint32_t*>(ob + (int64_t)row0 * DD + c) = pack2(o[dn][0] * i0, o[dn][1] * i0);
-    if (row1 < S) *reinterpret_cast<uint32_t*>(ob + (int64_t)row1 * DD + c) = pack2(o[dn][2] * i1, o[dn][3] * i1);
+    for (int dn = 0; dn < 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) chunk<8>(qf, sK, sV, c * 64, lane, o, m0, m1, l0, l1);
+    chunk<2>(qf, sK, sV, 256, lane, o, m0, m1, l0, l1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    bf16* ob = out + (int64_t)b * S * DD + h * DHD;
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn) {
+      const int c = dn * 8 + (lane & 3) * 2;
+      if (row0 < S) *reinterpret_cast<uint32_t*>(ob + (int64_t)row0 * DD + c) = pack2(o[dn][0] * i0, o[dn][1] * i0);
+      if (row1 < S) *reinterpret_cast<uint32_t*>(ob + (int64_t)row1 * DD + c) = pack2(o[dn][2] * i1, o[dn][3] * i1);
+    }
+    __syncthreads();             // buffer `cur` may be overwritten by the next iteration's prefetch
   }
+  cp_async_wait<0>();
 }
 
 inline int dino_attention(cudaStream_t st, const bf16* qkv, bf16* out, int B) {
   static bool attr = false;
   if (!attr) {
-    HVLA_CUDA(cudaFuncSetAttribute(dino_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    HVLA_CUDA(cudaFuncSetAttribute(dino_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    HVLA_CUDA(cudaFuncSetAttribute(dino_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSMEM));
     attr = true;
   }
-  dim3 grid(DH, B, QSPLIT);
+  const int n_items = B * DH;
+  const int grid = n_items < tc_num_sms() ? n_items : tc_num_sms();
   ProfScope ps(st, "dino_attention");
-  dino_attention_kernel<<<grid, WARPS * 32, SMEM, st>>>(qkv, out);
+  dino_attention_kernel<<<grid, PWARPS * 32, PSMEM, st>>>(qkv, out, n_items);
   HVLA_LAUNCH_CHECK("dino_attention");
   return HVLA_OK;
 }
