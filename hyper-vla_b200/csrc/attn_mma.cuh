@@ -43,30 +43,39 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// one chunk of NT*8 keys starting at key0
-template <int NT>
-__device__ __forceinline__ void chunk(const uint32_t (&qf)[4][4], uint32_t sK, uint32_t sV, int key0, int lane,
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// one chunk of NT*8 keys starting at key0.  kaddr / vaddr are this lane's ldmatrix base addresses
+// (row = lane-dependent, key 0); TAIL masks keys >= S (only the last chunk has any).
+template <int NT, bool TAIL>
+__device__ __forceinline__ void chunk(const uint32_t (&qf)[4][4], uint32_t kaddr, uint32_t vaddr, int key0, int lane,
                                       float (&o)[8][4], float& m0, float& m1, float& l0, float& l1) {
+  constexpr float LOG2E = 1.4426950408889634f;
   float s[NT][4];
+  const uint32_t ka = kaddr + (uint32_t)(key0 * ROW * 2), va = vaddr + (uint32_t)(key0 * ROW * 2);
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
     s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
     for (int kp = 0; kp < 2; ++kp) {   // pairs of 16-wide d steps
       uint32_t b0, b1, b2, b3;
-      const uint32_t addr = sK + (uint32_t)(((key0 + nt * 8 + (lane & 7)) * ROW + kp * 32 + (lane >> 3) * 8) * 2);
-      ldsm_x4(addr, b0, b1, b2, b3);
+      ldsm_x4(ka + (uint32_t)((nt * 8 * ROW + kp * 32) * 2), b0, b1, b2, b3);
       mma_bf16(s[nt], qf[2 * kp], b0, b1);
       mma_bf16(s[nt], qf[2 * kp + 1], b2, b3);
     }
   }
-  // mask padded keys (only in the tail chunk), running max
   float mx0 = m0, mx1 = m1;
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
-    const int kbase = key0 + nt * 8 + (lane & 3) * 2;
-    if (kbase >= S) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-    if (kbase + 1 >= S) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+    if (TAIL) {
+      const int kbase = key0 + nt * 8 + (lane & 3) * 2;
+      if (kbase >= S) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+      if (kbase + 1 >= S) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+    }
     mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
     mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
   }
@@ -74,23 +83,21 @@ __device__ __forceinline__ void chunk(const uint32_t (&qf)[4][4], uint32_t sK, u
   mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
   mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
   mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-  constexpr float LOG2E = 1.4426950408889634f;
-  const float c0 = exp2f((m0 - mx0) * LOG2E), c1 = exp2f((m1 - mx1) * LOG2E);   // m = -inf on the first chunk -> 0
+  const float n0 = -mx0 * LOG2E, n1 = -mx1 * LOG2E;
+  const float c0 = ex2_approx(fmaf(m0, LOG2E, n0)), c1 = ex2_approx(fmaf(m1, LOG2E, n1));   // m = -inf on the first chunk -> 0
   m0 = mx0; m1 = mx1;
   l0 *= c0; l1 *= c1;
 #pragma unroll
   for (int dn = 0; dn < 8; ++dn) { o[dn][0] *= c0; o[dn][1] *= c0; o[dn][2] *= c1; o[dn][3] *= c1; }
-  float r0 = 0.f, r1 = 0.f;
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
-    s[nt][0] = exp2f((s[nt][0] - mx0) * LOG2E);
-    s[nt][1] = exp2f((s[nt][1] - mx0) * LOG2E);
-    s[nt][2] = exp2f((s[nt][2] - mx1) * LOG2E);
-    s[nt][3] = exp2f((s[nt][3] - mx1) * LOG2E);
-    r0 += s[nt][0] + s[nt][1];
-    r1 += s[nt][2] + s[nt][3];
+    s[nt][0] = ex2_approx(fmaf(s[nt][0], LOG2E, n0));
+    s[nt][1] = ex2_approx(fmaf(s[nt][1], LOG2E, n0));
+    s[nt][2] = ex2_approx(fmaf(s[nt][2], LOG2E, n1));
+    s[nt][3] = ex2_approx(fmaf(s[nt][3], LOG2E, n1));
+    l0 += s[nt][0] + s[nt][1];
+    l1 += s[nt][2] + s[nt][3];
   }
-  l0 += r0; l1 += r1;   // per-thread partial sums; reduced across the quad at the end
   // O += P * V
 #pragma unroll
   for (int t = 0; t < NT / 2; ++t) {
@@ -102,9 +109,7 @@ __device__ __forceinline__ void chunk(const uint32_t (&qf)[4][4], uint32_t sK, u
 #pragma unroll
     for (int dp = 0; dp < 4; ++dp) {   // pairs of 8-wide d tiles
       uint32_t b0, b1, b2, b3;
-      const int i = lane >> 3;
-      const uint32_t addr = sV + (uint32_t)(((key0 + 16 * t + (i & 1) * 8 + (lane & 7)) * ROW + (dp * 2 + (i >> 1)) * 8) * 2);
-      ldsm_x4_t(addr, b0, b1, b2, b3);
+      ldsm_x4_t(va + (uint32_t)((16 * t * ROW + dp * 16) * 2), b0, b1, b2, b3);
       mma_bf16(o[2 * dp], pa, b0, b1);
       mma_bf16(o[2 * dp + 1], pa, b2, b3);
     }
@@ -175,9 +180,13 @@ dino_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int 
 #pragma unroll
     for (int dn = 0; dn < 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    // this lane's ldmatrix row addresses at key 0: K (non-transposed): row lane&7, 16-byte column (lane>>3);
+    // V (transposed): row (lane>>3 & 1)*8 + (lane&7), column ((lane>>4) * 8)
+    const uint32_t kaddr = sK + (uint32_t)(((lane & 7) * ROW + (lane >> 3) * 8) * 2);
+    const uint32_t vaddr = sV + (uint32_t)(((((lane >> 3) & 1) * 8 + (lane & 7)) * ROW + (lane >> 4) * 8) * 2);
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) chunk<8>(qf, sK, sV, c * 64, lane, o, m0, m1, l0, l1);
-    chunk<2>(qf, sK, sV, 256, lane, o, m0, m1, l0, l1);
+    for (int c = 0; c < 4; ++c) chunk<8, false>(qf, kaddr, vaddr, c * 64, lane, o, m0, m1, l0, l1);
+    chunk<2, true>(qf, kaddr, vaddr, 256, lane, o, m0, m1, l0, l1);
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
