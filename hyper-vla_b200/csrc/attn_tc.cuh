@@ -1,0 +1,326 @@
+// DINOv2 self-attention on tcgen05 tensor cores (257 tokens, 12 heads x 64, q pre-divided by sqrt(64)).
+//
+// Per (image, head) item the 257x257 problem is split so that the tensor-core part is a clean 256x256:
+//   * query rows 0..255 = two M=128 tiles; keys 0..255 = one N=256 MMA  (S = Q K^T, fp32 in TMEM);
+//   * key 256 (the last patch token) is a rank-1 correction done on CUDA cores by the softmax threads;
+//   * query row 256 is a single row handled by a dedicated warp on CUDA cores.
+// Softmax is a full-row (not online) two-pass softmax straight out of TMEM: pass 1 row max, pass 2
+// P = exp2(..) written back IN PLACE over S as bf16 (tcgen05.st), then O = P V runs with A from TMEM
+// (tcgen05.mma TS form) and V as an MN-major shared-memory operand.  O is double-buffered in TMEM so
+// the epilogue of one tile overlaps the S-MMA / softmax of the next.
+//
+// Warps: 0-3 softmax + epilogue (TMEM lane quarter = warp), 4 TMA producer, 5 MMA issuer, 6 row-256 warp.
+// Persistent: one CTA per SM loops over items; Q/K/V of the next item are prefetched (2 smem stages).
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace hvla {
+namespace attn5 {
+
+using namespace tc;
+
+constexpr int S_ = DTOK;                       // 257
+constexpr int NTHREADS = 7 * 32;
+constexpr int TILE_BYTES = 128 * 128;          // 128 rows x 64 bf16
+constexpr int STAGE_BYTES = 6 * TILE_BYTES;    // Q0 Q1 K0 K1 V0 V1
+constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 1024 + 256;
+constexpr int TM_S = 0, TM_O = 256;            // TMEM columns: S/P [0,256), O0 [256,320), O1 [320,384)
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accum), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2a(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// MN-major B operand (V[key][d], 128-byte rows, SWIZZLE_128B): 8-key groups 1024 B apart
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                    // leading byte offset: unused (N = 64 is one swizzle atom wide)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-key groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+constexpr uint32_t make_idesc_bmn(int M, int N) { return make_idesc(M, N) | (1u << 16); }   // B is MN-major
+
+__device__ __forceinline__ float dot8(const uint4& a, const uint4& b, float acc) {
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 x = __bfloat1622float2(pa[i]), y = __bfloat1622float2(pb[i]);
+    acc = fmaf(x.x, y.x, acc);
+    acc = fmaf(x.y, y.y, acc);
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict__ qkv, bf16* __restrict__ out, int n_items) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + 2 * STAGE_BYTES;
+  const uint32_t in_full = bars, in_empty = bars + 16, s_full = bars + 32, p_full = bars + 40;
+  const uint32_t o_full = bars + 48, o_free = bars + 64, tmem_slot = bars + 80;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  float* xrow = reinterpret_cast<float*>(smem_raw + (bars + 96 - smem_u32(smem_raw)));   // 32 floats scratch for warp 6 (unused otherwise)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(in_full + 8 * s, 1);
+      mbar_init(in_empty + 8 * s, 1);
+      mbar_init(o_full + 8 * s, 1);
+      mbar_init(o_free + 8 * s, 4);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  (void)xrow;
+
+  if (warp == 4) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const int b = item / DH, h = item % DH;
+        const uint32_t st = smem_base + s * STAGE_BYTES;
+        mbar_wait(in_empty + 8 * s, ph ^ 1);
+        mbar_expect_tx(in_full + 8 * s, STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          tma_load_2d(st + j * TILE_BYTES, &tmQKV, in_full + 8 * s, h * DHD, b * S_ + 128 * j);
+          tma_load_2d(st + (2 + j) * TILE_BYTES, &tmQKV, in_full + 8 * s, DD + h * DHD, b * S_ + 128 * j);
+          tma_load_2d(st + (4 + j) * TILE_BYTES, &tmQKV, in_full + 8 * s, 2 * DD + h * DHD, b * S_ + 128 * j);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(128, 256);
+      constexpr uint32_t idesc_o = make_idesc_bmn(128, 64);
+      int it = 0, t = 0;     // t = running tile counter (2 per item)
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint32_t st = smem_base + s * STAGE_BYTES;
+        mbar_wait(in_full + 8 * s, (it >> 1) & 1);
+        tc_fence_after();
+        const uint64_t dk = make_smem_desc(st + 2 * TILE_BYTES);
+        const uint64_t dv = make_smem_desc_mn(st + 4 * TILE_BYTES);
+        for (int j = 0; j < 2; ++j, ++t) {
+          // S = Q_j K^T   (issued after the previous tile's P V MMAs: the pipe executes in order, so the
+          //               S/P region is free by the time these run)
+          const uint64_t dq = make_smem_desc(st + j * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(s_full);
+          // O[t&1] = P V once the softmax warps have written P
+          const int ob = t & 1;
+          mbar_wait(o_free + 8 * ob, ((t >> 1) & 1) ^ 1);
+          mbar_wait(p_full, t & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            umma_bf16_ts(tmem_base + TM_O + 64 * ob, tmem_base + TM_S + 8 * k, dv + (uint64_t)(k * (2048 >> 4)), idesc_o, k != 0 ? 1u : 0u);
+          umma_commit(o_full + 8 * ob);
+          if (j == 1) umma_commit(in_empty + 8 * s);   // all MMAs reading this stage have retired
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ============================ softmax + epilogue ============================
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    int t = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int b = item / DH, h = item % DH;
+      const bf16* base = qkv + (int64_t)b * S_ * (3 * DD) + h * DHD;
+      // key 256 and value 256 of this item (rank-1 correction), shared by both tiles
+      uint4 kx[8], vx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        kx[i] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)256 * (3 * DD) + DD) + i);
+        vx[i] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)256 * (3 * DD) + 2 * DD) + i);
+      }
+      for (int j = 0; j < 2; ++j, ++t) {
+        const int row = j * 128 + warp * 32 + lane;
+        // score against key 256 on CUDA cores (overlaps the S MMA)
+        float sx = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 qv = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)row * (3 * DD)) + i);
+          sx = dot8(qv, kx[i], sx);
+        }
+        mbar_wait(s_full, t & 1);
+        tc_fence_after();
+        // pass 1: row max
+        float mx = sx;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          uint32_t r[32];
+          tmem_ld32(lane_base + TM_S + c * 32, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+        const float nm = -mx * LOG2E;
+        float sum = 0.f;
+        // pass 2: P = exp2((s - max) log2e) as bf16, in place over S (the bf16 row is half as wide)
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          uint32_t r[32];
+          tmem_ld32(lane_base + TM_S + c * 32, r);
+          tmem_wait_ld();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2a(fmaf(__uint_as_float(r[2 * i]), LOG2E, nm));
+            const float p1 = ex2a(fmaf(__uint_as_float(r[2 * i + 1]), LOG2E, nm));
+            sum += p0 + p1;
+            pk[i] = pack_bf16(p0, p1);
+          }
+          tmem_st16(lane_base + TM_S + c * 16, pk);
+        }
+        const float px = ex2a(fmaf(sx, LOG2E, nm));
+        sum += px;
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        // epilogue: O / sum (+ the key-256 term) -> bf16 -> global
+        const int ob = t & 1;
+        mbar_wait(o_full + 8 * ob, (t >> 1) & 1);
+        tc_fence_after();
+        const float inv = 1.0f / sum;
+        bf16* orow = out + ((int64_t)b * S_ + row) * DD + h * DHD;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld32(lane_base + TM_O + 64 * ob + c * 32, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&vx[c * 4 + i]);
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 v2 = __bfloat1622float2(pv[e]);
+              const float o0 = fmaf(px, v2.x, __uint_as_float(r[i * 8 + 2 * e])) * inv;
+              const float o1 = fmaf(px, v2.y, __uint_as_float(r[i * 8 + 2 * e + 1])) * inv;
+              w[e] = pack_bf16(o0, o1);
+            }
+            *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_free + 8 * ob);
+      }
+    }
+  } else {
+    // ============================ query row 256 (CUDA cores, one warp) ============================
+    float* ps = xrow;   // not enough scratch for 257 probabilities there; use registers (9 keys per lane)
+    (void)ps;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int b = item / DH, h = item % DH;
+      const bf16* base = qkv + (int64_t)b * S_ * (3 * DD) + h * DHD;
+      uint4 qv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) qv[i] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)256 * (3 * DD)) + i);
+      float sc[9];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int key = lane + 32 * i;
+        float a = -INFINITY;
+        if (key < S_) {
+          a = 0.f;
+          const uint4* kp = reinterpret_cast<const uint4*>(base + (int64_t)key * (3 * DD) + DD);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) a = dot8(qv[u], __ldg(kp + u), a);
+        }
+        sc[i] = a;
+        mx = fmaxf(mx, a);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        sc[i] = (lane + 32 * i < S_) ? ex2a((sc[i] - mx) * LOG2E) : 0.f;
+        sum += sc[i];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      // out[d] = sum_k p_k V[k][d]; lane owns d = 2*lane, 2*lane+1
+      float o0 = 0.f, o1 = 0.f;
+      const bf16* vb = base + 2 * DD + 2 * lane;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) {
+          const int key = l + 32 * i;
+          if (key >= S_) break;
+          const float p = __shfl_sync(0xffffffffu, sc[i], l);
+          const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + (int64_t)key * (3 * DD)));
+          o0 = fmaf(p, v2.x, o0);
+          o1 = fmaf(p, v2.y, o1);
+        }
+      }
+      const float inv = 1.0f / sum;
+      *reinterpret_cast<uint32_t*>(out + ((int64_t)b * S_ + 256) * DD + h * DHD + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+inline int dino_attention_tc(cudaStream_t st, const bf16* qkv, bf16* out, int B) {
+  static bool attr = false;
+  if (!attr) {
+    HVLA_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr = true;
+  }
+  CUtensorMap map;
+  HVLA_TRY(make_map_bf16(&map, qkv, (int64_t)B * S_, 3 * DD, 128));
+  const int n_items = B * DH;
+  const int grid = n_items < num_sms() ? n_items : num_sms();
+  ProfScope ps(st, "dino_attention");
+  attn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map, qkv, out, n_items);
+  HVLA_LAUNCH_CHECK("attn_tc");
+  return HVLA_OK;
+}
+
+}  // namespace attn5
+}  // namespace hvla

@@ -5,6 +5,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "attn_mma.cuh"
+#include "attn_tc.cuh"
 #include "base_fused.cuh"
 
 #include <stdlib.h>
@@ -236,6 +237,7 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
   bf16* A0 = HID;
   const bool simt_gemm = env_flag("HVLA_DEBUG_SIMT_GEMM");   // debugging aid: CUDA-core GEMMs on the bf16 data
   const bool simt_attn = env_flag("HVLA_DEBUG_SIMT_ATTN");
+  const bool mma_attn = env_flag("HVLA_ATTN_MMA");           // A/B switch: warp-level mma.sync attention instead of tcgen05
   const bool one_cta = env_flag("HVLA_GEMM_1CTA");           // A/B switch: single-CTA 128x256 tiles instead of CTA pairs
   {
     const int64_t total = (int64_t)B * NPATCH * PATCH_KP;
@@ -276,8 +278,10 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
       AttnP ap; memset(&ap, 0, sizeof ap);
       ap.qkv = QKV; ap.out = ATT; ap.S = DTOK; ap.H = DH; ap.nbatch = B; ap.mask = 0; ap.prescaled = 1;
       HVLA_TRY((attention_simt<bf16, bf16>(st, ap, DHD)));
-    } else {
+    } else if (mma_attn) {
       HVLA_TRY(attn::dino_attention(st, QKV, ATT, B));
+    } else {
+      HVLA_TRY(attn5::dino_attention_tc(st, QKV, ATT, B));
     }
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
@@ -600,6 +604,13 @@ int hvla_profile_report(char* buf, size_t cap) {
     off += (size_t)w;
   }
   return HVLA_OK;
+}
+
+int hvla_dino_attention(hvla_stream_t stream, const void* qkv, void* out, int B, int impl) {
+  if (!qkv || !out || B <= 0) return fail(HVLA_ERR_ARG, "hvla_dino_attention: bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (impl == 0) return attn::dino_attention(st, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B);
+  return attn5::dino_attention_tc(st, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B);
 }
 
 // ---- legacy XLA custom-call wrappers (no status channel in this ABI revision: errors are logged) ---------

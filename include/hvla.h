@@ -109,6 +109,9 @@ int hvla_act_host(hvla_stream_t stream, const float* dino_vec, const void* dino_
  * act: 0 none, 2 erf-GELU.  The tcgen05/TMEM/TMA GEMM used by the DINOv2 blocks. */
 int hvla_gemm_bf16(hvla_stream_t stream, const void* A, const void* Wt, const float* bias, void* C,
                    int M, int N, int K, int act);
+/* DINOv2 self-attention alone: qkv [B*257, 2304] bf16 (q | k | v, q pre-divided by sqrt(64)) -> out [B*257, 768] bf16.
+ * impl 0 = warp-level mma.sync kernel, 1 = tcgen05/TMEM kernel (the one the pipeline uses). */
+int hvla_dino_attention(hvla_stream_t stream, const void* qkv, void* out, int B, int impl);
 /* number of kernels launched by this library since load (for bench.py's gpu_launches) */
 int64_t hvla_launch_count(void);
 /* per-kernel-class CUDA-event timing on the launching stream (bench.py's live roofline numbers).

@@ -115,6 +115,30 @@ def test_tcgen05_gemm_against_torch(torch_cuda, shape):
     assert err < 1e-2
 
 
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("B", [1, 3, 13])
+def test_dino_attention_kernels_against_torch(torch_cuda, impl, B):
+    """Both attention kernels (mma.sync and tcgen05/TMEM) alone against softmax(q k^T) v in fp32."""
+    torch = torch_cuda
+    from hvla import _native as N
+    gen = torch.Generator(device="cuda").manual_seed(100 + B)
+    qkv = torch.randn(B * 257, 2304, device="cuda", generator=gen)
+    qkv[:, :768] *= 0.35            # q arrives pre-divided by sqrt(64); keep logits in a realistic range
+    qkv = qkv.to(torch.bfloat16)
+    out = torch.full((B * 257, 768), float("nan"), device="cuda", dtype=torch.bfloat16)
+    st = N.lib().hvla_dino_attention(int(torch.cuda.current_stream().cuda_stream), qkv.data_ptr(), out.data_ptr(), B, impl)
+    N.check(st, "hvla_dino_attention")
+    torch.cuda.synchronize()
+    x = qkv.float().view(B, 257, 3, 12, 64)
+    q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
+    ref = torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v
+    ref = ref.transpose(1, 2).reshape(B * 257, 768)
+    err = (out.float() - ref).abs().max().item() / ref.abs().max().item()
+    print(f"attention impl {impl} B={B}: rel err {err:.3e}")
+    assert torch.isfinite(out.float()).all()
+    assert err < 1e-2
+
+
 def test_debug_cuda_core_paths_agree_with_tensor_core_paths(models, torch_cuda):
     """bf16 mode: tcgen05 GEMM + mma.sync attention vs the same math on CUDA cores."""
     from hvla import synthetic as S
