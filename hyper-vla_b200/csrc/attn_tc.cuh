@@ -81,14 +81,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict
   const uint32_t in_full = bars, in_empty = bars + 16, s_full = bars + 32, p_full = bars + 40;
   const uint32_t o_full = bars + 48, o_free = bars + 64, tmem_slot = bars + 80;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  float* xrow = reinterpret_cast<float*>(smem_raw + (bars + 96 - smem_u32(smem_raw)));   // 32 floats scratch for warp 6 (unused otherwise)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     for (int s = 0; s < 2; ++s) {
       mbar_init(in_full + 8 * s, 1);
-      mbar_init(in_empty + 8 * s, 1);
+      mbar_init(in_empty + 8 * s, 2);     // MMA commit + the row-256 warp
       mbar_init(o_full + 8 * s, 1);
       mbar_init(o_free + 8 * s, 4);
     }
@@ -101,7 +100,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  (void)xrow;
 
   if (warp == 4) {
     // ============================ TMA producer ============================
@@ -162,13 +160,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / DH, h = item % DH;
       const bf16* base = qkv + (int64_t)b * S_ * (3 * DD) + h * DHD;
-      // key 256 and value 256 of this item (rank-1 correction), shared by both tiles
-      uint4 kx[8], vx[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        kx[i] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)256 * (3 * DD) + DD) + i);
-        vx[i] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)256 * (3 * DD) + 2 * DD) + i);
-      }
+      const uint4* kxp = reinterpret_cast<const uint4*>(base + (int64_t)256 * (3 * DD) + DD);        // key 256
+      const uint4* vxp = reinterpret_cast<const uint4*>(base + (int64_t)256 * (3 * DD) + 2 * DD);    // value 256
       for (int j = 0; j < 2; ++j, ++t) {
         const int row = j * 128 + warp * 32 + lane;
         // score against key 256 on CUDA cores (overlaps the S MMA)
@@ -176,37 +169,38 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const uint4 qv = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)row * (3 * DD)) + i);
-          sx = dot8(qv, kx[i], sx);
+          sx = dot8(qv, __ldg(kxp + i), sx);
         }
         mbar_wait(s_full, t & 1);
         tc_fence_after();
-        // pass 1: row max
+        uint32_t r[2][32];
+        // pass 1: row max (TMEM loads double-buffered against the max reduction)
         float mx = sx;
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          uint32_t r[32];
-          tmem_ld32(lane_base + TM_S + c * 32, r);
-          tmem_wait_ld();
+        tmem_ld32(lane_base + TM_S, r[0]);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        for (int c = 0; c < 8; ++c) {
+          tmem_wait_ld();
+          if (c < 7) tmem_ld32(lane_base + TM_S + (c + 1) * 32, r[(c + 1) & 1]);
+          else tmem_ld32(lane_base + TM_S, r[0]);            // first chunk of pass 2
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[c & 1][i]));
         }
         const float nm = -mx * LOG2E;
         float sum = 0.f;
         // pass 2: P = exp2((s - max) log2e) as bf16, in place over S (the bf16 row is half as wide)
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < 8; ++c) {
-          uint32_t r[32];
-          tmem_ld32(lane_base + TM_S + c * 32, r);
           tmem_wait_ld();
+          if (c < 7) tmem_ld32(lane_base + TM_S + (c + 1) * 32, r[(c + 1) & 1]);
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2a(fmaf(__uint_as_float(r[2 * i]), LOG2E, nm));
-            const float p1 = ex2a(fmaf(__uint_as_float(r[2 * i + 1]), LOG2E, nm));
+            const float p0 = ex2a(fmaf(__uint_as_float(r[c & 1][2 * i]), LOG2E, nm));
+            const float p1 = ex2a(fmaf(__uint_as_float(r[c & 1][2 * i + 1]), LOG2E, nm));
             sum += p0 + p1;
             pk[i] = pack_bf16(p0, p1);
           }
-          tmem_st16(lane_base + TM_S + c * 16, pk);
+          tmem_st16(lane_base + TM_S + c * 16, pk);           // columns [16c,16c+16) were consumed at chunk <= c
         }
         const float px = ex2a(fmaf(sx, LOG2E, nm));
         sum += px;
@@ -216,56 +210,61 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict
         if (lane == 0) mbar_arrive(p_full);
         // epilogue: O / sum (+ the key-256 term) -> bf16 -> global
         const int ob = t & 1;
-        mbar_wait(o_full + 8 * ob, (t >> 1) & 1);
-        tc_fence_after();
         const float inv = 1.0f / sum;
         bf16* orow = out + ((int64_t)b * S_ + row) * DD + h * DHD;
+        mbar_wait(o_full + 8 * ob, (t >> 1) & 1);
+        tc_fence_after();
+        tmem_ld32(lane_base + TM_O + 64 * ob, r[0]);
+        tmem_ld32(lane_base + TM_O + 64 * ob + 32, r[1]);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_free + 8 * ob);          // O is in registers now
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld32(lane_base + TM_O + 64 * ob + c * 32, r);
-          tmem_wait_ld();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&vx[c * 4 + i]);
+            const uint4 vq = __ldg(vxp + c * 4 + i);
+            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&vq);
             uint32_t w[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 v2 = __bfloat1622float2(pv[e]);
-              const float o0 = fmaf(px, v2.x, __uint_as_float(r[i * 8 + 2 * e])) * inv;
-              const float o1 = fmaf(px, v2.y, __uint_as_float(r[i * 8 + 2 * e + 1])) * inv;
+              const float o0 = fmaf(px, v2.x, __uint_as_float(r[c][i * 8 + 2 * e])) * inv;
+              const float o1 = fmaf(px, v2.y, __uint_as_float(r[c][i * 8 + 2 * e + 1])) * inv;
               w[e] = pack_bf16(o0, o1);
             }
             *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(o_free + 8 * ob);
       }
     }
   } else {
     // ============================ query row 256 (CUDA cores, one warp) ============================
-    float* ps = xrow;   // not enough scratch for 257 probabilities there; use registers (9 keys per lane)
-    (void)ps;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    // K/V rows 0..255 are read from the TMA-staged (128B-swizzled) shared-memory tiles; row 256 from global.
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int s = it & 1;
       const int b = item / DH, h = item % DH;
       const bf16* base = qkv + (int64_t)b * S_ * (3 * DD) + h * DHD;
+      const uint8_t* sk = smem_raw + (smem_base + s * STAGE_BYTES + 2 * TILE_BYTES - smem_u32(smem_raw));
+      const uint8_t* sv = sk + 2 * TILE_BYTES;
       uint4 qv[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) qv[i] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)256 * (3 * DD)) + i);
-      float sc[9];
-      float mx = -INFINITY;
+      float sx = 0.f;   // key 256 (every lane computes it; cheap)
 #pragma unroll
-      for (int i = 0; i < 9; ++i) {
+      for (int i = 0; i < 8; ++i) sx = dot8(qv[i], __ldg(reinterpret_cast<const uint4*>(base + (int64_t)256 * (3 * DD) + DD) + i), sx);
+      mbar_wait(in_full + 8 * s, (it >> 1) & 1);
+      float sc[8];
+      float mx = sx;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
         const int key = lane + 32 * i;
-        float a = -INFINITY;
-        if (key < S_) {
-          a = 0.f;
-          const uint4* kp = reinterpret_cast<const uint4*>(base + (int64_t)key * (3 * DD) + DD);
+        const uint8_t* kr = sk + key * 128;
+        float a = 0.f;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) a = dot8(qv[u], __ldg(kp + u), a);
-        }
+        for (int u = 0; u < 8; ++u) a = dot8(qv[u], *reinterpret_cast<const uint4*>(kr + ((u ^ (key & 7)) << 4)), a);
         sc[i] = a;
         mx = fmaxf(mx, a);
       }
@@ -273,26 +272,34 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        sc[i] = (lane + 32 * i < S_) ? ex2a((sc[i] - mx) * LOG2E) : 0.f;
+      for (int i = 0; i < 8; ++i) {
+        sc[i] = ex2a((sc[i] - mx) * LOG2E);
         sum += sc[i];
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      // out[d] = sum_k p_k V[k][d]; lane owns d = 2*lane, 2*lane+1
+      const float px = ex2a((sx - mx) * LOG2E);
+      sum += px;
+      // out[d] = sum_k p_k V[k][d]; lane owns d = 2*lane, 2*lane+1 (4 bytes at chunk lane>>2 of each row)
       float o0 = 0.f, o1 = 0.f;
-      const bf16* vb = base + 2 * DD + 2 * lane;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) {
+      for (int i = 0; i < 8; ++i) {
 #pragma unroll 8
         for (int l = 0; l < 32; ++l) {
           const int key = l + 32 * i;
-          if (key >= S_) break;
           const float p = __shfl_sync(0xffffffffu, sc[i], l);
-          const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + (int64_t)key * (3 * DD)));
+          const uint8_t* vr = sv + key * 128 + (((lane >> 2) ^ (key & 7)) << 4) + (lane & 3) * 4;
+          const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vr));
           o0 = fmaf(p, v2.x, o0);
           o1 = fmaf(p, v2.y, o1);
         }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(in_empty + 8 * s);         // done with this stage's shared memory
+      {
+        const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + (int64_t)256 * (3 * DD) + 2 * DD + 2 * lane));
+        o0 = fmaf(px, v2.x, o0);
+        o1 = fmaf(px, v2.y, o1);
       }
       const float inv = 1.0f / sum;
       *reinterpret_cast<uint32_t*>(out + ((int64_t)b * S_ + 256) * DD + h * DHD + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
