@@ -2,7 +2,8 @@
 //
 // Per (image, head) item the 257x257 problem is split so that the tensor-core part is a clean 256x256:
 //   * query rows 0..255 = two M=128 tiles; keys 0..255 = one N=256 MMA  (S = Q K^T, fp32 in TMEM);
-//   * key 256 (the last patch token) is a rank-1 correction done on CUDA cores by the softmax threads;
+//   * key 256 (the last patch token) rides along as a 16-key tail MMA (N=16 for S, a 17th K step for P V;
+//     the 15 padding keys get P = 0);
 //   * query row 256 is a single row handled by a dedicated warp on CUDA cores.
 // Softmax is a full-row (not online) two-pass softmax straight out of TMEM: pass 1 row max, pass 2
 // P = exp2(..) written back IN PLACE over S as bf16 (tcgen05.st), then O = P V runs with A from TMEM
@@ -22,9 +23,12 @@ using namespace tc;
 constexpr int S_ = DTOK;                       // 257
 constexpr int NTHREADS = 7 * 32;
 constexpr int TILE_BYTES = 128 * 128;          // 128 rows x 64 bf16
-constexpr int STAGE_BYTES = 6 * TILE_BYTES;    // Q0 Q1 K0 K1 V0 V1
+constexpr int KV_BYTES = 272 * 128;            // keys 0..271 (256 = last real key, 257.. = padding rows, P is 0 there)
+constexpr int OFF_K = 2 * TILE_BYTES, OFF_V = OFF_K + KV_BYTES;
+constexpr int STAGE_BYTES = OFF_V + KV_BYTES;  // Q0 Q1 | K[272] | V[272] = 100 KB
 constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 1024 + 256;
-constexpr int TM_S = 0, TM_O = 256;            // TMEM columns: S/P [0,256), O0 [256,320), O1 [320,384)
+constexpr int TM_S = 0, TM_O = 288;            // TMEM columns: S/P [0,272), O0 [288,352), O1 [352,416)
+static_assert(STAGE_BYTES % 1024 == 0 && OFF_V % 1024 == 0, "UMMA / TMA 128B-swizzle tiles need 1024-byte alignment");
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
@@ -42,6 +46,18 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
       "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2a(float x) {
@@ -74,7 +90,8 @@ __device__ __forceinline__ float dot8(const uint4& a, const uint4& b, float acc)
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict__ qkv, bf16* __restrict__ out, int n_items) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmTail, const bf16* __restrict__ qkv,
+               bf16* __restrict__ out, int n_items) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + 2 * STAGE_BYTES;
@@ -85,6 +102,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmTail);
     for (int s = 0; s < 2; ++s) {
       mbar_init(in_full + 8 * s, 1);
       mbar_init(in_empty + 8 * s, 2);     // MMA commit + the row-256 warp
@@ -115,15 +133,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           tma_load_2d(st + j * TILE_BYTES, &tmQKV, in_full + 8 * s, h * DHD, b * S_ + 128 * j);
-          tma_load_2d(st + (2 + j) * TILE_BYTES, &tmQKV, in_full + 8 * s, DD + h * DHD, b * S_ + 128 * j);
-          tma_load_2d(st + (4 + j) * TILE_BYTES, &tmQKV, in_full + 8 * s, 2 * DD + h * DHD, b * S_ + 128 * j);
+          tma_load_2d(st + OFF_K + j * TILE_BYTES, &tmQKV, in_full + 8 * s, DD + h * DHD, b * S_ + 128 * j);
+          tma_load_2d(st + OFF_V + j * TILE_BYTES, &tmQKV, in_full + 8 * s, 2 * DD + h * DHD, b * S_ + 128 * j);
         }
+        // rows 256..271: token 256 of this image, then 15 rows that only ever meet P == 0
+        tma_load_2d(st + OFF_K + 2 * TILE_BYTES, &tmTail, in_full + 8 * s, DD + h * DHD, b * S_ + 256);
+        tma_load_2d(st + OFF_V + 2 * TILE_BYTES, &tmTail, in_full + 8 * s, 2 * DD + h * DHD, b * S_ + 256);
       }
     }
   } else if (warp == 5) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc(128, 256);
+      constexpr uint32_t idesc_s2 = make_idesc(128, 16);
       constexpr uint32_t idesc_o = make_idesc_bmn(128, 64);
       int it = 0, t = 0;     // t = running tile counter (2 per item)
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -131,14 +153,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict
         const uint32_t st = smem_base + s * STAGE_BYTES;
         mbar_wait(in_full + 8 * s, (it >> 1) & 1);
         tc_fence_after();
-        const uint64_t dk = make_smem_desc(st + 2 * TILE_BYTES);
-        const uint64_t dv = make_smem_desc_mn(st + 4 * TILE_BYTES);
+        const uint64_t dk = make_smem_desc(st + OFF_K);
+        const uint64_t dk2 = make_smem_desc(st + OFF_K + 2 * TILE_BYTES);
+        const uint64_t dv = make_smem_desc_mn(st + OFF_V);
         for (int j = 0; j < 2; ++j, ++t) {
-          // S = Q_j K^T   (issued after the previous tile's P V MMAs: the pipe executes in order, so the
-          //               S/P region is free by the time these run)
+          // S = Q_j K^T over keys 0..255 (N=256) and 256..271 (N=16).  Issued after the previous tile's P V MMAs:
+          // the pipe executes in order, so the S/P region is free by the time these run.
           const uint64_t dq = make_smem_desc(st + j * TILE_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16(tmem_base + TM_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+            umma_bf16(tmem_base + TM_S + 256, dq + 2 * k, dk2 + 2 * k, idesc_s2, k != 0 ? 1u : 0u);
+          }
           umma_commit(s_full);
           // O[t&1] = P V once the softmax warps have written P
           const int ob = t & 1;
@@ -146,7 +172,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict
           mbar_wait(p_full, t & 1);
           tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < 16; ++k)
+          for (int k = 0; k < 17; ++k)
             umma_bf16_ts(tmem_base + TM_O + 64 * ob, tmem_base + TM_S + 8 * k, dv + (uint64_t)(k * (2048 >> 4)), idesc_o, k != 0 ? 1u : 0u);
           umma_commit(o_full + 8 * ob);
           if (j == 1) umma_commit(in_empty + 8 * s);   // all MMAs reading this stage have retired
@@ -160,55 +186,68 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / DH, h = item % DH;
       const bf16* base = qkv + (int64_t)b * S_ * (3 * DD) + h * DHD;
-      const uint4* kxp = reinterpret_cast<const uint4*>(base + (int64_t)256 * (3 * DD) + DD);        // key 256
-      const uint4* vxp = reinterpret_cast<const uint4*>(base + (int64_t)256 * (3 * DD) + 2 * DD);    // value 256
+      (void)base;
       for (int j = 0; j < 2; ++j, ++t) {
         const int row = j * 128 + warp * 32 + lane;
-        // score against key 256 on CUDA cores (overlaps the S MMA)
-        float sx = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 qv = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)row * (3 * DD)) + i);
-          sx = dot8(qv, __ldg(kxp + i), sx);
-        }
         mbar_wait(s_full, t & 1);
         tc_fence_after();
         uint32_t r[2][32];
-        // pass 1: row max (TMEM loads double-buffered against the max reduction)
-        float mx = sx;
+        uint32_t rt[16];
+        // pass 1: row max over keys 0..256 (TMEM loads double-buffered against the max reduction)
+        tmem_ld16(lane_base + TM_S + 256, rt);
         tmem_ld32(lane_base + TM_S, r[0]);
+        tmem_wait_ld();
+        const float sx = __uint_as_float(rt[0]);               // key 256; columns 257..271 are padding
+        float mx = sx;
+#pragma unroll 1
+        for (int c = 0; c < 8; c += 2) {
+          tmem_ld32(lane_base + TM_S + (c + 1) * 32, r[1]);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[0][i]));
           tmem_wait_ld();
-          if (c < 7) tmem_ld32(lane_base + TM_S + (c + 1) * 32, r[(c + 1) & 1]);
-          else tmem_ld32(lane_base + TM_S, r[0]);            // first chunk of pass 2
+          tmem_ld32(lane_base + TM_S + ((c + 2) & 7) * 32, r[0]);   // wraps to chunk 0 = first chunk of pass 2
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[c & 1][i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[1][i]));
+          tmem_wait_ld();
         }
         const float nm = -mx * LOG2E;
         float sum = 0.f;
         // pass 2: P = exp2((s - max) log2e) as bf16, in place over S (the bf16 row is half as wide)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          tmem_wait_ld();
-          if (c < 7) tmem_ld32(lane_base + TM_S + (c + 1) * 32, r[(c + 1) & 1]);
+#pragma unroll 1
+        for (int c = 0; c < 8; c += 2) {
+          tmem_ld32(lane_base + TM_S + (c + 1) * 32, r[1]);
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2a(fmaf(__uint_as_float(r[c & 1][2 * i]), LOG2E, nm));
-            const float p1 = ex2a(fmaf(__uint_as_float(r[c & 1][2 * i + 1]), LOG2E, nm));
+            const float p0 = ex2a(fmaf(__uint_as_float(r[0][2 * i]), LOG2E, nm));
+            const float p1 = ex2a(fmaf(__uint_as_float(r[0][2 * i + 1]), LOG2E, nm));
             sum += p0 + p1;
             pk[i] = pack_bf16(p0, p1);
           }
-          tmem_st16(lane_base + TM_S + c * 16, pk);           // columns [16c,16c+16) were consumed at chunk <= c
+          tmem_wait_ld();
+          tmem_st16(lane_base + TM_S + c * 16, pk);             // columns [16c,16c+16) were consumed at chunk <= c
+          if (c + 2 < 8) tmem_ld32(lane_base + TM_S + (c + 2) * 32, r[0]);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2a(fmaf(__uint_as_float(r[1][2 * i]), LOG2E, nm));
+            const float p1 = ex2a(fmaf(__uint_as_float(r[1][2 * i + 1]), LOG2E, nm));
+            sum += p0 + p1;
+            pk[i] = pack_bf16(p0, p1);
+          }
+          tmem_wait_ld();
+          tmem_st16(lane_base + TM_S + (c + 1) * 16, pk);
         }
-        const float px = ex2a(fmaf(sx, LOG2E, nm));
-        sum += px;
+        {
+          const float px = ex2a(fmaf(sx, LOG2E, nm));
+          sum += px;
+          uint32_t pt[8] = {pack_bf16(px, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // keys 256 | 257..271 (zero)
+          tmem_st8(lane_base + TM_S + 128, pt);
+        }
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
-        // epilogue: O / sum (+ the key-256 term) -> bf16 -> global
+        // epilogue: O / sum -> bf16 -> global
         const int ob = t & 1;
         const float inv = 1.0f / sum;
         bf16* orow = out + ((int64_t)b * S_ + row) * DD + h * DHD;
@@ -224,16 +263,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict
         for (int c = 0; c < 2; ++c) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const uint4 vq = __ldg(vxp + c * 4 + i);
-            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&vq);
             uint32_t w[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 v2 = __bfloat1622float2(pv[e]);
-              const float o0 = fmaf(px, v2.x, __uint_as_float(r[c][i * 8 + 2 * e])) * inv;
-              const float o1 = fmaf(px, v2.y, __uint_as_float(r[c][i * 8 + 2 * e + 1])) * inv;
-              w[e] = pack_bf16(o0, o1);
-            }
+            for (int e = 0; e < 4; ++e)
+              w[e] = pack_bf16(__uint_as_float(r[c][i * 8 + 2 * e]) * inv, __uint_as_float(r[c][i * 8 + 2 * e + 1]) * inv);
             *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
@@ -247,15 +280,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict
       const int s = it & 1;
       const int b = item / DH, h = item % DH;
       const bf16* base = qkv + (int64_t)b * S_ * (3 * DD) + h * DHD;
-      const uint8_t* sk = smem_raw + (smem_base + s * STAGE_BYTES + 2 * TILE_BYTES - smem_u32(smem_raw));
-      const uint8_t* sv = sk + 2 * TILE_BYTES;
+      const uint8_t* sk = smem_raw + (smem_base + s * STAGE_BYTES + OFF_K - smem_u32(smem_raw));
+      const uint8_t* sv = sk + KV_BYTES;
       uint4 qv[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) qv[i] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)256 * (3 * DD)) + i);
-      float sx = 0.f;   // key 256 (every lane computes it; cheap)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sx = dot8(qv[i], __ldg(reinterpret_cast<const uint4*>(base + (int64_t)256 * (3 * DD) + DD) + i), sx);
       mbar_wait(in_full + 8 * s, (it >> 1) & 1);
+      float sx = 0.f;   // key 256 (row 256 & 7 == 0: no swizzle); every lane computes it, cheap
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sx = dot8(qv[i], *reinterpret_cast<const uint4*>(sk + 256 * 128 + (i << 4)), sx);
       float sc[8];
       float mx = sx;
 #pragma unroll
@@ -294,13 +327,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const bf16* __restrict
           o1 = fmaf(p, v2.y, o1);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(in_empty + 8 * s);         // done with this stage's shared memory
       {
-        const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + (int64_t)256 * (3 * DD) + 2 * DD + 2 * lane));
+        const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sv + 256 * 128 + 4 * lane));
         o0 = fmaf(px, v2.x, o0);
         o1 = fmaf(px, v2.y, o1);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(in_empty + 8 * s);         // done with this stage's shared memory
       const float inv = 1.0f / sum;
       *reinterpret_cast<uint32_t*>(out + ((int64_t)b * S_ + 256) * DD + h * DHD + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
     }
@@ -319,12 +352,13 @@ inline int dino_attention_tc(cudaStream_t st, const bf16* qkv, bf16* out, int B)
     HVLA_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr = true;
   }
-  CUtensorMap map;
+  CUtensorMap map, tail;
   HVLA_TRY(make_map_bf16(&map, qkv, (int64_t)B * S_, 3 * DD, 128));
+  HVLA_TRY(make_map_bf16(&tail, qkv, (int64_t)B * S_, 3 * DD, 16));
   const int n_items = B * DH;
   const int grid = n_items < num_sms() ? n_items : num_sms();
   ProfScope ps(st, "dino_attention");
-  attn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map, qkv, out, n_items);
+  attn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map, tail, qkv, out, n_items);
   HVLA_LAUNCH_CHECK("attn_tc");
   return HVLA_OK;
 }
