@@ -2,15 +2,16 @@
 //
 // Per (image, head) item the 257x257 problem is split so that the tensor-core part is a clean 256x256:
 //   * query rows 0..255 = two M=128 tiles; keys 0..255 = one N=256 MMA  (S = Q K^T, fp32 in TMEM);
-//   * key 256 (the last patch token) rides along as a 16-key tail MMA (N=16 for S, a 17th K step for P V;
-//     the 15 padding keys get P = 0);
+//   * key 256 (the last patch token) is a rank-1 correction on CUDA cores, read from the staged smem tiles;
 //   * query row 256 is a single row handled by a dedicated warp on CUDA cores.
 // Softmax is a full-row (not online) two-pass softmax straight out of TMEM: pass 1 row max, pass 2
 // P = exp2(..) written back IN PLACE over S as bf16 (tcgen05.st), then O = P V runs with A from TMEM
-// (tcgen05.mma TS form) and V as an MN-major shared-memory operand.  O is double-buffered in TMEM so
-// the epilogue of one tile overlaps the S-MMA / softmax of the next.
+// (tcgen05.mma TS form) and V as an MN-major shared-memory operand; O lands in the free half of the same
+// TMEM region.  The two query tiles of an item are processed by two softmax warp groups in ping-pong (each
+// owns 256 TMEM columns), so one group's TMEM/MUFU work overlaps the other's MMA waits.
 //
-// Warps: 0-3 softmax + epilogue (TMEM lane quarter = warp), 4 TMA producer, 5 MMA issuer, 6 row-256 warp.
+// Warps: 0-3 / 4-7 softmax + epilogue of tile 0 / 1 (TMEM lane quarter = warp & 3), 8 TMA producer,
+// 9 MMA issuer, 10 query-row-256 warp.
 // Persistent: one CTA per SM loops over items; Q/K/V of the next item are prefetched (2 smem stages).
 #pragma once
 #include "gemm_tc.cuh"
@@ -21,13 +22,14 @@ namespace attn5 {
 using namespace tc;
 
 constexpr int S_ = DTOK;                       // 257
-constexpr int NTHREADS = 7 * 32;
+constexpr int W_TMA = 8, W_MMA = 9;           // warps 0-7: two softmax groups; 8: TMA; 9: MMA; 10: query row 256
+constexpr int NTHREADS = 11 * 32;
 constexpr int TILE_BYTES = 128 * 128;          // 128 rows x 64 bf16
 constexpr int KV_BYTES = 272 * 128;            // keys 0..271 (256 = last real key, 257.. = padding rows, P is 0 there)
 constexpr int OFF_K = 2 * TILE_BYTES, OFF_V = OFF_K + KV_BYTES;
 constexpr int STAGE_BYTES = OFF_V + KV_BYTES;  // Q0 Q1 | K[272] | V[272] = 100 KB
 constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 1024 + 256;
-constexpr int TM_S = 0, TM_O = 288;            // TMEM columns: S/P [0,272), O0 [288,352), O1 [352,416)
+constexpr int TM_OREL = 160;                   // TMEM: group g owns columns [256g, 256g+256): S fp32 -> P bf16 in [0,128), O in [160,224)
 static_assert(STAGE_BYTES % 1024 == 0 && OFF_V % 1024 == 0, "UMMA / TMA 128B-swizzle tiles need 1024-byte alignment");
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -95,31 +97,32 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + 2 * STAGE_BYTES;
-  const uint32_t in_full = bars, in_empty = bars + 16, s_full = bars + 32, p_full = bars + 40;
-  const uint32_t o_full = bars + 48, o_free = bars + 64, tmem_slot = bars + 80;
+  const uint32_t in_full = bars, in_empty = bars + 16, s_full = bars + 32, p_full = bars + 48;
+  const uint32_t o_full = bars + 64, o_free = bars + 80, tmem_slot = bars + 96;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmTail);
     for (int s = 0; s < 2; ++s) {
       mbar_init(in_full + 8 * s, 1);
-      mbar_init(in_empty + 8 * s, 2);     // MMA commit + the row-256 warp
+      mbar_init(in_empty + 8 * s, 10);    // MMA commit + row-256 warp + 8 softmax warps
+      mbar_init(s_full + 8 * s, 1);
+      mbar_init(p_full + 8 * s, 4);
       mbar_init(o_full + 8 * s, 1);
       mbar_init(o_free + 8 * s, 4);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 4) {
+  if (warp == W_TMA) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       int it = 0;
@@ -136,151 +139,162 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
           tma_load_2d(st + OFF_K + j * TILE_BYTES, &tmQKV, in_full + 8 * s, DD + h * DHD, b * S_ + 128 * j);
           tma_load_2d(st + OFF_V + j * TILE_BYTES, &tmQKV, in_full + 8 * s, 2 * DD + h * DHD, b * S_ + 128 * j);
         }
-        // rows 256..271: token 256 of this image, then 15 rows that only ever meet P == 0
+        // rows 256..271: token 256 of this image (read by the CUDA-core rank-1 paths) + 15 unused rows
         tma_load_2d(st + OFF_K + 2 * TILE_BYTES, &tmTail, in_full + 8 * s, DD + h * DHD, b * S_ + 256);
         tma_load_2d(st + OFF_V + 2 * TILE_BYTES, &tmTail, in_full + 8 * s, 2 * DD + h * DHD, b * S_ + 256);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == W_MMA) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc(128, 256);
-      constexpr uint32_t idesc_s2 = make_idesc(128, 16);
       constexpr uint32_t idesc_o = make_idesc_bmn(128, 64);
-      int it = 0, t = 0;     // t = running tile counter (2 per item)
+      int it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int s = it & 1;
         const uint32_t st = smem_base + s * STAGE_BYTES;
+        const uint32_t par = it & 1;        // every per-group barrier completes once per item
         mbar_wait(in_full + 8 * s, (it >> 1) & 1);
         tc_fence_after();
         const uint64_t dk = make_smem_desc(st + OFF_K);
-        const uint64_t dk2 = make_smem_desc(st + OFF_K + 2 * TILE_BYTES);
         const uint64_t dv = make_smem_desc_mn(st + OFF_V);
-        for (int j = 0; j < 2; ++j, ++t) {
-          // S = Q_j K^T over keys 0..255 (N=256) and 256..271 (N=16).  Issued after the previous tile's P V MMAs:
-          // the pipe executes in order, so the S/P region is free by the time these run.
-          const uint64_t dq = make_smem_desc(st + j * TILE_BYTES);
+        // S_g = Q_g K^T for both query tiles (group g owns TMEM columns [256g, 256g+256))
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_bf16(tmem_base + TM_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-            umma_bf16(tmem_base + TM_S + 256, dq + 2 * k, dk2 + 2 * k, idesc_s2, k != 0 ? 1u : 0u);
-          }
-          umma_commit(s_full);
-          // O[t&1] = P V once the softmax warps have written P
-          const int ob = t & 1;
-          mbar_wait(o_free + 8 * ob, ((t >> 1) & 1) ^ 1);
-          mbar_wait(p_full, t & 1);
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(o_free + 8 * g, par ^ 1);           // group g has read the previous item's O out of this region
+          tc_fence_after();
+          const uint64_t dq = make_smem_desc(st + g * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 256 * g, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(s_full + 8 * g);
+        }
+        // O_g = P_g V as soon as group g has written P_g (bf16, in place over S_g); O_g lives in the same region
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(p_full + 8 * g, par);
           tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < 17; ++k)
-            umma_bf16_ts(tmem_base + TM_O + 64 * ob, tmem_base + TM_S + 8 * k, dv + (uint64_t)(k * (2048 >> 4)), idesc_o, k != 0 ? 1u : 0u);
-          umma_commit(o_full + 8 * ob);
-          if (j == 1) umma_commit(in_empty + 8 * s);   // all MMAs reading this stage have retired
+          for (int k = 0; k < 16; ++k)
+            umma_bf16_ts(tmem_base + 256 * g + TM_OREL, tmem_base + 256 * g + 8 * k, dv + (uint64_t)(k * (2048 >> 4)), idesc_o,
+                         k != 0 ? 1u : 0u);
+          umma_commit(o_full + 8 * g);
         }
+        umma_commit(in_empty + 8 * s);                  // all MMAs reading this stage have retired
       }
     }
-  } else if (warp < 4) {
-    // ============================ softmax + epilogue ============================
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    int t = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  } else if (warp < 8) {
+    // ============================ softmax + epilogue: group g = warp / 4 owns query tile g ============================
+    const int g = warp >> 2, quarter = warp & 3;
+    const uint32_t tm = tmem_base + ((uint32_t)(quarter * 32) << 16) + 256 * g;
+    const int rl = quarter * 32 + lane;                 // row inside the tile
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t par = it & 1;
       const int b = item / DH, h = item % DH;
-      const bf16* base = qkv + (int64_t)b * S_ * (3 * DD) + h * DHD;
-      (void)base;
-      for (int j = 0; j < 2; ++j, ++t) {
-        const int row = j * 128 + warp * 32 + lane;
-        mbar_wait(s_full, t & 1);
-        tc_fence_after();
-        uint32_t r[2][32];
-        uint32_t rt[16];
-        // pass 1: row max over keys 0..256 (TMEM loads double-buffered against the max reduction)
-        tmem_ld16(lane_base + TM_S + 256, rt);
-        tmem_ld32(lane_base + TM_S, r[0]);
-        tmem_wait_ld();
-        const float sx = __uint_as_float(rt[0]);               // key 256; columns 257..271 are padding
-        float mx = sx;
+      const uint8_t* st = smem_al + s * STAGE_BYTES;
+      // score against key 256 on CUDA cores from the staged tiles (128B swizzle: chunk ^= row & 7)
+      mbar_wait(in_full + 8 * s, (it >> 1) & 1);
+      float sx = 0.f;
+      {
+        const uint8_t* qr = st + g * TILE_BYTES + rl * 128;
+        const uint8_t* kr = st + OFF_K + 256 * 128;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          sx = dot8(*reinterpret_cast<const uint4*>(qr + ((u ^ (rl & 7)) << 4)), *reinterpret_cast<const uint4*>(kr + (u << 4)), sx);
+      }
+      mbar_wait(s_full + 8 * g, par);
+      tc_fence_after();
+      uint32_t r[2][32];
+      // pass 1: row max (TMEM loads double-buffered against the max reduction)
+      float mx = sx;
+      tmem_ld32(tm, r[0]);
+      tmem_wait_ld();
 #pragma unroll 1
-        for (int c = 0; c < 8; c += 2) {
-          tmem_ld32(lane_base + TM_S + (c + 1) * 32, r[1]);
+      for (int c = 0; c < 8; c += 2) {
+        tmem_ld32(tm + (c + 1) * 32, r[1]);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[0][i]));
-          tmem_wait_ld();
-          tmem_ld32(lane_base + TM_S + ((c + 2) & 7) * 32, r[0]);   // wraps to chunk 0 = first chunk of pass 2
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[1][i]));
-          tmem_wait_ld();
-        }
-        const float nm = -mx * LOG2E;
-        float sum = 0.f;
-        // pass 2: P = exp2((s - max) log2e) as bf16, in place over S (the bf16 row is half as wide)
-#pragma unroll 1
-        for (int c = 0; c < 8; c += 2) {
-          tmem_ld32(lane_base + TM_S + (c + 1) * 32, r[1]);
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2a(fmaf(__uint_as_float(r[0][2 * i]), LOG2E, nm));
-            const float p1 = ex2a(fmaf(__uint_as_float(r[0][2 * i + 1]), LOG2E, nm));
-            sum += p0 + p1;
-            pk[i] = pack_bf16(p0, p1);
-          }
-          tmem_wait_ld();
-          tmem_st16(lane_base + TM_S + c * 16, pk);             // columns [16c,16c+16) were consumed at chunk <= c
-          if (c + 2 < 8) tmem_ld32(lane_base + TM_S + (c + 2) * 32, r[0]);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2a(fmaf(__uint_as_float(r[1][2 * i]), LOG2E, nm));
-            const float p1 = ex2a(fmaf(__uint_as_float(r[1][2 * i + 1]), LOG2E, nm));
-            sum += p0 + p1;
-            pk[i] = pack_bf16(p0, p1);
-          }
-          tmem_wait_ld();
-          tmem_st16(lane_base + TM_S + (c + 1) * 16, pk);
-        }
-        {
-          const float px = ex2a(fmaf(sx, LOG2E, nm));
-          sum += px;
-          uint32_t pt[8] = {pack_bf16(px, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // keys 256 | 257..271 (zero)
-          tmem_st8(lane_base + TM_S + 128, pt);
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
-        // epilogue: O / sum -> bf16 -> global
-        const int ob = t & 1;
-        const float inv = 1.0f / sum;
-        bf16* orow = out + ((int64_t)b * S_ + row) * DD + h * DHD;
-        mbar_wait(o_full + 8 * ob, (t >> 1) & 1);
-        tc_fence_after();
-        tmem_ld32(lane_base + TM_O + 64 * ob, r[0]);
-        tmem_ld32(lane_base + TM_O + 64 * ob + 32, r[1]);
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[0][i]));
         tmem_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(o_free + 8 * ob);          // O is in registers now
+        tmem_ld32(tm + ((c + 2) & 7) * 32, r[0]);        // wraps to chunk 0 = first chunk of pass 2
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[1][i]));
+        tmem_wait_ld();
+      }
+      const float nm = -mx * LOG2E;
+      float sum = 0.f;
+      // pass 2: P = exp2((s - max) log2e) as bf16, in place over S (the bf16 row is half as wide)
+#pragma unroll 1
+      for (int c = 0; c < 8; c += 2) {
+        tmem_ld32(tm + (c + 1) * 32, r[1]);
+        uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint32_t w[4];
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2a(fmaf(__uint_as_float(r[0][2 * i]), LOG2E, nm));
+          const float p1 = ex2a(fmaf(__uint_as_float(r[0][2 * i + 1]), LOG2E, nm));
+          sum += p0 + p1;
+          pk[i] = pack_bf16(p0, p1);
+        }
+        tmem_wait_ld();
+        tmem_st16(tm + c * 16, pk);                       // columns [16c,16c+16) were consumed at chunk <= c
+        if (c + 2 < 8) tmem_ld32(tm + (c + 2) * 32, r[0]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              w[e] = pack_bf16(__uint_as_float(r[c][i * 8 + 2 * e]) * inv, __uint_as_float(r[c][i * 8 + 2 * e + 1]) * inv);
-            *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2a(fmaf(__uint_as_float(r[1][2 * i]), LOG2E, nm));
+          const float p1 = ex2a(fmaf(__uint_as_float(r[1][2 * i + 1]), LOG2E, nm));
+          sum += p0 + p1;
+          pk[i] = pack_bf16(p0, p1);
+        }
+        tmem_wait_ld();
+        tmem_st16(tm + (c + 1) * 16, pk);
+      }
+      const float px = ex2a(fmaf(sx, LOG2E, nm));
+      sum += px;
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full + 8 * g);
+      // epilogue: (O + p_256 v_256) / sum -> bf16 -> global
+      const float inv = 1.0f / sum;
+      const float pxi = px * inv;
+      bf16* orow = out + ((int64_t)b * S_ + g * 128 + rl) * DD + h * DHD;
+      const uint8_t* vr = st + OFF_V + 256 * 128;
+      mbar_wait(o_full + 8 * g, par);
+      tc_fence_after();
+      tmem_ld32(tm + TM_OREL, r[0]);
+      tmem_ld32(tm + TM_OREL + 32, r[1]);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free + 8 * g);          // O is in registers now
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 vq = *reinterpret_cast<const uint4*>(vr + ((c * 4 + i) << 4));
+          const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&vq);
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 v2 = __bfloat1622float2(pv[e]);
+            w[e] = pack_bf16(fmaf(pxi, v2.x, __uint_as_float(r[c][i * 8 + 2 * e]) * inv),
+                             fmaf(pxi, v2.y, __uint_as_float(r[c][i * 8 + 2 * e + 1]) * inv));
           }
+          *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(in_empty + 8 * s);        // done reading this stage's shared memory
     }
   } else {
     // ============================ query row 256 (CUDA cores, one warp) ============================
-    // K/V rows 0..255 are read from the TMA-staged (128B-swizzled) shared-memory tiles; row 256 from global.
+    // K/V rows 0..256 are read from the TMA-staged (128B-swizzled) shared-memory tiles; the query row from global.
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int s = it & 1;
       const int b = item / DH, h = item % DH;
       const bf16* base = qkv + (int64_t)b * S_ * (3 * DD) + h * DHD;
-      const uint8_t* sk = smem_raw + (smem_base + s * STAGE_BYTES + OFF_K - smem_u32(smem_raw));
+      const uint8_t* sk = smem_al + s * STAGE_BYTES + OFF_K;
       const uint8_t* sv = sk + KV_BYTES;
       uint4 qv[8];
 #pragma unroll
@@ -340,7 +354,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
