@@ -3,7 +3,7 @@
 // Per (image, head) item the 257x257 problem is split so that the tensor-core part is a clean 256x256:
 //   * query rows 0..255 = two M=128 tiles; keys 0..255 = one N=256 MMA  (S = Q K^T, fp32 in TMEM);
 //   * key 256 (the last patch token) is a rank-1 correction on CUDA cores, read from the staged smem tiles;
-//   * query row 256 is a single row handled by a dedicated warp on CUDA cores.
+//   * query row 256 is a single row done on CUDA cores by the softmax warps (32 keys each, merged).
 // Softmax is a full-row (not online) two-pass softmax straight out of TMEM: pass 1 row max, pass 2
 // P = exp2(..) written back IN PLACE over S as bf16 (tcgen05.st), then O = P V runs with A from TMEM
 // (tcgen05.mma TS form) and V as an MN-major shared-memory operand; O lands in the free half of the same
@@ -11,10 +11,11 @@
 // owns 256 TMEM columns), so one group's TMEM/MUFU work overlaps the other's MMA waits.
 //
 // Warps: 0-3 / 4-7 softmax + epilogue of tile 0 / 1 (TMEM lane quarter = warp & 3), 8 TMA producer,
-// 9 MMA issuer, 10 query-row-256 warp.
+// 9 MMA issuer.  Query row 256 is shared out over the 8 softmax warps (32 keys each) and merged by warp 0.
 // Persistent: one CTA per SM loops over items; Q/K/V of the next item are prefetched (2 smem stages).
 #pragma once
 #include "gemm_tc.cuh"
+#include <stdlib.h>
 
 namespace hvla {
 namespace attn5 {
@@ -22,13 +23,14 @@ namespace attn5 {
 using namespace tc;
 
 constexpr int S_ = DTOK;                       // 257
-constexpr int W_TMA = 8, W_MMA = 9;           // warps 0-7: two softmax groups; 8: TMA; 9: MMA; 10: query row 256
-constexpr int NTHREADS = 11 * 32;
+constexpr int W_TMA = 8, W_MMA = 9;           // warps 0-7: two softmax groups (+ query row 256 cooperatively); 8: TMA; 9: MMA
+constexpr int NTHREADS = 10 * 32;
 constexpr int TILE_BYTES = 128 * 128;          // 128 rows x 64 bf16
 constexpr int KV_BYTES = 272 * 128;            // keys 0..271 (256 = last real key, 257.. = padding rows, P is 0 there)
 constexpr int OFF_K = 2 * TILE_BYTES, OFF_V = OFF_K + KV_BYTES;
-constexpr int STAGE_BYTES = OFF_V + KV_BYTES;  // Q0 Q1 | K[272] | V[272] = 100 KB
-constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 1024 + 256;
+constexpr int OFF_QT = OFF_V + KV_BYTES;        // query rows 256..271 (only row 256 is used)
+constexpr int STAGE_BYTES = OFF_QT + 16 * 128; // Q0 Q1 | K[272] | V[272] | Qtail[16] = 102 KB
+constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 1024 + 256 + 2 * 8 * 66 * 4;   // + row-256 partials (double-buffered)
 constexpr int TM_OREL = 160;                   // TMEM: group g owns columns [256g, 256g+256): S fp32 -> P bf16 in [0,128), O in [160,224)
 static_assert(STAGE_BYTES % 1024 == 0 && OFF_V % 1024 == 0, "UMMA / TMA 128B-swizzle tiles need 1024-byte alignment");
 constexpr float LOG2E = 1.4426950408889634f;
@@ -93,7 +95,7 @@ __device__ __forceinline__ float dot8(const uint4& a, const uint4& b, float acc)
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmTail, const bf16* __restrict__ qkv,
-               bf16* __restrict__ out, int n_items) {
+               bf16* __restrict__ out, int n_items, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + 2 * STAGE_BYTES;
@@ -101,6 +103,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   const uint32_t o_full = bars + 64, o_free = bars + 80, tmem_slot = bars + 96;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* part = reinterpret_cast<float*>(smem_raw + (bars + 256 - smem_u32(smem_raw)));   // [2][8][66]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == W_TMA && lane == 0) {
@@ -108,7 +111,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     tma_prefetch_desc(&tmTail);
     for (int s = 0; s < 2; ++s) {
       mbar_init(in_full + 8 * s, 1);
-      mbar_init(in_empty + 8 * s, 10);    // MMA commit + row-256 warp + 8 softmax warps
+      mbar_init(in_empty + 8 * s, 9);     // MMA commit + 8 softmax warps
       mbar_init(s_full + 8 * s, 1);
       mbar_init(p_full + 8 * s, 4);
       mbar_init(o_full + 8 * s, 1);
@@ -142,6 +145,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         // rows 256..271: token 256 of this image (read by the CUDA-core rank-1 paths) + 15 unused rows
         tma_load_2d(st + OFF_K + 2 * TILE_BYTES, &tmTail, in_full + 8 * s, DD + h * DHD, b * S_ + 256);
         tma_load_2d(st + OFF_V + 2 * TILE_BYTES, &tmTail, in_full + 8 * s, 2 * DD + h * DHD, b * S_ + 256);
+        tma_load_2d(st + OFF_QT, &tmTail, in_full + 8 * s, h * DHD, b * S_ + 256);
       }
     }
   } else if (warp == W_MMA) {
@@ -211,7 +215,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       tmem_ld32(tm, r[0]);
       tmem_wait_ld();
 #pragma unroll 1
-      for (int c = 0; c < 8; c += 2) {
+      for (int c = (dbg & 1) ? 8 : 0; c < 8; c += 2) {
         tmem_ld32(tm + (c + 1) * 32, r[1]);
 #pragma unroll
         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[0][i]));
@@ -230,8 +234,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2a(fmaf(__uint_as_float(r[0][2 * i]), LOG2E, nm));
-          const float p1 = ex2a(fmaf(__uint_as_float(r[0][2 * i + 1]), LOG2E, nm));
+          const float p0 = (dbg & 4) ? __uint_as_float(r[0][2 * i]) : ex2a(fmaf(__uint_as_float(r[0][2 * i]), LOG2E, nm));
+          const float p1 = (dbg & 4) ? __uint_as_float(r[0][2 * i + 1]) : ex2a(fmaf(__uint_as_float(r[0][2 * i + 1]), LOG2E, nm));
           sum += p0 + p1;
           pk[i] = pack_bf16(p0, p1);
         }
@@ -240,8 +244,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         if (c + 2 < 8) tmem_ld32(tm + (c + 2) * 32, r[0]);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2a(fmaf(__uint_as_float(r[1][2 * i]), LOG2E, nm));
-          const float p1 = ex2a(fmaf(__uint_as_float(r[1][2 * i + 1]), LOG2E, nm));
+          const float p0 = (dbg & 4) ? __uint_as_float(r[1][2 * i]) : ex2a(fmaf(__uint_as_float(r[1][2 * i]), LOG2E, nm));
+          const float p1 = (dbg & 4) ? __uint_as_float(r[1][2 * i + 1]) : ex2a(fmaf(__uint_as_float(r[1][2 * i + 1]), LOG2E, nm));
           sum += p0 + p1;
           pk[i] = pack_bf16(p0, p1);
         }
@@ -283,73 +287,64 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
           *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(in_empty + 8 * s);        // done reading this stage's shared memory
-    }
-  } else {
-    // ============================ query row 256 (CUDA cores, one warp) ============================
-    // K/V rows 0..256 are read from the TMA-staged (128B-swizzled) shared-memory tiles; the query row from global.
-    int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int s = it & 1;
-      const int b = item / DH, h = item % DH;
-      const bf16* base = qkv + (int64_t)b * S_ * (3 * DD) + h * DHD;
-      const uint8_t* sk = smem_al + s * STAGE_BYTES + OFF_K;
-      const uint8_t* sv = sk + KV_BYTES;
-      uint4 qv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) qv[i] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)256 * (3 * DD)) + i);
-      mbar_wait(in_full + 8 * s, (it >> 1) & 1);
-      float sx = 0.f;   // key 256 (row 256 & 7 == 0: no swizzle); every lane computes it, cheap
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sx = dot8(qv[i], *reinterpret_cast<const uint4*>(sk + 256 * 128 + (i << 4)), sx);
-      float sc[8];
-      float mx = sx;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int key = lane + 32 * i;
-        const uint8_t* kr = sk + key * 128;
+      // ---- query row 256 (one row per item), cooperatively: this warp takes keys [32*warp, 32*warp+32) ----
+      {
+        const uint8_t* sk = st + OFF_K;
+        const uint8_t* sv = st + OFF_V;
+        const uint8_t* q256 = st + OFF_QT;                 // row 0 of the tail tile: no swizzle offset
+        const int key = 32 * warp + lane;
         float a = 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) a = dot8(qv[u], *reinterpret_cast<const uint4*>(kr + ((u ^ (key & 7)) << 4)), a);
-        sc[i] = a;
-        mx = fmaxf(mx, a);
-      }
+        for (int u = 0; u < 8; ++u)
+          a = dot8(*reinterpret_cast<const uint4*>(q256 + (u << 4)), *reinterpret_cast<const uint4*>(sk + key * 128 + ((u ^ (key & 7)) << 4)), a);
+        float mw = a;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      float sum = 0.f;
+        for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+        const float pw = ex2a((a - mw) * LOG2E);
+        float lw = pw;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        sc[i] = ex2a((sc[i] - mx) * LOG2E);
-        sum += sc[i];
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      const float px = ex2a((sx - mx) * LOG2E);
-      sum += px;
-      // out[d] = sum_k p_k V[k][d]; lane owns d = 2*lane, 2*lane+1 (4 bytes at chunk lane>>2 of each row)
-      float o0 = 0.f, o1 = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
+        for (int o = 16; o > 0; o >>= 1) lw += __shfl_xor_sync(0xffffffffu, lw, o);
+        float o0 = 0.f, o1 = 0.f;                           // lane owns d = 2*lane, 2*lane+1
 #pragma unroll 8
         for (int l = 0; l < 32; ++l) {
-          const int key = l + 32 * i;
-          const float p = __shfl_sync(0xffffffffu, sc[i], l);
-          const uint8_t* vr = sv + key * 128 + (((lane >> 2) ^ (key & 7)) << 4) + (lane & 3) * 4;
-          const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vr));
+          const int k2 = 32 * warp + l;
+          const float p = __shfl_sync(0xffffffffu, pw, l);
+          const float2 v2 = __bfloat1622float2(
+              *reinterpret_cast<const __nv_bfloat162*>(sv + k2 * 128 + (((lane >> 2) ^ (k2 & 7)) << 4) + (lane & 3) * 4));
           o0 = fmaf(p, v2.x, o0);
           o1 = fmaf(p, v2.y, o1);
         }
-      }
-      {
-        const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sv + 256 * 128 + 4 * lane));
-        o0 = fmaf(px, v2.x, o0);
-        o1 = fmaf(px, v2.y, o1);
+        float* pp = part + ((it & 1) * 8 + warp) * 66;
+        if (lane == 0) { pp[0] = mw; pp[1] = lw; }
+        pp[2 + 2 * lane] = o0;
+        pp[3 + 2 * lane] = o1;
+        epi_bar_sync();                                      // the 8 softmax warps (256 threads)
+        if (warp == 0) {
+          float sx2 = 0.f;                                   // key 256 itself
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            sx2 = dot8(*reinterpret_cast<const uint4*>(q256 + (u << 4)), *reinterpret_cast<const uint4*>(sk + 256 * 128 + (u << 4)), sx2);
+          const float* p0 = part + (it & 1) * 8 * 66;
+          float M = sx2;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) M = fmaxf(M, p0[w * 66]);
+          const float ex = ex2a((sx2 - M) * LOG2E);
+          float L = ex;
+          const float2 vx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sv + 256 * 128 + 4 * lane));
+          float r0 = ex * vx.x, r1 = ex * vx.y;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) {
+            const float f = ex2a((p0[w * 66] - M) * LOG2E);
+            L = fmaf(f, p0[w * 66 + 1], L);
+            r0 = fmaf(f, p0[w * 66 + 2 + 2 * lane], r0);
+            r1 = fmaf(f, p0[w * 66 + 3 + 2 * lane], r1);
+          }
+          const float il = 1.0f / L;
+          *reinterpret_cast<uint32_t*>(out + ((int64_t)b * S_ + 256) * DD + h * DHD + 2 * lane) = pack_bf16(r0 * il, r1 * il);
+        }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(in_empty + 8 * s);         // done with this stage's shared memory
-      const float inv = 1.0f / sum;
-      *reinterpret_cast<uint32_t*>(out + ((int64_t)b * S_ + 256) * DD + h * DHD + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
+      if (lane == 0) mbar_arrive(in_empty + 8 * s);        // done reading this stage's shared memory
     }
   }
   tc_fence_before();
@@ -372,7 +367,9 @@ inline int dino_attention_tc(cudaStream_t st, const bf16* qkv, bf16* out, int B)
   const int n_items = B * DH;
   const int grid = n_items < num_sms() ? n_items : num_sms();
   ProfScope ps(st, "dino_attention");
-  attn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map, tail, qkv, out, n_items);
+  int dbg = 0;
+  if (const char* e = getenv("HVLA_ATTN_DEBUG")) dbg = atoi(e);     // timing experiments only (results are wrong when set)
+  attn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map, tail, qkv, out, n_items, dbg);
   HVLA_LAUNCH_CHECK("attn_tc");
   return HVLA_OK;
 }
