@@ -36,6 +36,15 @@ FLOP_DINO_GEMM_IMG = FLOP_DINO_IMG - FLOP_DINO_ATTN_IMG
 FLOP_BASE_IMG = 160_171_008
 
 
+def workload_config(B: int, world: int) -> dict:
+    return {
+        "workload": f"HyperVLA vit_t batch {B}/GPU SIMPLER-shaped synthetic obs, one generated weight set per env, "
+                    f"action_ensemble window_size=1 (BASELINE.json configs[1])",
+        "envs_per_gpu": B, "tasks_per_gpu": B, "image": "224x224x3 u8", "params": "random-init P1 seed 2025",
+        "parallelism": f"env-sharded dp{world}, no data-path collective",
+    }
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -110,7 +119,7 @@ def run_reference(args):
         "impl": "reference", "metric": "actions_per_sec", "value": v, "unit": "actions/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"HyperVLA vit_t batch {args.batch}/GPU SIMPLER-shaped synthetic obs, window_size=1 (configs[1]); CPU sample of {n} images/step"},
+        "config": dict(workload_config(args.batch, max(1, args.gpus)), cpu_sample=f"{n} images per step on the host cores (rank 0 only)"),
         "cpu_baseline": {"value": v, "unit": "actions/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "actions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -290,6 +299,14 @@ def run_ours(args):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); rt.act_device(img1, bp1.weights, None); b.record(); torch.cuda.synchronize()
         l1.append(a.elapsed_time(b))
+    # batch-1 end to end through the public API (numpy image in, numpy action out; CUDA-graph replay inside)
+    for _ in range(5):
+        model.sample_actions(inp1["images"], inp1["instruction_dict"], None, inp1["timestep_pad_mask"], bp1)
+    l1h = []
+    for _ in range(30):
+        t0 = time.perf_counter()
+        model.sample_actions(inp1["images"], inp1["instruction_dict"], None, inp1["timestep_pad_mask"], bp1)
+        l1h.append((time.perf_counter() - t0) * 1e3)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -302,14 +319,9 @@ def run_ours(args):
             "metric": "actions_per_sec", "value": value, "unit": "actions/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {
-                "workload": f"HyperVLA vit_t batch {B}/GPU SIMPLER-shaped synthetic obs, one generated weight set per env, "
-                            f"action_ensemble window_size=1 (BASELINE.json configs[1])",
-                "envs_per_gpu": B, "tasks_per_gpu": B, "image": "224x224x3 u8", "params": "random-init P1 seed 2025",
-                "l2": f"inputs+activations exceed L2: rotating {n_sets} input sets ({n_sets * B * 150528 / 1e6:.0f} MB) and "
-                      f"~{B * 257 * (768 * 4 + 768 * 2 * 3 + 2304 * 2 + 3072 * 2) / 1e6:.0f} MB of activations per step",
-                "parallelism": f"env-sharded dp{world}, no data-path collective",
-            },
+            "config": dict(workload_config(B, world),
+                           l2=f"inputs+activations exceed L2: rotating {n_sets} input sets ({n_sets * B * 150528 / 1e6:.0f} MB) and "
+                              f"~{B * 257 * (768 * 4 + 768 * 2 * 3 + 2304 * 2 + 3072 * 2) / 1e6:.0f} MB of activations per step"),
             "e2e": {"value": e2e_value, "unit": "actions/s", "h2d_bytes_per_step": B * 150528, "d2h_bytes_per_step": B * (28 + 4) * 4,
                     "ms_per_step": e2e_ms / args.steps, "api": "HyperVLA.sample_actions(host pinned uint8 images) -> numpy actions"},
             "gpu_launches": launches,
@@ -318,7 +330,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "kernel_ms_per_step": kernel_ms,
             "p50_step_ms": float(np.median(lat)), "p95_step_ms": float(np.percentile(lat, 95)),
-            "batch1_p50_latency_ms": float(np.median(l1)),
+            "batch1_p50_latency_ms": float(np.median(l1)), "batch1_e2e_p50_latency_ms": float(np.median(l1h)),
             "hypernet_gen_ms": {"tasks": B, "p50": float(np.median(gen_ms))},
             "tflops_step": (FLOP_DINO_IMG + FLOP_BASE_IMG) * B / (step_ms / 1e3) / 1e12,
         }

@@ -213,6 +213,24 @@ def test_grouped_equals_per_sample_and_is_deterministic(models, torch_cuda):
     assert np.isfinite(a1).all() and np.abs(a1[..., :6]).max() <= 5.0
 
 
+def test_cuda_graph_host_path_equals_eager_path(models, torch_cuda):
+    """Small host batches replay a captured CUDA graph; results must be bit-identical to the eager C-ABI call,
+    also after the weights (task switch) or the batch size change."""
+    from hvla import synthetic as S
+    m = models["bf16"]
+    rt = m.runtime
+    for ci, B in ((1, 1), (8, 3), (1, 1)):
+        inp = S.make_inputs(ci, B, B)
+        bp, tasks, _ = m.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"])
+        a_graph, i_graph = m.sample_actions(inp["images"], None, tasks, None, bp)          # numpy in -> graph replay
+        a_graph2, _ = m.sample_actions(inp["images"], None, tasks, None, bp)
+        img = torch_cuda.from_numpy(inp["images"]).to(rt.device)
+        a_eager, i_eager = m.sample_actions(img, None, tasks, None, bp)                    # CUDA in -> eager launches
+        assert np.array_equal(a_graph, a_eager.cpu().numpy()) and np.array_equal(a_graph, a_graph2)
+        assert np.array_equal(i_graph["gripper_logits"], i_eager["gripper_logits"].cpu().numpy())
+    assert len(rt._graphs) >= 2
+
+
 def test_edge_cases(models, torch_cuda):
     from hvla import _native as N
     from hvla import synthetic as S
