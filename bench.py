@@ -287,6 +287,8 @@ def run_ours(args):
             "traffic": None,
         }
     kernel_ms = {k: round(v[1], 4) for k, v in prof.items()}
+    gen_prof = rt.profile(lambda: model.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"]), repeats=2)
+    gen_kernel_ms = {k: [v[0], round(v[1], 4)] for k, v in gen_prof.items()}
 
     # ---- batch-1 latency (configs[0] shape on the GPU) ----------------------------------------------------
     inp1 = S.make_inputs(1, 1, 1)
@@ -331,7 +333,7 @@ def run_ours(args):
             "kernel_ms_per_step": kernel_ms,
             "p50_step_ms": float(np.median(lat)), "p95_step_ms": float(np.percentile(lat, 95)),
             "batch1_p50_latency_ms": float(np.median(l1)), "batch1_e2e_p50_latency_ms": float(np.median(l1h)),
-            "hypernet_gen_ms": {"tasks": B, "p50": float(np.median(gen_ms))},
+            "hypernet_gen_ms": {"tasks": B, "p50": float(np.median(gen_ms)), "kernel_launches_ms": gen_kernel_ms},
             "tflops_step": (FLOP_DINO_IMG + FLOP_BASE_IMG) * B / (step_ms / 1e3) / 1e12,
         }
         print(json.dumps(out))

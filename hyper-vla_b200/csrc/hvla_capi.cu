@@ -7,6 +7,7 @@
 #include "attn_mma.cuh"
 #include "attn_tc.cuh"
 #include "base_fused.cuh"
+#include "heads_mma.cuh"
 
 #include <stdlib.h>
 #include <type_traits>
@@ -124,6 +125,7 @@ static int generate_impl(cudaStream_t st, const float* hn, const void* heads_w, 
       st, gemm_params(init_cls, DD, hn + L::img_w, CD, hn + L::img_b, IPj, CD, T, CD, DD), 1)));
   {
     const int64_t total = (int64_t)M * CD;
+    ProfScope ps(st, "ctx_assemble");
     ctx_assemble_kernel<<<cdiv(total, 256), 256, 0, st>>>(TPj, IPj, hn + L::task_pos, hn + L::img_pos, hn + L::layer_pos, X, T);
     HVLA_LAUNCH_CHECK("ctx_assemble");
   }
@@ -157,6 +159,9 @@ static int generate_impl(cudaStream_t st, const float* hn, const void* heads_w, 
     HVLA_TRY((layernorm<float, float>(st, ln, CD)));
   }
   // K3: all 73 output heads as one skinny GEMM (hypernetwork.py:205-217, 227)
+  if (std::is_same<TW, bf16>::value && !env_flag("HVLA_DEBUG_SIMT_HEADS"))
+    return heads::heads_gemm_bf16(st, E, reinterpret_cast<const bf16*>(heads_w), heads_b, reinterpret_cast<bf16*>(out_w), T);
+  ProfScope ps(st, "heads_gemm");
   heads_gemm_kernel<TW, TW><<<cdiv(NGP, 1024), 256, 0, st>>>(E, reinterpret_cast<const TW*>(heads_w), heads_b,
                                                              reinterpret_cast<TW*>(out_w), T);
   HVLA_LAUNCH_CHECK("heads_gemm");
@@ -178,6 +183,7 @@ static int dino_f32(cudaStream_t st, const float* dv, const float* dm, const uin
   float* P = QKV;    // patch projections alias the qkv buffer
   {
     const int64_t total = (int64_t)B * NPATCH * PATCH_KP;
+    ProfScope ps(st, "im2col");
     im2col_norm_kernel<float><<<cdiv(total, 256), 256, 0, st>>>(images, A0, B);
     HVLA_LAUNCH_CHECK("im2col");
   }
@@ -241,8 +247,12 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
   const bool one_cta = env_flag("HVLA_GEMM_1CTA");           // A/B switch: single-CTA 128x256 tiles instead of CTA pairs
   {
     const int64_t total = (int64_t)B * NPATCH * PATCH_KP;
-    im2col_norm_kernel<bf16><<<cdiv(total, 256), 256, 0, st>>>(images, A0, B);
-    HVLA_LAUNCH_CHECK("im2col");
+    {
+      ProfScope ps(st, "im2col");
+      im2col_norm_kernel<bf16><<<cdiv(total, 256), 256, 0, st>>>(images, A0, B);
+      HVLA_LAUNCH_CHECK("im2col");
+    }
+    ProfScope ps2(st, "cls_rows");
     dino_cls_rows_kernel<<<cdiv(B * DD, 256), 256, 0, st>>>(dv + V::cls, dv + V::pos, X, B);
     HVLA_LAUNCH_CHECK("dino_cls_rows");
   }
@@ -366,6 +376,7 @@ static int base_generic(cudaStream_t st, const TE* emb, const TW* weights, const
       HVLA_TRY((gemm_simt<float, TW, TW, float>(st, g, B)));
     }
   }
+  ProfScope ps(st, "mix_head");
   mix_head_kernel<TW><<<cdiv(B, 4), 128, 0, st>>>(X, weights, tidx, out_action, out_logit, B);
   HVLA_LAUNCH_CHECK("mix_head");
   return HVLA_OK;
