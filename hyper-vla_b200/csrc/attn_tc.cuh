@@ -95,7 +95,7 @@ __device__ __forceinline__ float dot8(const uint4& a, const uint4& b, float acc)
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmTail, const bf16* __restrict__ qkv,
-               bf16* __restrict__ out, int n_items, int dbg) {
+               bf16* __restrict__ out, int n_items, int dbg, long long* __restrict__ tstamp) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + 2 * STAGE_BYTES;
@@ -162,7 +162,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         tc_fence_after();
         const uint64_t dk = make_smem_desc(st + OFF_K);
         const uint64_t dv = make_smem_desc_mn(st + OFF_V);
-        // S_g = Q_g K^T for both query tiles (group g owns TMEM columns [256g, 256g+256))
+        // Group g owns TMEM columns [256g, 256g+256).  The two groups are deliberately staggered: S_1 is only
+        // issued once group 0 has finished its exponentials (p_full[0]), so the MUFU pipe -- the real bound of
+        // this kernel (16 ex2/clk/SM) -- is used by one group while the other runs its epilogue / row-256 share.
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           mbar_wait(o_free + 8 * g, par ^ 1);           // group g has read the previous item's O out of this region
@@ -171,10 +173,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 256 * g, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
           umma_commit(s_full + 8 * g);
-        }
-        // O_g = P_g V as soon as group g has written P_g (bf16, in place over S_g); O_g lives in the same region
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
+          // O_g = P_g V as soon as group g has written P_g (bf16, in place over S_g); O_g lives in the same region
           mbar_wait(p_full + 8 * g, par);
           tc_fence_after();
 #pragma unroll
@@ -189,6 +188,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   } else if (warp < 8) {
     // ============================ softmax + epilogue: group g = warp / 4 owns query tile g ============================
     const int g = warp >> 2, quarter = warp & 3;
+#define HVLA_TS(k) do { if (tstamp && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4) && it < 6) tstamp[((warp >> 2) * 6 + it) * 8 + (k)] = clock64(); } while (0)
     const uint32_t tm = tmem_base + ((uint32_t)(quarter * 32) << 16) + 256 * g;
     const int rl = quarter * 32 + lane;                 // row inside the tile
     int it = 0;
@@ -198,7 +198,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       const int b = item / DH, h = item % DH;
       const uint8_t* st = smem_al + s * STAGE_BYTES;
       // score against key 256 on CUDA cores from the staged tiles (128B swizzle: chunk ^= row & 7)
+      HVLA_TS(0);
       mbar_wait(in_full + 8 * s, (it >> 1) & 1);
+      HVLA_TS(1);
       float sx = 0.f;
       {
         const uint8_t* qr = st + g * TILE_BYTES + rl * 128;
@@ -209,6 +211,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       }
       mbar_wait(s_full + 8 * g, par);
       tc_fence_after();
+      HVLA_TS(2);
       uint32_t r[2][32];
       // pass 1: row max (TMEM loads double-buffered against the max reduction)
       float mx = sx;
@@ -227,6 +230,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       }
       const float nm = -mx * LOG2E;
       float sum = 0.f;
+      HVLA_TS(3);
       // pass 2: P = exp2((s - max) log2e) as bf16, in place over S (the bf16 row is half as wide)
 #pragma unroll 1
       for (int c = 0; c < 8; c += 2) {
@@ -258,35 +262,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full + 8 * g);
-      // epilogue: (O + p_256 v_256) / sum -> bf16 -> global
-      const float inv = 1.0f / sum;
-      const float pxi = px * inv;
-      bf16* orow = out + ((int64_t)b * S_ + g * 128 + rl) * DD + h * DHD;
-      const uint8_t* vr = st + OFF_V + 256 * 128;
-      mbar_wait(o_full + 8 * g, par);
-      tc_fence_after();
-      tmem_ld32(tm + TM_OREL, r[0]);
-      tmem_ld32(tm + TM_OREL + 32, r[1]);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_free + 8 * g);          // O is in registers now
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint4 vq = *reinterpret_cast<const uint4*>(vr + ((c * 4 + i) << 4));
-          const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&vq);
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 v2 = __bfloat1622float2(pv[e]);
-            w[e] = pack_bf16(fmaf(pxi, v2.x, __uint_as_float(r[c][i * 8 + 2 * e]) * inv),
-                             fmaf(pxi, v2.y, __uint_as_float(r[c][i * 8 + 2 * e + 1]) * inv));
-          }
-          *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-      }
+      HVLA_TS(4);
       // ---- query row 256 (one row per item), cooperatively: this warp takes keys [32*warp, 32*warp+32) ----
       {
         const uint8_t* sk = st + OFF_K;
@@ -318,6 +294,42 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         if (lane == 0) { pp[0] = mw; pp[1] = lw; }
         pp[2 + 2 * lane] = o0;
         pp[3 + 2 * lane] = o1;
+      }
+      // epilogue: (O + p_256 v_256) / sum -> bf16 -> global
+      const float inv = 1.0f / sum;
+      const float pxi = px * inv;
+      bf16* orow = out + ((int64_t)b * S_ + g * 128 + rl) * DD + h * DHD;
+      const uint8_t* vr = st + OFF_V + 256 * 128;
+      mbar_wait(o_full + 8 * g, par);
+      tc_fence_after();
+      HVLA_TS(5);
+      tmem_ld32(tm + TM_OREL, r[0]);
+      tmem_ld32(tm + TM_OREL + 32, r[1]);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free + 8 * g);          // O is in registers now
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 vq = *reinterpret_cast<const uint4*>(vr + ((c * 4 + i) << 4));
+          const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&vq);
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 v2 = __bfloat1622float2(pv[e]);
+            w[e] = pack_bf16(fmaf(pxi, v2.x, __uint_as_float(r[c][i * 8 + 2 * e]) * inv),
+                             fmaf(pxi, v2.y, __uint_as_float(r[c][i * 8 + 2 * e + 1]) * inv));
+          }
+          *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      HVLA_TS(6);
+      {
+        const uint8_t* sk = st + OFF_K;
+        const uint8_t* sv = st + OFF_V;
+        const uint8_t* q256 = st + OFF_QT;
         epi_bar_sync();                                      // the 8 softmax warps (256 threads)
         if (warp == 0) {
           float sx2 = 0.f;                                   // key 256 itself
@@ -345,8 +357,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(in_empty + 8 * s);        // done reading this stage's shared memory
+      HVLA_TS(7);
     }
   }
+#undef HVLA_TS
   tc_fence_before();
   __syncthreads();
   if (warp == W_MMA) {
@@ -369,7 +383,19 @@ inline int dino_attention_tc(cudaStream_t st, const bf16* qkv, bf16* out, int B)
   ProfScope ps(st, "dino_attention");
   int dbg = 0;
   if (const char* e = getenv("HVLA_ATTN_DEBUG")) dbg = atoi(e);     // timing experiments only (results are wrong when set)
-  attn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map, tail, qkv, out, n_items, dbg);
+  static long long* d_ts = nullptr;
+  if ((dbg & 32) && !d_ts) { cudaMalloc(&d_ts, 2 * 6 * 8 * sizeof(long long)); cudaMemset(d_ts, 0, 2 * 6 * 8 * sizeof(long long)); }
+  attn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map, tail, qkv, out, n_items, dbg, (dbg & 32) ? d_ts : nullptr);
+  if (dbg & 32) {
+    long long h[96];
+    cudaMemcpy(h, d_ts, sizeof h, cudaMemcpyDeviceToHost);
+    for (int g = 0; g < 2; ++g)
+      for (int it = 0; it < 6; ++it) {
+        const long long* t = h + (g * 6 + it) * 8;
+        fprintf(stderr, "ts g%d it%d: start %lld | in_full +%lld s_full +%lld pass1 +%lld pass2 +%lld o_full +%lld epi +%lld row256 +%lld\n", g, it,
+                t[0] - h[0], t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6]);
+      }
+  }
   HVLA_LAUNCH_CHECK("attn_tc");
   return HVLA_OK;
 }
