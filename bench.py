@@ -224,14 +224,14 @@ def run_ours(args):
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
-    l0 = N.lib().hvla_launch_count()
+    l0 = rt.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
         step_dev(i)
     e1.record()
     barrier()
-    launches = int(N.lib().hvla_launch_count() - l0)
+    launches = int(rt.launch_count() - l0)
     sampler.stop_flag.set()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:

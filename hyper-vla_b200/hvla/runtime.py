@@ -36,7 +36,9 @@ class Runtime:
         self._ws_key = (0, 0)
         self._pinned = {}
         self._graphs = {}
-        self.graph_max_batch = 16       # host-path calls with B <= this replay a captured CUDA graph (launch-bound regime)
+        self.use_graphs = True          # replay a captured CUDA graph of the act step instead of ~110 eager launches
+        self._profiling = False
+        self.replayed_launches = 0      # kernels launched through graph replays (the C counter only sees eager launches)
         self.upload(params)
 
     # ---- parameters -------------------------------------------------------------------------------
@@ -78,6 +80,10 @@ class Runtime:
             self._pinned[name] = t
         return t[:n].view(*shape)
 
+    def launch_count(self) -> int:
+        """Kernels of libhvla launched so far on behalf of this runtime (eager + replayed through CUDA graphs)."""
+        return int(self.lib.hvla_launch_count()) + self.replayed_launches
+
     def stream(self) -> int:
         return int(_torch().cuda.current_stream(self.device).cuda_stream)
 
@@ -110,7 +116,7 @@ class Runtime:
         N.check(st, "hvla_generate")
         return out, ctx
 
-    # ---- act --------------------------------------------------------------------------------------------
+    # ---- act: one CUDA graph (~110 kernels) per (batch, weights, task map), replayed every control step ------------
     def _tidx(self, task_index, B, T):
         torch = _torch()
         if task_index is None:
@@ -121,83 +127,73 @@ class Runtime:
         ti = ti.to(self.device).to(torch.int32).contiguous()
         if tuple(ti.shape) != (B,):
             raise ValueError("task_index must have shape (B,)")
+        if int(ti.min()) < 0 or int(ti.max()) >= T:
+            raise ValueError("task_index out of range")
         return ti, ti.data_ptr()
 
-    def act_device(self, images, weights, task_index=None):
-        """images: uint8 CUDA tensor (B,224,224,3); returns (action, logit) CUDA tensors (async)."""
-        torch = _torch()
-        B, T = int(images.shape[0]), int(weights.shape[0])
-        if tuple(images.shape[1:]) != (Cfg.IMAGE_SIZE, Cfg.IMAGE_SIZE, 3) or images.dtype != torch.uint8:
-            raise ValueError("Input image size must be 224x224 (uint8, NHWC)")   # base_vit.py:87-89
-        images = images.contiguous()
-        keep, tptr = self._tidx(task_index, B, T)
-        act = torch.empty((B, Cfg.ACTION_HORIZON, Cfg.ACTION_DIM), dtype=torch.float32, device=self.device)
-        logit = torch.empty((B, Cfg.ACTION_HORIZON), dtype=torch.float32, device=self.device)
-        if B == 0:
-            return act, logit
+    def _act_eager(self, img_dev, weights, tptr, B, T, act_dev, logit_dev):
         ws, ws_bytes = self.workspace(B, 0)
-        st = self.lib.hvla_act(self.stream(), self.dino_vec.data_ptr(), self.dino_mat.data_ptr(), images.data_ptr(),
-                               weights.data_ptr(), tptr, B, T, act.data_ptr(), logit.data_ptr(), ws, ws_bytes, self.dtype)
-        N.check(st, "hvla_act")
-        return act, logit
+        N.check(self.lib.hvla_act(self.stream(), self.dino_vec.data_ptr(), self.dino_mat.data_ptr(), img_dev.data_ptr(),
+                                  weights.data_ptr(), tptr, B, T, act_dev.data_ptr(), logit_dev.data_ptr(), ws, ws_bytes,
+                                  self.dtype), "hvla_act")
 
-    # ---- CUDA-graph replay of one act step (small batches are launch-bound: ~110 kernels per step) -------------
-    def _graph(self, B, weights, tidx_t):
+    def _graph(self, B, weights, task_index):
+        """Static device buffers + captured graph of hvla_act for this (B, weights, task map)."""
         torch = _torch()
-        key = (B, int(weights.data_ptr()), int(tidx_t.data_ptr()) if tidx_t is not None else 0)
-        g = self._graphs.get(key)
-        if g is not None:
-            return g
+        T = int(weights.shape[0])
+        tkey = None if task_index is None else np.asarray(task_index.cpu() if torch.is_tensor(task_index) else task_index).tobytes()
+        key = (B, int(weights.data_ptr()), tkey)
+        st = self._graphs.get(key)
+        if st is not None and st["ws_key"] == self._ws_key:
+            return st
         if len(self._graphs) >= 8:
             self._graphs.pop(next(iter(self._graphs)))
-        T = int(weights.shape[0])
+        tidx_t, tptr = self._tidx(task_index, B, T)
         st = {
-            "img_pin": torch.empty((B, Cfg.IMAGE_SIZE, Cfg.IMAGE_SIZE, 3), dtype=torch.uint8).pin_memory(),
             "img_dev": torch.empty((B, Cfg.IMAGE_SIZE, Cfg.IMAGE_SIZE, 3), dtype=torch.uint8, device=self.device),
             "act_dev": torch.empty((B, Cfg.ACTION_HORIZON, Cfg.ACTION_DIM), dtype=torch.float32, device=self.device),
             "logit_dev": torch.empty((B, Cfg.ACTION_HORIZON), dtype=torch.float32, device=self.device),
-            "act_pin": torch.empty((B, Cfg.ACTION_HORIZON, Cfg.ACTION_DIM), dtype=torch.float32).pin_memory(),
-            "logit_pin": torch.empty((B, Cfg.ACTION_HORIZON), dtype=torch.float32).pin_memory(),
-            "weights": weights, "tidx": tidx_t,
+            "weights": weights, "tidx": tidx_t, "tptr": tptr, "T": T, "graph": None,
         }
-        ws, ws_bytes = self.workspace(B, 0)
-        tptr = tidx_t.data_ptr() if tidx_t is not None else None
-
-        def launch():
-            N.check(self.lib.hvla_act(self.stream(), self.dino_vec.data_ptr(), self.dino_mat.data_ptr(), st["img_dev"].data_ptr(),
-                                      weights.data_ptr(), tptr, B, T, st["act_dev"].data_ptr(), st["logit_dev"].data_ptr(),
-                                      ws, ws_bytes, self.dtype), "hvla_act")
-
-        launch()                          # eager warm-up: one-time kernel attribute setup happens outside the capture
-        torch.cuda.synchronize(self.device)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            st["img_dev"].copy_(st["img_pin"], non_blocking=True)
-            launch()
-            st["act_pin"].copy_(st["act_dev"], non_blocking=True)
-            st["logit_pin"].copy_(st["logit_dev"], non_blocking=True)
-        st["graph"] = graph
+        self.workspace(B, 0)
+        if self.use_graphs and not self._profiling:
+            st["img_dev"].zero_()
+            n0 = int(self.lib.hvla_launch_count())
+            self._act_eager(st["img_dev"], weights, tptr, B, T, st["act_dev"], st["logit_dev"])   # one-time kernel setup outside capture
+            st["n_launches"] = int(self.lib.hvla_launch_count()) - n0
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._act_eager(st["img_dev"], weights, tptr, B, T, st["act_dev"], st["logit_dev"])
+            st["graph"] = graph
         st["ws_key"] = self._ws_key
         self._graphs[key] = st
         return st
 
-    def act_host_graphed(self, arr, weights, task_index=None):
-        """Host numpy images -> numpy actions through a replayed CUDA graph (H2D + ~110 kernels + D2H)."""
+    def _run(self, st, B):
+        if st["graph"] is not None and not self._profiling:
+            st["graph"].replay()
+            self.replayed_launches += st["n_launches"]
+        else:
+            self._act_eager(st["img_dev"], st["weights"], st["tptr"], B, st["T"], st["act_dev"], st["logit_dev"])
+
+    def act_device(self, images, weights, task_index=None):
+        """images: uint8 CUDA tensor (B,224,224,3); returns (action, logit) CUDA tensors (asynchronous)."""
         torch = _torch()
-        B, T = int(arr.shape[0]), int(weights.shape[0])
-        tidx_t, _ = self._tidx(task_index, B, T)
-        st = self._graph(B, weights, tidx_t)
-        if st["ws_key"] != self._ws_key:          # the workspace was re-allocated since capture: re-capture
-            self._graphs.clear()
-            st = self._graph(B, weights, tidx_t)
-        st["img_pin"].numpy()[...] = arr
-        st["graph"].replay()
-        torch.cuda.current_stream(self.device).synchronize()
-        return st["act_pin"].numpy().copy(), st["logit_pin"].numpy().copy()
+        B = int(images.shape[0])
+        if tuple(images.shape[1:]) != (Cfg.IMAGE_SIZE, Cfg.IMAGE_SIZE, 3) or images.dtype != torch.uint8:
+            raise ValueError("Input image size must be 224x224 (uint8, NHWC)")   # base_vit.py:87-89
+        if B == 0:
+            return (torch.empty((0, Cfg.ACTION_HORIZON, Cfg.ACTION_DIM), dtype=torch.float32, device=self.device),
+                    torch.empty((0, Cfg.ACTION_HORIZON), dtype=torch.float32, device=self.device))
+        st = self._graph(B, weights, task_index)
+        st["img_dev"].copy_(images, non_blocking=True)
+        self._run(st, B)
+        return st["act_dev"].clone(), st["logit_dev"].clone()
 
     def act_host(self, images, weights, task_index=None):
         """images: host uint8 (numpy or pinned torch CPU tensor) (B,224,224,3); returns numpy
-        (action (B,4,7), logit (B,4)).  Includes H2D + D2H + one stream sync."""
+        (action (B,4,7), logit (B,4)).  H2D copy + graph replay + D2H copy + one stream sync."""
         torch = _torch()
         if torch.is_tensor(images):
             if images.dtype != torch.uint8 or tuple(images.shape[1:]) != (Cfg.IMAGE_SIZE, Cfg.IMAGE_SIZE, 3):
@@ -207,32 +203,33 @@ class Runtime:
             arr = np.ascontiguousarray(images)
             if arr.dtype != np.uint8 or arr.shape[1:] != (Cfg.IMAGE_SIZE, Cfg.IMAGE_SIZE, 3):
                 raise ValueError("Input image size must be 224x224 (uint8, NHWC)")
-            if 0 < arr.shape[0] <= self.graph_max_batch:
-                return self.act_host_graphed(arr, weights, task_index)
             src = self.pinned("img", arr.shape, torch.uint8)
             if arr.size:
                 src.numpy()[...] = arr
-        B, T = int(src.shape[0]), int(weights.shape[0])
+        B = int(src.shape[0])
         if B == 0:
             return (np.zeros((0, Cfg.ACTION_HORIZON, Cfg.ACTION_DIM), np.float32), np.zeros((0, Cfg.ACTION_HORIZON), np.float32))
-        keep, tptr = self._tidx(task_index, B, T)
+        st = self._graph(B, weights, task_index)
         act = self.pinned("act", (B, Cfg.ACTION_HORIZON, Cfg.ACTION_DIM), torch.float32)
         logit = self.pinned("logit", (B, Cfg.ACTION_HORIZON), torch.float32)
-        ws, ws_bytes = self.workspace(B, 0)
-        st = self.lib.hvla_act_host(self.stream(), self.dino_vec.data_ptr(), self.dino_mat.data_ptr(), src.data_ptr(),
-                                    weights.data_ptr(), tptr, B, T, act.data_ptr(), logit.data_ptr(), ws, ws_bytes, self.dtype)
-        N.check(st, "hvla_act_host")
+        st["img_dev"].copy_(src, non_blocking=True)
+        self._run(st, B)
+        act.copy_(st["act_dev"], non_blocking=True)
+        logit.copy_(st["logit_dev"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
         return act.numpy().copy(), logit.numpy().copy()
 
     def profile(self, fn, repeats: int = 1) -> dict:
         """Run ``fn`` with per-kernel-class event timing on; -> {class: (launches, total_ms)} per repeat."""
         self.lib.hvla_profile_enable(1)
+        self._profiling = True
         try:
             for _ in range(repeats):
                 fn()
             buf = C.create_string_buffer(4096)
             N.check(self.lib.hvla_profile_report(buf, 4096), "hvla_profile_report")
         finally:
+            self._profiling = False
             self.lib.hvla_profile_enable(0)
         out = {}
         for line in buf.value.decode().splitlines():

@@ -213,22 +213,33 @@ def test_grouped_equals_per_sample_and_is_deterministic(models, torch_cuda):
     assert np.isfinite(a1).all() and np.abs(a1[..., :6]).max() <= 5.0
 
 
-def test_cuda_graph_host_path_equals_eager_path(models, torch_cuda):
-    """Small host batches replay a captured CUDA graph; results must be bit-identical to the eager C-ABI call,
-    also after the weights (task switch) or the batch size change."""
+def test_cuda_graph_replay_equals_eager_launches(models, torch_cuda):
+    """The act step is replayed from a captured CUDA graph; results must be bit-identical to eager launches through
+    the C ABI, also after the weights (task switch), the task map or the batch size change."""
     from hvla import synthetic as S
     m = models["bf16"]
     rt = m.runtime
-    for ci, B in ((1, 1), (8, 3), (1, 1)):
-        inp = S.make_inputs(ci, B, B)
+    for ci, B, T in ((1, 1, 1), (8, 3, 3), (5, 6, 2), (1, 1, 1)):
+        inp = S.make_inputs(ci, B, T)
+        ti = None if T in (1, B) else inp["task_index"]
         bp, tasks, _ = m.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"])
-        a_graph, i_graph = m.sample_actions(inp["images"], None, tasks, None, bp)          # numpy in -> graph replay
-        a_graph2, _ = m.sample_actions(inp["images"], None, tasks, None, bp)
+        a_graph, i_graph = m.sample_actions(inp["images"], None, tasks, None, bp, task_index=ti)
+        a_graph2, _ = m.sample_actions(inp["images"], None, tasks, None, bp, task_index=ti)
         img = torch_cuda.from_numpy(inp["images"]).to(rt.device)
-        a_eager, i_eager = m.sample_actions(img, None, tasks, None, bp)                    # CUDA in -> eager launches
-        assert np.array_equal(a_graph, a_eager.cpu().numpy()) and np.array_equal(a_graph, a_graph2)
-        assert np.array_equal(i_graph["gripper_logits"], i_eager["gripper_logits"].cpu().numpy())
-    assert len(rt._graphs) >= 2
+        a_dev, _ = m.sample_actions(img, None, tasks, None, bp, task_index=ti)
+        rt.use_graphs = False
+        rt._graphs.clear()
+        try:
+            a_eager, i_eager = m.sample_actions(inp["images"], None, tasks, None, bp, task_index=ti)
+        finally:
+            rt.use_graphs = True
+            rt._graphs.clear()
+        assert np.array_equal(a_graph, a_eager) and np.array_equal(a_graph, a_graph2) and np.array_equal(a_graph, a_dev.cpu().numpy())
+        assert np.array_equal(i_graph["gripper_logits"], i_eager["gripper_logits"])
+    n0 = rt.launch_count()
+    m.sample_actions(inp["images"], None, tasks, None, bp)
+    m.sample_actions(inp["images"], None, tasks, None, bp)
+    assert rt.launch_count() - n0 >= 2 * 60
 
 
 def test_edge_cases(models, torch_cuda):
