@@ -104,6 +104,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   float* part = reinterpret_cast<float*>(smem_raw + (bars + 256 - smem_u32(smem_raw)));   // [2][8][66]
+  int* cnt = reinterpret_cast<int*>(smem_raw + (bars + 128 - smem_u32(smem_raw)));           // [2] arrival counters
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == W_TMA && lane == 0) {
@@ -117,6 +118,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       mbar_init(o_full + 8 * s, 1);
       mbar_init(o_free + 8 * s, 4);
     }
+    cnt[0] = 0;
+    cnt[1] = 0;
     fence_barrier_init();
   }
   if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
@@ -162,9 +165,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         tc_fence_after();
         const uint64_t dk = make_smem_desc(st + OFF_K);
         const uint64_t dv = make_smem_desc_mn(st + OFF_V);
-        // Group g owns TMEM columns [256g, 256g+256).  The two groups are deliberately staggered: S_1 is only
-        // issued once group 0 has finished its exponentials (p_full[0]), so the MUFU pipe -- the real bound of
-        // this kernel (16 ex2/clk/SM) -- is used by one group while the other runs its epilogue / row-256 share.
+        // Group g owns TMEM columns [256g, 256g+256): S_g = Q_g K^T for both query tiles first ...
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           mbar_wait(o_free + 8 * g, par ^ 1);           // group g has read the previous item's O out of this region
@@ -173,7 +174,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 256 * g, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
           umma_commit(s_full + 8 * g);
-          // O_g = P_g V as soon as group g has written P_g (bf16, in place over S_g); O_g lives in the same region
+        }
+        // ... then O_g = P_g V as soon as group g has written P_g (bf16, in place over S_g); O_g lives in the same region
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
           mbar_wait(p_full + 8 * g, par);
           tc_fence_after();
 #pragma unroll
@@ -330,13 +334,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         const uint8_t* sk = st + OFF_K;
         const uint8_t* sv = st + OFF_V;
         const uint8_t* q256 = st + OFF_QT;
-        epi_bar_sync();                                      // the 8 softmax warps (256 threads)
-        if (warp == 0) {
+        // the last of the 8 warps to publish its share merges them (no CTA-wide barrier: the groups stay decoupled)
+        __threadfence_block();
+        __syncwarp();
+        int prev = 0;
+        if (lane == 0) prev = atomicAdd(cnt + (it & 1), 1);
+        prev = __shfl_sync(0xffffffffu, prev, 0);
+        if (prev == 7) {
+          __threadfence_block();
+          if (lane == 0) cnt[it & 1] = 0;
           float sx2 = 0.f;                                   // key 256 itself
 #pragma unroll
           for (int u = 0; u < 8; ++u)
             sx2 = dot8(*reinterpret_cast<const uint4*>(q256 + (u << 4)), *reinterpret_cast<const uint4*>(sk + 256 * 128 + (u << 4)), sx2);
-          const float* p0 = part + (it & 1) * 8 * 66;
+          const volatile float* p0 = part + (it & 1) * 8 * 66;
           float M = sx2;
 #pragma unroll
           for (int w = 0; w < 8; ++w) M = fmaxf(M, p0[w * 66]);
