@@ -1,0 +1,288 @@
+// Hypernetwork context encoder in ONE kernel (bf16 tensor-core path): token / initial-image projections +
+// position embeddings, the 34-token block-masked 6-layer pre-LN transformer (4 heads x 32, mlp 512, tanh-GELU),
+// encoder_norm on the layer token and the 1/sqrt(128) scaling.
+//   reference: hypervla/components/hypernetwork.py:99-197, transformer.py:127-262.
+//
+// One CTA per task, 8 warps.  The fp32 residual stream (34 x 128), the bf16 A operands and q|k|v / the MLP
+// hidden stay in shared memory for the whole network; the (task-shared) weights are streamed from L2 in
+// 32-row K chunks with double-buffered cp.async and consumed by warp-level mma.sync m16n8k16 (M = 34 rows is far
+// below a tcgen05 tile; the kernel is latency-bound, the 2.8 MB of bf16 weights per task come from L2).
+#pragma once
+#include "common.cuh"
+#include "attn_mma.cuh"
+
+namespace hvla {
+namespace ctxf {
+
+using attn::cp_async16;
+using attn::cp_async_commit;
+using attn::cp_async_wait;
+using attn::ldsm_x4;
+using attn::ldsm_x4_t;
+using attn::mma_bf16;
+using attn::pack2;
+
+constexpr int NTH = 256, MT = 3;                         // 8 warps; 3 m-tiles = 48 rows (34 used)
+constexpr int XLD = 132, ALD = 136, QLD = 392, HLD = 520, ELD = 776, WCH = 32;
+constexpr int OFF_X = 0;                                 // fp32 [48][132]
+constexpr int OFF_A = OFF_X + 48 * XLD * 4;              // bf16 [48][136]  LN output / attention output
+constexpr int OFF_BIG = OFF_A + 48 * ALD * 2;            // bf16: q|k|v [48][392]  |  hidden [48][520]  |  token emb [32][776]
+constexpr int BIG_BYTES = 48 * HLD * 2;
+constexpr int OFF_W = OFF_BIG + BIG_BYTES;               // 2 x weight chunk [32][<=520] bf16
+constexpr int WBUF_BYTES = WCH * HLD * 2;
+constexpr int OFF_MISC = OFF_W + 2 * WBUF_BYTES;         // key-valid flags [34]
+constexpr int SMEM = OFF_MISC + 256;
+static_assert(32 * ELD * 2 <= BIG_BYTES && 48 * QLD * 2 <= BIG_BYTES, "BIG region");
+
+// C[48 x N] (+)= A[48 x K] (bf16 smem, row stride lda) * W[K x N] (bf16 global, row-major), warp w owns N/8 columns.
+// epi(row, col, v0, v1) is called for column pairs (col, col+1) of rows < 34.
+template <int N, int K, class Epi>
+__device__ __forceinline__ void cta_gemm(uint8_t* smem, const bf16* As, int lda, const bf16* __restrict__ Wg, Epi epi) {
+  constexpr int NTW = N / 64;                            // n-tiles (8 columns) per warp
+  constexpr int WLD = N + 8;
+  constexpr int NCH = K / WCH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sW = (uint32_t)__cvta_generic_to_shared(smem + OFF_W);
+  const uint32_t sA = (uint32_t)__cvta_generic_to_shared(As);
+  float acc[MT][NTW][4];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int n = 0; n < NTW; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
+  auto stage = [&](int c) {
+    const uint32_t dst = sW + (uint32_t)((c & 1) * WBUF_BYTES);
+    const bf16* src = Wg + (int64_t)c * WCH * N;
+    for (int i = threadIdx.x; i < WCH * (N / 8); i += NTH) {
+      const int r = i / (N / 8), cc = (i % (N / 8)) * 8;
+      cp_async16(dst + (uint32_t)((r * WLD + cc) * 2), src + (int64_t)r * N + cc);
+    }
+    cp_async_commit();
+  };
+  stage(0);
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    if (c + 1 < NCH) { stage(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const uint32_t wb = sW + (uint32_t)((c & 1) * WBUF_BYTES);
+#pragma unroll
+    for (int ks = 0; ks < WCH / 16; ++ks) {
+      uint32_t a[MT][4];
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+        ldsm_x4(sA + (uint32_t)(((m * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * lda + c * WCH + ks * 16 + (lane >> 4) * 8) * 2), a[m][0], a[m][1],
+                a[m][2], a[m][3]);
+#pragma unroll
+      for (int np = 0; np < NTW / 2; ++np) {
+        uint32_t b0, b1, b2, b3;
+        const int i = lane >> 3;
+        ldsm_x4_t(wb + (uint32_t)(((ks * 16 + (i & 1) * 8 + (lane & 7)) * WLD + warp * (N / 8) + (np * 2 + (i >> 1)) * 8) * 2), b0, b1, b2, b3);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          mma_bf16(acc[m][2 * np], a[m], b0, b1);
+          mma_bf16(acc[m][2 * np + 1], a[m], b2, b3);
+        }
+      }
+    }
+    __syncthreads();                                     // chunk buffer (c & 1) is free for the prefetch of chunk c + 2
+  }
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int n = 0; n < NTW; ++n) {
+      const int col = warp * (N / 8) + n * 8 + (lane & 3) * 2;
+      const int r0 = m * 16 + (lane >> 2);
+      if (r0 < CTOK) epi(r0, col, acc[m][n][0], acc[m][n][1]);
+      if (r0 + 8 < CTOK) epi(r0 + 8, col, acc[m][n][2], acc[m][n][3]);
+    }
+}
+
+// flax LayerNorm of the 34 residual rows -> bf16 A operand (one warp per row, 4 values per lane)
+__device__ __forceinline__ void ln_rows(const float* X, bf16* A, const float* __restrict__ sc, const float* __restrict__ bi) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4 g = __ldg(reinterpret_cast<const float4*>(sc) + lane), b = __ldg(reinterpret_cast<const float4*>(bi) + lane);
+  for (int r = warp; r < CTOK; r += 8) {
+    const float4 v = *reinterpret_cast<const float4*>(X + r * XLD + lane * 4);
+    float s = (v.x + v.y) + (v.z + v.w);
+    float q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    const float mean = s * (1.f / 128.f);
+    const float rstd = 1.0f / sqrtf(fmaxf(0.f, q * (1.f / 128.f) - mean * mean) + 1e-6f);
+    const uint32_t p0 = pack2((v.x - mean) * (rstd * g.x) + b.x, (v.y - mean) * (rstd * g.y) + b.y);
+    const uint32_t p1 = pack2((v.z - mean) * (rstd * g.z) + b.z, (v.w - mean) * (rstd * g.w) + b.w);
+    *reinterpret_cast<uint2*>(A + r * ALD + lane * 4) = make_uint2(p0, p1);
+  }
+}
+
+__global__ void __launch_bounds__(NTH, 1)
+ctx_fused_kernel(const float* __restrict__ hn, const bf16* __restrict__ hnb, const float* __restrict__ tok_emb,
+                 const int32_t* __restrict__ tok_mask, const uint8_t* __restrict__ lang_pad, const float* __restrict__ init_cls,
+                 float* __restrict__ out_ctx) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  typedef HnLayout L;
+  const int t = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* X = reinterpret_cast<float*>(smem + OFF_X);
+  bf16* A = reinterpret_cast<bf16*>(smem + OFF_A);
+  bf16* BIG = reinterpret_cast<bf16*>(smem + OFF_BIG);
+  int* kvalid = reinterpret_cast<int*>(smem + OFF_MISC);
+
+  // ---- inputs: token embeddings -> bf16 A operand [32][776]; key-valid flags ----
+  for (int i = threadIdx.x; i < LANG * (LANGD / 4); i += NTH) {
+    const int r = i / (LANGD / 4), c = (i % (LANGD / 4)) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(tok_emb + ((int64_t)t * LANG + r) * LANGD + c));
+    *reinterpret_cast<uint2*>(BIG + r * ELD + c) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+  }
+  // (rows 32..47 of this A operand alias the weight-chunk buffers: their products land in output rows that are never read)
+  if (threadIdx.x < CTOK) {
+    const int j = threadIdx.x;
+    const bool pad = lang_pad ? lang_pad[t] != 0 : true;
+    kvalid[j] = j < LANG ? ((tok_mask[t * LANG + j] != 0) && pad) : 1;          // hypernetwork.py:151-163 (key 33: see attention)
+  }
+  for (int i = threadIdx.x; i < 48 * XLD; i += NTH) X[i] = 0.f;
+  for (int i = threadIdx.x; i < 48 * ALD / 2; i += NTH) reinterpret_cast<uint32_t*>(A)[i] = 0u;
+  __syncthreads();
+  // ---- K1: task tokens = tok_emb * W + b + task_pos (hypernetwork.py:112-115) --------------------------------------
+  cta_gemm<CD, LANGD>(smem, BIG, ELD, hnb + L::tok_w, [&](int r, int c, float v0, float v1) {
+    if (r < LANG) {
+      X[r * XLD + c] = v0 + hn[L::tok_b + c] + hn[L::task_pos + r * CD + c];
+      X[r * XLD + c + 1] = v1 + hn[L::tok_b + c + 1] + hn[L::task_pos + r * CD + c + 1];
+    }
+  });
+  // initial-image token (row 32): cls * W + b + pos (hypernetwork.py:126-127) as a second small GEMM whose only
+  // live row is row 0 of the A operand; layer token (row 33) = 0 + pos (hypernetwork.py:144-145)
+  __syncthreads();
+  for (int i = threadIdx.x; i < DD / 4; i += NTH) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(init_cls + (int64_t)t * DD) + i);
+    *reinterpret_cast<uint2*>(BIG + i * 4) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+  }
+  if (threadIdx.x < CD) X[33 * XLD + threadIdx.x] = hn[L::layer_pos + threadIdx.x];
+  __syncthreads();
+  cta_gemm<CD, DD>(smem, BIG, ELD, hnb + L::img_w, [&](int r, int c, float v0, float v1) {
+    if (r == 0) {
+      X[32 * XLD + c] = v0 + hn[L::img_b + c] + hn[L::img_pos + c];
+      X[32 * XLD + c + 1] = v1 + hn[L::img_b + c + 1] + hn[L::img_pos + c + 1];
+    }
+  });
+  __syncthreads();
+
+  // ---- K2: 6 encoder blocks ----------------------------------------------------------------------------------------
+  for (int l = 0; l < CL; ++l) {
+    const float* lw = hn + L::layers + (int64_t)l * L::layer_size;
+    const bf16* lb = hnb + L::layers + (int64_t)l * L::layer_size;
+    ln_rows(X, A, lw + L::ln0_s, lw + L::ln0_b);
+    __syncthreads();
+    // q|k|v = LN(x) Wqkv + b; q pre-divided by sqrt(32)
+    cta_gemm<3 * CD, CD>(smem, A, ALD, lb + L::wqkv, [&](int r, int c, float v0, float v1) {
+      v0 += lw[L::bqkv + c];
+      v1 += lw[L::bqkv + c + 1];
+      if (c < CD) { v0 *= 0.17677669529663687f; v1 *= 0.17677669529663687f; }
+      *reinterpret_cast<uint32_t*>(BIG + r * QLD + c) = pack2(v0, v1);
+    });
+    __syncthreads();
+    // attention on CUDA cores: (head, query) pairs over the warps; 34 keys, block mask of hypernetwork.py:151-181
+    for (int p = warp; p < CH * CTOK; p += 8) {
+      const int h = p / CTOK, q = p % CTOK;
+      float s0 = -INFINITY, s1 = -INFINITY;               // keys lane and lane + 32
+      {
+        const bf16* qp = BIG + q * QLD + h * CHD;
+        float a0 = 0.f, a1 = 0.f;
+        const bf16* k0 = BIG + lane * QLD + CD + h * CHD;
+        const bf16* k1 = BIG + (32 + (lane & 1)) * QLD + CD + h * CHD;
+#pragma unroll
+        for (int u = 0; u < CHD / 8; ++u) {
+          const uint4 qv = *reinterpret_cast<const uint4*>(qp + u * 8);
+          const uint4 kv0 = *reinterpret_cast<const uint4*>(k0 + u * 8);
+          const uint4 kv1 = *reinterpret_cast<const uint4*>(k1 + u * 8);
+          const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&qv);
+          const __nv_bfloat162* b0 = reinterpret_cast<const __nv_bfloat162*>(&kv0);
+          const __nv_bfloat162* b1 = reinterpret_cast<const __nv_bfloat162*>(&kv1);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 x = __bfloat1622float2(a[e]), y0 = __bfloat1622float2(b0[e]), y1 = __bfloat1622float2(b1[e]);
+            a0 = fmaf(x.x, y0.x, fmaf(x.y, y0.y, a0));
+            a1 = fmaf(x.x, y1.x, fmaf(x.y, y1.y, a1));
+          }
+        }
+        if (kvalid[lane]) s0 = a0;
+        if (lane == 0) s1 = a1;                            // key 32 (initial image): always visible
+        else if (lane == 1 && q == CTOK - 1) s1 = a1;      // key 33 (layer token): only the layer token sees it
+      }
+      float mx = fmaxf(s0, s1);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float e0 = s0 == -INFINITY ? 0.f : __expf(s0 - mx), e1 = s1 == -INFINITY ? 0.f : __expf(s1 - mx);
+      float sum = e0 + e1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float inv = 1.0f / sum;
+      float acc = 0.f;                                    // lane owns dim d = lane of this head
+      const bf16* vp = BIG + 2 * CD + h * CHD + lane;
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) acc = fmaf(__shfl_sync(0xffffffffu, e0, k), __bfloat162float(vp[k * QLD]), acc);
+      acc = fmaf(__shfl_sync(0xffffffffu, e1, 0), __bfloat162float(vp[32 * QLD]), acc);
+      acc = fmaf(__shfl_sync(0xffffffffu, e1, 1), __bfloat162float(vp[33 * QLD]), acc);
+      A[q * ALD + h * CHD + lane] = __float2bfloat16_rn(acc * inv);
+    }
+    __syncthreads();
+    // x += attn Wo + b
+    cta_gemm<CD, CD>(smem, A, ALD, lb + L::wo, [&](int r, int c, float v0, float v1) {
+      X[r * XLD + c] += v0 + lw[L::bo + c];
+      X[r * XLD + c + 1] += v1 + lw[L::bo + c + 1];
+    });
+    __syncthreads();
+    ln_rows(X, A, lw + L::ln1_s, lw + L::ln1_b);
+    __syncthreads();
+    // h = gelu_tanh(LN(x) W0 + b0)
+    cta_gemm<CF, CD>(smem, A, ALD, lb + L::w0, [&](int r, int c, float v0, float v1) {
+      *reinterpret_cast<uint32_t*>(BIG + r * HLD + c) = pack2(gelu_tanh_f(v0 + lw[L::b0 + c]), gelu_tanh_f(v1 + lw[L::b0 + c + 1]));
+    });
+    __syncthreads();
+    // x += h W1 + b1
+    cta_gemm<CD, CF>(smem, BIG, HLD, lb + L::w1, [&](int r, int c, float v0, float v1) {
+      X[r * XLD + c] += v0 + lw[L::b1 + c];
+      X[r * XLD + c + 1] += v1 + lw[L::b1 + c + 1];
+    });
+    __syncthreads();
+  }
+  // ---- encoder_norm on the layer token, / sqrt(128)  (hypernetwork.py:188-192) --------------------------------------
+  if (warp == 0) {
+    const float4 v = *reinterpret_cast<const float4*>(X + (CTOK - 1) * XLD + lane * 4);
+    float s = (v.x + v.y) + (v.z + v.w);
+    float q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    const float mean = s * (1.f / 128.f);
+    const float rstd = 1.0f / sqrtf(fmaxf(0.f, q * (1.f / 128.f) - mean * mean) + 1e-6f);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(hn + L::encn_s) + lane), b = __ldg(reinterpret_cast<const float4*>(hn + L::encn_b) + lane);
+    const float d = sqrtf((float)CD);
+    float4 o;
+    o.x = ((v.x - mean) * (rstd * g.x) + b.x) / d;
+    o.y = ((v.y - mean) * (rstd * g.y) + b.y) / d;
+    o.z = ((v.z - mean) * (rstd * g.z) + b.z) / d;
+    o.w = ((v.w - mean) * (rstd * g.w) + b.w) / d;
+    *reinterpret_cast<float4*>(out_ctx + (int64_t)t * CD + lane * 4) = o;
+  }
+}
+
+inline int ctx_encode_bf16(cudaStream_t st, const float* hn, const bf16* hnb, const float* tok_emb, const int32_t* tok_mask,
+                           const uint8_t* lang_pad, const float* init_cls, int T, float* out_ctx) {
+  static bool attr = false;
+  if (!attr) {
+    HVLA_CUDA(cudaFuncSetAttribute(ctx_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr = true;
+  }
+  ProfScope ps(st, "ctx_fused");
+  ctx_fused_kernel<<<T, NTH, SMEM, st>>>(hn, hnb, tok_emb, tok_mask, lang_pad, init_cls, out_ctx);
+  HVLA_LAUNCH_CHECK("ctx_fused");
+  return HVLA_OK;
+}
+
+}  // namespace ctxf
+}  // namespace hvla

@@ -8,6 +8,7 @@
 #include "attn_tc.cuh"
 #include "base_fused.cuh"
 #include "heads_mma.cuh"
+#include "ctx_fused.cuh"
 
 #include <stdlib.h>
 #include <type_traits>
@@ -105,7 +106,7 @@ static bool env_flag(const char* name) {
 
 // ---- generate (K1-K3) ---------------------------------------------------------------------------------
 template <typename TW>
-static int generate_impl(cudaStream_t st, const float* hn, const void* heads_w, const float* heads_b, const float* tok_emb,
+static int generate_impl(cudaStream_t st, const float* hn, const void* hn_lp, const void* heads_w, const float* heads_b, const float* tok_emb,
                          const int32_t* tok_mask, const uint8_t* lang_pad, const float* init_cls, int T, void* out_w,
                          float* out_ctx, uint8_t* ws, const Plan& pl) {
   float* TPj = reinterpret_cast<float*>(ws + pl.tp);
@@ -118,6 +119,11 @@ static int generate_impl(cudaStream_t st, const float* hn, const void* heads_w, 
   float* E = out_ctx ? out_ctx : reinterpret_cast<float*>(ws + pl.e);
   const int M = T * CTOK;
   typedef HnLayout L;
+  if (std::is_same<TW, bf16>::value && hn_lp && !env_flag("HVLA_DEBUG_GENERIC_CTX")) {
+    // bf16 tensor-core path: the whole context encoder is one kernel, the 73 heads another
+    HVLA_TRY(ctxf::ctx_encode_bf16(st, hn, reinterpret_cast<const bf16*>(hn_lp), tok_emb, tok_mask, lang_pad, init_cls, T, E));
+    return heads::heads_gemm_bf16(st, E, reinterpret_cast<const bf16*>(heads_w), heads_b, reinterpret_cast<bf16*>(out_w), T);
+  }
   // K1: projections (hypernetwork.py:112, 126)
   HVLA_TRY((gemm_simt<float, float, float, float>(
       st, gemm_params(tok_emb, LANGD, hn + L::tok_w, CD, hn + L::tok_b, TPj, CD, T * LANG, CD, LANGD), 1)));
@@ -504,9 +510,9 @@ int64_t hvla_layout_offset(const char* name) {
 
 size_t hvla_workspace_bytes(int B, int T, int dtype) { return make_plan(B, T, dtype).total; }
 
-int hvla_generate(hvla_stream_t stream, const float* hn_blob, const void* heads_w, const float* heads_b, const float* tok_emb,
-                  const int32_t* tok_mask, const uint8_t* lang_pad, const float* init_cls, int T, void* out_weights,
-                  float* out_ctx, void* workspace, size_t workspace_bytes, int dtype) {
+int hvla_generate(hvla_stream_t stream, const float* hn_blob, const void* hn_blob_bf16, const void* heads_w, const float* heads_b,
+                  const float* tok_emb, const int32_t* tok_mask, const uint8_t* lang_pad, const float* init_cls, int T,
+                  void* out_weights, float* out_ctx, void* workspace, size_t workspace_bytes, int dtype) {
   if (!hn_blob || !heads_w || !heads_b || !tok_emb || !tok_mask || !init_cls || !out_weights)
     return fail(HVLA_ERR_ARG, "hvla_generate: NULL argument");
   HVLA_TRY(check_common(0, T, dtype, workspace, workspace_bytes));
@@ -515,8 +521,8 @@ int hvla_generate(hvla_stream_t stream, const float* hn_blob, const void* heads_
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   if (dtype == HVLA_F32)
-    return generate_impl<float>(st, hn_blob, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, out_weights, out_ctx, ws, pl);
-  return generate_impl<bf16>(st, hn_blob, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, out_weights, out_ctx, ws, pl);
+    return generate_impl<float>(st, hn_blob, nullptr, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, out_weights, out_ctx, ws, pl);
+  return generate_impl<bf16>(st, hn_blob, hn_blob_bf16, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, out_weights, out_ctx, ws, pl);
 }
 
 int hvla_dino_forward(hvla_stream_t stream, const float* dino_vec, const void* dino_mat, const uint8_t* images, int B,
@@ -628,8 +634,8 @@ int hvla_dino_attention(hvla_stream_t stream, const void* qkv, void* out, int B,
 void hvla_xla_generate(void* stream, void** b, const char* opaque, size_t opaque_len) {
   if (opaque_len < sizeof(hvla_xla_opaque)) return;
   hvla_xla_opaque o; memcpy(&o, opaque, sizeof o);
-  int r = hvla_generate(stream, (const float*)b[0], b[1], (const float*)b[2], (const float*)b[3], (const int32_t*)b[4],
-                        (const uint8_t*)b[5], (const float*)b[6], o.T, b[7], (float*)b[8], b[9], (size_t)o.workspace_bytes, o.dtype);
+  int r = hvla_generate(stream, (const float*)b[0], b[1], b[2], (const float*)b[3], (const float*)b[4], (const int32_t*)b[5],
+                        (const uint8_t*)b[6], (const float*)b[7], o.T, b[8], (float*)b[9], b[10], (size_t)o.workspace_bytes, o.dtype);
   if (r != HVLA_OK) fprintf(stderr, "hvla_xla_generate: %s\n", hvla_last_error());
 }
 void hvla_xla_act(void* stream, void** b, const char* opaque, size_t opaque_len) {

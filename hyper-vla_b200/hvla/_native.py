@@ -24,7 +24,7 @@ SIGNATURES = {
     "hvla_dino_mat_elems": (c_i64, []),
     "hvla_layout_offset": (c_i64, [C.c_char_p]),
     "hvla_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "hvla_generate": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
+    "hvla_generate": (c_int, [c_void_p] * 9 + [c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
     "hvla_dino_forward": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_void_p, c_size_t, c_int]),
     "hvla_base_act": (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
     "hvla_act": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),

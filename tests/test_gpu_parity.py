@@ -67,7 +67,7 @@ def test_generate_and_act_match_golden(models, golden, prec, case):
     e_act = rel_err(action[..., :6], g["action"][..., :6])
     e_logit = rel_err(logit, g["logit"])
     print(f"[{prec} {case}] ctx {e_ctx:.2e} rows {e_rows:.2e} abs-sum {e_sum:.2e} action {e_act:.2e} logit {e_logit:.2e}")
-    assert e_ctx <= (1e-5 if prec == "fp32" else 1e-5)       # the context encoder is fp32 in both modes
+    assert e_ctx <= tol
     assert e_rows <= tol
     assert e_sum <= tol
     assert e_act <= tol
@@ -155,6 +155,32 @@ def test_debug_cuda_core_paths_agree_with_tensor_core_paths(models, torch_cuda):
     e = rel_err(fast, slow)
     print(f"tensor-core vs CUDA-core bf16 DINOv2: {e:.2e}")
     assert e < 2e-2
+
+
+def test_fused_context_encoder_matches_generic_fp32_kernels(models, torch_cuda):
+    """K1/K2: the one-kernel-per-task bf16 context encoder vs the generic fp32 CUDA-core kernels (same inputs),
+    including fully padded instructions (lang_pad False) and maximum-length masks."""
+    from hvla import synthetic as S
+    rt = models["bf16"].runtime
+    inp = S.make_inputs(4, 1, 37)
+    lang = inp["instruction_dict"]["language_instruction"]
+    am = lang["attention_mask"].copy()
+    am[0, :] = 1            # every token valid
+    am[1, :] = 0            # no valid token at all: only the image token is visible
+    pad = np.ones(37, bool)
+    pad[2] = False          # pad_mask_dict False masks the whole instruction
+    cls = inp["initial_state"]["patch_embeddings"][:, 0]
+    w_fused, c_fused = rt.generate(lang["token_embedding"], am, cls, pad)
+    os.environ["HVLA_DEBUG_GENERIC_CTX"] = "1"
+    try:
+        w_gen, c_gen = rt.generate(lang["token_embedding"], am, cls, pad)
+    finally:
+        os.environ.pop("HVLA_DEBUG_GENERIC_CTX")
+    e_c = rel_err(c_fused.cpu().numpy(), c_gen.cpu().numpy())
+    e_w = rel_err(w_fused.float().cpu().numpy(), w_gen.float().cpu().numpy())
+    print(f"fused context encoder vs generic fp32: ctx {e_c:.2e}, weights {e_w:.2e}")
+    assert e_c < 2e-2 and e_w < 2e-2
+    assert np.isfinite(c_fused.cpu().numpy()).all()
 
 
 def test_fused_base_kernel_matches_generic_path_and_oracle(models, params_p1, torch_cuda):

@@ -112,4 +112,4 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     from hvla import _native as N
     assert lib.hvla_act(None, None, None, None, None, None, 1, 1, None, None, None, 0, 1) == -1
     assert b"NULL" in lib.hvla_last_error()
-    assert lib.hvla_generate(None, None, None, None, None, None, None, None, 1, None, None, None, 0, 0) == -1
+    assert lib.hvla_generate(None, None, None, None, None, None, None, None, None, 1, None, None, None, 0, 0) == -1
