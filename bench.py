@@ -197,13 +197,22 @@ def run_ours(args):
     base_params, tasks, _ = model.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"])
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    gen_ms = []
-    for _ in range(3):
+    gen_ms, gen_dev_ms = [], []
+    lang = inp["instruction_dict"]["language_instruction"]
+    dev_instr = {"language_instruction": {"input_ids": lang["input_ids"], "attention_mask": torch.from_numpy(lang["attention_mask"]).to(dev),
+                                          "token_embedding": torch.from_numpy(lang["token_embedding"]).to(dev)}}
+    dev_state = {"patch_embeddings": torch.from_numpy(inp["initial_state"]["patch_embeddings"]).to(dev)}
+    for _ in range(5):
         ev[0].record()
         base_params, tasks, _ = model.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"])
         ev[1].record()
         torch.cuda.synchronize()
         gen_ms.append(ev[0].elapsed_time(ev[1]))
+        ev[0].record()
+        model.create_tasks(instruction_dict=dev_instr, initial_state=dev_state)
+        ev[1].record()
+        torch.cuda.synchronize()
+        gen_dev_ms.append(ev[0].elapsed_time(ev[1]))
     # ---- inputs: rotate through image sets totalling more than L2 (126 MB) ----------------------------
     n_sets = max(2, -(-160_000_000 // (B * 150528)))
     n_sets = min(n_sets, 64)
@@ -333,7 +342,9 @@ def run_ours(args):
             "kernel_ms_per_step": kernel_ms,
             "p50_step_ms": float(np.median(lat)), "p95_step_ms": float(np.percentile(lat, 95)),
             "batch1_p50_latency_ms": float(np.median(l1)), "batch1_e2e_p50_latency_ms": float(np.median(l1h)),
-            "hypernet_gen_ms": {"tasks": B, "p50": float(np.median(gen_ms)), "kernel_launches_ms": gen_kernel_ms},
+            "hypernet_gen_ms": {"tasks": B, "p50": float(np.median(gen_dev_ms)), "p50_host_inputs": float(np.median(gen_ms)),
+                                "note": "create_tasks for all tasks of the batch; p50 = embeddings already on the GPU, p50_host_inputs = numpy inputs (pageable H2D inside)",
+                                "kernel_launches_ms": gen_kernel_ms},
             "tflops_step": (FLOP_DINO_IMG + FLOP_BASE_IMG) * B / (step_ms / 1e3) / 1e12,
         }
         print(json.dumps(out))

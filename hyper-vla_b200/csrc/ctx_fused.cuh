@@ -1,15 +1,16 @@
-// Hypernetwork context encoder in ONE kernel (bf16 tensor-core path): token / initial-image projections +
+// Hypernetwork context encoder in ONE kernel (fp16-operand tensor-core path of HVLA_BF16 mode): token / initial-image projections +
 // position embeddings, the 34-token block-masked 6-layer pre-LN transformer (4 heads x 32, mlp 512, tanh-GELU),
 // encoder_norm on the layer token and the 1/sqrt(128) scaling.
 //   reference: hypervla/components/hypernetwork.py:99-197, transformer.py:127-262.
 //
-// One CTA per task, 8 warps.  The fp32 residual stream (34 x 128), the bf16 A operands and q|k|v / the MLP
+// One CTA per task, 8 warps.  The fp32 residual stream (34 x 128), the fp16 A operands and q|k|v / the MLP
 // hidden stay in shared memory for the whole network; the (task-shared) weights are streamed from L2 in
 // 32-row K chunks with double-buffered cp.async and consumed by warp-level mma.sync m16n8k16 (M = 34 rows is far
-// below a tcgen05 tile; the kernel is latency-bound, the 2.8 MB of bf16 weights per task come from L2).
+// below a tcgen05 tile; the kernel is latency-bound, the 2.8 MB of fp16 weights per task come from L2).
 #pragma once
 #include "common.cuh"
 #include "attn_mma.cuh"
+#include <cuda_fp16.h>
 
 namespace hvla {
 namespace ctxf {
@@ -19,25 +20,37 @@ using attn::cp_async_commit;
 using attn::cp_async_wait;
 using attn::ldsm_x4;
 using attn::ldsm_x4_t;
-using attn::mma_bf16;
-using attn::pack2;
+
+// fp16 operands (fp32 accumulate): LN-normalised activations and O(0.1) weights fit fp16 comfortably and its 11-bit
+// mantissa keeps the context embedding ~8x closer to the fp32 reference than bf16 would .
+typedef __half lp;
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __half2 t = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack2(const void* p) { return __half22float2(*reinterpret_cast<const __half2*>(p)); }
 
 constexpr int NTH = 256, MT = 3;                         // 8 warps; 3 m-tiles = 48 rows (34 used)
 constexpr int XLD = 132, ALD = 136, QLD = 392, HLD = 520, ELD = 776, WCH = 32;
 constexpr int OFF_X = 0;                                 // fp32 [48][132]
-constexpr int OFF_A = OFF_X + 48 * XLD * 4;              // bf16 [48][136]  LN output / attention output
-constexpr int OFF_BIG = OFF_A + 48 * ALD * 2;            // bf16: q|k|v [48][392]  |  hidden [48][520]  |  token emb [32][776]
+constexpr int OFF_A = OFF_X + 48 * XLD * 4;              // fp16 [48][136]  LN output / attention output
+constexpr int OFF_BIG = OFF_A + 48 * ALD * 2;            // fp16: q|k|v [48][392]  |  hidden [48][520]  |  token emb [32][776]
 constexpr int BIG_BYTES = 48 * HLD * 2;
-constexpr int OFF_W = OFF_BIG + BIG_BYTES;               // 2 x weight chunk [32][<=520] bf16
+constexpr int OFF_W = OFF_BIG + BIG_BYTES;               // 2 x weight chunk [32][<=520] fp16
 constexpr int WBUF_BYTES = WCH * HLD * 2;
 constexpr int OFF_MISC = OFF_W + 2 * WBUF_BYTES;         // key-valid flags [34]
 constexpr int SMEM = OFF_MISC + 256;
 static_assert(32 * ELD * 2 <= BIG_BYTES && 48 * QLD * 2 <= BIG_BYTES, "BIG region");
 
-// C[48 x N] (+)= A[48 x K] (bf16 smem, row stride lda) * W[K x N] (bf16 global, row-major), warp w owns N/8 columns.
+// C[48 x N] (+)= A[48 x K] (fp16 smem, row stride lda) * W[K x N] (fp16 global, row-major), warp w owns N/8 columns.
 // epi(row, col, v0, v1) is called for column pairs (col, col+1) of rows < 34.
 template <int N, int K, class Epi>
-__device__ __forceinline__ void cta_gemm(uint8_t* smem, const bf16* As, int lda, const bf16* __restrict__ Wg, Epi epi) {
+__device__ __forceinline__ void cta_gemm(uint8_t* smem, const lp* As, int lda, const lp* __restrict__ Wg, Epi epi) {
   constexpr int NTW = N / 64;                            // n-tiles (8 columns) per warp
   constexpr int WLD = N + 8;
   constexpr int NCH = K / WCH;
@@ -51,7 +64,7 @@ __device__ __forceinline__ void cta_gemm(uint8_t* smem, const bf16* As, int lda,
     for (int n = 0; n < NTW; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
   auto stage = [&](int c) {
     const uint32_t dst = sW + (uint32_t)((c & 1) * WBUF_BYTES);
-    const bf16* src = Wg + (int64_t)c * WCH * N;
+    const lp* src = Wg + (int64_t)c * WCH * N;
     for (int i = threadIdx.x; i < WCH * (N / 8); i += NTH) {
       const int r = i / (N / 8), cc = (i % (N / 8)) * 8;
       cp_async16(dst + (uint32_t)((r * WLD + cc) * 2), src + (int64_t)r * N + cc);
@@ -78,8 +91,8 @@ __device__ __forceinline__ void cta_gemm(uint8_t* smem, const bf16* As, int lda,
         ldsm_x4_t(wb + (uint32_t)(((ks * 16 + (i & 1) * 8 + (lane & 7)) * WLD + warp * (N / 8) + (np * 2 + (i >> 1)) * 8) * 2), b0, b1, b2, b3);
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
-          mma_bf16(acc[m][2 * np], a[m], b0, b1);
-          mma_bf16(acc[m][2 * np + 1], a[m], b2, b3);
+          mma_f16(acc[m][2 * np], a[m], b0, b1);
+          mma_f16(acc[m][2 * np + 1], a[m], b2, b3);
         }
       }
     }
@@ -96,8 +109,8 @@ __device__ __forceinline__ void cta_gemm(uint8_t* smem, const bf16* As, int lda,
     }
 }
 
-// flax LayerNorm of the 34 residual rows -> bf16 A operand (one warp per row, 4 values per lane)
-__device__ __forceinline__ void ln_rows(const float* X, bf16* A, const float* __restrict__ sc, const float* __restrict__ bi) {
+// flax LayerNorm of the 34 residual rows -> fp16 A operand (one warp per row, 4 values per lane)
+__device__ __forceinline__ void ln_rows(const float* X, lp* A, const float* __restrict__ sc, const float* __restrict__ bi) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4 g = __ldg(reinterpret_cast<const float4*>(sc) + lane), b = __ldg(reinterpret_cast<const float4*>(bi) + lane);
   for (int r = warp; r < CTOK; r += 8) {
@@ -118,7 +131,7 @@ __device__ __forceinline__ void ln_rows(const float* X, bf16* A, const float* __
 }
 
 __global__ void __launch_bounds__(NTH, 1)
-ctx_fused_kernel(const float* __restrict__ hn, const bf16* __restrict__ hnb, const float* __restrict__ tok_emb,
+ctx_fused_kernel(const float* __restrict__ hn, const lp* __restrict__ hnb, const float* __restrict__ tok_emb,
                  const int32_t* __restrict__ tok_mask, const uint8_t* __restrict__ lang_pad, const float* __restrict__ init_cls,
                  float* __restrict__ out_ctx) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -126,11 +139,11 @@ ctx_fused_kernel(const float* __restrict__ hn, const bf16* __restrict__ hnb, con
   const int t = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* X = reinterpret_cast<float*>(smem + OFF_X);
-  bf16* A = reinterpret_cast<bf16*>(smem + OFF_A);
-  bf16* BIG = reinterpret_cast<bf16*>(smem + OFF_BIG);
+  lp* A = reinterpret_cast<lp*>(smem + OFF_A);
+  lp* BIG = reinterpret_cast<lp*>(smem + OFF_BIG);
   int* kvalid = reinterpret_cast<int*>(smem + OFF_MISC);
 
-  // ---- inputs: token embeddings -> bf16 A operand [32][776]; key-valid flags ----
+  // ---- inputs: token embeddings -> fp16 A operand [32][776]; key-valid flags ----
   for (int i = threadIdx.x; i < LANG * (LANGD / 4); i += NTH) {
     const int r = i / (LANGD / 4), c = (i % (LANGD / 4)) * 4;
     const float4 v = __ldg(reinterpret_cast<const float4*>(tok_emb + ((int64_t)t * LANG + r) * LANGD + c));
@@ -172,7 +185,7 @@ ctx_fused_kernel(const float* __restrict__ hn, const bf16* __restrict__ hnb, con
   // ---- K2: 6 encoder blocks ----------------------------------------------------------------------------------------
   for (int l = 0; l < CL; ++l) {
     const float* lw = hn + L::layers + (int64_t)l * L::layer_size;
-    const bf16* lb = hnb + L::layers + (int64_t)l * L::layer_size;
+    const lp* lb = hnb + L::layers + (int64_t)l * L::layer_size;
     ln_rows(X, A, lw + L::ln0_s, lw + L::ln0_b);
     __syncthreads();
     // q|k|v = LN(x) Wqkv + b; q pre-divided by sqrt(32)
@@ -188,21 +201,21 @@ ctx_fused_kernel(const float* __restrict__ hn, const bf16* __restrict__ hnb, con
       const int h = p / CTOK, q = p % CTOK;
       float s0 = -INFINITY, s1 = -INFINITY;               // keys lane and lane + 32
       {
-        const bf16* qp = BIG + q * QLD + h * CHD;
+        const lp* qp = BIG + q * QLD + h * CHD;
         float a0 = 0.f, a1 = 0.f;
-        const bf16* k0 = BIG + lane * QLD + CD + h * CHD;
-        const bf16* k1 = BIG + (32 + (lane & 1)) * QLD + CD + h * CHD;
+        const lp* k0 = BIG + lane * QLD + CD + h * CHD;
+        const lp* k1 = BIG + (32 + (lane & 1)) * QLD + CD + h * CHD;
 #pragma unroll
         for (int u = 0; u < CHD / 8; ++u) {
           const uint4 qv = *reinterpret_cast<const uint4*>(qp + u * 8);
           const uint4 kv0 = *reinterpret_cast<const uint4*>(k0 + u * 8);
           const uint4 kv1 = *reinterpret_cast<const uint4*>(k1 + u * 8);
-          const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&qv);
-          const __nv_bfloat162* b0 = reinterpret_cast<const __nv_bfloat162*>(&kv0);
-          const __nv_bfloat162* b1 = reinterpret_cast<const __nv_bfloat162*>(&kv1);
+          const uint32_t* a = reinterpret_cast<const uint32_t*>(&qv);
+          const uint32_t* b0 = reinterpret_cast<const uint32_t*>(&kv0);
+          const uint32_t* b1 = reinterpret_cast<const uint32_t*>(&kv1);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float2 x = __bfloat1622float2(a[e]), y0 = __bfloat1622float2(b0[e]), y1 = __bfloat1622float2(b1[e]);
+            const float2 x = unpack2(a + e), y0 = unpack2(b0 + e), y1 = unpack2(b1 + e);
             a0 = fmaf(x.x, y0.x, fmaf(x.y, y0.y, a0));
             a1 = fmaf(x.x, y1.x, fmaf(x.y, y1.y, a1));
           }
@@ -220,12 +233,12 @@ ctx_fused_kernel(const float* __restrict__ hn, const bf16* __restrict__ hnb, con
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       const float inv = 1.0f / sum;
       float acc = 0.f;                                    // lane owns dim d = lane of this head
-      const bf16* vp = BIG + 2 * CD + h * CHD + lane;
+      const lp* vp = BIG + 2 * CD + h * CHD + lane;
 #pragma unroll 8
-      for (int k = 0; k < 32; ++k) acc = fmaf(__shfl_sync(0xffffffffu, e0, k), __bfloat162float(vp[k * QLD]), acc);
-      acc = fmaf(__shfl_sync(0xffffffffu, e1, 0), __bfloat162float(vp[32 * QLD]), acc);
-      acc = fmaf(__shfl_sync(0xffffffffu, e1, 1), __bfloat162float(vp[33 * QLD]), acc);
-      A[q * ALD + h * CHD + lane] = __float2bfloat16_rn(acc * inv);
+      for (int k = 0; k < 32; ++k) acc = fmaf(__shfl_sync(0xffffffffu, e0, k), __half2float(vp[k * QLD]), acc);
+      acc = fmaf(__shfl_sync(0xffffffffu, e1, 0), __half2float(vp[32 * QLD]), acc);
+      acc = fmaf(__shfl_sync(0xffffffffu, e1, 1), __half2float(vp[33 * QLD]), acc);
+      A[q * ALD + h * CHD + lane] = __float2half_rn(acc * inv);
     }
     __syncthreads();
     // x += attn Wo + b
@@ -271,7 +284,7 @@ ctx_fused_kernel(const float* __restrict__ hn, const bf16* __restrict__ hnb, con
   }
 }
 
-inline int ctx_encode_bf16(cudaStream_t st, const float* hn, const bf16* hnb, const float* tok_emb, const int32_t* tok_mask,
+inline int ctx_encode_lp(cudaStream_t st, const float* hn, const lp* hnb, const float* tok_emb, const int32_t* tok_mask,
                            const uint8_t* lang_pad, const float* init_cls, int T, float* out_ctx) {
   static bool attr = false;
   if (!attr) {

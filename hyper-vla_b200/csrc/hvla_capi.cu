@@ -121,7 +121,7 @@ static int generate_impl(cudaStream_t st, const float* hn, const void* hn_lp, co
   typedef HnLayout L;
   if (std::is_same<TW, bf16>::value && hn_lp && !env_flag("HVLA_DEBUG_GENERIC_CTX")) {
     // bf16 tensor-core path: the whole context encoder is one kernel, the 73 heads another
-    HVLA_TRY(ctxf::ctx_encode_bf16(st, hn, reinterpret_cast<const bf16*>(hn_lp), tok_emb, tok_mask, lang_pad, init_cls, T, E));
+    HVLA_TRY(ctxf::ctx_encode_lp(st, hn, reinterpret_cast<const ctxf::lp*>(hn_lp), tok_emb, tok_mask, lang_pad, init_cls, T, E));
     return heads::heads_gemm_bf16(st, E, reinterpret_cast<const bf16*>(heads_w), heads_b, reinterpret_cast<bf16*>(out_w), T);
   }
   // K1: projections (hypernetwork.py:112, 126)
@@ -510,7 +510,7 @@ int64_t hvla_layout_offset(const char* name) {
 
 size_t hvla_workspace_bytes(int B, int T, int dtype) { return make_plan(B, T, dtype).total; }
 
-int hvla_generate(hvla_stream_t stream, const float* hn_blob, const void* hn_blob_bf16, const void* heads_w, const float* heads_b,
+int hvla_generate(hvla_stream_t stream, const float* hn_blob, const void* hn_blob_f16, const void* heads_w, const float* heads_b,
                   const float* tok_emb, const int32_t* tok_mask, const uint8_t* lang_pad, const float* init_cls, int T,
                   void* out_weights, float* out_ctx, void* workspace, size_t workspace_bytes, int dtype) {
   if (!hn_blob || !heads_w || !heads_b || !tok_emb || !tok_mask || !init_cls || !out_weights)
@@ -522,7 +522,7 @@ int hvla_generate(hvla_stream_t stream, const float* hn_blob, const void* hn_blo
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   if (dtype == HVLA_F32)
     return generate_impl<float>(st, hn_blob, nullptr, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, out_weights, out_ctx, ws, pl);
-  return generate_impl<bf16>(st, hn_blob, hn_blob_bf16, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, out_weights, out_ctx, ws, pl);
+  return generate_impl<bf16>(st, hn_blob, hn_blob_f16, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, out_weights, out_ctx, ws, pl);
 }
 
 int hvla_dino_forward(hvla_stream_t stream, const float* dino_vec, const void* dino_mat, const uint8_t* images, int B,

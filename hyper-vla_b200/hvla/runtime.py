@@ -48,7 +48,7 @@ class Runtime:
         hn = P.pack_hn_blob(params)
         assert hn.size == self.lib.hvla_hn_blob_elems()
         self.hn_blob = torch.from_numpy(hn).to(dev)
-        self.hn_blob_bf16 = self.hn_blob.to(torch.bfloat16) if self.precision == "bf16" else None
+        self.hn_blob_f16 = self.hn_blob.to(torch.float16) if self.precision == "bf16" else None
         W, b = P.pack_heads(params)
         self.heads_w = torch.from_numpy(W).to(self.tdtype).to(dev)
         self.heads_b = torch.from_numpy(b).to(dev)
@@ -112,7 +112,7 @@ class Runtime:
         ctx = torch.empty((T, Cfg.CTX_DIM), dtype=torch.float32, device=dev)
         ws, ws_bytes = self.workspace(0, T)
         st = self.lib.hvla_generate(self.stream(), self.hn_blob.data_ptr(),
-                                    self.hn_blob_bf16.data_ptr() if self.hn_blob_bf16 is not None else None,
+                                    self.hn_blob_f16.data_ptr() if self.hn_blob_f16 is not None else None,
                                     self.heads_w.data_ptr(), self.heads_b.data_ptr(),
                                     tok.data_ptr(), am.data_ptr(), pad_ptr, cls.data_ptr(), T, out.data_ptr(), ctx.data_ptr(),
                                     ws, ws_bytes, self.dtype)

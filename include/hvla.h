@@ -72,9 +72,10 @@ size_t hvla_workspace_bytes(int B, int T, int dtype);
  *   init_cls  [T,768]    f32  initial_state.patch_embeddings[:, 0]   (hypernetwork.py:126)
  *   out_weights [T,NGP] (dtype)  packed generated base-net weights, one row per task
  *   out_ctx   [T,128] f32 or NULL  context embedding (second return of HyperNetwork.__call__)
- *   hn_blob_bf16: the HN blob converted element-wise to bf16 (same offsets); used by the HVLA_BF16 fused
- *   context-encoder kernel.  NULL (or HVLA_F32) selects the fp32 CUDA-core path. */
-int hvla_generate(hvla_stream_t stream, const float* hn_blob, const void* hn_blob_bf16, const void* heads_w,
+ *   hn_blob_f16: the HN blob converted element-wise to IEEE fp16 (same offsets); operands of the fused
+ *   context-encoder kernel of HVLA_BF16 mode (fp16 keeps the context embedding ~8x closer to the fp32
+ *   reference than bf16).  NULL (or HVLA_F32) selects the fp32 CUDA-core path. */
+int hvla_generate(hvla_stream_t stream, const float* hn_blob, const void* hn_blob_f16, const void* heads_w,
                   const float* heads_b, const float* tok_emb, const int32_t* tok_mask, const uint8_t* lang_pad,
                   const float* init_cls, int T, void* out_weights, float* out_ctx, void* workspace,
                   size_t workspace_bytes, int dtype);
