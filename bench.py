@@ -285,15 +285,20 @@ def run_ours(args):
     if os.path.exists(pk):
         with open(pk) as f:
             peaks = json.load(f)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp) and B == 64:
+        with open(tp) as f:
+            traffic = json.load(f).get("gemm_tc_bytes_per_launch")
     if gemm_ms > 0:
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         achieved = FLOP_DINO_GEMM_IMG * B / (gemm_ms / 1e3) / 1e12
         roofline = {
-            "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all DINOv2 GEMMs of one step)",
+            "bound": "tensor", "kernel": "gemm_tc2_kernel (tcgen05 cta_group::2; the 49 DINOv2 GEMMs of one step)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
             "launches_per_step": gemm_n, "ms_per_step": gemm_ms, "share_of_step": gemm_ms / sum(v[1] for v in prof.values()),
-            "traffic": None,
+            "traffic": traffic, "traffic_note": "dram read+write bytes per GEMM launch, ncu --set full capture of this config (profiles/)",
         }
     kernel_ms = {k: round(v[1], 4) for k, v in prof.items()}
     gen_prof = rt.profile(lambda: model.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"]), repeats=2)
