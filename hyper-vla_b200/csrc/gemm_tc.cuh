@@ -260,14 +260,14 @@ constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 2048;
 template <int EPI>
 __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensorMap* tmO, float* sepi, uint32_t sstage,
                                                   uint32_t tfull_bar_addr, uint32_t aph, int as, uint32_t tmem_base, int m0,
-                                                  int n0, int warp, int lane) {
+                                                  int n0, int warp, int lane, bool add_bias = true) {
   const int ew = warp - 2;
   const int quarter = warp & 3;
   const int half = ew >> 2;
   const int te = threadIdx.x - 64;
   float* sb = sepi + as * 512;
   float* sl = sb + 256;
-  sb[te] = __ldg(ep.bias + n0 + te);
+  sb[te] = add_bias ? __ldg(ep.bias + n0 + te) : 0.f;      // split-K: only the first K split contributes the bias
   if (EPI == EPI_RESIDUAL_F32) sl[te] = __ldg(ep.ls + n0 + te);
   const int row0 = m0 + quarter * 32;
   const uint32_t slab = sstage + (uint32_t)ew * 2048u;

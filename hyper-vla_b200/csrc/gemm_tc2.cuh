@@ -74,7 +74,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmO, EpiP ep, int M, int N, int K) {
+                const __grid_constant__ CUtensorMap tmO, EpiP ep, int M, int N, int K, int splits) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
@@ -92,8 +92,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int n_tiles_n = N / BN;
   const int n_tiles_m = (M + BM2 - 1) / BM2;
-  const int n_tiles = n_tiles_m * n_tiles_n;
-  const int n_kb = K / BK;
+  const int n_tiles = n_tiles_m * n_tiles_n * splits;   // work units: (tile, K split); splits > 1 only with the reduce-add epilogue
+  const int n_kb = K / BK / splits;                     // K blocks per unit
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -121,14 +121,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+      for (int unit = pair; unit < n_tiles; unit += n_pairs) {
+        const int tile = unit / splits, kb0 = (unit % splits) * n_kb;
         const int m0 = (tile / n_tiles_n) * BM2 + (int)rank * 128;
         const int n0 = (tile % n_tiles_n) * BN + (int)rank * 128;
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(empty_bar + 8 * s, ph ^ 1);
           if (rank == 0) mbar_expect_tx(full_bar + 8 * s, 2 * (A2_BYTES + B2_BYTES));
-          tma_load_2d_2sm(sA + s * A2_BYTES, &tmA, full_bar + 8 * s, kb * BK, m0);
-          tma_load_2d_2sm(sB + s * B2_BYTES, &tmB, full_bar + 8 * s, kb * BK, n0);
+          tma_load_2d_2sm(sA + s * A2_BYTES, &tmA, full_bar + 8 * s, (kb0 + kb) * BK, m0);
+          tma_load_2d_2sm(sB + s * B2_BYTES, &tmB, full_bar + 8 * s, (kb0 + kb) * BK, n0);
           if (++s == STAGES2) { s = 0; ph ^= 1; }
         }
       }
@@ -162,12 +163,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     // ===================== epilogue warps (both CTAs, own 128 TMEM lanes) =====================
     int it = 0;
-    for (int tile = pair; tile < n_tiles; tile += n_pairs, ++it) {
+    for (int unit = pair; unit < n_tiles; unit += n_pairs, ++it) {
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
+      const int tile = unit / splits;
       const int m0 = (tile / n_tiles_n) * BM2 + (int)rank * 128, n0 = (tile % n_tiles_n) * BN;
       if (EPI == EPI_PATCH_F32) epilogue_tile_direct<EPI>(ep, sepi, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, M, warp, lane);
-      else epilogue_tile_tma<EPI>(ep, &tmO, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane);
+      else epilogue_tile_tma<EPI>(ep, &tmO, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane, unit % splits == 0);
       if (lane == 0) mbar_arrive_remote(tempty_bar + 8 * as, 0);
     }
     if (lane == 0) bulk_wait0();
@@ -189,12 +191,20 @@ inline int launch_one2(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap
     HVLA_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
     attr_set = true;
   }
-  const int tiles = ((M + BM2 - 1) / BM2) * (N / BN);
+  const int tiles0 = ((M + BM2 - 1) / BM2) * (N / BN);
   int pairs = num_sms() / 2;
+  // split K over several CTA pairs when there are too few tiles to fill the chip (small batches); only the
+  // residual epilogue can do that for free: its TMA reduce-add accumulates the partial products in the fp32 stream
+  int splits = 1;
+  if (EPI == EPI_RESIDUAL_F32) {
+    const int nkb = K / BK;
+    while (splits < 4 && tiles0 * splits * 2 <= pairs && nkb % (splits * 2) == 0) splits *= 2;
+  }
+  const int tiles = tiles0 * splits;
   if (const char* e = getenv("HVLA_GEMM_MAX_PAIRS")) { const int v = atoi(e); if (v > 0 && v < pairs) pairs = v; }   // experiment knob
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
   ProfScope ps(st, "gemm_tc");
-  gemm_tc2_kernel<EPI><<<grid, NUM_THREADS, SMEM2_BYTES, st>>>(ma, mb, mo, ep, M, N, K);
+  gemm_tc2_kernel<EPI><<<grid, NUM_THREADS, SMEM2_BYTES, st>>>(ma, mb, mo, ep, M, N, K, splits);
   HVLA_LAUNCH_CHECK("gemm_tc2");
   return HVLA_OK;
 }
