@@ -195,8 +195,11 @@ inline int launch_one2(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap
   int pairs = num_sms() / 2;
   // split K over several CTA pairs when there are too few tiles to fill the chip (small batches); only the
   // residual epilogue can do that for free: its TMA reduce-add accumulates the partial products in the fp32 stream
+  // OFF by default: the order of the fp32 reduce-adds of different splits is not fixed, which would make small batches
+  // non-deterministic and batch-size dependent in the last bits (tests require bit-exact batch invariance).
   int splits = 1;
-  if (EPI == EPI_RESIDUAL_F32) {
+  static const bool splitk = getenv("HVLA_GEMM_SPLITK") != nullptr;
+  if (EPI == EPI_RESIDUAL_F32 && splitk) {
     const int nkb = K / BK;
     while (splits < 4 && tiles0 * splits * 2 <= pairs && nkb % (splits * 2) == 0) splits *= 2;
   }
