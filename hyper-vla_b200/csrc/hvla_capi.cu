@@ -9,6 +9,7 @@
 #include "base_fused.cuh"
 #include "heads_mma.cuh"
 #include "ctx_fused.cuh"
+#include "postprocess.cuh"
 
 #include <stdlib.h>
 #include <type_traits>
@@ -628,6 +629,26 @@ int hvla_dino_attention(hvla_stream_t stream, const void* qkv, void* out, int B,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (impl == 0) return attn::dino_attention(st, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B);
   return attn5::dino_attention_tc(st, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B);
+}
+
+int64_t hvla_postprocess_state_floats(void) { return post::STATE_FLOATS; }
+
+int hvla_postprocess(hvla_stream_t stream, const float* raw_action, float* state, const uint8_t* reset, int B, int norm_type,
+                     const float* stat_a, const float* stat_b, const uint8_t* mask, int ensemble, float temp, int policy_setup,
+                     int sticky_repeat, float* out_raw, float* out_action) {
+  if (!raw_action || !state || !stat_a || !stat_b || !out_raw || !out_action || B < 0) return fail(HVLA_ERR_ARG, "hvla_postprocess: bad argument");
+  if (norm_type < 0 || norm_type > 1 || policy_setup < 0 || policy_setup > 2) return fail(HVLA_ERR_UNSUPPORTED, "hvla_postprocess: unknown mode");
+  if (B == 0) return HVLA_OK;
+  post::PostP p;
+  memset(&p, 0, sizeof p);
+  p.raw = raw_action; p.state = state; p.reset = reset; p.out_raw = out_raw; p.out_action = out_action;
+  for (int d = 0; d < AD; ++d) { p.a[d] = stat_a[d]; p.b[d] = stat_b[d]; p.mask[d] = mask ? mask[d] : 1; }
+  p.B = B; p.norm_type = norm_type; p.ensemble = ensemble; p.temp = temp; p.policy = policy_setup; p.sticky_repeat = sticky_repeat;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ProfScope ps(st, "postprocess");
+  post::postprocess_kernel<<<cdiv(B, 128), 128, 0, st>>>(p);
+  HVLA_LAUNCH_CHECK("postprocess");
+  return HVLA_OK;
 }
 
 // ---- legacy XLA custom-call wrappers (no status channel in this ABI revision: errors are logged) ---------

@@ -31,6 +31,9 @@ SIGNATURES = {
     "hvla_act_host": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
     "hvla_gemm_bf16": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int]),
     "hvla_dino_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
+    "hvla_postprocess_state_floats": (c_i64, []),
+    "hvla_postprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                 C.c_float, c_int, c_int, c_void_p, c_void_p]),
     "hvla_launch_count": (c_i64, []),
     "hvla_profile_enable": (c_int, [c_int]),
     "hvla_profile_report": (c_int, [C.c_char_p, c_size_t]),

@@ -149,6 +149,27 @@ class HyperVLA:
             self._runtime = Runtime(self.params, self.precision, self.device)
         return self._runtime
 
+    # ---- initial-image encoder --------------------------------------------------------------
+    def set_initial_image_encoder(self, dino_tree: Optional[dict]) -> None:
+        """Use a separate frozen DINOv2-base param tree (HF Flax names) for the initial image, as the reference's eval
+        loop does with the pretrained facebook/dinov2-base (data/simpler/evaluate.py:146-163, scripts/train.py:187-194).
+        ``None`` (default) re-uses the model's own shared image_encoder leaves."""
+        self._init_encoder_blobs = None if dino_tree is None else self.runtime.pack_dino_tree(dino_tree)
+
+    def encode_initial_image(self, images):
+        """DINO_encode_image of the reference (data/simpler/evaluate.py:155-163) on the GPU: uint8 (T,224,224,3) host or
+        CUDA images -> ``initial_state`` dict whose ``patch_embeddings`` (T,257,768) stay on the device, so a task switch
+        (encode -> create_tasks) never leaves the GPU."""
+        import torch
+        rt = self.runtime
+        img = images if torch.is_tensor(images) else torch.from_numpy(np.ascontiguousarray(images))
+        if img.dim() == 5 and img.shape[1] == 1:
+            img = img[:, 0]
+        img = img.to(rt.device)
+        hidden = rt.dino_forward(img, getattr(self, "_init_encoder_blobs", None))
+        return {"image_primary": images, "patch_embeddings": hidden.float(),
+                "pad_mask_dict": {"image_primary": np.ones((int(img.shape[0]), 1))}}
+
     # ---- generate ------------------------------------------------------------------------------------
     def create_tasks(self, goals=None, instruction_dict: dict = None, initial_state=None):
         """Build the ``tasks`` dict and generate base-net parameters (reference: model.py:35-83).

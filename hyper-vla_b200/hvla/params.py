@@ -314,9 +314,13 @@ def dino_mat_layout(transposed: bool) -> Dict[str, Tuple[int, Tuple[int, int]]]:
 
 
 def pack_dino(params: dict, transposed: bool) -> Tuple[np.ndarray, np.ndarray]:
-    """(vec blob fp32, matrix blob fp32).  The caller casts the matrix blob to bf16 for the
-    tensor-core path.  The position table is interpolated here, once."""
-    t = dino_tree_from_params(params)
+    """(vec blob fp32, matrix blob fp32) of the shared DINOv2 leaves held in the hypernetwork params."""
+    return pack_dino_tree(dino_tree_from_params(params), transposed)
+
+
+def pack_dino_tree(t: dict, transposed: bool) -> Tuple[np.ndarray, np.ndarray]:
+    """(vec blob fp32, matrix blob fp32) of a HF DINOv2-base param tree.  The caller casts the matrix blob to
+    bf16 for the tensor-core path.  The position table is interpolated here, once."""
     D = C.DINO_DIM
     vl, ml = dino_vec_layout(), dino_mat_layout(transposed)
     vec = np.zeros((vl["__total__"][0],), F32)

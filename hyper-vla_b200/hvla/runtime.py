@@ -240,12 +240,23 @@ class Runtime:
             out[name] = (int(n) / repeats, float(ms) / repeats)
         return out
 
-    def dino_forward(self, images):
+    def pack_dino_tree(self, tree: dict):
+        """Upload another DINOv2-base param tree (e.g. the frozen pretrained encoder of the initial image,
+        data/simpler/evaluate.py:146-163) -> (vec, mat) device blobs for ``dino_forward(..., blobs=...)``."""
+        torch = _torch()
+        vec, mat = P.pack_dino_tree(tree, transposed=(self.precision == "bf16"))
+        return torch.from_numpy(vec).to(self.device), torch.from_numpy(mat).to(self.tdtype).to(self.device)
+
+    def dino_forward(self, images, blobs=None):
+        """images uint8 CUDA (B,224,224,3) -> last_hidden_state (B,257,768) in the runtime dtype."""
         torch = _torch()
         B = int(images.shape[0])
+        if tuple(images.shape[1:]) != (Cfg.IMAGE_SIZE, Cfg.IMAGE_SIZE, 3) or images.dtype != torch.uint8:
+            raise ValueError("Input image size must be 224x224 (uint8, NHWC)")
+        vec, mat = blobs if blobs is not None else (self.dino_vec, self.dino_mat)
         out = torch.empty((B, Cfg.DINO_TOKENS, Cfg.DINO_DIM), dtype=self.tdtype, device=self.device)
         ws, ws_bytes = self.workspace(B, 0)
-        st = self.lib.hvla_dino_forward(self.stream(), self.dino_vec.data_ptr(), self.dino_mat.data_ptr(),
+        st = self.lib.hvla_dino_forward(self.stream(), vec.data_ptr(), mat.data_ptr(),
                                         images.contiguous().data_ptr(), B, out.data_ptr(), ws, ws_bytes, self.dtype)
         N.check(st, "hvla_dino_forward")
         return out

@@ -116,6 +116,17 @@ int hvla_gemm_bf16(hvla_stream_t stream, const void* A, const void* Wt, const fl
 /* DINOv2 self-attention alone: qkv [B*257, 2304] bf16 (q | k | v, q pre-divided by sqrt(64)) -> out [B*257, 768] bf16.
  * impl 0 = warp-level mma.sync kernel, 1 = tcgen05/TMEM kernel (the one the pipeline uses). */
 int hvla_dino_attention(hvla_stream_t stream, const void* qkv, void* out, int B, int impl);
+/* ---- batched action post-processing: replaces the host code after the model call in
+ * InferenceWrapper.step (data/utils/hypervla_interface.py:219-300) and BatchActionEnsembler
+ * (data/utils/action_ensemble.py:6-27) for B environments at once.
+ *   raw_action [B,4,7] f32 (device)   state [B, hvla_postprocess_state_floats()] f32 (device, zero-initialised)
+ *   reset [B] u8 or NULL (1 = first step of an episode)      stat_a/stat_b/mask: HOST arrays of 7
+ *   norm_type 0 = NORMAL (a=std, b=mean), 1 = BOUNDS (a=p01, b=p99); policy_setup 0 google_robot, 1 widowx_bridge, 2 libero
+ *   out_raw [B,7] un-normalised (ensembled) action; out_action [B,7] = world_vector | rot_axangle | gripper */
+int64_t hvla_postprocess_state_floats(void);
+int hvla_postprocess(hvla_stream_t stream, const float* raw_action, float* state, const uint8_t* reset, int B, int norm_type,
+                     const float* stat_a, const float* stat_b, const uint8_t* mask, int ensemble, float temp,
+                     int policy_setup, int sticky_repeat, float* out_raw, float* out_action);
 /* number of kernels launched by this library since load (for bench.py's gpu_launches) */
 int64_t hvla_launch_count(void);
 /* per-kernel-class CUDA-event timing on the launching stream (bench.py's live roofline numbers).

@@ -268,6 +268,68 @@ def test_cuda_graph_replay_equals_eager_launches(models, torch_cuda):
     assert rt.launch_count() - n0 >= 2 * 60
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_task_switch_on_gpu_initial_image_encoder(models, params_p1, prec):
+    """frozen DINOv2 encode of the initial image -> create_tasks -> act, everything on the GPU, vs the
+    oracle doing the same (a separately initialised 'pretrained' encoder for the initial image)."""
+    from hvla import metadata as M, params as P, synthetic as S
+    from oracle import hypervla_oracle as O
+    m = models[prec]
+    frozen = P._init_dinov2(np.random.default_rng(77), "P1")
+    m.set_initial_image_encoder(frozen)
+    try:
+        inp = S.make_inputs(6, 2, 2)
+        init_imgs = np.random.default_rng(5).integers(0, 256, (2, 224, 224, 3), dtype=np.uint8)
+        state = m.encode_initial_image(init_imgs)
+        assert state["patch_embeddings"].is_cuda and tuple(state["patch_embeddings"].shape) == (2, 257, 768)
+        bp, tasks, _ = m.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=state)
+        act, _ = m.sample_actions(inp["images"], None, tasks, None, bp)
+    finally:
+        m.set_initial_image_encoder(None)
+    hid = O.dinov2_forward(frozen, init_imgs, np.float64)
+    lang = inp["instruction_dict"]["language_instruction"]
+    gen, emb = O.generate(params_p1, lang["token_embedding"], lang["attention_mask"], hid[:, 0], dtype=np.float64,
+                          generated_paths=M.generated_leaves_canonical())
+    ref, _ = O.sample_actions(P.dino_tree_from_params(params_p1), O.to_tree(gen), inp["images"][:, 0], dtype=np.float64)
+    e_h = rel_err(state["patch_embeddings"].cpu().numpy()[:, 0], hid[:, 0])
+    e_c = rel_err(bp.context_embedding.cpu().numpy(), emb[:, 0])
+    e_a = rel_err(act[..., :6], ref[..., :6])
+    print(f"[{prec}] task switch on GPU: initial CLS {e_h:.2e}, context {e_c:.2e}, action {e_a:.2e}")
+    tol = TOL[prec]
+    assert e_h <= tol and e_c <= tol and e_a <= tol
+
+
+@pytest.mark.parametrize("policy,norm", [("google_robot", "normal"), ("widowx_bridge", "bounds"), ("libero", "normal")])
+def test_batched_postprocessing_matches_per_env_oracle(torch_cuda, policy, norm):
+    """un-normalise + temporal ensemble + axis-angle + gripper handling for 33 envs over 24 steps with
+    mid-run episode resets, against the per-env NumPy restatement of InferenceWrapper.step's post-processing."""
+    from hvla.postprocess import BatchedActionPostprocessor
+    from oracle.postprocess_oracle import EnvPostprocessor
+    rng = np.random.default_rng(42)
+    B = 33
+    stats = {"mean": rng.normal(0, 0.1, 7), "std": rng.uniform(0.05, 0.5, 7), "p01": rng.uniform(-1, -0.2, 7), "p99": rng.uniform(0.2, 1, 7),
+             "mask": np.array([1, 1, 1, 1, 1, 1, 0], bool)}
+    pp = BatchedActionPostprocessor(B, policy, norm, stats, action_ensemble=True, action_ensemble_temp=0.3)
+    envs = [EnvPostprocessor(policy, norm, stats, True, 0.3) for _ in range(B)]
+    worst = 0.0
+    for step in range(24):
+        raw = rng.uniform(-3, 3, (B, 4, 7)).astype(np.float32)
+        raw[..., 6] = (rng.uniform(size=(B, 4)) > 0.5)                       # the mix head emits 0/1 gripper actions
+        if step in (7, 15):
+            who = rng.uniform(size=B) > 0.5
+            pp.reset(who)
+            for e in np.nonzero(who)[0]:
+                envs[e].reset()
+        g_raw, g_act = pp.step(raw)
+        g_raw, g_act = g_raw.cpu().numpy(), g_act.cpu().numpy()
+        for e in range(B):
+            r_raw, r_act = envs[e].step(raw[e])
+            worst = max(worst, np.abs(g_raw[e] - r_raw).max(), np.abs(g_act[e] - r_act).max())
+            assert g_act[e][6] == np.float32(r_act[6]) or policy == "libero", (step, e)
+    print(f"postprocess {policy}/{norm}: max abs diff {worst:.2e}")
+    assert worst < 2e-6
+
+
 def test_edge_cases(models, torch_cuda):
     from hvla import _native as N
     from hvla import synthetic as S

@@ -114,3 +114,24 @@ def test_mix_head_semantics():
     assert act.shape == (1, 4, 7)
     assert np.allclose(act[0, :, :6].ravel(), np.tanh((np.arange(24) - 10.0) / 5) * 5, atol=1e-6)
     assert act[0, :, 6].tolist() == [0.0, 1.0, 1.0, 1.0]
+
+
+def test_postprocess_oracle_euler_matches_scipy_and_ensemble_rule():
+    """The transforms3d.euler2axangle restatement is pinned against scipy (extrinsic xyz == 'sxyz'); the ensemble rule
+    of data/utils/action_ensemble.py (older predictions, later horizon step, more weight) on a hand-checkable case."""
+    from scipy.spatial.transform import Rotation as R
+    from oracle.postprocess_oracle import EnvPostprocessor, euler2axangle
+    rng = np.random.default_rng(0)
+    for e in rng.uniform(-3, 3, (50, 3)):
+        ax, ang = euler2axangle(*e)
+        rv = R.from_euler("xyz", e).as_rotvec()
+        # same rotation (axis-angle is unique up to the 2*pi wrap transforms3d does not apply)
+        assert np.allclose(R.from_rotvec(ax * ang).as_matrix(), R.from_rotvec(rv).as_matrix(), atol=1e-12)
+    stats = {"mean": np.zeros(7), "std": np.ones(7)}
+    env = EnvPostprocessor("libero", "normal", stats, True, 0.0)
+    a0 = np.arange(28, dtype=np.float32).reshape(4, 7)
+    r0, _ = env.step(a0)
+    assert np.allclose(r0, a0[0])
+    r1, act = env.step(a0 + 100)
+    assert np.allclose(r1, 0.5 * (a0[1] + (a0 + 100)[0]))          # oldest prediction contributes its step 1
+    assert np.isclose(act[6], 2 * r1[6] - 1)
