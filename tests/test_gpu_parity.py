@@ -325,7 +325,8 @@ def test_batched_postprocessing_matches_per_env_oracle(torch_cuda, policy, norm)
         for e in range(B):
             r_raw, r_act = envs[e].step(raw[e])
             worst = max(worst, np.abs(g_raw[e] - r_raw).max(), np.abs(g_act[e] - r_act).max())
-            assert g_act[e][6] == np.float32(r_act[6]) or policy == "libero", (step, e)
+            if policy == "widowx_bridge":                                    # binarised gripper: must be exact
+                assert g_act[e][6] == np.float32(r_act[6]), (step, e)
     print(f"postprocess {policy}/{norm}: max abs diff {worst:.2e}")
     assert worst < 2e-6
 
