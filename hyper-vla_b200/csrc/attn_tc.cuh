@@ -96,6 +96,7 @@ __device__ __forceinline__ float dot8(const uint4& a, const uint4& b, float acc)
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmTail, const bf16* __restrict__ qkv,
                bf16* __restrict__ out, int n_items, int dbg, long long* __restrict__ tstamp) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + 2 * STAGE_BYTES;
@@ -127,6 +128,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();
 
   if (warp == W_TMA) {
     // ============================ TMA producer ============================
@@ -396,7 +398,7 @@ inline int dino_attention_tc(cudaStream_t st, const bf16* qkv, bf16* out, int B)
   if (const char* e = getenv("HVLA_ATTN_DEBUG")) dbg = atoi(e);     // timing experiments only (results are wrong when set)
   static long long* d_ts = nullptr;
   if ((dbg & 32) && !d_ts) { cudaMalloc(&d_ts, 2 * 6 * 8 * sizeof(long long)); cudaMemset(d_ts, 0, 2 * 6 * 8 * sizeof(long long)); }
-  attn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map, tail, qkv, out, n_items, dbg, (dbg & 32) ? d_ts : nullptr);
+  launch_k(attn_tc_kernel, dim3(grid), dim3(NTHREADS), (size_t)SMEM_BYTES, st, map, tail, qkv, out, n_items, dbg, (dbg & 32) ? d_ts : (long long*)nullptr);
   if (dbg & 32) {
     long long h[96];
     cudaMemcpy(h, d_ts, sizeof h, cudaMemcpyDeviceToHost);

@@ -183,6 +183,8 @@ __device__ __forceinline__ void warp_ln64(const float* x, const float* sc, const
 __global__ void __launch_bounds__(NT, 1)
 base_fused_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ weights, const int* __restrict__ tidx,
                   float* __restrict__ action, float* __restrict__ logit_out) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t smem[];
   typedef GenLayout G;
   const int b = blockIdx.x;
@@ -525,7 +527,7 @@ inline int base_act_bf16(cudaStream_t st, const bf16* emb, const bf16* weights, 
     attr = true;
   }
   ProfScope ps(st, "base_fused");
-  base_fused_kernel<<<B, NT, SMEM, st>>>(emb, weights, tidx, action, logit);
+  launch_k(base_fused_kernel, dim3(B), dim3(NT), (size_t)SMEM, st, emb, weights, tidx, action, logit);
   HVLA_LAUNCH_CHECK("base_fused");
   return HVLA_OK;
 }

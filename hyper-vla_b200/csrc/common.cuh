@@ -126,6 +126,28 @@ struct ProfScope {
     if (r__ != HVLA_OK) return r__; \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// Every kernel of the act path starts with pdl_trigger() (its successor in the stream may be scheduled as soon as
+// all CTAs of this grid have started), does its local prologue (barrier init, TMEM alloc, descriptor prefetch) and
+// only then pdl_wait()s for the full completion + memory flush of its predecessor before touching global memory.
+// This hides launch latency and prologue behind the predecessor's tail (~90 kernel boundaries per control step).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+extern bool g_pdl;
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- dtype helpers -------------------------------------------------------------------------
 typedef __nv_bfloat16 bf16;
 __device__ __forceinline__ float to_f(float v) { return v; }

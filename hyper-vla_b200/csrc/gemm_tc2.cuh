@@ -75,6 +75,7 @@ template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, EpiP ep, int M, int N, int K, int splits) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
@@ -115,6 +116,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();          // peer barriers are initialised before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();                  // predecessor's outputs (A operand, residual stream) are complete and visible
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -207,7 +209,7 @@ inline int launch_one2(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap
   if (const char* e = getenv("HVLA_GEMM_MAX_PAIRS")) { const int v = atoi(e); if (v > 0 && v < pairs) pairs = v; }   // experiment knob
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
   ProfScope ps(st, "gemm_tc");
-  gemm_tc2_kernel<EPI><<<grid, NUM_THREADS, SMEM2_BYTES, st>>>(ma, mb, mo, ep, M, N, K, splits);
+  launch_k(gemm_tc2_kernel<EPI>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM2_BYTES, st, ma, mb, mo, ep, M, N, K, splits);
   HVLA_LAUNCH_CHECK("gemm_tc2");
   return HVLA_OK;
 }

@@ -19,6 +19,7 @@ namespace hvla {
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
 ProfState g_prof;
+bool g_pdl = getenv("HVLA_NO_PDL") == nullptr;
 
 static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -231,6 +232,8 @@ static int dino_f32(cudaStream_t st, const float* dv, const float* dm, const uin
 
 // cls rows of the residual stream: X[b,0,:] = cls + pos[0]
 __global__ void dino_cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ X, int B) {
+  pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * DD) return;
   const int c = idx % DD, b = idx / DD;
@@ -256,11 +259,11 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
     const int64_t total = (int64_t)B * NPATCH * PATCH_KP;
     {
       ProfScope ps(st, "im2col");
-      im2col_norm_kernel<bf16><<<cdiv(total, 256), 256, 0, st>>>(images, A0, B);
+      launch_k(im2col_norm_kernel<bf16>, dim3(cdiv(total, 256)), dim3(256), 0, st, images, A0, B);
       HVLA_LAUNCH_CHECK("im2col");
     }
     ProfScope ps2(st, "cls_rows");
-    dino_cls_rows_kernel<<<cdiv(B * DD, 256), 256, 0, st>>>(dv + V::cls, dv + V::pos, X, B);
+    launch_k(dino_cls_rows_kernel, dim3(cdiv(B * DD, 256)), dim3(256), 0, st, dv + V::cls, dv + V::pos, X, B);
     HVLA_LAUNCH_CHECK("dino_cls_rows");
   }
   auto gemm = [&](const bf16* A, const bf16* Wt, int m, int n, int k, int epi, const tc::EpiP& ep) -> int {

@@ -199,6 +199,8 @@ __global__ void __launch_bounds__(128) layernorm_kernel(LnP p) {
 template <typename TO>
 __global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restrict__ x, TO* __restrict__ y,
                                                            const float* __restrict__ scale, const float* __restrict__ bias, int rows) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -239,8 +241,8 @@ template <typename TS, typename TO>
 inline int layernorm(cudaStream_t st, const LnP& p, int D) {
   if (D == 768 && std::is_same<TS, float>::value && p.sS == 0 && p.ldx == 768 && p.ldy == 768 && p.post_div == 0.f) {
     ProfScope ps(st, "layernorm");
-    layernorm768_kernel<TO><<<cdiv(p.rows, 8), 256, 0, st>>>(p.x, reinterpret_cast<TO*>(p.y), reinterpret_cast<const float*>(p.scale),
-                                                             reinterpret_cast<const float*>(p.bias), p.rows);
+    launch_k(layernorm768_kernel<TO>, dim3(cdiv(p.rows, 8)), dim3(256), 0, st, p.x, reinterpret_cast<TO*>(p.y),
+             reinterpret_cast<const float*>(p.scale), reinterpret_cast<const float*>(p.bias), p.rows);
     HVLA_LAUNCH_CHECK("layernorm768");
     return HVLA_OK;
   }
@@ -356,6 +358,8 @@ inline int attention_simt(cudaStream_t st, const AttnP& p, int dh) {
 // (u8/255 - mean)/std, im2col of the VALID 14x14/14 conv: A0[b*256+p, k], k = (kh,kw,c), K padded to 640.
 template <typename TO>
 __global__ void im2col_norm_kernel(const uint8_t* __restrict__ img, TO* __restrict__ out, int B) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)B * NPATCH * PATCH_KP;
   if (idx >= total) return;
