@@ -2,67 +2,31 @@
 //
 // Per (image, head) item the 257x257 problem is split so that the tensor-core part is a clean 256x256:
 //   * query rows 0..255 = two M=128 tiles; keys 0..255 = one N=256 MMA  (S = Q K^T, fp32 in TMEM);
-//   * key 256 (the last patch token) is a rank-1 correction on CUDA cores, read from the staged smem tiles;
-//   * query row 256 is a single row done on CUDA cores by the softmax warps (32 keys each, merged).
-// Softmax is a full-row (not online) two-pass softmax straight out of TMEM: pass 1 row max, pass 2
-// P = exp2(..) written back IN PLACE over S as bf16 (tcgen05.st), then O = P V runs with A from TMEM
-// (tcgen05.mma TS form) and V as an MN-major shared-memory operand; O lands in the free half of the same
-// TMEM region.  The two query tiles of an item are processed by two softmax warp groups in ping-pong (each
-// owns 256 TMEM columns), so one group's TMEM/MUFU work overlaps the other's MMA waits.
-//
-// Warps: 0-3 / 4-7 softmax + epilogue of tile 0 / 1 (TMEM lane quarter = warp & 3), 8 TMA producer,
-// 9 MMA issuer.  Query row 256 is shared out over the 8 softmax warps (32 keys each) and merged by warp 0.
-// Persistent: one CTA per SM loops over items; Q/K/V of the next item are prefetched (2 smem stages).
+//   * key 256 (the last patch token) is a rank-1 column and query row 256 a single row: both are done by helper warps with
+//     warp-level mma.sync matrix-vector products from the staged shared-memory tiles.
+// P = exp2(..) goes back to TMEM as bf16 and O = P V runs with A from TMEM (tcgen05.mma TS form) and V as an MN-major
+// shared-memory operand.  Measured facts that shaped the design (profiles/README.md): MUFU.EX2 is 16 results/clk/SM whatever the
+// operand type, TMEM reads are ~64 B/clk per scheduler, and with four roles on every scheduler the kernel is bound by instruction
+// issue and hand-off latency rather than by any single pipe -- hence packed fp32x2 math, mma.sync helpers and TMA stores.
 #pragma once
 #include "gemm_tc.cuh"
+#include "attn_mma.cuh"
 #include <stdlib.h>
 
 namespace hvla {
-namespace attn5 {
+namespace attn_tc {
 
 using namespace tc;
 
 constexpr int S_ = DTOK;                       // 257
-constexpr int W_TMA = 8, W_MMA = 9;           // warps 0-7: two softmax groups (+ query row 256 cooperatively); 8: TMA; 9: MMA
-constexpr int NTHREADS = 10 * 32;
 constexpr int TILE_BYTES = 128 * 128;          // 128 rows x 64 bf16
-constexpr int KV_BYTES = 272 * 128;            // keys 0..271 (256 = last real key, 257.. = padding rows, P is 0 there)
+constexpr int KV_BYTES = 272 * 128;            // keys 0..271 (256 = last real key, 257.. = padding rows never read as keys)
 constexpr int OFF_K = 2 * TILE_BYTES, OFF_V = OFF_K + KV_BYTES;
 constexpr int OFF_QT = OFF_V + KV_BYTES;        // query rows 256..271 (only row 256 is used)
 constexpr int STAGE_BYTES = OFF_QT + 16 * 128; // Q0 Q1 | K[272] | V[272] | Qtail[16] = 102 KB
-constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 1024 + 256 + 2 * 8 * 66 * 4;   // + row-256 partials (double-buffered)
-constexpr int TM_OREL = 160;                   // TMEM: group g owns columns [256g, 256g+256): S fp32 -> P bf16 in [0,128), O in [160,224)
 static_assert(STAGE_BYTES % 1024 == 0 && OFF_V % 1024 == 0, "UMMA / TMA 128B-swizzle tiles need 1024-byte alignment");
 constexpr float LOG2E = 1.4426950408889634f;
 
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
-      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accum), "r"(0u)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2a(float x) {
   float y;
@@ -81,389 +45,10 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
 }
 constexpr uint32_t make_idesc_bmn(int M, int N) { return make_idesc(M, N) | (1u << 16); }   // B is MN-major
 
-__device__ __forceinline__ float dot8(const uint4& a, const uint4& b, float acc) {
-  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
-  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 x = __bfloat1622float2(pa[i]), y = __bfloat1622float2(pb[i]);
-    acc = fmaf(x.x, y.x, acc);
-    acc = fmaf(x.y, y.y, acc);
-  }
-  return acc;
-}
-
-__global__ void __launch_bounds__(NTHREADS, 1)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmTail, const bf16* __restrict__ qkv,
-               bf16* __restrict__ out, int n_items, int dbg, long long* __restrict__ tstamp) {
-  pdl_trigger();
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = smem_base + 2 * STAGE_BYTES;
-  const uint32_t in_full = bars, in_empty = bars + 16, s_full = bars + 32, p_full = bars + 48;
-  const uint32_t o_full = bars + 64, o_free = bars + 80, tmem_slot = bars + 96;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  const uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  float* part = reinterpret_cast<float*>(smem_raw + (bars + 256 - smem_u32(smem_raw)));   // [2][8][66]
-  int* cnt = reinterpret_cast<int*>(smem_raw + (bars + 128 - smem_u32(smem_raw)));           // [2] arrival counters
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (warp == W_TMA && lane == 0) {
-    tma_prefetch_desc(&tmQKV);
-    tma_prefetch_desc(&tmTail);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(in_full + 8 * s, 1);
-      mbar_init(in_empty + 8 * s, 9);     // MMA commit + 8 softmax warps
-      mbar_init(s_full + 8 * s, 1);
-      mbar_init(p_full + 8 * s, 4);
-      mbar_init(o_full + 8 * s, 1);
-      mbar_init(o_free + 8 * s, 4);
-    }
-    cnt[0] = 0;
-    cnt[1] = 0;
-    fence_barrier_init();
-  }
-  if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-  pdl_wait();
-
-  if (warp == W_TMA) {
-    // ============================ TMA producer ============================
-    if (lane == 0) {
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int s = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        const int b = item / DH, h = item % DH;
-        const uint32_t st = smem_base + s * STAGE_BYTES;
-        mbar_wait(in_empty + 8 * s, ph ^ 1);
-        mbar_expect_tx(in_full + 8 * s, STAGE_BYTES);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          tma_load_2d(st + j * TILE_BYTES, &tmQKV, in_full + 8 * s, h * DHD, b * S_ + 128 * j);
-          tma_load_2d(st + OFF_K + j * TILE_BYTES, &tmQKV, in_full + 8 * s, DD + h * DHD, b * S_ + 128 * j);
-          tma_load_2d(st + OFF_V + j * TILE_BYTES, &tmQKV, in_full + 8 * s, 2 * DD + h * DHD, b * S_ + 128 * j);
-        }
-        // rows 256..271: token 256 of this image (read by the CUDA-core rank-1 paths) + 15 unused rows
-        tma_load_2d(st + OFF_K + 2 * TILE_BYTES, &tmTail, in_full + 8 * s, DD + h * DHD, b * S_ + 256);
-        tma_load_2d(st + OFF_V + 2 * TILE_BYTES, &tmTail, in_full + 8 * s, 2 * DD + h * DHD, b * S_ + 256);
-        tma_load_2d(st + OFF_QT, &tmTail, in_full + 8 * s, h * DHD, b * S_ + 256);
-      }
-    }
-  } else if (warp == W_MMA) {
-    // ============================ MMA issuer ============================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc(128, 256);
-      constexpr uint32_t idesc_o = make_idesc_bmn(128, 64);
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int s = it & 1;
-        const uint32_t st = smem_base + s * STAGE_BYTES;
-        const uint32_t par = it & 1;        // every per-group barrier completes once per item
-        mbar_wait(in_full + 8 * s, (it >> 1) & 1);
-        tc_fence_after();
-        const uint64_t dk = make_smem_desc(st + OFF_K);
-        const uint64_t dv = make_smem_desc_mn(st + OFF_V);
-        // Group g owns TMEM columns [256g, 256g+256): S_g = Q_g K^T for both query tiles first ...
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          mbar_wait(o_free + 8 * g, par ^ 1);           // group g has read the previous item's O out of this region
-          tc_fence_after();
-          const uint64_t dq = make_smem_desc(st + g * TILE_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + 256 * g, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(s_full + 8 * g);
-        }
-        // ... then O_g = P_g V as soon as group g has written P_g (bf16, in place over S_g); O_g lives in the same region
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          mbar_wait(p_full + 8 * g, par);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 16; ++k)
-            umma_bf16_ts(tmem_base + 256 * g + TM_OREL, tmem_base + 256 * g + 8 * k, dv + (uint64_t)(k * (2048 >> 4)), idesc_o,
-                         k != 0 ? 1u : 0u);
-          umma_commit(o_full + 8 * g);
-        }
-        umma_commit(in_empty + 8 * s);                  // all MMAs reading this stage have retired
-      }
-    }
-  } else if (warp < 8) {
-    // ============================ softmax + epilogue: group g = warp / 4 owns query tile g ============================
-    const int g = warp >> 2, quarter = warp & 3;
-#define HVLA_TS(k) do { if (tstamp && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4) && it < 6) tstamp[((warp >> 2) * 6 + it) * 8 + (k)] = clock64(); } while (0)
-    const uint32_t tm = tmem_base + ((uint32_t)(quarter * 32) << 16) + 256 * g;
-    const int rl = quarter * 32 + lane;                 // row inside the tile
-    int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int s = it & 1;
-      const uint32_t par = it & 1;
-      const int b = item / DH, h = item % DH;
-      const uint8_t* st = smem_al + s * STAGE_BYTES;
-      // score against key 256 on CUDA cores from the staged tiles (128B swizzle: chunk ^= row & 7)
-      HVLA_TS(0);
-      mbar_wait(in_full + 8 * s, (it >> 1) & 1);
-      HVLA_TS(1);
-      float sx = 0.f;
-      {
-        const uint8_t* qr = st + g * TILE_BYTES + rl * 128;
-        const uint8_t* kr = st + OFF_K + 256 * 128;
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          sx = dot8(*reinterpret_cast<const uint4*>(qr + ((u ^ (rl & 7)) << 4)), *reinterpret_cast<const uint4*>(kr + (u << 4)), sx);
-      }
-      mbar_wait(s_full + 8 * g, par);
-      tc_fence_after();
-      HVLA_TS(2);
-      uint32_t r[2][32];
-      // pass 1: row max (TMEM loads double-buffered against the max reduction)
-      float mx = sx;
-      tmem_ld32(tm, r[0]);
-      tmem_wait_ld();
-#pragma unroll 1
-      for (int c = (dbg & 1) ? 8 : 0; c < 8; c += 2) {
-        tmem_ld32(tm + (c + 1) * 32, r[1]);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[0][i]));
-        tmem_wait_ld();
-        tmem_ld32(tm + ((c + 2) & 7) * 32, r[0]);        // wraps to chunk 0 = first chunk of pass 2
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[1][i]));
-        tmem_wait_ld();
-      }
-      const float nm = -mx * LOG2E;
-      float sum = 0.f;
-      HVLA_TS(3);
-      // pass 2: P = exp2((s - max) log2e) as bf16, in place over S (the bf16 row is half as wide)
-#pragma unroll 1
-      for (int c = 0; c < 8; c += 2) {
-        tmem_ld32(tm + (c + 1) * 32, r[1]);
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = (dbg & 4) ? __uint_as_float(r[0][2 * i]) : ex2a(fmaf(__uint_as_float(r[0][2 * i]), LOG2E, nm));
-          const float p1 = (dbg & 4) ? __uint_as_float(r[0][2 * i + 1]) : ex2a(fmaf(__uint_as_float(r[0][2 * i + 1]), LOG2E, nm));
-          sum += p0 + p1;
-          pk[i] = pack_bf16(p0, p1);
-        }
-        tmem_wait_ld();
-        tmem_st16(tm + c * 16, pk);                       // columns [16c,16c+16) were consumed at chunk <= c
-        if (c + 2 < 8) tmem_ld32(tm + (c + 2) * 32, r[0]);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = (dbg & 4) ? __uint_as_float(r[1][2 * i]) : ex2a(fmaf(__uint_as_float(r[1][2 * i]), LOG2E, nm));
-          const float p1 = (dbg & 4) ? __uint_as_float(r[1][2 * i + 1]) : ex2a(fmaf(__uint_as_float(r[1][2 * i + 1]), LOG2E, nm));
-          sum += p0 + p1;
-          pk[i] = pack_bf16(p0, p1);
-        }
-        tmem_wait_ld();
-        tmem_st16(tm + (c + 1) * 16, pk);
-      }
-      const float px = ex2a(fmaf(sx, LOG2E, nm));
-      sum += px;
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full + 8 * g);
-      HVLA_TS(4);
-      // ---- query row 256 (one row per item), cooperatively: this warp takes keys [32*warp, 32*warp+32) ----
-      {
-        const uint8_t* sk = st + OFF_K;
-        const uint8_t* sv = st + OFF_V;
-        const uint8_t* q256 = st + OFF_QT;                 // row 0 of the tail tile: no swizzle offset
-        const int key = 32 * warp + lane;
-        float a = 0.f;
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          a = dot8(*reinterpret_cast<const uint4*>(q256 + (u << 4)), *reinterpret_cast<const uint4*>(sk + key * 128 + ((u ^ (key & 7)) << 4)), a);
-        float mw = a;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
-        const float pw = ex2a((a - mw) * LOG2E);
-        float lw = pw;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) lw += __shfl_xor_sync(0xffffffffu, lw, o);
-        float o0 = 0.f, o1 = 0.f;                           // lane owns d = 2*lane, 2*lane+1
-#pragma unroll 8
-        for (int l = 0; l < 32; ++l) {
-          const int k2 = 32 * warp + l;
-          const float p = __shfl_sync(0xffffffffu, pw, l);
-          const float2 v2 = __bfloat1622float2(
-              *reinterpret_cast<const __nv_bfloat162*>(sv + k2 * 128 + (((lane >> 2) ^ (k2 & 7)) << 4) + (lane & 3) * 4));
-          o0 = fmaf(p, v2.x, o0);
-          o1 = fmaf(p, v2.y, o1);
-        }
-        float* pp = part + ((it & 1) * 8 + warp) * 66;
-        if (lane == 0) { pp[0] = mw; pp[1] = lw; }
-        pp[2 + 2 * lane] = o0;
-        pp[3 + 2 * lane] = o1;
-      }
-      // epilogue: (O + p_256 v_256) / sum -> bf16 -> global
-      const float inv = 1.0f / sum;
-      const float pxi = px * inv;
-      bf16* orow = out + ((int64_t)b * S_ + g * 128 + rl) * DD + h * DHD;
-      const uint8_t* vr = st + OFF_V + 256 * 128;
-      mbar_wait(o_full + 8 * g, par);
-      tc_fence_after();
-      HVLA_TS(5);
-      tmem_ld32(tm + TM_OREL, r[0]);
-      tmem_ld32(tm + TM_OREL + 32, r[1]);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_free + 8 * g);          // O is in registers now
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint4 vq = *reinterpret_cast<const uint4*>(vr + ((c * 4 + i) << 4));
-          const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&vq);
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 v2 = __bfloat1622float2(pv[e]);
-            w[e] = pack_bf16(fmaf(pxi, v2.x, __uint_as_float(r[c][i * 8 + 2 * e]) * inv),
-                             fmaf(pxi, v2.y, __uint_as_float(r[c][i * 8 + 2 * e + 1]) * inv));
-          }
-          *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-      }
-      HVLA_TS(6);
-      {
-        const uint8_t* sk = st + OFF_K;
-        const uint8_t* sv = st + OFF_V;
-        const uint8_t* q256 = st + OFF_QT;
-        // the last of the 8 warps to publish its share merges them (no CTA-wide barrier: the groups stay decoupled)
-        __threadfence_block();
-        __syncwarp();
-        int prev = 0;
-        if (lane == 0) prev = atomicAdd(cnt + (it & 1), 1);
-        prev = __shfl_sync(0xffffffffu, prev, 0);
-        if (prev == 7) {
-          __threadfence_block();
-          if (lane == 0) cnt[it & 1] = 0;
-          float sx2 = 0.f;                                   // key 256 itself
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            sx2 = dot8(*reinterpret_cast<const uint4*>(q256 + (u << 4)), *reinterpret_cast<const uint4*>(sk + 256 * 128 + (u << 4)), sx2);
-          const volatile float* p0 = part + (it & 1) * 8 * 66;
-          float M = sx2;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) M = fmaxf(M, p0[w * 66]);
-          const float ex = ex2a((sx2 - M) * LOG2E);
-          float L = ex;
-          const float2 vx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sv + 256 * 128 + 4 * lane));
-          float r0 = ex * vx.x, r1 = ex * vx.y;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) {
-            const float f = ex2a((p0[w * 66] - M) * LOG2E);
-            L = fmaf(f, p0[w * 66 + 1], L);
-            r0 = fmaf(f, p0[w * 66 + 2 + 2 * lane], r0);
-            r1 = fmaf(f, p0[w * 66 + 3 + 2 * lane], r1);
-          }
-          const float il = 1.0f / L;
-          *reinterpret_cast<uint32_t*>(out + ((int64_t)b * S_ + 256) * DD + h * DHD + 2 * lane) = pack_bf16(r0 * il, r1 * il);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(in_empty + 8 * s);        // done reading this stage's shared memory
-      HVLA_TS(7);
-    }
-  }
-#undef HVLA_TS
-  tc_fence_before();
-  __syncthreads();
-  if (warp == W_MMA) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-inline int dino_attention_tc(cudaStream_t st, const bf16* qkv, bf16* out, int B) {
-  static bool attr = false;
-  if (!attr) {
-    HVLA_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr = true;
-  }
-  CUtensorMap map, tail;
-  HVLA_TRY(make_map_bf16(&map, qkv, (int64_t)B * S_, 3 * DD, 128));
-  HVLA_TRY(make_map_bf16(&tail, qkv, (int64_t)B * S_, 3 * DD, 16));
-  const int n_items = B * DH;
-  const int grid = n_items < num_sms() ? n_items : num_sms();
-  ProfScope ps(st, "dino_attention");
-  int dbg = 0;
-  if (const char* e = getenv("HVLA_ATTN_DEBUG")) dbg = atoi(e);     // timing experiments only (results are wrong when set)
-  static long long* d_ts = nullptr;
-  if ((dbg & 32) && !d_ts) { cudaMalloc(&d_ts, 2 * 6 * 8 * sizeof(long long)); cudaMemset(d_ts, 0, 2 * 6 * 8 * sizeof(long long)); }
-  launch_k(attn_tc_kernel, dim3(grid), dim3(NTHREADS), (size_t)SMEM_BYTES, st, map, tail, qkv, out, n_items, dbg, (dbg & 32) ? d_ts : (long long*)nullptr);
-  if (dbg & 32) {
-    long long h[96];
-    cudaMemcpy(h, d_ts, sizeof h, cudaMemcpyDeviceToHost);
-    for (int g = 0; g < 2; ++g)
-      for (int it = 0; it < 6; ++it) {
-        const long long* t = h + (g * 6 + it) * 8;
-        fprintf(stderr, "ts g%d it%d: start %lld | in_full +%lld s_full +%lld pass1 +%lld pass2 +%lld o_full +%lld epi +%lld row256 +%lld\n", g, it,
-                t[0] - h[0], t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6]);
-      }
-  }
-  HVLA_LAUNCH_CHECK("attn_tc");
-  return HVLA_OK;
-}
-
-}  // namespace attn5
-
-// ====================================================================================================================
-// v9 (the pipeline's kernel): per CTA ONE softmax group (4 warps) + 4 helper warps + TMA warp + MMA warp, 256 TMEM columns,
-// one shared-memory stage, TWO CTAs per SM.
-//   * The two query tiles of an item run back to back in a CTA; one tile's MUFU/TMEM work overlaps the other CTA's MMA,
-//     loads and stores because the two co-resident CTAs drift freely against each other.
-//   * Everything that is not a 128x256 tile -- the scores against key 256 (a rank-1 column for all 256 rows) and the whole
-//     of query row 256 -- is CUDA-core work done by the helper warps OFF the softmax warps' critical path; the softmax warps
-//     pick the key-256 score up from shared memory at the end of their max pass.
-//   * The stage is refilled in three parts with their own full/empty barriers (Q0,K | V | Q1): Q0 and K of the next item
-//     stream in as soon as this item's second S = Q K^T has retired, V as soon as its second P V has, so one stage is enough.
-//   * Output rows leave through shared memory (the dead Q tile, 128B-swizzled) and one TMA store per warp: a row-per-thread
-//     global store costs one LSU cycle per row and was 1-2 k cycles of every tile's critical path.
-//   * Registers are moved between roles with setmaxnreg (softmax 160, helpers 40, TMA/MMA 40).
-// Small batches (units < CTA slots) split an item into its two tiles (unit = one query tile).
-// ====================================================================================================================
-namespace attn9 {
-using namespace attn5;
-
-constexpr int NT9 = 12 * 32;                        // warps 0-3 softmax, 4-7 helpers, 8 TMA, 9 MMA, 10-11 register donors
-constexpr int A_BYTES = 3 * TILE_BYTES + 2 * 16 * 128;   // Q0 | K[0..255] | K[256..271] | Q[256..271]
-constexpr int B_BYTES = TILE_BYTES;                      // Q1
-constexpr int C_BYTES = 2 * TILE_BYTES + 16 * 128;       // V[0..271]
-static_assert(A_BYTES + B_BYTES + C_BYTES == STAGE_BYTES, "stage parts");
-constexpr int OFF_BAR = STAGE_BYTES;
-constexpr int OFF_SX = OFF_BAR + 256;               // float [2][256]: score of every query row against key 256 (double-buffered by item)
-constexpr int OFF_PS = OFF_SX + 2 * 256 * 4;        // float [264]: un-normalised probabilities of query row 256
-constexpr int OFF_RED = OFF_PS + 264 * 4;           // float [8]
-constexpr int OFF_OP = OFF_RED + 32;                // float [4][64]: per-warp partial outputs of query row 256
-constexpr int SMEM9 = 1024 + OFF_OP + 4 * 64 * 4;
-static_assert(2 * (SMEM9 + 1024) <= 233472, "two CTAs per SM");
-
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-__device__ __forceinline__ void helper_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
-__device__ __forceinline__ void cvt8(const uint4& a, float (&f)[8]) {
-  f[0] = bf_lo(a.x); f[1] = bf_hi(a.x); f[2] = bf_lo(a.y); f[3] = bf_hi(a.y);
-  f[4] = bf_lo(a.z); f[5] = bf_hi(a.z); f[6] = bf_lo(a.w); f[7] = bf_hi(a.w);
-}
-__device__ __forceinline__ float dot8f(const uint4& a, const float (&k)[8], float acc) {
-  acc = fmaf(bf_lo(a.x), k[0], acc); acc = fmaf(bf_hi(a.x), k[1], acc);
-  acc = fmaf(bf_lo(a.y), k[2], acc); acc = fmaf(bf_hi(a.y), k[3], acc);
-  acc = fmaf(bf_lo(a.z), k[4], acc); acc = fmaf(bf_hi(a.z), k[5], acc);
-  acc = fmaf(bf_lo(a.w), k[6], acc); acc = fmaf(bf_hi(a.w), k[7], acc);
-  return acc;
-}
-// MMA issue with the 64-bit shared-memory descriptors kept as (lo, hi) words: stepping K only touches the 14-bit address field in
-// lo, so the single issuing thread spends one 32-bit add per MMA instead of 64-bit arithmetic on a serial dependency chain.
 // The K-step offsets are added INSIDE the asm block so that the compiler cannot hoist 24 pre-stepped descriptors out of the item loop
 // (they would not fit the issuing warp's 40 registers).
 template <bool ACC, int KOFF>
@@ -493,170 +78,230 @@ __device__ __forceinline__ void umma_ts2(uint32_t tmem_d, uint32_t tmem_a, uint3
       "}" ::"r"(tmem_d), "r"(tmem_a), "r"(blo), "r"(bhi), "r"(idesc), "n"(AOFF), "n"(BOFF), "n"(ACC ? 1 : 0)
       : "memory");
 }
+
+// ====================================================================================================================
+// One CTA per SM, 20 warps, both TMEM halves in flight, softmax warps that never wait.
+//   warps 0-7   softmax: TWO threads per query row (warp w: TMEM lane quarter w & 3, key half w >> 2).  A thread pulls its 128
+//               scores out of TMEM ONCE, keeps them in registers for both the max and the exp pass, and swaps the row max with
+//               its partner through shared memory (64-thread named barrier).  All eight warps work on the same tile, so a tile's
+//               softmax takes half as long and the MUFU pipes are fed back to back: while tile n is in softmax, S(n+1) = Q K^T
+//               is already sitting in the other TMEM half, and P(n-1) V, its epilogue and the loads of the next item run under it.
+//   warps 8-11  epilogue: O out of TMEM, + p_256 v_256, / row sum, bf16, staged (128B-swizzled) in the dead Q tile, one TMA
+//               store per warp.
+//   warps 12-15 helpers: the key-256 score of all 256 rows and the whole of query row 256 (mma.sync matrix-vector products), one
+//               item ahead of the softmax warps.
+//   warp 16 TMA producer (two 102 KB stages), warp 17 MMA issuer, warps 18-19 register donors (setmaxnreg: 168 / 72 / 40 / 32).
+// TMEM half s (256 columns): S fp32 [0,256) -> P bf16 of keys 0..127 in [0,64), of keys 128..255 in [128,192), O in [192,256).
+// Work is split by TILE: CTA c owns tiles [c T / grid, (c+1) T / grid) (tile = item * 2 + half), so SMs differ by at most one
+// tile; an item cut by a range boundary is staged by both neighbours.
+// ====================================================================================================================
+constexpr int NTHREADS = 20 * 32;
+constexpr int W_EPI = 8, W_HELP = 12, W_TMA = 16, W_MMA = 17;
+constexpr int OFF_BAR = 2 * STAGE_BYTES;
+constexpr int OFF_SX = OFF_BAR + 256;               // float [2 stages][256]: score of every query row against key 256
+constexpr int OFF_MX = OFF_SX + 2 * 256 * 4;        // float [2 slots][2 halves][128]: partial row maxima
+constexpr int OFF_SUM = OFF_MX + 2 * 2 * 128 * 4;   // float [2 slots][2 halves][128]: partial row sums
+constexpr int OFF_PX = OFF_SUM + 2 * 2 * 128 * 4;   // float [2 slots][128]: un-normalised probability of key 256
+constexpr int OFF_PS = OFF_PX + 2 * 128 * 4;        // float [264]: un-normalised probabilities of query row 256
+constexpr int OFF_RED = OFF_PS + 264 * 4;           // float [8]
+constexpr int OFF_OP = OFF_RED + 32;                // float [4][64]: per-warp partial outputs of query row 256
+constexpr int OFF_VF = OFF_OP + 4 * 64 * 4;         // float [2 stages][64]: value row of key 256 in fp32
+constexpr int OFF_PB = OFF_VF + 2 * 64 * 4;         // bf16 [256]: probabilities of query row 256 as the A operand of its P V
+constexpr int SMEM_BYTES = 1024 + OFF_PB + 256 * 2;
+static_assert(SMEM_BYTES <= 232448, "shared memory");
+
+// TMEM store without a compiler memory barrier: the exp pipeline below is scheduled across these stores
+__device__ __forceinline__ void tmem_st8_nc(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]));
+}
+__device__ __forceinline__ void pair_sync(int q) { asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory"); }
+__device__ __forceinline__ void helper_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 template <int K>
 __device__ __forceinline__ void pv_chain(uint32_t tmem_d, uint32_t tmem_a, uint32_t vlo, uint32_t vhi, uint32_t idesc) {
   if constexpr (K < 16) {
-    umma_ts2<K != 0, 8 * K, K * (2048 >> 4)>(tmem_d, tmem_a, vlo, vhi, idesc);
+    umma_ts2<K != 0, 8 * K + (K >= 8 ? 64 : 0), K * (2048 >> 4)>(tmem_d, tmem_a, vlo, vhi, idesc);
     pv_chain<K + 1>(tmem_d, tmem_a, vlo, vhi, idesc);
   }
 }
 
-__global__ void __launch_bounds__(NT9, 2)
-attn_tc9_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmTail, const __grid_constant__ CUtensorMap tmOut,
-                int n_units, int split_dbg, long long* __restrict__ tstamp, bf16* __restrict__ out) {
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmTail, const __grid_constant__ CUtensorMap tmOut,
+               int n_tiles, long long* __restrict__ tstamp, bf16* __restrict__ out) {
   pdl_trigger();
-  const int split = split_dbg & 1, dbg = split_dbg >> 4;
+  long long ts_c0 = 0, ts_g0 = 0;
+  if (tstamp && threadIdx.x == 0) {
+    ts_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_g0));
+  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + OFF_BAR;
-  const uint32_t a_full = bars, b_full = bars + 8, c_full = bars + 16, a_empty = bars + 24, b_empty = bars + 32, c_empty = bars + 40;
-  const uint32_t s_full = bars + 48, p_full = bars + 56, o_full = bars + 64, o_free = bars + 72, sx_full = bars + 80 /* [2]: one per tile index, completes once per item */, tmem_slot = bars + 96;
-  uint8_t* st = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t* tmem_slot_ptr = reinterpret_cast<const uint32_t*>(st + OFF_BAR + 96);
-  float* sxs = reinterpret_cast<float*>(st + OFF_SX);
+  // [2] each: in_full, in_empty (per stage); s_full, p_full, o_full, o_free (per TMEM half); sx_full (per stage)
+  const uint32_t in_full = bars, in_empty = bars + 16, s_full = bars + 32, p_full = bars + 48, o_full = bars + 64, o_free = bars + 80;
+  const uint32_t sx_full = bars + 96, tmem_slot = bars + 112;
+  uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t* tmem_slot_ptr = reinterpret_cast<const uint32_t*>(sm + OFF_BAR + 112);
+  float* sxs = reinterpret_cast<float*>(sm + OFF_SX);
+  float* mxs = reinterpret_cast<float*>(sm + OFF_MX);
+  float* sums = reinterpret_cast<float*>(sm + OFF_SUM);
+  float* pxs = reinterpret_cast<float*>(sm + OFF_PX);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int begin = (int)((long long)blockIdx.x * n_tiles / gridDim.x), end = (int)((long long)(blockIdx.x + 1) * n_tiles / gridDim.x);
+  const int item0 = begin >> 1;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmTail);
     tma_prefetch_desc(&tmOut);
-    mbar_init(a_full, 1);
-    mbar_init(b_full, 1);
-    mbar_init(c_full, 1);
-    mbar_init(a_empty, 9);        // MMA commit (last S of the unit retired) + 4 helper warps + 4 softmax warps (tile-0 output staged in Q0 has left)
-    mbar_init(b_empty, 9);        // same for Q1
-    mbar_init(c_empty, 9);        // MMA commit (last PV retired) + 4 helper warps + 4 softmax warps (key-256 value row)
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
-    mbar_init(o_full, 1);
-    mbar_init(o_free, 4);
-    mbar_init(sx_full, 4);
-    mbar_init(sx_full + 8, 4);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(in_full + 8 * s, 1);
+      mbar_init(in_empty + 8 * s, 9);     // MMA commit + 4 helper warps + 4 epilogue warps
+      mbar_init(s_full + 8 * s, 1);
+      mbar_init(p_full + 8 * s, 8);
+      mbar_init(o_full + 8 * s, 1);
+      mbar_init(o_free + 8 * s, 4);
+      mbar_init(sx_full + 8 * s, 4);
+    }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, 256);
+  if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_wait();
 
-  if (warp >= 8) {
-    reg_dec<40>();
-    if (warp == 8 && lane == 0) {
+  if (warp >= W_TMA) {
+    reg_dec<32>();
+    if (warp == W_TMA && lane == 0) {
       // ============================ TMA producer ============================
-      int it = 0;
-      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
-        const int item = split ? (unit >> 1) : unit;
+      const int item1 = (end + 1) >> 1;
+      for (int item = item0; item < item1; ++item) {
+        const int il = item - item0, s = il & 1;
         const int b = item / DH, h = item % DH;
-        const uint32_t ph = it & 1;
-        mbar_wait(a_empty, ph ^ 1);
-        mbar_expect_tx(a_full, A_BYTES);
-        tma_load_2d(smem_base, &tmQKV, a_full, h * DHD, b * S_);
-        tma_load_2d(smem_base + OFF_K, &tmQKV, a_full, DD + h * DHD, b * S_);
-        tma_load_2d(smem_base + OFF_K + TILE_BYTES, &tmQKV, a_full, DD + h * DHD, b * S_ + 128);
-        tma_load_2d(smem_base + OFF_K + 2 * TILE_BYTES, &tmTail, a_full, DD + h * DHD, b * S_ + 256);
-        tma_load_2d(smem_base + OFF_QT, &tmTail, a_full, h * DHD, b * S_ + 256);
-        mbar_wait(c_empty, ph ^ 1);
-        mbar_expect_tx(c_full, C_BYTES);
-        tma_load_2d(smem_base + OFF_V, &tmQKV, c_full, 2 * DD + h * DHD, b * S_);
-        tma_load_2d(smem_base + OFF_V + TILE_BYTES, &tmQKV, c_full, 2 * DD + h * DHD, b * S_ + 128);
-        tma_load_2d(smem_base + OFF_V + 2 * TILE_BYTES, &tmTail, c_full, 2 * DD + h * DHD, b * S_ + 256);
-        mbar_wait(b_empty, ph ^ 1);
-        mbar_expect_tx(b_full, B_BYTES);
-        tma_load_2d(smem_base + TILE_BYTES, &tmQKV, b_full, h * DHD, b * S_ + 128);
+        const uint32_t st = smem_base + s * STAGE_BYTES;
+        mbar_wait(in_empty + 8 * s, ((il >> 1) & 1) ^ 1);
+        mbar_expect_tx(in_full + 8 * s, STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          tma_load_2d(st + j * TILE_BYTES, &tmQKV, in_full + 8 * s, h * DHD, b * S_ + 128 * j);
+          tma_load_2d(st + OFF_K + j * TILE_BYTES, &tmQKV, in_full + 8 * s, DD + h * DHD, b * S_ + 128 * j);
+          tma_load_2d(st + OFF_V + j * TILE_BYTES, &tmQKV, in_full + 8 * s, 2 * DD + h * DHD, b * S_ + 128 * j);
+        }
+        tma_load_2d(st + OFF_K + 2 * TILE_BYTES, &tmTail, in_full + 8 * s, DD + h * DHD, b * S_ + 256);
+        tma_load_2d(st + OFF_V + 2 * TILE_BYTES, &tmTail, in_full + 8 * s, 2 * DD + h * DHD, b * S_ + 256);
+        tma_load_2d(st + OFF_QT, &tmTail, in_full + 8 * s, h * DHD, b * S_ + 256);
       }
-    } else if (warp == 9 && lane == 0) {
+    } else if (warp == W_MMA && lane == 0) {
       // ============================ MMA issuer ============================
       constexpr uint32_t idesc_s = make_idesc(128, 256);
       constexpr uint32_t idesc_o = make_idesc_bmn(128, 64);
       const uint64_t dk = make_smem_desc(smem_base + OFF_K);
       const uint64_t dv = make_smem_desc_mn(smem_base + OFF_V);
       const uint32_t klo = (uint32_t)dk, khi = (uint32_t)(dk >> 32), vlo = (uint32_t)dv, vhi = (uint32_t)(dv >> 32);
-      int it = 0;
-      uint32_t n = 0;                                   // tiles so far: every per-tile barrier completes once per tile
-      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
-        const int t0 = split ? (unit & 1) : 0, t1 = split ? t0 + 1 : 2;
-        mbar_wait(a_full, it & 1);
-        for (int t = t0; t < t1; ++t, ++n) {
-          if (t == 1) mbar_wait(b_full, it & 1);
-          mbar_wait(o_free, (n & 1) ^ 1);               // the previous tile's O has been read out of TMEM
-          tc_fence_after();
-          const uint32_t qlo = klo - ((OFF_K - t * TILE_BYTES) >> 4);     // same descriptor fields, Q tile t's address
-          umma_ss2<false, 0>(tmem_base, qlo, klo, khi, idesc_s);
-          umma_ss2<true, 2>(tmem_base, qlo, klo, khi, idesc_s);
-          umma_ss2<true, 4>(tmem_base, qlo, klo, khi, idesc_s);
-          umma_ss2<true, 6>(tmem_base, qlo, klo, khi, idesc_s);
-          umma_commit(s_full);
-          if (t == t1 - 1) {                            // Q and K may be overwritten once these MMAs retire
-            umma_commit(a_empty);
-            umma_commit(b_empty);
-          }
-          mbar_wait(p_full, n & 1);
-          if (t == t0) mbar_wait(c_full, it & 1);
-          tc_fence_after();
-          if (!(dbg & 1)) pv_chain<0>(tmem_base + TM_OREL, tmem_base, vlo, vhi, idesc_o);
-          umma_commit(o_full);
-        }
-        umma_commit(c_empty);
+      // S(g) = Q K^T of tile g into TMEM half (g - begin) & 1, as soon as that half's previous O has been read out
+      auto issue_qk = [&](int g) {
+        const int n = g - begin, slot = n & 1, t = g & 1, il = (g >> 1) - item0, s = il & 1;
+        if (t == 0 || g == begin) mbar_wait(in_full + 8 * s, (il >> 1) & 1);
+        mbar_wait(o_free + 8 * slot, ((n >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t ks = klo + s * (STAGE_BYTES >> 4);
+        const uint32_t qs = ks - ((OFF_K - t * TILE_BYTES) >> 4);     // same descriptor fields, Q tile t's address
+        const uint32_t d = tmem_base + 256 * slot;
+        umma_ss2<false, 0>(d, qs, ks, khi, idesc_s);
+        umma_ss2<true, 2>(d, qs, ks, khi, idesc_s);
+        umma_ss2<true, 4>(d, qs, ks, khi, idesc_s);
+        umma_ss2<true, 6>(d, qs, ks, khi, idesc_s);
+        umma_commit(s_full + 8 * slot);
+      };
+      if (begin < end) issue_qk(begin);
+      for (int g = begin; g < end; ++g) {
+        if (g + 1 < end) issue_qk(g + 1);
+        const int n = g - begin, slot = n & 1, t = g & 1, il = (g >> 1) - item0, s = il & 1;
+        mbar_wait(p_full + 8 * slot, (n >> 1) & 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + 256 * slot;
+        pv_chain<0>(d + 192, d, vlo + s * (STAGE_BYTES >> 4), vhi, idesc_o);
+        umma_commit(o_full + 8 * slot);
+        if (t == 1 || g == end - 1) umma_commit(in_empty + 8 * s);    // every MMA reading this stage has been issued
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= W_HELP) {
     // ============================ helpers: key-256 column for all rows, and query row 256 ============================
     reg_dec<40>();
-    const int hw = warp - 4, tid = hw * 32 + lane, sw = tid & 7;
-    const uint8_t* sk = st + OFF_K;
-    const uint8_t* sv = st + OFF_V;
-    float* ps = reinterpret_cast<float*>(st + OFF_PS);
-    float* red = reinterpret_cast<float*>(st + OFF_RED);
-    float* op = reinterpret_cast<float*>(st + OFF_OP);
-    int it = 0;
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
-      const int item = split ? (unit >> 1) : unit;
-      const int t0 = split ? (unit & 1) : 0, t1 = split ? t0 + 1 : 2;
-      const bool own256 = t1 == 2;                         // the unit holding tile 1 also produces query row 256
+    // Warp-level mma.sync (m16n8k16, bf16 -> fp32) with the vector in column / row 0 of the B / A fragment: a matrix-vector product
+    // costs 1 ldmatrix + 1 mma per 16 x 16 block instead of ~500 CUDA-core instructions, which matters because this kernel is bound by
+    // instruction issue, not by any pipe.
+    const int hw = warp - W_HELP, tid = hw * 32 + lane, g = lane >> 2, tq = lane & 3, mi = lane >> 3, rr = lane & 7;
+    float* ps = reinterpret_cast<float*>(sm + OFF_PS);
+    float* red = reinterpret_cast<float*>(sm + OFF_RED);
+    float* op = reinterpret_cast<float*>(sm + OFF_OP);
+    const uint32_t* pbw = reinterpret_cast<const uint32_t*>(sm + OFF_PB);
+    const int item1 = (end + 1) >> 1;
+    for (int item = item0; item < item1; ++item) {
+      const int il = item - item0, s = il & 1;
+      const bool own256 = 2 * item + 1 >= begin && 2 * item + 1 < end;     // the CTA holding tile 1 also produces query row 256
       const int b = item / DH, h = item % DH;
-      const uint32_t par = it & 1;
-      float* sxw = sxs + par * 256;
-      mbar_wait(a_full, par);
-      // thread tid: row tid against key 256; query 256 against keys tid, 128 + tid and 256 (128B swizzle: chunk ^= row & 7)
-      float a0 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f;
-#pragma unroll 2
-      for (int u = 0; u < 8; ++u) {
-        const int cs = (u ^ sw) << 4;
-        float kc[8], qc[8];
-        cvt8(*reinterpret_cast<const uint4*>(sk + 256 * 128 + (u << 4)), kc);
-        a0 = dot8f(*reinterpret_cast<const uint4*>(st + tid * 128 + cs), kc, a0);
-        cvt8(*reinterpret_cast<const uint4*>(st + OFF_QT + (u << 4)), qc);
+      const uint8_t* st = sm + s * STAGE_BYTES;
+      const uint32_t st_u = smem_base + s * STAGE_BYTES;
+      mbar_wait(in_full + 8 * s, (il >> 1) & 1);
+      // ---- key-256 column: rows [64 hw, 64 hw + 64) of Q times k_256 (B fragment column 0 = lanes 0..3) ----
+      {
+        uint32_t vb[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) a2 = fmaf(qc[e], kc[e], a2);
-        b0 = dot8f(*reinterpret_cast<const uint4*>(sk + tid * 128 + cs), qc, b0);
-        b1 = dot8f(*reinterpret_cast<const uint4*>(sk + (128 + tid) * 128 + cs), qc, b1);
-      }
-      if (t0 == 0) {
-        sxw[tid] = a0;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sx_full);
-      }
-      if (t1 == 2) {
-        mbar_wait(b_full, par);
-        float a1 = 0.f;                                    // row 128 + tid against key 256
-#pragma unroll 2
-        for (int u = 0; u < 8; ++u) {
-          float kc[8];
-          cvt8(*reinterpret_cast<const uint4*>(sk + 256 * 128 + (u << 4)), kc);
-          a1 = dot8f(*reinterpret_cast<const uint4*>(st + TILE_BYTES + tid * 128 + ((u ^ sw) << 4)), kc, a1);
+        for (int i = 0; i < 8; ++i) vb[i] = lane < 4 ? *reinterpret_cast<const uint32_t*>(st + OFF_K + 256 * 128 + 4 * (4 * i + tq)) : 0u;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          const int row = 64 * hw + 16 * mt + (mi & 1) * 8 + rr;          // this lane's ldmatrix row (row & 7 == rr)
+          const uint32_t base = st_u + (row >> 7) * TILE_BYTES + (row & 127) * 128;
+          float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            uint32_t af[4];
+            attn::ldsm_x4(base + (((2 * ks + (mi >> 1)) ^ rr) << 4), af[0], af[1], af[2], af[3]);
+            attn::mma_bf16(c, af, vb[2 * ks], vb[2 * ks + 1]);
+          }
+          if (tq == 0) {
+            sxs[s * 256 + 64 * hw + 16 * mt + g] = c[0];
+            sxs[s * 256 + 64 * hw + 16 * mt + g + 8] = c[2];
+          }
         }
-        sxw[128 + tid] = a1;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sx_full + 8);
+      }
+      if (hw == 0) {                                       // value row of key 256 in fp32 for the epilogue warps
+        const uint32_t v2 = *reinterpret_cast<const uint32_t*>(st + OFF_V + 256 * 128 + lane * 4);
+        *reinterpret_cast<float2*>(sm + OFF_VF + s * 256 + lane * 8) = make_float2(bf_lo(v2), bf_hi(v2));
       }
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(a_empty);
-        mbar_arrive(b_empty);
-      }
+      if (lane == 0) mbar_arrive(sx_full + 8 * s);
       if (own256) {
+        // ---- scores of query 256: keys [64 hw, 64 hw + 64) of K (and key 256 on warp 0) times q_256 ----
+        uint32_t vb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vb[i] = lane < 4 ? *reinterpret_cast<const uint32_t*>(st + OFF_QT + 4 * (4 * i + tq)) : 0u;
+#pragma unroll
+        for (int mt = 0; mt < 5; ++mt) {
+          if (mt == 4 && hw != 0) break;
+          const int row = (mt < 4 ? 64 * hw + 16 * mt : 256) + (mi & 1) * 8 + rr;
+          const uint32_t base = st_u + OFF_K + row * 128;
+          float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            uint32_t af[4];
+            attn::ldsm_x4(base + (((2 * ks + (mi >> 1)) ^ rr) << 4), af[0], af[1], af[2], af[3]);
+            attn::mma_bf16(c, af, vb[2 * ks], vb[2 * ks + 1]);
+          }
+          if (mt < 4) {
+            if (tq == 0) {
+              ps[64 * hw + 16 * mt + g] = c[0];
+              ps[64 * hw + 16 * mt + g + 8] = c[2];
+            }
+          } else if (lane == 0) {
+            ps[256] = c[0];
+          }
+        }
+        helper_sync();
+        const float b0 = ps[tid], b1 = ps[128 + tid], a2 = ps[256];
         float m = fmaxf(fmaxf(b0, b1), a2);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -667,217 +312,234 @@ attn_tc9_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         float l = p0 + p1;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-        ps[tid] = p0;
-        ps[128 + tid] = p1;
+        reinterpret_cast<bf16*>(sm + OFF_PB)[tid] = __float2bfloat16_rn(p0);
+        reinterpret_cast<bf16*>(sm + OFF_PB)[128 + tid] = __float2bfloat16_rn(p1);
         if (lane == 0) red[4 + hw] = l;
         helper_sync();
         l = red[4] + red[5] + red[6] + red[7] + p2;
-        mbar_wait(c_full, par);
-        float o0 = 0.f, o1 = 0.f;                           // warp hw: keys [64 hw, 64 hw + 64); lane owns d = 2 lane, 2 lane + 1
-#pragma unroll 8
-        for (int j = 0; j < 64; ++j) {
-          const int k2 = 64 * hw + j;
-          const float p = ps[k2];
-          const uint32_t v2 = *reinterpret_cast<const uint32_t*>(sv + k2 * 128 + (((lane >> 2) ^ (k2 & 7)) << 4) + (lane & 3) * 4);
-          o0 = fmaf(p, bf_lo(v2), o0);
-          o1 = fmaf(p, bf_hi(v2), o1);
-        }
-        if (hw == 0) {
-          const uint32_t v2 = *reinterpret_cast<const uint32_t*>(sv + 256 * 128 + lane * 4);
-          o0 = fmaf(p2, bf_lo(v2), o0);
-          o1 = fmaf(p2, bf_hi(v2), o1);
-        }
-        op[hw * 64 + 2 * lane] = o0;
-        op[hw * 64 + 2 * lane + 1] = o1;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(c_empty);
-        helper_sync();
-        if (hw == 0) {
-          const float il = 1.0f / l;
-          const float r0 = (op[2 * lane] + op[64 + 2 * lane]) + (op[128 + 2 * lane] + op[192 + 2 * lane]);
-          const float r1 = (op[2 * lane + 1] + op[64 + 2 * lane + 1]) + (op[128 + 2 * lane + 1] + op[192 + 2 * lane + 1]);
-          *reinterpret_cast<uint32_t*>(out + ((int64_t)b * S_ + 256) * DD + h * DHD + 2 * lane) = pack_bf16(r0 * il, r1 * il);
-        }
-      } else if (lane == 0) {
-        mbar_arrive(c_empty);
-      }
-    }
-  } else {
-    // ============================ softmax + epilogue (TMEM lane quarter = warp) ============================
-    reg_inc<160>();
-#define TS9(k) do { if (tstamp && blockIdx.x == 0 && threadIdx.x == 0 && n < 6) tstamp[n * 8 + (k)] = clock64(); } while (0)
-    const uint32_t tm = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const int rl = warp * 32 + lane;
-    const uint8_t* vr = st + OFF_V + 256 * 128;
-    int it = 0;
-    uint32_t n = 0;
-    int pending = -1;                                      // tile whose staged output (in its Q tile) is still being read by TMA
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
-      const int item = split ? (unit >> 1) : unit;
-      const int t0 = split ? (unit & 1) : 0, t1 = split ? t0 + 1 : 2;
-      const int b = item / DH, h = item % DH;
-      const uint32_t par = it & 1;
-      for (int t = t0; t < t1; ++t, ++n) {
-        TS9(0);
-        mbar_wait(s_full, n & 1);
-        tc_fence_after();
-        TS9(1);
-        if (pending >= 0) {                                // long done by now: release the previous tile's Q buffer to the producer
-          if (lane == 0) {
-            bulk_wait_read0();
-            mbar_arrive(pending == 0 ? a_empty : b_empty);
-          }
-          pending = -1;
-        }
-        uint32_t r[2][32];
-        // pass 1: row max (TMEM loads double-buffered against the max reduction)
-        float mx = -3.0e38f;
-        tmem_ld32(tm, r[0]);
-        tmem_wait_ld();
-#pragma unroll 1
-        for (int c = 0; c < 8; c += 2) {
-          tmem_ld32(tm + (c + 1) * 32, r[1]);
+        // ---- O_256 = p V over keys [64 hw, 64 hw + 64): p in row 0 of the A fragment (lanes 0..3), V through ldmatrix.trans ----
+        uint32_t pa[8];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[0][i]));
-          tmem_wait_ld();
-          tmem_ld32(tm + ((c + 2) & 7) * 32, r[0]);        // wraps to chunk 0 = first chunk of pass 2
+        for (int i = 0; i < 8; ++i) pa[i] = lane < 4 ? pbw[8 * (4 * hw + (i >> 1)) + 4 * (i & 1) + tq] : 0u;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[1][i]));
-          tmem_wait_ld();
-        }
-        mbar_wait(sx_full + 8 * t, par);                   // the helpers' key-256 column of this tile
-        const float sx = sxs[par * 256 + t * 128 + rl];
-        mx = fmaxf(mx, sx);
-        const float nm = -mx * LOG2E;
-        float sum = 0.f;
-        TS9(2);
-        // pass 2: P = exp2((s - max) log2e) as bf16, in place over S (the bf16 row is half as wide)
-#pragma unroll 1
-        for (int c = 0; c < 8; c += 2) {
-          tmem_ld32(tm + (c + 1) * 32, r[1]);
-          uint32_t pk[16];
+        for (int half = 0; half < 2; ++half) {
+          float c[4][4];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2a(fmaf(__uint_as_float(r[0][2 * i]), LOG2E, nm));
-            const float p1 = ex2a(fmaf(__uint_as_float(r[0][2 * i + 1]), LOG2E, nm));
-            sum += p0 + p1;
-            pk[i] = pack_bf16(p0, p1);
-          }
-          tmem_wait_ld();
-          tmem_st16(tm + c * 16, pk);                       // columns [16c,16c+16) were consumed at chunk <= c
-          if (c + 2 < 8) tmem_ld32(tm + (c + 2) * 32, r[0]);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2a(fmaf(__uint_as_float(r[1][2 * i]), LOG2E, nm));
-            const float p1 = ex2a(fmaf(__uint_as_float(r[1][2 * i + 1]), LOG2E, nm));
-            sum += p0 + p1;
-            pk[i] = pack_bf16(p0, p1);
-          }
-          tmem_wait_ld();
-          tmem_st16(tm + (c + 1) * 16, pk);
-        }
-        const float px = ex2a(fmaf(sx, LOG2E, nm));
-        sum += px;
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
-        TS9(3);
-        // epilogue: (O + p_256 v_256) / sum -> bf16 -> this warp's 32 x 128 B slice of the dead Q tile -> one TMA store
-        const float inv = 1.0f / sum;
-        const float pxi = px * inv;
-        uint8_t* stg = st + t * TILE_BYTES + warp * 4096 + lane * 128;
-        mbar_wait(o_full, n & 1);
-        if (t == t0) mbar_wait(c_full, par);               // makes the TMA-written V row 256 visible to this thread
-        tc_fence_after();
-        TS9(4);
-        tmem_ld32(tm + TM_OREL, r[0]);
-        tmem_ld32(tm + TM_OREL + 32, r[1]);
-        tmem_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(o_free);                  // O is in registers now: the next tile's S may overwrite it
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+          for (int j = 0; j < 4; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const uint4 vq = *reinterpret_cast<const uint4*>(vr + ((c * 4 + i) << 4));
-            const uint32_t vw[4] = {vq.x, vq.y, vq.z, vq.w};
-            uint32_t w[4];
+            const int row = 16 * (4 * hw + i) + (mi & 1) * 8 + rr;
+            const uint32_t af[4] = {pa[2 * i], 0u, pa[2 * i + 1], 0u};
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              w[e] = pack_bf16(fmaf(pxi, bf_lo(vw[e]), __uint_as_float(r[c][i * 8 + 2 * e]) * inv),
-                               fmaf(pxi, bf_hi(vw[e]), __uint_as_float(r[c][i * 8 + 2 * e + 1]) * inv));
-            *reinterpret_cast<uint4*>(stg + (((c * 4 + i) ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int ntp = 0; ntp < 2; ++ntp) {
+              uint32_t bf[4];
+              attn::ldsm_x4_t(st_u + OFF_V + row * 128 + (((2 * (2 * half + ntp) + (mi >> 1)) ^ rr) << 4), bf[0], bf[1], bf[2], bf[3]);
+              attn::mma_bf16(c[2 * ntp], af, bf[0], bf[1]);
+              attn::mma_bf16(c[2 * ntp + 1], af, bf[2], bf[3]);
+            }
+          }
+          if (lane < 4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<float2*>(op + hw * 64 + 8 * (4 * half + j) + 2 * tq) = make_float2(c[j][0], c[j][1]);
           }
         }
-        fence_proxy_async();
         __syncwarp();
-        if (lane == 0 && !(dbg & 2)) {
-          tma_store_2d(&tmOut, smem_base + t * TILE_BYTES + warp * 4096, h * DHD, b * S_ + t * 128 + warp * 32);
-          bulk_commit();
+        if (lane == 0) mbar_arrive(in_empty + 8 * s);        // this warp is done reading the stage
+        helper_sync();
+        if (hw == 0) {
+          const float il2 = 1.0f / l;
+          const float2 vx = *reinterpret_cast<const float2*>(sm + OFF_VF + s * 256 + lane * 8);
+          const float r0 = (op[2 * lane] + op[64 + 2 * lane]) + (op[128 + 2 * lane] + op[192 + 2 * lane]) + p2 * vx.x;
+          const float r1 = (op[2 * lane + 1] + op[64 + 2 * lane + 1]) + (op[128 + 2 * lane + 1] + op[192 + 2 * lane + 1]) + p2 * vx.y;
+          *reinterpret_cast<uint32_t*>(out + ((int64_t)b * S_ + 256) * DD + h * DHD + 2 * lane) = pack_bf16(r0 * il2, r1 * il2);
         }
-        pending = t;
-        if (split) {                                       // one tile per unit: nothing later in this unit could release the buffers
-          if (lane == 0) {
-            bulk_wait_read0();
-            mbar_arrive(a_empty);
-            mbar_arrive(b_empty);
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(in_empty + 8 * s);
+      }
+    }
+  } else if (warp >= W_EPI) {
+    // ============================ epilogue (TMEM lane quarter = warp & 3) ============================
+    reg_dec<72>();
+    const int q = warp & 3, rl = q * 32 + lane;
+    for (int g = begin; g < end; ++g) {
+      const int n = g - begin, slot = n & 1, t = g & 1, item = g >> 1, il = item - item0, s = il & 1;
+      const uint32_t ph = (n >> 1) & 1;
+      const int b = item / DH, h = item % DH;
+      uint8_t* st = sm + s * STAGE_BYTES;
+      const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + 256 * slot + 192;
+      if (t == 0 || g == begin) mbar_wait(sx_full + 8 * s, (il >> 1) & 1);     // the helpers' fp32 copy of V row 256 (and, through them, the stage)
+      mbar_wait(p_full + 8 * slot, ph);                                         // ... and the softmax warps' row statistics
+      const float inv = 1.0f / (sums[(slot * 2 + 0) * 128 + rl] + sums[(slot * 2 + 1) * 128 + rl]);
+      const float px = pxs[slot * 128 + rl];
+      const float2 inv2 = make_float2(inv, inv), px2 = make_float2(px, px);
+      mbar_wait(o_full + 8 * slot, ph);
+      tc_fence_after();
+      uint8_t* stg = st + t * TILE_BYTES + q * 4096 + lane * 128;     // this warp's 32 x 128 B slice of the dead Q tile
+      const float4* vf = reinterpret_cast<const float4*>(sm + OFF_VF + s * 256);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tm + 32 * c, r);
+        tmem_wait_ld();
+        if (c == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_free + 8 * slot);      // O is in registers now: the next S may overwrite this TMEM half
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                         // (O + p_256 v_256) / sum on the packed fp32x2 pipe
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float4 v4 = vf[c * 8 + i * 2 + e];
+            const float2 lo = __fmul2_rn(__ffma2_rn(px2, make_float2(v4.x, v4.y), make_float2(__uint_as_float(r[i * 8 + 4 * e]), __uint_as_float(r[i * 8 + 4 * e + 1]))), inv2);
+            const float2 hi = __fmul2_rn(__ffma2_rn(px2, make_float2(v4.z, v4.w), make_float2(__uint_as_float(r[i * 8 + 4 * e + 2]), __uint_as_float(r[i * 8 + 4 * e + 3]))), inv2);
+            w[2 * e] = pack_bf16(lo.x, lo.y);
+            w[2 * e + 1] = pack_bf16(hi.x, hi.y);
           }
-          pending = -1;
+          *reinterpret_cast<uint4*>(stg + (((c * 4 + i) ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        TS9(5);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tmOut, smem_base + s * STAGE_BYTES + t * TILE_BYTES + q * 4096, h * DHD, b * S_ + t * 128 + q * 32);
+        bulk_commit();
+        if (t == 1 || g == end - 1) {                        // last tile of the item here: hand the stage back once TMA has read the staging
+          bulk_wait_read0();
+          mbar_arrive(in_empty + 8 * s);
+        }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(c_empty);                 // done reading the value tile's row 256
     }
-    if (lane == 0) bulk_wait0();                           // the last staged tile must have left before the CTA's shared memory goes away
-#undef TS9
+    if (lane == 0) bulk_wait0();
+  } else {
+    // ============================ softmax: 2 threads per row (lane quarter q, key half hf) ============================
+    reg_inc<168>();
+#define TS(k) do { if (tstamp && blockIdx.x == 0 && threadIdx.x == 0 && n < 6) tstamp[n * 8 + (k)] = clock64(); } while (0)
+    const int q = warp & 3, hf = warp >> 2, rl = q * 32 + lane;
+    for (int g = begin; g < end; ++g) {
+      const int n = g - begin, slot = n & 1, t = g & 1, il = (g >> 1) - item0, s = il & 1;
+      const uint32_t ph = (n >> 1) & 1;
+      const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + 256 * slot + 128 * hf;
+      TS(0);
+      mbar_wait(s_full + 8 * slot, ph);
+      tc_fence_after();
+      TS(1);
+      uint32_t r[4][32];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tmem_ld32(tm + 32 * j, r[j]);
+      tmem_wait_ld();
+      float mx = -3.0e38f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[j][i]));
+      float sx = 0.f;
+      if (hf == 1) {
+        if (t == 0 || g == begin) mbar_wait(sx_full + 8 * s, (il >> 1) & 1);     // the helpers' key-256 column of this item
+        sx = sxs[s * 256 + t * 128 + rl];
+        mx = fmaxf(mx, sx);
+      }
+      mxs[(slot * 2 + hf) * 128 + rl] = mx;
+      pair_sync(q);
+      mx = fmaxf(mx, mxs[(slot * 2 + (hf ^ 1)) * 128 + rl]);
+      const float nm = -mx * LOG2E;
+      TS(2);
+      // P = exp2((s - max) log2e) as bf16 into this thread's own (already consumed) half: columns [128 hf, 128 hf + 64).
+      // The kernel is instruction-issue bound (four roles share every scheduler), so the scale/shift and the row sum use the packed
+      // fp32x2 pipe: per key 0.5 FFMA2 + 1 MUFU + 0.5 FADD2 + 0.5 F2FP.  Blocks of 16 keys are software-pipelined: the MUFU ops of
+      // block b + 1 are issued before the adds / packs / TMEM store of block b.
+      const float2 l2 = make_float2(LOG2E, LOG2E), nm2 = make_float2(nm, nm);
+      float2 acc = make_float2(0.f, 0.f);
+      float2 e[2][8];
+      auto exp_block = [&](int blk, float2 (&o)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(r[blk >> 1][16 * (blk & 1) + 2 * i]), __uint_as_float(r[blk >> 1][16 * (blk & 1) + 2 * i + 1])), l2, nm2);
+          o[i] = make_float2(ex2a(x.x), ex2a(x.y));
+        }
+      };
+      exp_block(0, e[0]);
+#pragma unroll
+      for (int blk = 0; blk < 8; ++blk) {
+        if (blk + 1 < 8) exp_block(blk + 1, e[(blk + 1) & 1]);
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc = __fadd2_rn(acc, e[blk & 1][i]);
+          pk[i] = pack_bf16(e[blk & 1][i].x, e[blk & 1][i].y);
+        }
+        tmem_st8_nc(tm + 8 * blk, pk);
+      }
+      float sum = acc.x + acc.y;
+      if (hf == 1) {
+        const float px = ex2a(fmaf(sx, LOG2E, nm));
+        sum += px;
+        pxs[slot * 128 + rl] = px;
+      }
+      sums[(slot * 2 + hf) * 128 + rl] = sum;
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full + 8 * slot);
+      TS(3);
+    }
+#undef TS10
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (tstamp && threadIdx.x == 0) {
+    long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    tstamp[48 + 3 * blockIdx.x] = clock64() - ts_c0;
+    tstamp[48 + 3 * blockIdx.x + 1] = ts_g0;
+    tstamp[48 + 3 * blockIdx.x + 2] = g1;
+  }
+  if (warp == W_MMA) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
-inline int dino_attention_tc9(cudaStream_t st, const bf16* qkv, bf16* out, int B) {
+inline int dino_attention_tc(cudaStream_t st, const bf16* qkv, bf16* out, int B) {
   static bool attr = false;
   if (!attr) {
-    HVLA_CUDA(cudaFuncSetAttribute(attn_tc9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM9));
+    HVLA_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr = true;
   }
   CUtensorMap map, tail, omap;
   HVLA_TRY(make_map_bf16(&map, qkv, (int64_t)B * S_, 3 * DD, 128));
   HVLA_TRY(make_map_bf16(&tail, qkv, (int64_t)B * S_, 3 * DD, 16));
   HVLA_TRY(make_map_bf16(&omap, out, (int64_t)B * S_, DD, 32));
-  const int n_items = B * DH;
-  const int slots = 2 * num_sms();
-  const int split = (2 * n_items <= slots) ? 1 : 0;          // small batches: one query tile per CTA
-  const int n_units = split ? 2 * n_items : n_items;
-  const int grid = n_units < slots ? n_units : slots;
+  const int n_tiles = 2 * B * DH;
+  const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
   ProfScope ps(st, "dino_attention");
   static long long* d_ts = nullptr;
-  const bool ts = getenv("HVLA_ATTN_TS") != nullptr;            // phase timestamps of CTA 0 (experiments)
-  if (ts && !d_ts) { cudaMalloc(&d_ts, 48 * sizeof(long long)); cudaMemset(d_ts, 0, 48 * sizeof(long long)); }
-  int dbg = 0;
-  if (const char* e = getenv("HVLA_ATTN_DEBUG")) dbg = atoi(e);      // timing experiments only (results are wrong when set)
-  launch_k(attn_tc9_kernel, dim3(grid), dim3(NT9), (size_t)SMEM9, st, map, tail, omap, n_units, split | (dbg << 4),
-           ts ? d_ts : (long long*)nullptr, out);
+  const bool ts = getenv("HVLA_ATTN_TS") != nullptr;            // experiments: phase timestamps of CTA 0, cycle counts of every CTA
+  if (ts && !d_ts) { cudaMalloc(&d_ts, 1024 * sizeof(long long)); cudaMemset(d_ts, 0, 1024 * sizeof(long long)); }
+  launch_k(attn_tc_kernel, dim3(grid), dim3(NTHREADS), (size_t)SMEM_BYTES, st, map, tail, omap, n_tiles, ts ? d_ts : (long long*)nullptr, out);
   if (ts) {
-    long long h[48];
+    long long h[1024];
     cudaMemcpy(h, d_ts, sizeof h, cudaMemcpyDeviceToHost);
+    long long cmin = 1LL << 60, cmax = 0, g0 = 1LL << 62, g1 = 0, csum = 0;
+    for (int c = 0; c < grid; ++c) {
+      const long long cy = h[48 + 3 * c];
+      cmin = cy < cmin ? cy : cmin; cmax = cy > cmax ? cy : cmax; csum += cy;
+      g0 = h[48 + 3 * c + 1] < g0 ? h[48 + 3 * c + 1] : g0;
+      g1 = h[48 + 3 * c + 2] > g1 ? h[48 + 3 * c + 2] : g1;
+    }
+    fprintf(stderr, "attn_tc CTAs %d: cycles min %lld avg %lld max %lld | wall %lld ns first start -> last end (%.0f MHz)\n", grid, cmin, csum / grid, cmax,
+            g1 - g0, 1e3 * cmax / (double)(g1 - g0));
     for (int n = 0; n < 6; ++n) {
       const long long* t = h + n * 8;
-      fprintf(stderr, "ts9 tile %d: start %lld | s_full +%lld pass1 +%lld pass2 +%lld o_full +%lld epi +%lld\n", n, t[0] - h[0], t[1] - t[0],
-              t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4]);
+      fprintf(stderr, "attn_tc tile %d: start %lld | s_full +%lld max +%lld exp +%lld\n", n, t[0] - h[0], t[1] - t[0], t[2] - t[1], t[3] - t[2]);
     }
   }
-  HVLA_LAUNCH_CHECK("attn_tc9");
+  HVLA_LAUNCH_CHECK("attn_tc");
   return HVLA_OK;
 }
 
-}  // namespace attn9
-
+}  // namespace attn_tc
 }  // namespace hvla

@@ -254,7 +254,6 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
   const bool simt_gemm = env_flag("HVLA_DEBUG_SIMT_GEMM");   // debugging aid: CUDA-core GEMMs on the bf16 data
   const bool simt_attn = env_flag("HVLA_DEBUG_SIMT_ATTN");
   const bool mma_attn = env_flag("HVLA_ATTN_MMA");           // A/B switch: warp-level mma.sync attention instead of tcgen05
-  const bool attn_v7 = env_flag("HVLA_ATTN_V7");             // A/B switch: one CTA per SM with two softmax groups (previous design)
   const bool one_cta = env_flag("HVLA_GEMM_1CTA");           // A/B switch: single-CTA 128x256 tiles instead of CTA pairs
   {
     const int64_t total = (int64_t)B * NPATCH * PATCH_KP;
@@ -301,10 +300,8 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
       HVLA_TRY((attention_simt<bf16, bf16>(st, ap, DHD)));
     } else if (mma_attn) {
       HVLA_TRY(attn::dino_attention(st, QKV, ATT, B));
-    } else if (attn_v7) {
-      HVLA_TRY(attn5::dino_attention_tc(st, QKV, ATT, B));
     } else {
-      HVLA_TRY(attn9::dino_attention_tc9(st, QKV, ATT, B));
+      HVLA_TRY(attn_tc::dino_attention_tc(st, QKV, ATT, B));
     }
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
@@ -634,8 +631,7 @@ int hvla_dino_attention(hvla_stream_t stream, const void* qkv, void* out, int B,
   if (!qkv || !out || B <= 0) return fail(HVLA_ERR_ARG, "hvla_dino_attention: bad argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (impl == 0) return attn::dino_attention(st, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B);
-  if (impl == 1) return attn5::dino_attention_tc(st, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B);
-  return attn9::dino_attention_tc9(st, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B);
+  return attn_tc::dino_attention_tc(st, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), B);
 }
 
 int64_t hvla_postprocess_state_floats(void) { return post::STATE_FLOATS; }

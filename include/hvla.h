@@ -114,8 +114,7 @@ int hvla_act_host(hvla_stream_t stream, const float* dino_vec, const void* dino_
 int hvla_gemm_bf16(hvla_stream_t stream, const void* A, const void* Wt, const float* bias, void* C,
                    int M, int N, int K, int act);
 /* DINOv2 self-attention alone: qkv [B*257, 2304] bf16 (q | k | v, q pre-divided by sqrt(64)) -> out [B*257, 768] bf16.
- * impl 0 = warp-level mma.sync kernel, 1 = tcgen05/TMEM kernel with one CTA per SM, 2 = tcgen05/TMEM kernel with two CTAs
- * per SM (the one the pipeline uses). */
+ * impl 0 = warp-level mma.sync kernel, 1 = tcgen05/TMEM kernel (the one the pipeline uses). */
 int hvla_dino_attention(hvla_stream_t stream, const void* qkv, void* out, int B, int impl);
 /* ---- batched action post-processing: replaces the host code after the model call in
  * InferenceWrapper.step (data/utils/hypervla_interface.py:219-300) and BatchActionEnsembler

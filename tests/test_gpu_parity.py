@@ -115,10 +115,10 @@ def test_tcgen05_gemm_against_torch(torch_cuda, shape):
     assert err < 1e-2
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 1])
 @pytest.mark.parametrize("B", [1, 3, 13, 40])
 def test_dino_attention_kernels_against_torch(torch_cuda, impl, B):
-    """The attention kernels (mma.sync, tcgen05/TMEM one and two CTAs per SM; B = 1, 3 take the per-tile split) alone against softmax(q k^T) v in fp32."""
+    """Both attention kernels (mma.sync and tcgen05/TMEM; B = 1, 3: fewer tiles than SMs, 13 / 40: items cut by range boundaries) alone against softmax(q k^T) v in fp32."""
     torch = torch_cuda
     from hvla import _native as N
     gen = torch.Generator(device="cuda").manual_seed(100 + B)

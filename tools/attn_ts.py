@@ -15,6 +15,6 @@ st = int(torch.cuda.current_stream().cuda_stream)
 qkv = (torch.randn(B * 257, 2304, device="cuda") * 0.5).to(torch.bfloat16)
 out = torch.empty(B * 257, 768, device="cuda", dtype=torch.bfloat16)
 for _ in range(3):
-    N.check(lib.hvla_dino_attention(st, qkv.data_ptr(), out.data_ptr(), B, 2), "attn")
+    N.check(lib.hvla_dino_attention(st, qkv.data_ptr(), out.data_ptr(), B, 1), "attn")
     torch.cuda.synchronize()
     print("----", file=sys.stderr)
