@@ -86,26 +86,27 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.cpu_sample
     steps, warm = max(1, args.steps), max(0, args.warmup)
     from hvla import metadata as M, params as P, synthetic as S
     from oracle import hypervla_oracle as O
     params = P.init_params(2025, "P1")
     dino = P.dino_tree_from_params(params)
     pos = O.interpolate_pos_table(dino["embeddings"]["position_embeddings"])
+    # exactly K timed + W warm-up steps; the per-step sample (n images of the workload) is sized so the run stays within ~150 s
+    probe = S.make_inputs(2, 1, 1)
+    lang = probe["instruction_dict"]["language_instruction"]
+    gen, _ = O.generate(params, lang["token_embedding"], lang["attention_mask"], probe["initial_state"]["patch_embeddings"][:, 0],
+                        generated_paths=M.generated_leaves_canonical())
+    t0 = time.perf_counter()
+    O.sample_actions(dino, O.to_tree(gen), probe["images"][:, 0], pos_table=pos)
+    one = time.perf_counter() - t0
+    n = int(max(1, min(args.cpu_sample, 150.0 / ((steps + warm) * max(one, 1e-3)))))
     inp = S.make_inputs(2, n, n)
     lang = inp["instruction_dict"]["language_instruction"]
     gen, _ = O.generate(params, lang["token_embedding"], lang["attention_mask"], inp["initial_state"]["patch_embeddings"][:, 0],
                         generated_paths=M.generated_leaves_canonical())
     tree = O.to_tree(gen)
     imgs = inp["images"][:, 0]
-    # bound the run: at most ~90 s of CPU work in total
-    t0 = time.perf_counter()
-    O.sample_actions(dino, tree, imgs, pos_table=pos)
-    one = time.perf_counter() - t0
-    budget = 90.0
-    steps = max(1, min(steps, int(budget / max(one, 1e-3)) - 1))
-    warm = min(warm, 1)
     for _ in range(warm):
         O.sample_actions(dino, tree, imgs, pos_table=pos)
     t0 = time.perf_counter()
