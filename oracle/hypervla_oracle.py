@@ -11,16 +11,23 @@ function, each citing the reference file:line it follows (paths relative to
 rounding noise of both this oracle and the CUDA path.
 
 PARITY STATUS
-  * The reference ships no tests, fixtures or golden vectors, and JAX/Flax
-    are not installable here (F3), so the oracle cannot be pinned against the reference
-    itself: **parity unpinned** for the HyperVLA-specific glue (hypernetwork.py,
-    transformer.py, base_vit.py, action_heads.py), which is restated from the source.
+  * The reference ships no tests, fixtures or golden vectors and JAX/Flax
+    are not installable here (F3).  The oracle is pinned instead against the reference's
+    OWN hot-path code executed in this container through `oracle/refshim/` (NumPy
+    stand-ins for the jax/flax primitives only): committed fixtures
+    tests/golden/ref_*.npz (generator: tests/golden/make_ref_golden.py), checked in
+    tests/test_reference_pin.py.  Pinned that way: hypernetwork.py, transformer.py,
+    base_vit.py, base_network.py, action_heads.py (MixActionHead), model.py
+    (from_config / init_base_net / create_tasks / sample_actions).
+  * Restated rather than executed (flax 0.8.1 / jax sources are not on this box): Dense,
+    LayerNorm, MultiHeadDotProductAttention, gelu — once in refshim/flaxlite.py for the
+    reference run and once below for the oracle.
   * The DINOv2 arithmetic lives in un-vendored `transformers==4.50.0`
     (`FlaxDinov2Module`, requirements_full_install.txt:22).  Its block stack is pinned
-    here against the *torch* `transformers.Dinov2Model` of the local transformers 5.5.0
+    against the *torch* `transformers.Dinov2Model` of the local transformers 5.5.0
     (same published architecture) in tests/test_oracle_dinov2_torch.py; only the
     bicubic position-table interpolation (`jax.image.scale_and_translate`) remains
-    unpinned and is isolated in `interpolate_pos_table`.
+    **unpinned** and is isolated in `interpolate_pos_table`.
 """
 from __future__ import annotations
 

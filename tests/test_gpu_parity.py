@@ -16,6 +16,8 @@ pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": 1e-5, "bf16": 2e-2}
 CASES = {"c1_b1_t1": (1, 1, 1), "c2_b3_t3": (2, 3, 3), "c5_b6_t2": (5, 6, 2)}
+# the same cases against fixtures produced by executing the reference's own code (tests/golden/make_ref_golden.py)
+CASES.update({"ref_" + k: v for k, v in list(CASES.items())})
 
 
 def rel_err(x, ref):
