@@ -25,6 +25,9 @@ using attn::ldsm_x4;
 using attn::ldsm_x4_t;
 using attn::mma_bf16;
 using attn::pack2;
+using attn::cp_async16;
+using attn::cp_async_commit;
+using attn::cp_async_wait;
 
 constexpr int NW = 9, NT = NW * 32;
 constexpr int XLD = 72;                 // fp32 residual row stride (floats): conflict-free float2 C-fragment access
@@ -45,7 +48,10 @@ constexpr int V_LN0S = 0, V_LN0B = 64, V_BQ = 128, V_BK = 192, V_BV = 256, V_BO 
               V_B1 = 640, V_COUNT = 704;
 constexpr int OFF_ACT = OFF_VEC + V_COUNT * 4;          // action-token scratch (fp32)
 constexpr int A_X = 0, A_XN = 64, A_Q = 128, A_K = 192, A_V = 256, A_O = 320, A_H = 384, A_P = 512, A_COUNT = 512 + 264;
-constexpr int SMEM = OFF_ACT + A_COUNT * 4;
+constexpr int OFF_VECB = OFF_ACT + A_COUNT * 4;       // the layer's vectors as they arrive (bf16), converted into VEC
+constexpr int SMEM = OFF_VECB + V_COUNT * 2;
+constexpr int ELD = 72;                               // staged embedding chunk [256][72] bf16 (two of them fill the X region)
+static_assert(2 * 256 * ELD * 2 <= OFF_K, "embedding chunks are double-buffered in the (not yet written) X region");
 static_assert(768 * PLD * 2 <= OFF_VEC - OFF_K, "projection kernel staging must fit in the K/V/W region");
 static_assert(SMEM <= 232448, "shared memory budget");
 
@@ -153,6 +159,17 @@ __device__ __forceinline__ void stage_matrix(uint8_t* smem, int off, const bf16*
     *reinterpret_cast<uint4*>(smem + off + (r * ld + c) * 2) = v;
   }
 }
+// the same through cp.async (16-byte pieces, no register round trip): issue everything, wait once
+__device__ __forceinline__ void stage_matrix_async(uint32_t sdst, const bf16* g, int rows, int cols, int ld) {
+  const int per_row = cols / 8;
+  for (int i = threadIdx.x; i < rows * per_row; i += NT) {
+    const int r = i / per_row, c = (i % per_row) * 8;
+    cp_async16(sdst + (uint32_t)((r * ld + c) * 2), g + (int64_t)r * cols + c);
+  }
+}
+__device__ __forceinline__ void stage_vec_async(uint32_t sdst, const bf16* g, int n) {   // n % 8 == 0
+  if (threadIdx.x < n / 8) cp_async16(sdst + threadIdx.x * 16, g + threadIdx.x * 8);
+}
 __device__ __forceinline__ void stage_vec(float* dst, const bf16* g, int n) {
   for (int i = threadIdx.x; i < n; i += NT) dst[i] = __bfloat162float(g[i]);
 }
@@ -180,14 +197,57 @@ __device__ __forceinline__ void warp_ln64(const float* x, const float* sc, const
   out[lane + 32] = (v1 - m) * (r * sc[lane + 32]) + bi[lane + 32];
 }
 
-__global__ void __launch_bounds__(NT, 1)
+// phase timestamps of CTA 0 (experiments only: build with HVLA_NVCC_EXTRA=-DHVLA_BASE_TS)
+#ifdef HVLA_BASE_TS
+#define BASE_TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) ts_[i] = clock64(); } while (0)
+#else
+#define BASE_TS(i) do { } while (0)
+#endif
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// copy 16 bytes of this CTA's shared memory to the same offset of CTA `peer` of the cluster (distributed shared memory)
+__device__ __forceinline__ void copy16_to_peer(uint32_t local_addr, uint32_t peer) {
+  uint32_t r, v0, v1, v2, v3;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(local_addr) : "memory");
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(peer));
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(r), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+}
+// all warps of the CTA meet on the (sleeping) CTA barrier first, so nobody spins on the cluster barrier while
+// a slower warp of the same SM is still working
+__device__ __forceinline__ void cluster_sync_after_cta() {
+  __syncthreads();
+  cluster_barrier();
+}
+
+// C = CTAs per environment (a thread-block cluster): each CTA owns 256/C patch rows (residual stream, Q, MLP) and
+// broadcasts the K/V rows it computes into every CTA of the cluster through distributed shared memory; the action
+// token lives in rank 0.  C = 2 puts 128 CTAs on the 148 SMs at 64 envs and halves the batch-1 latency.
+template <int C>
+__global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(NT, 1)
 base_fused_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ weights, const int* __restrict__ tidx,
                   float* __restrict__ action, float* __restrict__ logit_out) {
+  constexpr int ROWS = 256 / C;          // patch rows of this CTA
+  constexpr int MT = 2 / C;              // 16-row m-tiles per patch warp
+  static_assert(C == 1 || C == 2, "cluster size");
   pdl_trigger();
   pdl_wait();
+#ifdef HVLA_BASE_TS
+  long long ts_[16];
+#endif
+  BASE_TS(0);
   extern __shared__ __align__(16) uint8_t smem[];
   typedef GenLayout G;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / C;
+  const uint32_t rank = C > 1 ? cluster_rank() : 0u;
+  const int grow0 = (int)rank * ROWS;     // first global patch row of this CTA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bf16* wrow = weights + (int64_t)(tidx ? tidx[b] : b) * NGP;
   const bf16* erow = emb + ((int64_t)b * DTOK + 1) * DD;     // skip the CLS row (base_vit.py:122)
@@ -200,81 +260,108 @@ base_fused_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ weights
   const uint32_t sK = sbase + OFF_K, sV = sbase + OFF_V;
 
   // ------------------------------------------------------------------ P0: projection + pos-emb
-  stage_matrix(smem, OFF_K, wrow + G::proj_w, DD, BD, PLD);
+  // The 768x64 kernel is staged once; the sample's 256x768 embeddings stream through two 256x64 chunks
+  // (cp.async, double-buffered in the X region, which is only written after the last chunk is consumed).
+  const uint32_t sE = sbase + OFF_X;
+  auto stage_emb = [&](int kc) {
+    const uint32_t dst = sE + (uint32_t)((kc & 1) * 256 * ELD * 2);
+    for (int i = threadIdx.x; i < ROWS * 8; i += NT) {
+      const int r = i >> 3, c = (i & 7) * 8;
+      cp_async16(dst + (uint32_t)((r * ELD + c) * 2), erow + (int64_t)(grow0 + r) * DD + kc * 64 + c);
+    }
+  };
+  stage_matrix_async(sK, wrow + G::proj_w, DD, BD, PLD);
+  stage_emb(0);
+  cp_async_commit();
   stage_vec(VEC, wrow + G::proj_b, BD);
-  __syncthreads();
-  if (warp < 8) {
-    float acc[2][8][4];
-    zero8(acc[0]); zero8(acc[1]);
-    const int r0 = warp * 32 + (lane >> 2);
-    const bf16* e0 = erow + (int64_t)r0 * DD + (lane & 3) * 2;
-#pragma unroll 2
-    for (int ks = 0; ks < DD / 16; ++ks) {
-      uint32_t a[2][1][4];
+  BASE_TS(1);
+  float acc[MT][8][4];
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const bf16* p = e0 + (int64_t)t * 16 * DD + ks * 16;
-        a[t][0][0] = __ldg(reinterpret_cast<const uint32_t*>(p));
-        a[t][0][1] = __ldg(reinterpret_cast<const uint32_t*>(p + 8 * DD));
-        a[t][0][2] = __ldg(reinterpret_cast<const uint32_t*>(p + 8));
-        a[t][0][3] = __ldg(reinterpret_cast<const uint32_t*>(p + 8 * DD + 8));
-      }
+  for (int t = 0; t < MT; ++t) zero8(acc[t]);
+#pragma unroll 1
+  for (int kc = 0; kc < DD / 64; ++kc) {
+    cp_async_wait<0>();
+    __syncthreads();                                   // chunk kc landed; everyone is done with chunk kc-1
+    if (kc + 1 < DD / 64) { stage_emb(kc + 1); cp_async_commit(); }
+    if (warp < 8) {
+      const uint32_t src = sE + (uint32_t)((kc & 1) * 256 * ELD * 2);
       const int i = lane >> 3;
 #pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        uint32_t b0, b1, b2, b3;
-        const uint32_t addr = sK + (uint32_t)(((ks * 16 + (i & 1) * 8 + (lane & 7)) * PLD + (np * 2 + (i >> 1)) * 8) * 2);
-        ldsm_x4_t(addr, b0, b1, b2, b3);
-        mma_bf16(acc[0][2 * np], a[0][0], b0, b1);
-        mma_bf16(acc[0][2 * np + 1], a[0][0], b2, b3);
-        mma_bf16(acc[1][2 * np], a[1][0], b0, b1);
-        mma_bf16(acc[1][2 * np + 1], a[1][0], b2, b3);
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a[MT][4];
+#pragma unroll
+        for (int t = 0; t < MT; ++t)
+          ldsm_x4(src + (uint32_t)((((warp * MT + t) * 16 + (lane & 7) + (i & 1) * 8) * ELD + ks * 16 + (i >> 1) * 8) * 2),
+                  a[t][0], a[t][1], a[t][2], a[t][3]);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          uint32_t b0, b1, b2, b3;
+          const uint32_t addr = sK + (uint32_t)(((kc * 64 + ks * 16 + (i & 1) * 8 + (lane & 7)) * PLD + (np * 2 + (i >> 1)) * 8) * 2);
+          ldsm_x4_t(addr, b0, b1, b2, b3);
+#pragma unroll
+          for (int t = 0; t < MT; ++t) {
+            mma_bf16(acc[t][2 * np], a[t], b0, b1);
+            mma_bf16(acc[t][2 * np + 1], a[t], b2, b3);
+          }
+        }
       }
     }
+  }
+  __syncthreads();                                     // the X region is free: every warp has consumed the last chunk
+  if (warp < 8) {
     const bf16* pos = wrow + G::pos;
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int row0 = warp * 32 + t * 16;
+    for (int t = 0; t < MT; ++t) {
+      const int row0 = (warp * MT + t) * 16;             // local row in X
       add_bias(acc[t], VEC, lane);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int col = j * 8 + (lane & 3) * 2;
-        const __nv_bfloat162 pa = *reinterpret_cast<const __nv_bfloat162*>(pos + (row0 + (lane >> 2)) * BD + col);
-        const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(pos + (row0 + 8 + (lane >> 2)) * BD + col);
+        const __nv_bfloat162 pa = *reinterpret_cast<const __nv_bfloat162*>(pos + (grow0 + row0 + (lane >> 2)) * BD + col);
+        const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(pos + (grow0 + row0 + 8 + (lane >> 2)) * BD + col);
         acc[t][j][0] += __low2float(pa); acc[t][j][1] += __high2float(pa);
         acc[t][j][2] += __low2float(pb); acc[t][j][3] += __high2float(pb);
       }
       store_x(X, row0, lane, acc[t]);
     }
-  } else {
+  } else if (rank == 0) {
     // action token: zeros + pos_embedding[256]  (base_vit.py:182-204)
     const bf16* pos = wrow + G::pos + 256 * BD;
     ACT[A_X + lane] = __bfloat162float(pos[lane]);
     ACT[A_X + lane + 32] = __bfloat162float(pos[lane + 32]);
   }
   __syncthreads();
+  BASE_TS(2);
 
   // ------------------------------------------------------------------ encoder blocks
   for (int l = 0; l < BL; ++l) {
     const bf16* lw = wrow + G::layers + (int64_t)l * G::layer_size;
-    stage_matrix(smem, OFF_WQ, lw + G::wq, 64, 64, KLD);
-    stage_matrix(smem, OFF_WK, lw + G::wk, 64, 64, KLD);
-    stage_matrix(smem, OFF_WV, lw + G::wv, 64, 64, KLD);
-    stage_matrix(smem, OFF_WO, lw + G::wo, 64, 64, KLD);
-    stage_matrix(smem, OFF_W0, lw + G::w0, 64, 128, W0LD);
-    stage_matrix(smem, OFF_W1, lw + G::w1, 128, 64, KLD);
-    stage_vec(VEC + V_LN0S, lw + G::ln0_s, 64); stage_vec(VEC + V_LN0B, lw + G::ln0_b, 64);
-    stage_vec(VEC + V_BQ, lw + G::bq, 64); stage_vec(VEC + V_BK, lw + G::bk, 64);
-    stage_vec(VEC + V_BV, lw + G::bv, 64); stage_vec(VEC + V_BO, lw + G::bo, 64);
-    stage_vec(VEC + V_LN1S, lw + G::ln1_s, 64); stage_vec(VEC + V_LN1B, lw + G::ln1_b, 64);
-    stage_vec(VEC + V_B0, lw + G::b0, 128); stage_vec(VEC + V_B1, lw + G::b1, 64);
+    stage_matrix_async(sbase + OFF_WQ, lw + G::wq, 64, 64, KLD);
+    stage_matrix_async(sbase + OFF_WK, lw + G::wk, 64, 64, KLD);
+    stage_matrix_async(sbase + OFF_WV, lw + G::wv, 64, 64, KLD);
+    stage_matrix_async(sbase + OFF_WO, lw + G::wo, 64, 64, KLD);
+    stage_matrix_async(sbase + OFF_W0, lw + G::w0, 64, 128, W0LD);
+    stage_matrix_async(sbase + OFF_W1, lw + G::w1, 128, 64, KLD);
+    {
+      const uint32_t sv = sbase + OFF_VECB;
+      stage_vec_async(sv + V_LN0S * 2, lw + G::ln0_s, 128);     // ln0 scale | bias are adjacent in the row
+      stage_vec_async(sv + V_BQ * 2, lw + G::bq, 64); stage_vec_async(sv + V_BK * 2, lw + G::bk, 64);
+      stage_vec_async(sv + V_BV * 2, lw + G::bv, 64); stage_vec_async(sv + V_BO * 2, lw + G::bo, 64);
+      stage_vec_async(sv + V_LN1S * 2, lw + G::ln1_s, 128);     // ln1 scale | bias
+      stage_vec_async(sv + V_B0 * 2, lw + G::b0, 128); stage_vec_async(sv + V_B1 * 2, lw + G::b1, 64);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
+    for (int i = threadIdx.x; i < V_COUNT; i += NT) VEC[i] = __bfloat162float(reinterpret_cast<const bf16*>(smem + OFF_VECB)[i]);
+    __syncthreads();
+    BASE_TS(3 + 3 * l);
 
     // ---- phase A: K and V of every token -------------------------------------------------------
     if (warp < 8) {
 #pragma unroll 1
-      for (int t = 0; t < 2; ++t) {
-        const int row0 = warp * 32 + t * 16;
+      for (int t = 0; t < MT; ++t) {
+        const int row0 = (warp * MT + t) * 16;
         float c[8][4];
         load_x(X, row0, lane, c);
         uint32_t a[4][4];
@@ -284,15 +371,26 @@ base_fused_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ weights
           zero8(c);
           gemm_tile<8, 4>(c, a, sbase + (kv ? OFF_WV : OFF_WK), KLD, 0, 0, lane);
           add_bias(c, VEC + (kv ? V_BV : V_BK), lane);
-          bf16* dst = (kv ? Vs : Ks) + (row0 + (lane >> 2)) * KLD + (lane & 3) * 2;
+          // K/V rows are indexed globally; every CTA of the cluster gets a copy
+          const uint32_t dst = (kv ? sV : sK) + (uint32_t)(((grow0 + row0 + (lane >> 2)) * KLD + (lane & 3) * 2) * 2);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            *reinterpret_cast<uint32_t*>(dst + j * 8) = pack2(c[j][0], c[j][1]);
-            *reinterpret_cast<uint32_t*>(dst + 8 * KLD + j * 8) = pack2(c[j][2], c[j][3]);
+            const uint32_t lo = pack2(c[j][0], c[j][1]), hi = pack2(c[j][2], c[j][3]);
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + j * 16), "r"(lo) : "memory");
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + 8 * KLD * 2 + j * 16), "r"(hi) : "memory");
+          }
+          if (C > 1) {                                   // the warp's 16 x 64 tile goes to the peer in 16-byte pieces
+            __syncwarp();
+            const uint32_t tile = (kv ? sV : sK) + (uint32_t)((grow0 + row0) * KLD * 2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int piece = lane + 32 * i;               // 16 rows x 8 pieces
+              copy16_to_peer(tile + (uint32_t)((piece >> 3) * KLD * 2 + (piece & 7) * 16), rank ^ 1u);
+            }
           }
         }
       }
-    } else {
+    } else if (rank == 0) {
       warp_ln64(ACT + A_X, VEC + V_LN0S, VEC + V_LN0B, ACT + A_XN, lane);
       __syncwarp();
 #pragma unroll
@@ -303,14 +401,15 @@ base_fused_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ weights
         ACT[A_V + n] = gemv_col<64>(ACT + A_XN, reinterpret_cast<const bf16*>(smem + OFF_WV), KLD, n) + VEC[V_BV + n];
       }
     }
-    __syncthreads();
+    if (C > 1) cluster_sync_after_cta(); else __syncthreads();      // all 256 K/V rows are in place (in every CTA)
+    BASE_TS(4 + 3 * l);
 
     // ---- phase B ------------------------------------------------------------------------------------
     if (warp < 8) {
       if (l < BL - 1) {
 #pragma unroll 1
-        for (int t = 0; t < 2; ++t) {
-          const int row0 = warp * 32 + t * 16;
+        for (int t = 0; t < MT; ++t) {
+          const int row0 = (warp * MT + t) * 16;
           float c[8][4];
           load_x(X, row0, lane, c);
           uint32_t a[4][4];
@@ -419,8 +518,11 @@ base_fused_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ weights
           store_x(X, row0, lane, c);
         }
       }
-    } else {
+    } else if (rank == 0) {
       // ---- action token (fp32, CUDA cores): attends to 256 patch keys + itself ----------------------------
+#ifdef HVLA_BASE_TS
+      const long long tb0_ = clock64();
+#endif
       float* P = ACT + A_P;
 #pragma unroll 1
       for (int h = 0; h < BH; ++h) {
@@ -486,12 +588,16 @@ base_fused_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ weights
         ACT[A_X + n] += v;
       }
       __syncwarp();
+#ifdef HVLA_BASE_TS
+      if (blockIdx.x == 0 && lane == 0) printf("base_ts action-token warp, layer %d phase B: %lld cycles\n", l, clock64() - tb0_);
+#endif
     }
-    __syncthreads();
+    if (C > 1) cluster_sync_after_cta(); else __syncthreads();      // nobody reads this layer's K/V any more
+    BASE_TS(5 + 3 * l);
   }
 
   // ------------------------------------------------------------------ encoder_norm + mix head (warp 8)
-  if (warp == 8) {
+  if (warp == 8 && rank == 0) {
     const float v0 = ACT[A_X + lane], v1 = ACT[A_X + lane + 32];
     float s = v0 + v1, q = fmaf(v0, v0, v1 * v1);
 #pragma unroll
@@ -518,16 +624,27 @@ base_fused_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ weights
       if (logit_out) logit_out[(int64_t)b * AH + j] = a;
     }
   }
+#ifdef HVLA_BASE_TS
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    printf("base_ts:");
+    for (int i = 1; i < 15; ++i) printf(" %lld", ts_[i] - ts_[i - 1]);
+    printf("\n");
+  }
+#endif
 }
 
 inline int base_act_bf16(cudaStream_t st, const bf16* emb, const bf16* weights, const int* tidx, int B, float* action, float* logit) {
   static bool attr = false;
   if (!attr) {
-    HVLA_CUDA(cudaFuncSetAttribute(base_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    HVLA_CUDA(cudaFuncSetAttribute(base_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    HVLA_CUDA(cudaFuncSetAttribute(base_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr = true;
   }
+  static const int force = getenv("HVLA_BASE_CLUSTER") ? atoi(getenv("HVLA_BASE_CLUSTER")) : 0;   // experiments: 1 or 2 CTAs per environment
+  const int c = force ? force : 2;
   ProfScope ps(st, "base_fused");
-  launch_k(base_fused_kernel, dim3(B), dim3(NT), (size_t)SMEM, st, emb, weights, tidx, action, logit);
+  if (c == 2) launch_k(base_fused_kernel<2>, dim3(B * 2), dim3(NT), (size_t)SMEM, st, emb, weights, tidx, action, logit);
+  else launch_k(base_fused_kernel<1>, dim3(B), dim3(NT), (size_t)SMEM, st, emb, weights, tidx, action, logit);
   HVLA_LAUNCH_CHECK("base_fused");
   return HVLA_OK;
 }
