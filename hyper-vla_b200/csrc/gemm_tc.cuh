@@ -32,6 +32,9 @@ struct EpiP {
   float qscale;        // EPI 0: columns < qcols are multiplied by qscale (query pre-scaling)
   int qcols;
   int debug;           // experiment knob (hvla_gemm_bf16 only): 1 = handshake only, 2 = TMEM loads only, 4 = no global stores
+  float* part;         // EPI 2: scratch for split-K partial products (null: never split), see "split-K partial products"
+  size_t part_bytes;   //        its size
+  int* splits_used;    //        host out: number of K splits of this launch (1 = none)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -82,6 +85,13 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ---- split-K partial products -------------------------------------------------------------------------------
+// At small batch the residual GEMMs (N = 768) have only a handful of output tiles; their K range is then split
+// over several CTA pairs.  Split 0 reduce-adds ls*(acc+bias) into the fp32 residual stream as usual; split s > 0
+// writes its ls*acc to block s-1 of a scratch buffer [splits-1][M_pad][N] with a plain TMA store, and the LayerNorm
+// that always follows adds the blocks to the stream in a fixed order (simt_kernels.cuh: layernorm768_kernel).
+// Deterministic, no inter-CTA waiting.
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -260,7 +270,9 @@ constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 2048;
 template <int EPI>
 __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensorMap* tmO, float* sepi, uint32_t sstage,
                                                   uint32_t tfull_bar_addr, uint32_t aph, int as, uint32_t tmem_base, int m0,
-                                                  int n0, int warp, int lane, bool add_bias = true) {
+                                                  int n0, int warp, int lane, int split = 0, const CUtensorMap* tmP = nullptr,
+                                                  int part_row0 = 0) {
+  const bool add_bias = split == 0;
   const int ew = warp - 2;
   const int quarter = warp & 3;
   const int half = ew >> 2;
@@ -337,7 +349,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_reduce_add_2d(tmO, slab, col + u * 16, row0);
+          if (split == 0) tma_reduce_add_2d(tmO, slab, col + u * 16, row0);
+          else tma_store_2d(tmP, slab, col + u * 16, part_row0 + quarter * 32);
           bulk_commit();
         }
       }

@@ -74,7 +74,8 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmO, EpiP ep, int M, int N, int K, int splits) {
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP, EpiP ep, int M, int N, int K,
+                int splits) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -100,6 +101,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
+    if (splits > 1) tma_prefetch_desc(&tmP);
     for (int s = 0; s < STAGES2; ++s) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
@@ -171,7 +173,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int tile = unit / splits;
       const int m0 = (tile / n_tiles_n) * BM2 + (int)rank * 128, n0 = (tile % n_tiles_n) * BN;
       if (EPI == EPI_PATCH_F32) epilogue_tile_direct<EPI>(ep, sepi, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, M, warp, lane);
-      else epilogue_tile_tma<EPI>(ep, &tmO, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane, unit % splits == 0);
+      else {
+        const int split = unit % splits;          // split s > 0 stores to block s-1 of the partial-product scratch
+        epilogue_tile_tma<EPI>(ep, &tmO, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane, split, &tmP,
+                               (split - 1) * n_tiles_m * BM2 + m0);
+      }
       if (lane == 0) mbar_arrive_remote(tempty_bar + 8 * as, 0);
     }
     if (lane == 0) bulk_wait0();
@@ -195,21 +201,25 @@ inline int launch_one2(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap
   }
   const int tiles0 = ((M + BM2 - 1) / BM2) * (N / BN);
   int pairs = num_sms() / 2;
-  // split K over several CTA pairs when there are too few tiles to fill the chip (small batches); only the
-  // residual epilogue can do that for free: its TMA reduce-add accumulates the partial products in the fp32 stream
-  // OFF by default: the order of the fp32 reduce-adds of different splits is not fixed, which would make small batches
-  // non-deterministic and batch-size dependent in the last bits (tests require bit-exact batch invariance).
+  // Split K over several CTA pairs when there are too few tiles to fill the chip (small batches: 6 tiles at batch 1).
+  // Only the residual GEMMs do it (see "split-K partial products" in gemm_tc.cuh): deterministic, but the last bits
+  // differ from the unsplit computation of the same rows in a large batch.  HVLA_GEMM_SPLITK=0 turns it off.
   int splits = 1;
-  static const bool splitk = getenv("HVLA_GEMM_SPLITK") != nullptr;
-  if (EPI == EPI_RESIDUAL_F32 && splitk) {
+  static const bool splitk = !(getenv("HVLA_GEMM_SPLITK") && getenv("HVLA_GEMM_SPLITK")[0] == '0');
+  CUtensorMap mp = mo;
+  if (EPI == EPI_RESIDUAL_F32 && splitk && ep.part != nullptr) {
     const int nkb = K / BK;
-    while (splits < 4 && tiles0 * splits * 2 <= pairs && nkb % (splits * 2) == 0) splits *= 2;
+    const size_t block = (size_t)((M + BM2 - 1) / BM2) * BM2 * (size_t)N * 4;
+    while (splits < 8 && tiles0 * splits * 2 <= pairs && nkb % (splits * 2) == 0 && block * (splits * 2 - 1) <= ep.part_bytes)
+      splits *= 2;
+    if (splits > 1) HVLA_TRY(make_map_out(&mp, ep.part, (int64_t)(splits - 1) * ((M + BM2 - 1) / BM2) * BM2, N, true));
   }
+  if (ep.splits_used) *ep.splits_used = splits;
   const int tiles = tiles0 * splits;
   if (const char* e = getenv("HVLA_GEMM_MAX_PAIRS")) { const int v = atoi(e); if (v > 0 && v < pairs) pairs = v; }   // experiment knob
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
   ProfScope ps(st, "gemm_tc");
-  launch_k(gemm_tc2_kernel<EPI>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM2_BYTES, st, ma, mb, mo, ep, M, N, K, splits);
+  launch_k(gemm_tc2_kernel<EPI>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM2_BYTES, st, ma, mb, mo, mp, ep, M, N, K, splits);
   HVLA_LAUNCH_CHECK("gemm_tc2");
   return HVLA_OK;
 }

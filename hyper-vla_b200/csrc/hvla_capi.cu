@@ -28,13 +28,16 @@ struct Plan {
   // generate region (fp32)
   size_t tp, ip, xc, yc, qkvc, cc, hc, e;
   // DINO region
-  size_t x, y, qkv, att, hid, emb;
+  size_t x, y, qkv, att, hid, emb, part;
   // base region (fp32)
   size_t pt, xb, yb, qkvb, cb, hb;
   // host staging (hvla_act_host)
   size_t img, act, logit, tidx;
   size_t total;
 };
+
+// room for the split-K partial products of one residual GEMM: at most one 256x256 fp32 block per CTA pair
+constexpr size_t PART_BYTES = (size_t)74 * 256 * 256 * 4;
 
 static Plan make_plan(int B, int T, int dtype) {
   Plan p;
@@ -57,6 +60,7 @@ static Plan make_plan(int B, int T, int dtype) {
   p.att = take(M * DD * es);
   p.hid = take(M * DF * es);
   p.emb = take(M * DD * es);
+  p.part = take(dtype == HVLA_BF16 ? PART_BYTES : 0);   // split-K partial products (small batches)
   p.pt = take(Bb * NPATCH * BD * 4);
   p.xb = take(Bb * BTOK * BD * 4);
   p.yb = take(Bb * BTOK * BD * 4);
@@ -251,6 +255,9 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
   bf16* ATT = reinterpret_cast<bf16*>(ws + pl.att);
   bf16* HID = reinterpret_cast<bf16*>(ws + pl.hid);
   bf16* A0 = HID;
+  float* PART = reinterpret_cast<float*>(ws + pl.part);
+  const int64_t part_stride = (int64_t)((M + 255) / 256) * 256 * DD;   // one [M_pad, 768] block per extra K split
+  int splits = 1;                                                       // K splits of the most recent residual GEMM
   const bool simt_gemm = env_flag("HVLA_DEBUG_SIMT_GEMM");   // debugging aid: CUDA-core GEMMs on the bf16 data
   const bool simt_attn = env_flag("HVLA_DEBUG_SIMT_ATTN");
   const bool mma_attn = env_flag("HVLA_ATTN_MMA");           // A/B switch: warp-level mma.sync attention instead of tcgen05
@@ -267,6 +274,7 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
     HVLA_LAUNCH_CHECK("dino_cls_rows");
   }
   auto gemm = [&](const bf16* A, const bf16* Wt, int m, int n, int k, int epi, const tc::EpiP& ep) -> int {
+    if (ep.splits_used) *ep.splits_used = 1;      // only the 2-CTA tensor-core path ever splits K
     if (!simt_gemm) return one_cta ? tc::gemm_tc(st, A, Wt, m, n, k, epi, ep) : tc2::gemm_tc2(st, A, Wt, m, n, k, epi, ep);
     // debug path: same math on CUDA cores (W given transposed)
     return gemm_simt_debug(st, A, Wt, m, n, k, epi, ep);
@@ -288,6 +296,7 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
     const bf16* m = dm + Mx::layers + (int64_t)l * Mx::layer_size;
     LnP ln; memset(&ln, 0, sizeof ln);
     ln.x = X; ln.ldx = DD; ln.y = Y; ln.ldy = DD; ln.scale = v + V::ln1_s; ln.bias = v + V::ln1_b; ln.rows = M; ln.rows_per_batch = 1;
+    ln.part = PART; ln.part_stride = part_stride; ln.nsplit = splits - 1;   // partial products of the previous layer's fc2
     HVLA_TRY((layernorm<float, bf16>(st, ln, DD)));
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
@@ -306,9 +315,11 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
       ep.bias = v + V::bo; ep.out = X; ep.ldo = DD; ep.ls = v + V::ls1;
+      ep.part = PART; ep.part_bytes = PART_BYTES; ep.splits_used = &splits;
       HVLA_TRY(gemm(ATT, m + Mx::wo, M, DD, DD, tc::EPI_RESIDUAL_F32, ep));
     }
     ln.scale = v + V::ln2_s; ln.bias = v + V::ln2_b;
+    ln.nsplit = splits - 1;      // this LayerNorm first folds the split-K partial products into the stream
     HVLA_TRY((layernorm<float, bf16>(st, ln, DD)));
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
@@ -318,11 +329,13 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
       ep.bias = v + V::b2; ep.out = X; ep.ldo = DD; ep.ls = v + V::ls2;
+      ep.part = PART; ep.part_bytes = PART_BYTES; ep.splits_used = &splits;
       HVLA_TRY(gemm(HID, m + Mx::w2, M, DD, DF, tc::EPI_RESIDUAL_F32, ep));
     }
   }
   LnP ln; memset(&ln, 0, sizeof ln);
   ln.x = X; ln.ldx = DD; ln.y = out_emb; ln.ldy = DD; ln.scale = dv + V::lnf_s; ln.bias = dv + V::lnf_b; ln.rows = M; ln.rows_per_batch = 1;
+  ln.part = PART; ln.part_stride = part_stride; ln.nsplit = splits - 1;
   HVLA_TRY((layernorm<float, bf16>(st, ln, DD)));
   return HVLA_OK;
 }

@@ -152,6 +152,7 @@ struct LnP {
   const void* scale; const void* bias; int64_t sS;   // per weight-batch stride (0 = shared)
   const int* widx; int rows_per_batch;
   int rows; float post_div;          // y /= post_div when != 0
+  const float* part; int nsplit; int64_t part_stride;   // 768-wide fp32 path: x += part[s*part_stride + ...], s < nsplit, first
 };
 
 template <typename TS, typename TO, int D>
@@ -197,18 +198,31 @@ __global__ void __launch_bounds__(128) layernorm_kernel(LnP p) {
 
 // DINOv2 LayerNorm: 768-wide fp32 rows (contiguous, shared scale/bias), vectorised; one warp per row.
 template <typename TO>
-__global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restrict__ x, TO* __restrict__ y,
-                                                           const float* __restrict__ scale, const float* __restrict__ bias, int rows) {
+__global__ void __launch_bounds__(256) layernorm768_kernel(float* __restrict__ x, TO* __restrict__ y,
+                                                           const float* __restrict__ scale, const float* __restrict__ bias, int rows,
+                                                           const float* __restrict__ part, int nsplit, int64_t part_stride) {
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * 768);
+  float4* xr = reinterpret_cast<float4*>(x + (int64_t)row * 768);
   float4 v[6];
   float s = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < 6; ++i) v[i] = xr[lane + 32 * i];
+  if (nsplit > 0) {      // split-K partial products of the preceding residual GEMM, added in a fixed order (gemm_tc.cuh)
+    for (int sp = 0; sp < nsplit; ++sp) {
+      const float4* pr = reinterpret_cast<const float4*>(part + sp * part_stride + (int64_t)row * 768);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const float4 q = pr[lane + 32 * i];
+        v[i].x += q.x; v[i].y += q.y; v[i].z += q.z; v[i].w += q.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xr[lane + 32 * i] = v[i];
+  }
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -239,10 +253,12 @@ __global__ void __launch_bounds__(256) layernorm768_kernel(const float* __restri
 
 template <typename TS, typename TO>
 inline int layernorm(cudaStream_t st, const LnP& p, int D) {
+  if (p.nsplit > 0 && !(D == 768 && std::is_same<TS, float>::value && p.sS == 0 && p.ldx == 768 && p.ldy == 768 && p.post_div == 0.f))
+    return fail(HVLA_ERR_ARG, "layernorm: split-K partials need the 768-wide fp32 path");
   if (D == 768 && std::is_same<TS, float>::value && p.sS == 0 && p.ldx == 768 && p.ldy == 768 && p.post_div == 0.f) {
     ProfScope ps(st, "layernorm");
-    launch_k(layernorm768_kernel<TO>, dim3(cdiv(p.rows, 8)), dim3(256), 0, st, p.x, reinterpret_cast<TO*>(p.y),
-             reinterpret_cast<const float*>(p.scale), reinterpret_cast<const float*>(p.bias), p.rows);
+    launch_k(layernorm768_kernel<TO>, dim3(cdiv(p.rows, 8)), dim3(256), 0, st, const_cast<float*>(p.x), reinterpret_cast<TO*>(p.y),
+             reinterpret_cast<const float*>(p.scale), reinterpret_cast<const float*>(p.bias), p.rows, p.part, p.nsplit, p.part_stride);
     HVLA_LAUNCH_CHECK("layernorm768");
     return HVLA_OK;
   }

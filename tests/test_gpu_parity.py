@@ -223,8 +223,10 @@ def test_fused_base_kernel_matches_generic_path_and_oracle(models, params_p1, to
 
 
 def test_grouped_equals_per_sample_and_is_deterministic(models, torch_cuda):
-    """Full-size property test (B=64): a batch with mixed task weights gives bit-identical actions to
-    evaluating every env alone with its own task's weights; and the step is deterministic."""
+    """Full-size property test (B=64): a batch with mixed task weights gives the same actions as evaluating envs with
+    their own task's weights in other batch compositions, and the step is deterministic.  Bit-identical among batches
+    that use the same GEMM K-split configuration (sub-batches of 16 here); a batch of ONE env splits K of the residual
+    GEMMs over more CTAs (ordered, deterministic), so it agrees to fp32 summation-order noise instead."""
     from hvla import synthetic as S
     m = models["bf16"]
     rt = m.runtime
@@ -235,9 +237,16 @@ def test_grouped_equals_per_sample_and_is_deterministic(models, torch_cuda):
     a1, i1 = m.sample_actions(inp["images"], None, tasks, None, bp, task_index=ti)
     a2, i2 = m.sample_actions(inp["images"], None, tasks, None, bp, task_index=ti)
     assert np.array_equal(a1, a2) and np.array_equal(i1["gripper_logits"], i2["gripper_logits"])
+    for b0 in (0, 48):
+        ab, _ = m.sample_actions(inp["images"][b0:b0 + 16], None, tasks, None, bp, task_index=ti[b0:b0 + 16])
+        assert np.array_equal(ab, a1[b0:b0 + 16]), b0
     for b in (0, 17, 63):
-        ab, _ = m.sample_actions(inp["images"][b:b + 1], None, tasks, None, bp, task_index=ti[b:b + 1])
-        assert np.array_equal(ab[0], a1[b]), b
+        ab, ib = m.sample_actions(inp["images"][b:b + 1], None, tasks, None, bp, task_index=ti[b:b + 1])
+        ab2, _ = m.sample_actions(inp["images"][b:b + 1], None, tasks, None, bp, task_index=ti[b:b + 1])
+        assert np.array_equal(ab, ab2), b                                    # deterministic at batch 1 too
+        assert rel_err(ab[0][:, :6], a1[b][:, :6]) < 5e-3, b
+        sure = np.abs(i1["gripper_logits"][b]) > 2e-2 * np.abs(i1["gripper_logits"]).max()
+        assert np.array_equal(ab[0][:, 6][sure], a1[b][:, 6][sure]), b
     assert np.isfinite(a1).all() and np.abs(a1[..., :6]).max() <= 5.0
 
 
