@@ -194,6 +194,22 @@ __device__ __forceinline__ float gelu_erf_tanhfit(float x) {
   return fmaf(hx, th, hx);
 }
 
+// two elements at a time on the packed fp32 pipe (FMUL2 / FFMA2): 6 packed + 2 FMNMX + 2 MUFU per pair instead of 14 + 2
+__device__ __forceinline__ float2 gelu_erf_tanhfit2(float2 x) {
+  float2 t = __fmul2_rn(x, x);
+  t.x = fminf(t.x, 80.0f);
+  t.y = fminf(t.y, 80.0f);
+  float2 w = __ffma2_rn(make_float2(-0.00035151678755022096f, -0.00035151678755022096f), t,
+                        make_float2(0.0370056460170224f, 0.0370056460170224f));
+  w = __ffma2_rn(w, t, make_float2(0.7975078842849359f, 0.7975078842849359f));
+  const float2 a = __fmul2_rn(x, w);
+  float2 th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(a.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(a.y));
+  const float2 hx = __fmul2_rn(make_float2(0.5f, 0.5f), x);
+  return __ffma2_rn(hx, th, hx);
+}
+
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace hvla

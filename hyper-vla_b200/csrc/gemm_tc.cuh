@@ -84,6 +84,8 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- split-K partial products -------------------------------------------------------------------------------
@@ -267,7 +269,7 @@ __device__ __forceinline__ void epilogue_tile_direct(const EpiP& ep, float* sepi
 // residual stream, so x += ls * (acc + bias) needs no read of x through the SM at all.
 constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 2048;
 
-template <int EPI>
+template <int EPI, int NSLAB = 1>
 __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensorMap* tmO, float* sepi, uint32_t sstage,
                                                   uint32_t tfull_bar_addr, uint32_t aph, int as, uint32_t tmem_base, int m0,
                                                   int n0, int warp, int lane, int split = 0, const CUtensorMap* tmP = nullptr,
@@ -282,8 +284,9 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
   sb[te] = add_bias ? __ldg(ep.bias + n0 + te) : 0.f;      // split-K: only the first K split contributes the bias
   if (EPI == EPI_RESIDUAL_F32) sl[te] = __ldg(ep.ls + n0 + te);
   const int row0 = m0 + quarter * 32;
-  const uint32_t slab = sstage + (uint32_t)ew * 2048u;
-  const uint32_t my = slab + (uint32_t)lane * 64u;
+  // NSLAB 2 KB slabs per warp: with two, the TMA store of one chunk reads its slab while the next chunk is written
+  const uint32_t slab0 = sstage + (uint32_t)ew * (2048u * NSLAB);
+  const uint32_t my0 = slab0 + (uint32_t)lane * 64u;
   const uint32_t sw = (uint32_t)((lane >> 1) & 3);          // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
   epi_bar_sync();
   mbar_wait(tfull_bar_addr, aph);
@@ -303,20 +306,23 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 b4 = *reinterpret_cast<const float4*>(sb + cl + j);
-      v[j] = __uint_as_float(rc[j]) + b4.x;
-      v[j + 1] = __uint_as_float(rc[j + 1]) + b4.y;
-      v[j + 2] = __uint_as_float(rc[j + 2]) + b4.z;
-      v[j + 3] = __uint_as_float(rc[j + 3]) + b4.w;
+      const float2 lo = __fadd2_rn(make_float2(__uint_as_float(rc[j]), __uint_as_float(rc[j + 1])), make_float2(b4.x, b4.y));
+      const float2 hi = __fadd2_rn(make_float2(__uint_as_float(rc[j + 2]), __uint_as_float(rc[j + 3])), make_float2(b4.z, b4.w));
+      v[j] = lo.x; v[j + 1] = lo.y; v[j + 2] = hi.x; v[j + 3] = hi.y;
     }
     if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
       if (EPI == EPI_BIAS_GELU_BF16) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_tanhfit(v[j]);
+        for (int j = 0; j < 32; j += 2) {
+          const float2 g = gelu_erf_tanhfit2(make_float2(v[j], v[j + 1]));
+          v[j] = g.x; v[j + 1] = g.y;
+        }
       } else if (col < ep.qcols) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= ep.qscale;
       }
-      if (lane == 0) bulk_wait_read0();       // the slab's previous TMA store has finished reading it
+      const uint32_t slab = slab0 + (uint32_t)((c % NSLAB) * 2048), my = my0 + (uint32_t)((c % NSLAB) * 2048);
+      if (lane == 0) bulk_wait_read<NSLAB - 1>();       // the slab's previous TMA store has finished reading it
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -335,7 +341,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
     } else {   // EPI_RESIDUAL_F32: two units of 16 fp32 columns, reduce-added into the residual stream
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        if (lane == 0) bulk_wait_read0();
+        const uint32_t slab = slab0 + (uint32_t)((u % NSLAB) * 2048), my = my0 + (uint32_t)((u % NSLAB) * 2048);
+        if (lane == 0) bulk_wait_read<NSLAB - 1>();
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {

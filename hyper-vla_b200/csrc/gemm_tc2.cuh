@@ -18,9 +18,11 @@ using namespace tc;   // PTX wrappers, EpiP, Epi, descriptors
 
 constexpr int BM2 = 256;                         // pair tile rows (128 per CTA)
 constexpr int STAGES2 = 6;
+constexpr int NSLAB2 = 1;                         // TMA-store slabs per epilogue warp (2 = double-buffered: measured no gain, and costs a pipeline stage)
 constexpr int A2_BYTES = 128 * BK * 2;           // 16 KB
 constexpr int B2_BYTES = 128 * BK * 2;           // 16 KB
-constexpr int SMEM2_BYTES = STAGES2 * (A2_BYTES + B2_BYTES) + 1024 + 256 + 4096 + 1024 + 8 * 2048;
+constexpr int SMEM2_BYTES = STAGES2 * (A2_BYTES + B2_BYTES) + 1024 + 256 + 4096 + 1024 + 8 * 2048 * NSLAB2;
+static_assert(SMEM2_BYTES <= 232448, "shared memory budget");
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -175,7 +177,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (EPI == EPI_PATCH_F32) epilogue_tile_direct<EPI>(ep, sepi, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, M, warp, lane);
       else {
         const int split = unit % splits;          // split s > 0 stores to block s-1 of the partial-product scratch
-        epilogue_tile_tma<EPI>(ep, &tmO, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane, split, &tmP,
+        epilogue_tile_tma<EPI, NSLAB2>(ep, &tmO, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane, split, &tmP,
                                (split - 1) * n_tiles_m * BM2 + m0);
       }
       if (lane == 0) mbar_arrive_remote(tempty_bar + 8 * as, 0);
