@@ -10,6 +10,7 @@
 #include "heads_mma.cuh"
 #include "ctx_fused.cuh"
 #include "postprocess.cuh"
+#include "preprocess.cuh"
 
 #include <stdlib.h>
 #include <type_traits>
@@ -664,6 +665,38 @@ int hvla_postprocess(hvla_stream_t stream, const float* raw_action, float* state
   ProfScope ps(st, "postprocess");
   post::postprocess_kernel<<<cdiv(B, 128), 128, 0, st>>>(p);
   HVLA_LAUNCH_CHECK("postprocess");
+  return HVLA_OK;
+}
+
+size_t hvla_resize_workspace_bytes(int B, int H, int W, int S, int crop) {
+  if (B <= 0 || H <= 0 || W <= 0 || S <= 0) return 0;
+  return align_up((size_t)B * S * W * 3 * 4) + (crop ? align_up((size_t)B * S * S * 3 * 4) : 0);
+}
+
+int hvla_resize_lanczos3(hvla_stream_t stream, const uint8_t* images, int B, int H, int W, int S, const int32_t* starts_y,
+                         const float* weights_y, int span_y, const int32_t* starts_x, const float* weights_x, int span_x, int crop,
+                         const float* crop_params, uint8_t* out, void* workspace, size_t workspace_bytes) {
+  if (B < 0 || H <= 0 || W <= 0 || S <= 1 || span_y <= 0 || span_x <= 0) return fail(HVLA_ERR_ARG, "hvla_resize_lanczos3: bad sizes");
+  if (B == 0) return HVLA_OK;
+  if (!images || !starts_y || !weights_y || !starts_x || !weights_x || !out || !workspace || (crop && !crop_params))
+    return fail(HVLA_ERR_ARG, "hvla_resize_lanczos3: null argument");
+  if (workspace_bytes < hvla_resize_workspace_bytes(B, H, W, S, crop)) return fail(HVLA_ERR_WORKSPACE, "hvla_resize_lanczos3: workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* tmp = reinterpret_cast<float*>(workspace);
+  float* full = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + align_up((size_t)B * S * W * 3 * 4));
+  ProfScope ps(st, "resize");
+  const int64_t n1 = (int64_t)B * S * W * 3, n2 = (int64_t)B * S * S * 3;
+  prep::resize_rows_kernel<<<cdiv(n1, 256), 256, 0, st>>>(images, tmp, starts_y, weights_y, span_y, H, W * 3, S, n1);
+  HVLA_LAUNCH_CHECK("resize_rows");
+  if (!crop) {
+    prep::resize_cols_kernel<uint8_t><<<cdiv(n2, 256), 256, 0, st>>>(tmp, out, starts_x, weights_x, span_x, W, S, n2);
+    HVLA_LAUNCH_CHECK("resize_cols");
+  } else {
+    prep::resize_cols_kernel<float><<<cdiv(n2, 256), 256, 0, st>>>(tmp, full, starts_x, weights_x, span_x, W, S, n2);
+    HVLA_LAUNCH_CHECK("resize_cols");
+    prep::crop_bilinear_kernel<<<cdiv(n2, 256), 256, 0, st>>>(full, out, S, crop_params[0], crop_params[1], crop_params[2], crop_params[3], n2);
+    HVLA_LAUNCH_CHECK("crop_bilinear");
+  }
   return HVLA_OK;
 }
 

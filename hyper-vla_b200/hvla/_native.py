@@ -34,6 +34,9 @@ SIGNATURES = {
     "hvla_postprocess_state_floats": (c_i64, []),
     "hvla_postprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                  C.c_float, c_int, c_int, c_void_p, c_void_p]),
+    "hvla_resize_workspace_bytes": (c_size_t, [c_int] * 5),
+    "hvla_resize_lanczos3": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                     c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t]),
     "hvla_launch_count": (c_i64, []),
     "hvla_profile_enable": (c_int, [c_int]),
     "hvla_profile_report": (c_int, [C.c_char_p, c_size_t]),

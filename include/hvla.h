@@ -127,6 +127,18 @@ int64_t hvla_postprocess_state_floats(void);
 int hvla_postprocess(hvla_stream_t stream, const float* raw_action, float* state, const uint8_t* reset, int B, int norm_type,
                      const float* stat_a, const float* stat_b, const uint8_t* mask, int ensemble, float temp,
                      int policy_setup, int sticky_repeat, float* out_raw, float* out_action);
+/* ---- per-step image preprocessing: replaces InferenceWrapper._resize_image
+ * (data/utils/hypervla_interface.py:89-121: tf.image.resize lanczos3 antialias -> optional centre crop_and_resize
+ * -> round/clip/uint8) for B camera frames at once.
+ *   images [B,H,W,3] u8 (device) -> out [B,S,S,3] u8 (device; the buffer hvla_act reads when S = 224)
+ *   starts_y, starts_x, weights_y, weights_x (device): span start and normalised lanczos3 weights per output row / column,
+ *     weights_y [S, span_y], weights_x [S, span_x] (computed once per input size by the caller: hvla/preprocess.py)
+ *   crop 0/1; crop_params (HOST, 4 floats): y1*(S-1), x1*(S-1), height_scale, width_scale of the crop box
+ *   workspace (device): hvla_resize_workspace_bytes(B,H,W,S,crop) */
+size_t hvla_resize_workspace_bytes(int B, int H, int W, int S, int crop);
+int hvla_resize_lanczos3(hvla_stream_t stream, const uint8_t* images, int B, int H, int W, int S, const int32_t* starts_y,
+                         const float* weights_y, int span_y, const int32_t* starts_x, const float* weights_x, int span_x, int crop,
+                         const float* crop_params, uint8_t* out, void* workspace, size_t workspace_bytes);
 /* number of kernels launched by this library since load (for bench.py's gpu_launches) */
 int64_t hvla_launch_count(void);
 /* per-kernel-class CUDA-event timing on the launching stream (bench.py's live roofline numbers).
