@@ -106,8 +106,10 @@ class HyperVLA:
     def load_pretrained(cls, checkpoint_path: str, step: Optional[int] = None, *, precision: str = "bf16",
                         device=None) -> "HyperVLA":
         """Reads ``config.json`` / ``dataset_statistics.json`` like the reference (model.py:152-189).
-        Parameters: a flat ``params_<step>.npz`` ("a/b/c" keys, Flax names).  orbax checkpoints cannot be
-        read in this environment (orbax/tensorflow absent) -- convert them offline."""
+        Parameters (hvla/checkpoint.py): the EMA pickle ``<step>/EMA_params.pkl`` the reference's eval loop prefers
+        (data/simpler/evaluate.py:441-443, scripts/train.py:697-699), read without jax, or a flat
+        ``params_<step>.npz`` ("a/b/c" keys, Flax names) written by ``save_pretrained`` / tools/convert_orbax_checkpoint.py.
+        The orbax on-disk format itself (tensorstore/OCDBT) is not parsed here -- convert it once where orbax exists."""
         with open(os.path.join(checkpoint_path, "config.json")) as f:
             config = json.load(f)
         stats = None
@@ -115,17 +117,8 @@ class HyperVLA:
         if os.path.exists(sp):
             with open(sp) as f:
                 stats = json.load(f)
-        cand = [n for n in os.listdir(checkpoint_path) if n.startswith("params") and n.endswith(".npz")]
-        if step is not None:
-            cand = [n for n in cand if n == f"params_{step}.npz"]
-        if not cand:
-            raise FileNotFoundError(
-                f"no params*.npz under {checkpoint_path}; orbax PyTree checkpoints must be converted offline "
-                "(see INTEGRATION.md) -- orbax is not available here")
-        flat = np.load(os.path.join(checkpoint_path, sorted(cand)[-1]))
-        params: dict = {}
-        for k in flat.files:
-            M.set_path(params, tuple(k.split("/")), flat[k])
+        from . import checkpoint as CK
+        params = CK.load_params(checkpoint_path, step)
         if "shared_modules" in config.get("hypernet_kwargs", {}):
             config["hypernet_kwargs"]["shared_modules"] = tuple(config["hypernet_kwargs"]["shared_modules"])
         return cls.from_config(config, None, None, stats, precision=precision, device=device, params=params)
