@@ -686,14 +686,27 @@ int hvla_resize_lanczos3(hvla_stream_t stream, const uint8_t* images, int B, int
   float* full = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + align_up((size_t)B * S * W * 3 * 4));
   ProfScope ps(st, "resize");
   const int64_t n1 = (int64_t)B * S * W * 3, n2 = (int64_t)B * S * S * 3;
-  prep::resize_rows_kernel<<<cdiv(n1, 256), 256, 0, st>>>(images, tmp, starts_y, weights_y, span_y, H, W * 3, S, n1);
-  HVLA_LAUNCH_CHECK("resize_rows");
-  if (!crop) {
-    prep::resize_cols_kernel<uint8_t><<<cdiv(n2, 256), 256, 0, st>>>(tmp, out, starts_x, weights_x, span_x, W, S, n2);
-    HVLA_LAUNCH_CHECK("resize_cols");
+  const size_t row_bytes = (size_t)W * 3 * 4;
+  if (row_bytes <= 48 * 1024) {
+    // fused path: no float32 intermediate in HBM (preprocess.cuh)
+    const bool vec = (W * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(images) & 3) == 0;
+    const dim3 grid(S, B);
+    if (!crop) {
+      if (vec) prep::resize_fused_kernel<uint8_t, true><<<grid, 256, row_bytes, st>>>(images, out, starts_y, weights_y, span_y, starts_x, weights_x, span_x, H, W, S);
+      else prep::resize_fused_kernel<uint8_t, false><<<grid, 256, row_bytes, st>>>(images, out, starts_y, weights_y, span_y, starts_x, weights_x, span_x, H, W, S);
+    } else {
+      if (vec) prep::resize_fused_kernel<float, true><<<grid, 256, row_bytes, st>>>(images, full, starts_y, weights_y, span_y, starts_x, weights_x, span_x, H, W, S);
+      else prep::resize_fused_kernel<float, false><<<grid, 256, row_bytes, st>>>(images, full, starts_y, weights_y, span_y, starts_x, weights_x, span_x, H, W, S);
+    }
+    HVLA_LAUNCH_CHECK("resize_fused");
   } else {
-    prep::resize_cols_kernel<float><<<cdiv(n2, 256), 256, 0, st>>>(tmp, full, starts_x, weights_x, span_x, W, S, n2);
+    prep::resize_rows_kernel<<<cdiv(n1, 256), 256, 0, st>>>(images, tmp, starts_y, weights_y, span_y, H, W * 3, S, n1);
+    HVLA_LAUNCH_CHECK("resize_rows");
+    if (!crop) prep::resize_cols_kernel<uint8_t><<<cdiv(n2, 256), 256, 0, st>>>(tmp, out, starts_x, weights_x, span_x, W, S, n2);
+    else prep::resize_cols_kernel<float><<<cdiv(n2, 256), 256, 0, st>>>(tmp, full, starts_x, weights_x, span_x, W, S, n2);
     HVLA_LAUNCH_CHECK("resize_cols");
+  }
+  if (crop) {
     prep::crop_bilinear_kernel<<<cdiv(n2, 256), 256, 0, st>>>(full, out, S, crop_params[0], crop_params[1], crop_params[2], crop_params[3], n2);
     HVLA_LAUNCH_CHECK("crop_bilinear");
   }

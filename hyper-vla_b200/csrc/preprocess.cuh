@@ -13,6 +13,12 @@
 namespace hvla {
 namespace prep {
 
+// byte i of a 32-bit word as an exact float without the quarter-rate I2F: 0x4B0000xx is 8388608 + xx
+template <int I>
+__device__ __forceinline__ float byte_to_float(uint32_t u) {
+  return __fsub_rn(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7650 + I)), 8388608.0f);
+}
+
 __device__ __forceinline__ uint8_t round_clip_u8(float v) {
   return (uint8_t)fminf(fmaxf(rintf(v), 0.f), 255.f);       // tf.round = half to even
 }
@@ -51,6 +57,57 @@ resize_cols_kernel(const float* __restrict__ tmp, TO* __restrict__ out, const in
   for (int k = 0; k < span && c0 + k < W; ++k) acc = __fadd_rn(acc, __fmul_rn(__ldg(w + k), __ldg(src + 3 * k)));
   if (sizeof(TO) == 1) out[idx] = (TO)round_clip_u8(acc);
   else out[idx] = (TO)acc;
+}
+
+// Both passes in one kernel: a CTA owns one output row of one frame; the row pass lands in shared memory (W*3 floats),
+// the column pass reads it from there, so the float32 intermediate never touches HBM.  Same arithmetic, same order.
+// VEC: W*3 % 4 == 0 (and a 4-byte aligned frame base): the row pass reads four bytes per load.
+template <typename TO, bool VEC>
+__global__ void __launch_bounds__(256)
+resize_fused_kernel(const uint8_t* __restrict__ in, TO* __restrict__ out, const int* __restrict__ sy, const float* __restrict__ wy,
+                    int span_y, const int* __restrict__ sx, const float* __restrict__ wx, int span_x, int H, int W, int S) {
+  extern __shared__ float row[];                       // [W*3]
+  const int oy = blockIdx.x;
+  const int64_t b = blockIdx.y;
+  const int WC = W * 3;
+  const int r0 = sy[oy];
+  const float* w = wy + (int64_t)oy * span_y;
+  const int taps = min(span_y, H - r0);
+  const uint8_t* src = in + (b * H + r0) * (int64_t)WC;
+  if (VEC) {
+    for (int x4 = threadIdx.x; x4 < WC / 4; x4 += blockDim.x) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < taps; ++k) {
+        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(src + (int64_t)k * WC) + x4);
+        const float wk = __ldg(w + k);
+        a0 = __fadd_rn(a0, __fmul_rn(wk, byte_to_float<0>(u)));
+        a1 = __fadd_rn(a1, __fmul_rn(wk, byte_to_float<1>(u)));
+        a2 = __fadd_rn(a2, __fmul_rn(wk, byte_to_float<2>(u)));
+        a3 = __fadd_rn(a3, __fmul_rn(wk, byte_to_float<3>(u)));
+      }
+      *reinterpret_cast<float4*>(row + 4 * x4) = make_float4(a0, a1, a2, a3);
+    }
+  } else {
+    for (int xc = threadIdx.x; xc < WC; xc += blockDim.x) {
+      float acc = 0.f;
+      for (int k = 0; k < taps; ++k) acc = __fadd_rn(acc, __fmul_rn(__ldg(w + k), (float)__ldg(src + (int64_t)k * WC + xc)));
+      row[xc] = acc;
+    }
+  }
+  __syncthreads();
+  TO* dst = out + (b * S + oy) * (int64_t)S * 3;
+  for (int o = threadIdx.x; o < S * 3; o += blockDim.x) {
+    const int ox = o / 3, c = o - ox * 3;
+    const int c0 = sx[ox];
+    const float* wc = wx + (int64_t)ox * span_x;
+    const int tx = min(span_x, W - c0);
+    float acc = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < tx; ++k) acc = __fadd_rn(acc, __fmul_rn(__ldg(wc + k), row[(c0 + k) * 3 + c]));
+    if (sizeof(TO) == 1) dst[o] = (TO)round_clip_u8(acc);
+    else dst[o] = (TO)acc;
+  }
 }
 
 // tf.image.crop_and_resize (bilinear, extrapolation 0) of the SxS float image with one box, then round/clip

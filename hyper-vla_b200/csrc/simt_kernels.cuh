@@ -197,10 +197,10 @@ __global__ void __launch_bounds__(128) layernorm_kernel(LnP p) {
 }
 
 // DINOv2 LayerNorm: 768-wide fp32 rows (contiguous, shared scale/bias), vectorised; one warp per row.
-template <typename TO>
+template <typename TO, int NS>
 __global__ void __launch_bounds__(256) layernorm768_kernel(float* __restrict__ x, TO* __restrict__ y,
                                                            const float* __restrict__ scale, const float* __restrict__ bias, int rows,
-                                                           const float* __restrict__ part, int nsplit, int64_t part_stride) {
+                                                           const float* __restrict__ part, int64_t part_stride) {
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -211,14 +211,18 @@ __global__ void __launch_bounds__(256) layernorm768_kernel(float* __restrict__ x
   float s = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < 6; ++i) v[i] = xr[lane + 32 * i];
-  if (nsplit > 0) {      // split-K partial products of the preceding residual GEMM, added in a fixed order (gemm_tc.cuh)
-    for (int sp = 0; sp < nsplit; ++sp) {
+  if (NS > 0) {          // split-K partial products of the preceding residual GEMM, added in a fixed order (gemm_tc.cuh);
+    float4 q[NS > 0 ? NS : 1][6];     // every load is issued before the first add: one memory round trip (small batches are latency-bound)
+#pragma unroll
+    for (int sp = 0; sp < NS; ++sp) {
       const float4* pr = reinterpret_cast<const float4*>(part + sp * part_stride + (int64_t)row * 768);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const float4 q = pr[lane + 32 * i];
-        v[i].x += q.x; v[i].y += q.y; v[i].z += q.z; v[i].w += q.w;
-      }
+      for (int i = 0; i < 6; ++i) q[sp][i] = pr[lane + 32 * i];
+    }
+#pragma unroll
+    for (int sp = 0; sp < NS; ++sp) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { v[i].x += q[sp][i].x; v[i].y += q[sp][i].y; v[i].z += q[sp][i].z; v[i].w += q[sp][i].w; }
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) xr[lane + 32 * i] = v[i];
@@ -257,8 +261,18 @@ inline int layernorm(cudaStream_t st, const LnP& p, int D) {
     return fail(HVLA_ERR_ARG, "layernorm: split-K partials need the 768-wide fp32 path");
   if (D == 768 && std::is_same<TS, float>::value && p.sS == 0 && p.ldx == 768 && p.ldy == 768 && p.post_div == 0.f) {
     ProfScope ps(st, "layernorm");
-    launch_k(layernorm768_kernel<TO>, dim3(cdiv(p.rows, 8)), dim3(256), 0, st, const_cast<float*>(p.x), reinterpret_cast<TO*>(p.y),
-             reinterpret_cast<const float*>(p.scale), reinterpret_cast<const float*>(p.bias), p.rows, p.part, p.nsplit, p.part_stride);
+    float* xp = const_cast<float*>(p.x);
+    TO* yp = reinterpret_cast<TO*>(p.y);
+    const float* sc = reinterpret_cast<const float*>(p.scale);
+    const float* bi = reinterpret_cast<const float*>(p.bias);
+    const dim3 grid(cdiv(p.rows, 8)), block(256);
+    switch (p.nsplit) {
+      case 0: launch_k(layernorm768_kernel<TO, 0>, grid, block, 0, st, xp, yp, sc, bi, p.rows, p.part, p.part_stride); break;
+      case 1: launch_k(layernorm768_kernel<TO, 1>, grid, block, 0, st, xp, yp, sc, bi, p.rows, p.part, p.part_stride); break;
+      case 3: launch_k(layernorm768_kernel<TO, 3>, grid, block, 0, st, xp, yp, sc, bi, p.rows, p.part, p.part_stride); break;
+      case 7: launch_k(layernorm768_kernel<TO, 7>, grid, block, 0, st, xp, yp, sc, bi, p.rows, p.part, p.part_stride); break;
+      default: return fail(HVLA_ERR_ARG, "layernorm: unsupported number of split-K partial blocks");
+    }
     HVLA_LAUNCH_CHECK("layernorm768");
     return HVLA_OK;
   }
