@@ -35,6 +35,7 @@ struct EpiP {
   float* part;         // EPI 2: scratch for split-K partial products (null: never split), see "split-K partial products"
   size_t part_bytes;   //        its size
   int* splits_used;    //        host out: number of K splits of this launch (1 = none)
+  int patch_rows;      // EPI 2 used for the patch embedding: GEMM row b*256+p lands in stream row b*257+1+p; ls == null means 1
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -282,8 +283,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
   float* sb = sepi + as * 512;
   float* sl = sb + 256;
   sb[te] = add_bias ? __ldg(ep.bias + n0 + te) : 0.f;      // split-K: only the first K split contributes the bias
-  if (EPI == EPI_RESIDUAL_F32) sl[te] = __ldg(ep.ls + n0 + te);
-  const int row0 = m0 + quarter * 32;
+  if (EPI == EPI_RESIDUAL_F32) sl[te] = ep.ls ? __ldg(ep.ls + n0 + te) : 1.0f;
+  const int row0 = m0 + quarter * 32 + (ep.patch_rows ? m0 / 256 + 1 : 0);
   // NSLAB 2 KB slabs per warp: with two, the TMA store of one chunk reads its slab while the next chunk is written
   const uint32_t slab0 = sstage + (uint32_t)ew * (2048u * NSLAB);
   const uint32_t my0 = slab0 + (uint32_t)lane * 64u;
@@ -525,6 +526,7 @@ inline int make_map_out(CUtensorMap* map, const void* ptr, int64_t rows, int64_t
 }
 // rows of the output tensor as the epilogue addresses them (patch epilogue does not use the map)
 inline int make_out_map_for(CUtensorMap* mo, int epi, const EpiP& ep, int M) {
+  if (epi == EPI_PATCH_F32 && ep.patch_rows) return make_map_out(mo, ep.out, (int64_t)(M / 256) * 257, ep.ldo, true);
   if (epi == EPI_PATCH_F32) { memset(mo, 0, sizeof *mo); return HVLA_OK; }
   return make_map_out(mo, ep.out, M, ep.ldo, epi == EPI_RESIDUAL_F32);
 }

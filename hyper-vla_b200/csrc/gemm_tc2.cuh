@@ -174,7 +174,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t aph = (it >> 1) & 1;
       const int tile = unit / splits;
       const int m0 = (tile / n_tiles_n) * BM2 + (int)rank * 128, n0 = (tile % n_tiles_n) * BN;
-      if (EPI == EPI_PATCH_F32) epilogue_tile_direct<EPI>(ep, sepi, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, M, warp, lane);
+      if (EPI == EPI_PATCH_F32 && ep.patch_rows)      // patch embedding accumulated onto the pre-initialised stream rows (TMA reduce-add)
+        epilogue_tile_tma<EPI_RESIDUAL_F32, NSLAB2>(ep, &tmO, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane);
+      else if (EPI == EPI_PATCH_F32) epilogue_tile_direct<EPI>(ep, sepi, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, M, warp, lane);
       else {
         const int split = unit % splits;          // split s > 0 stores to block s-1 of the partial-product scratch
         epilogue_tile_tma<EPI, NSLAB2>(ep, &tmO, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane, split, &tmP,

@@ -245,6 +245,23 @@ __global__ void dino_cls_rows_kernel(const float* __restrict__ cls, const float*
   X[(int64_t)b * DTOK * DD + c] = cls[c] + pos[c];
 }
 
+// whole residual stream before the patch-embedding GEMM accumulates onto it: X[b,r,:] = pos[r,:] (+ cls on row 0)
+__global__ void __launch_bounds__(256) dino_init_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ X,
+                                                             int64_t total4) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int c4 = (int)(i % (DD / 4));
+  const int r = (int)((i / (DD / 4)) % DTOK);
+  float4 v = __ldg(reinterpret_cast<const float4*>(pos + (int64_t)r * DD) + c4);
+  if (r == 0) {
+    const float4 c = __ldg(reinterpret_cast<const float4*>(cls) + c4);
+    v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+  }
+  reinterpret_cast<float4*>(X)[i] = v;
+}
+
 static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uint8_t* images, int B, bf16* out_emb,
                      uint8_t* ws, const Plan& pl) {
   typedef DvecLayout V;
@@ -267,11 +284,16 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
     const int64_t total = (int64_t)B * NPATCH * PATCH_KP;
     {
       ProfScope ps(st, "im2col");
-      launch_k(im2col_norm_kernel<bf16>, dim3(cdiv(total, 256)), dim3(256), 0, st, images, A0, B);
+      launch_k(im2col_norm_bf16_kernel, dim3(cdiv(total / 8, 256 * 4)), dim3(256), 0, st, images, A0, B);
       HVLA_LAUNCH_CHECK("im2col");
     }
     ProfScope ps2(st, "cls_rows");
-    launch_k(dino_cls_rows_kernel, dim3(cdiv(B * DD, 256)), dim3(256), 0, st, dv + V::cls, dv + V::pos, X, B);
+    if (one_cta || simt_gemm) {
+      launch_k(dino_cls_rows_kernel, dim3(cdiv(B * DD, 256)), dim3(256), 0, st, dv + V::cls, dv + V::pos, X, B);
+    } else {
+      const int64_t total4 = (int64_t)M * DD / 4;
+      launch_k(dino_init_rows_kernel, dim3(cdiv(total4, 256)), dim3(256), 0, st, dv + V::cls, dv + V::pos, X, total4);
+    }
     HVLA_LAUNCH_CHECK("dino_cls_rows");
   }
   auto gemm = [&](const bf16* A, const bf16* Wt, int m, int n, int k, int epi, const tc::EpiP& ep) -> int {
@@ -290,6 +312,7 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
   } else {
     tc::EpiP ep; memset(&ep, 0, sizeof ep);
     ep.bias = dv + V::patch_b; ep.out = X; ep.ldo = DD; ep.pos = dv + V::pos;
+    ep.patch_rows = one_cta ? 0 : 1;     // 2-CTA path: the stream already holds cls/pos, the GEMM reduce-adds onto it
     HVLA_TRY(gemm(A0, dm + Mx::patch_w, B * NPATCH, DD, PATCH_KP, tc::EPI_PATCH_F32, ep));
   }
   for (int l = 0; l < DL; ++l) {
