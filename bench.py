@@ -275,6 +275,39 @@ def run_ours(args):
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
     assert act_np.shape == (B, 4, 7) and np.isfinite(act_np).all()
 
+    # ---- the widened caller path (SURVEY 8(f) rows 3 + 1): camera frames on the host -> GPU resize -> act ->
+    #      GPU post-processing -> (B,7) env actions on the host; what InferenceWrapper.step does around the model call
+    wrapper = None
+    try:
+        from hvla.postprocess import BatchedActionPostprocessor
+        from hvla.preprocess import BatchedImagePreprocessor
+        pre = BatchedImagePreprocessor(224, device=dev)
+        stats = {"mean": np.zeros(7), "std": np.ones(7), "mask": np.array([1, 1, 1, 1, 1, 1, 0], bool)}
+        post = BatchedActionPostprocessor(B, "widowx_bridge", "normal", stats, device=dev)
+        cams = [torch.from_numpy(rng.integers(0, 256, size=(B, 480, 640, 3), dtype=np.uint8)).pin_memory() for _ in range(3)]
+
+        def step_wrapper(i):
+            a_dev, _ = rt.act_device(pre(cams[i % 3]), W, None)
+            return post.step(a_dev)[1].cpu().numpy()
+        for i in range(3):
+            step_wrapper(i)
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for i in range(args.steps):
+            env_act = step_wrapper(i)
+        w1.record()
+        barrier()
+        wms = torch.tensor([w0.elapsed_time(w1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(wms, op=dist.ReduceOp.MAX)
+        assert env_act.shape == (B, 7) and np.isfinite(env_act).all()
+        wrapper = {"value": world * B * args.steps / (float(wms.item()) / 1e3), "unit": "actions/s", "ms_per_step": float(wms.item()) / args.steps,
+                   "h2d_bytes_per_step": B * 480 * 640 * 3, "d2h_bytes_per_step": B * 7 * 4,
+                   "api": "480x640 uint8 camera frames (pinned host) -> BatchedImagePreprocessor -> act -> BatchedActionPostprocessor -> numpy (B,7)"}
+    except Exception as exc:  # the headline numbers above do not depend on this leg
+        wrapper = {"error": repr(exc)}
+
     # ---- live per-kernel-class timing (CUDA events on the launching stream) -----------------------------
     prof = rt.profile(lambda: step_dev(0), repeats=3)
     torch.cuda.synchronize()
@@ -341,6 +374,7 @@ def run_ours(args):
                               f"~{B * 257 * (768 * 4 + 768 * 2 * 3 + 2304 * 2 + 3072 * 2) / 1e6:.0f} MB of activations per step"),
             "e2e": {"value": e2e_value, "unit": "actions/s", "h2d_bytes_per_step": B * 150528, "d2h_bytes_per_step": B * (28 + 4) * 4,
                     "ms_per_step": e2e_ms / args.steps, "api": "HyperVLA.sample_actions(host pinned uint8 images) -> numpy actions"},
+            "wrapper_e2e": wrapper,
             "gpu_launches": launches,
             "clocks": sampler.result(),
             "roofline": roofline,

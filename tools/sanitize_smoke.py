@@ -19,3 +19,14 @@ for prec in ("bf16", "fp32"):
     a, _ = m.sample_actions(inp["images"], None, tasks, None, bp)
     print(prec, a[0, 0])
     del m
+
+# the steps either side of the model call
+from hvla.postprocess import BatchedActionPostprocessor  # noqa: E402
+from hvla.preprocess import BatchedImagePreprocessor  # noqa: E402
+
+frames = np.random.default_rng(0).integers(0, 256, (2, 97, 131, 3), dtype=np.uint8)
+for crop in (False, True):
+    print("resize crop", crop, BatchedImagePreprocessor(224, crop=crop)(frames).float().mean().item())
+stats = {"mean": np.zeros(7), "std": np.ones(7), "mask": np.ones(7, bool)}
+pp = BatchedActionPostprocessor(2, "google_robot", "normal", stats)
+print("post", pp.step(a)[1].cpu().numpy()[0])
