@@ -41,10 +41,12 @@ constexpr int OFF_X = 0;                                 // fp32 [48][132]
 constexpr int OFF_A = OFF_X + 48 * XLD * 4;              // fp16 [48][136]  LN output / attention output
 constexpr int OFF_BIG = OFF_A + 48 * ALD * 2;            // fp16: q|k|v [48][392]  |  hidden [48][520]  |  token emb [32][776]
 constexpr int BIG_BYTES = 48 * HLD * 2;
-constexpr int OFF_W = OFF_BIG + BIG_BYTES;               // 2 x weight chunk [32][<=520] fp16
+constexpr int NSTG = 4;                                  // weight-chunk ring: 3 chunks in flight while one is consumed
+constexpr int OFF_W = OFF_BIG + BIG_BYTES;               // NSTG x weight chunk [32][<=520] fp16
 constexpr int WBUF_BYTES = WCH * HLD * 2;
-constexpr int OFF_MISC = OFF_W + 2 * WBUF_BYTES;         // key-valid flags [34]
+constexpr int OFF_MISC = OFF_W + NSTG * WBUF_BYTES;      // key-valid flags [34]
 constexpr int SMEM = OFF_MISC + 256;
+static_assert(SMEM <= 232448, "shared memory budget");
 static_assert(32 * ELD * 2 <= BIG_BYTES && 48 * QLD * 2 <= BIG_BYTES, "BIG region");
 
 // C[48 x N] (+)= A[48 x K] (fp16 smem, row stride lda) * W[K x N] (fp16 global, row-major), warp w owns N/8 columns.
@@ -62,21 +64,28 @@ __device__ __forceinline__ void cta_gemm(uint8_t* smem, const lp* As, int lda, c
   for (int m = 0; m < MT; ++m)
 #pragma unroll
     for (int n = 0; n < NTW; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
+  // The kernel is bound by L2 round trips (one CTA streams 2.8 MB of weights in 32-row chunks, ~200 of them per task):
+  // a 4-deep cp.async ring keeps three chunks in flight.  One commit group per iteration (empty past the end) keeps
+  // the wait_group arithmetic uniform.
   auto stage = [&](int c) {
-    const uint32_t dst = sW + (uint32_t)((c & 1) * WBUF_BYTES);
-    const lp* src = Wg + (int64_t)c * WCH * N;
-    for (int i = threadIdx.x; i < WCH * (N / 8); i += NTH) {
-      const int r = i / (N / 8), cc = (i % (N / 8)) * 8;
-      cp_async16(dst + (uint32_t)((r * WLD + cc) * 2), src + (int64_t)r * N + cc);
+    if (c < NCH) {
+      const uint32_t dst = sW + (uint32_t)((c % NSTG) * WBUF_BYTES);
+      const lp* src = Wg + (int64_t)c * WCH * N;
+      for (int i = threadIdx.x; i < WCH * (N / 8); i += NTH) {
+        const int r = i / (N / 8), cc = (i % (N / 8)) * 8;
+        cp_async16(dst + (uint32_t)((r * WLD + cc) * 2), src + (int64_t)r * N + cc);
+      }
     }
     cp_async_commit();
   };
-  stage(0);
+#pragma unroll
+  for (int c = 0; c < NSTG - 1; ++c) stage(c);
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
-    if (c + 1 < NCH) { stage(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();
-    const uint32_t wb = sW + (uint32_t)((c & 1) * WBUF_BYTES);
+    cp_async_wait<NSTG - 2>();                           // chunk c has landed (this thread's copies) ...
+    __syncthreads();                                     // ... and everyone's; everyone is also done with chunk c - 1
+    stage(c + NSTG - 1);                                 // refills the buffer chunk c - 1 was read from
+    const uint32_t wb = sW + (uint32_t)((c % NSTG) * WBUF_BYTES);
 #pragma unroll
     for (int ks = 0; ks < WCH / 16; ++ks) {
       uint32_t a[MT][4];
@@ -96,8 +105,9 @@ __device__ __forceinline__ void cta_gemm(uint8_t* smem, const lp* As, int lda, c
         }
       }
     }
-    __syncthreads();                                     // chunk buffer (c & 1) is free for the prefetch of chunk c + 2
   }
+  cp_async_wait<0>();
+  __syncthreads();                                       // the ring is free for the next GEMM's prologue
 #pragma unroll
   for (int m = 0; m < MT; ++m)
 #pragma unroll
@@ -196,49 +206,92 @@ ctx_fused_kernel(const float* __restrict__ hn, const lp* __restrict__ hnb, const
       *reinterpret_cast<uint32_t*>(BIG + r * QLD + c) = pack2(v0, v1);
     });
     __syncthreads();
-    // attention on CUDA cores: (head, query) pairs over the warps; 34 keys, block mask of hypernetwork.py:151-181
-    for (int p = warp; p < CH * CTOK; p += 8) {
-      const int h = p / CTOK, q = p % CTOK;
-      float s0 = -INFINITY, s1 = -INFINITY;               // keys lane and lane + 32
-      {
-        const lp* qp = BIG + q * QLD + h * CHD;
-        float a0 = 0.f, a1 = 0.f;
-        const lp* k0 = BIG + lane * QLD + CD + h * CHD;
-        const lp* k1 = BIG + (32 + (lane & 1)) * QLD + CD + h * CHD;
+    // attention with warp-level mma: a unit is (head, 16-query m-tile), 12 units over the 8 warps; the 48 key slots
+    // (34 live) are one chunk.  Block mask of hypernetwork.py:151-181: keys 0..31 = token mask & language pad, key 32
+    // (initial image) always visible, key 33 (layer token) only to query 33.  Rows 34..47 of V are zeroed first: their
+    // probabilities are exactly 0, but 0 x (stale fp16 Inf/NaN) would still poison the accumulator.
+    for (int i = threadIdx.x; i < (48 - CTOK) * (CD / 8); i += NTH) {
+      const int r = CTOK + i / (CD / 8), c = (i % (CD / 8)) * 8;
+      *reinterpret_cast<uint4*>(BIG + r * QLD + 2 * CD + c) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    {
+      const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(BIG);
+      const int i4 = lane >> 3;
+      for (int unit = warp; unit < CH * MT; unit += 8) {
+        const int h = unit / MT, mt = unit % MT;
+        uint32_t qa[2][4];
 #pragma unroll
-        for (int u = 0; u < CHD / 8; ++u) {
-          const uint4 qv = *reinterpret_cast<const uint4*>(qp + u * 8);
-          const uint4 kv0 = *reinterpret_cast<const uint4*>(k0 + u * 8);
-          const uint4 kv1 = *reinterpret_cast<const uint4*>(k1 + u * 8);
-          const uint32_t* a = reinterpret_cast<const uint32_t*>(&qv);
-          const uint32_t* b0 = reinterpret_cast<const uint32_t*>(&kv0);
-          const uint32_t* b1 = reinterpret_cast<const uint32_t*>(&kv1);
+        for (int ks = 0; ks < 2; ++ks)
+          ldsm_x4(sQ + (uint32_t)(((mt * 16 + (lane & 7) + (i4 & 1) * 8) * QLD + h * CHD + ks * 16 + (i4 >> 1) * 8) * 2), qa[ks][0], qa[ks][1],
+                  qa[ks][2], qa[ks][3]);
+        float sc[6][4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 x = unpack2(a + e), y0 = unpack2(b0 + e), y1 = unpack2(b1 + e);
-            a0 = fmaf(x.x, y0.x, fmaf(x.y, y0.y, a0));
-            a1 = fmaf(x.x, y1.x, fmaf(x.y, y1.y, a1));
+        for (int np = 0; np < 3; ++np) {
+          sc[2 * np][0] = sc[2 * np][1] = sc[2 * np][2] = sc[2 * np][3] = 0.f;
+          sc[2 * np + 1][0] = sc[2 * np + 1][1] = sc[2 * np + 1][2] = sc[2 * np + 1][3] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(sQ + (uint32_t)((((np * 2 + (i4 >> 1)) * 8 + (lane & 7)) * QLD + CD + h * CHD + ks * 16 + (i4 & 1) * 8) * 2), b0, b1, b2, b3);
+            mma_f16(sc[2 * np], qa[ks], b0, b1);
+            mma_f16(sc[2 * np + 1], qa[ks], b2, b3);
           }
         }
-        if (kvalid[lane]) s0 = a0;
-        if (lane == 0) s1 = a1;                            // key 32 (initial image): always visible
-        else if (lane == 1 && q == CTOK - 1) s1 = a1;      // key 33 (layer token): only the layer token sees it
+        const int r0 = mt * 16 + (lane >> 2);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int key = nt * 8 + (lane & 3) * 2 + e;
+            const bool vis = key < LANG ? kvalid[key] != 0 : key == LANG;
+            const bool v0 = vis || (key == CTOK - 1 && r0 == CTOK - 1), v1 = vis || (key == CTOK - 1 && r0 + 8 == CTOK - 1);
+            sc[nt][e] = v0 ? sc[nt][e] : -INFINITY;
+            sc[nt][2 + e] = v1 ? sc[nt][2 + e] : -INFINITY;
+            mx0 = fmaxf(mx0, sc[nt][e]);
+            mx1 = fmaxf(mx1, sc[nt][2 + e]);
+          }
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            sc[nt][e] = sc[nt][e] == -INFINITY ? 0.f : __expf(sc[nt][e] - mx0);
+            sc[nt][2 + e] = sc[nt][2 + e] == -INFINITY ? 0.f : __expf(sc[nt][2 + e] - mx1);
+            l0 += sc[nt][e];
+            l1 += sc[nt][2 + e];
+          }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        float o[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          uint32_t pa[4];
+          pa[0] = pack2(sc[2 * kt][0], sc[2 * kt][1]); pa[1] = pack2(sc[2 * kt][2], sc[2 * kt][3]);
+          pa[2] = pack2(sc[2 * kt + 1][0], sc[2 * kt + 1][1]); pa[3] = pack2(sc[2 * kt + 1][2], sc[2 * kt + 1][3]);
+#pragma unroll
+          for (int dp = 0; dp < 2; ++dp) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4_t(sQ + (uint32_t)(((16 * kt + (i4 & 1) * 8 + (lane & 7)) * QLD + 2 * CD + h * CHD + (dp * 2 + (i4 >> 1)) * 8) * 2), b0, b1, b2, b3);
+            mma_f16(o[2 * dp], pa, b0, b1);
+            mma_f16(o[2 * dp + 1], pa, b2, b3);
+          }
+        }
+        const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int col = h * CHD + nt * 8 + (lane & 3) * 2;
+          if (r0 < CTOK) *reinterpret_cast<uint32_t*>(A + r0 * ALD + col) = pack2(o[nt][0] * inv0, o[nt][1] * inv0);
+          if (r0 + 8 < CTOK) *reinterpret_cast<uint32_t*>(A + (r0 + 8) * ALD + col) = pack2(o[nt][2] * inv1, o[nt][3] * inv1);
+        }
       }
-      float mx = fmaxf(s0, s1);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const float e0 = s0 == -INFINITY ? 0.f : __expf(s0 - mx), e1 = s1 == -INFINITY ? 0.f : __expf(s1 - mx);
-      float sum = e0 + e1;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      const float inv = 1.0f / sum;
-      float acc = 0.f;                                    // lane owns dim d = lane of this head
-      const lp* vp = BIG + 2 * CD + h * CHD + lane;
-#pragma unroll 8
-      for (int k = 0; k < 32; ++k) acc = fmaf(__shfl_sync(0xffffffffu, e0, k), __half2float(vp[k * QLD]), acc);
-      acc = fmaf(__shfl_sync(0xffffffffu, e1, 0), __half2float(vp[32 * QLD]), acc);
-      acc = fmaf(__shfl_sync(0xffffffffu, e1, 1), __half2float(vp[33 * QLD]), acc);
-      A[q * ALD + h * CHD + lane] = __float2half_rn(acc * inv);
     }
     __syncthreads();
     // x += attn Wo + b
