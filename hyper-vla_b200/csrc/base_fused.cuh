@@ -29,7 +29,7 @@ using attn::cp_async16;
 using attn::cp_async_commit;
 using attn::cp_async_wait;
 
-constexpr int NW = 9, NT = NW * 32;
+constexpr int NW = 12, NT = NW * 32;      // warps 0..7: patch rows; warps 8..11: the action token (rank 0), one head each
 constexpr int XLD = 72;                 // fp32 residual row stride (floats): conflict-free float2 C-fragment access
 constexpr int KLD = 72;                 // bf16 row stride for 64-wide matrices (144 B)
 constexpr int W0LD = 136;               // bf16 row stride for the 64x128 Dense_0 kernel
@@ -47,7 +47,7 @@ constexpr int OFF_VEC = OFF_W1 + 128 * KLD * 2;         // fp32 vectors
 constexpr int V_LN0S = 0, V_LN0B = 64, V_BQ = 128, V_BK = 192, V_BV = 256, V_BO = 320, V_LN1S = 384, V_LN1B = 448, V_B0 = 512,
               V_B1 = 640, V_COUNT = 704;
 constexpr int OFF_ACT = OFF_VEC + V_COUNT * 4;          // action-token scratch (fp32)
-constexpr int A_X = 0, A_XN = 64, A_Q = 128, A_K = 192, A_V = 256, A_O = 320, A_H = 384, A_P = 512, A_COUNT = 512 + 264;
+constexpr int A_X = 0, A_XN = 64, A_Q = 128, A_K = 192, A_V = 256, A_O = 320, A_H = 384, A_P = 512, A_COUNT = 512 + 4 * 264;   // A_P: one probability row per head
 constexpr int OFF_VECB = OFF_ACT + A_COUNT * 4;       // the layer's vectors as they arrive (bf16), converted into VEC
 constexpr int SMEM = OFF_VECB + V_COUNT * 2;
 constexpr int ELD = 72;                               // staged embedding chunk [256][72] bf16 (two of them fill the X region)
@@ -181,6 +181,19 @@ __device__ __forceinline__ float gemv_col(const float* x, const bf16* W, int ld,
 #pragma unroll 8
   for (int k = 0; k < K; ++k) a = fmaf(x[k], __bfloat162float(W[k * ld + n]), a);
   return a;
+}
+
+// barrier among the four action-token warps (threads 256..383)
+__device__ __forceinline__ void act_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// out[n] for n = n0 + (lane & 15): the two 16-lane halves of the warp each sum half of the K range
+template <int K>
+__device__ __forceinline__ float gemv_col_split(const float* x, const bf16* W, int ld, int n0, int lane) {
+  const int n = n0 + (lane & 15), k0 = (lane >> 4) * (K / 2);
+  float a = 0.f;
+#pragma unroll 8
+  for (int k = k0; k < k0 + K / 2; ++k) a = fmaf(x[k], __bfloat162float(W[k * ld + n]), a);
+  return a + __shfl_xor_sync(0xffffffffu, a, 16);
 }
 
 __device__ __forceinline__ void warp_ln64(const float* x, const float* sc, const float* bi, float* out, int lane) {
@@ -324,7 +337,7 @@ base_fused_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ weights
       }
       store_x(X, row0, lane, acc[t]);
     }
-  } else if (rank == 0) {
+  } else if (rank == 0 && warp == 8) {
     // action token: zeros + pos_embedding[256]  (base_vit.py:182-204)
     const bf16* pos = wrow + G::pos + 256 * BD;
     ACT[A_X + lane] = __bfloat162float(pos[lane]);
@@ -391,14 +404,20 @@ base_fused_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ weights
         }
       }
     } else if (rank == 0) {
-      warp_ln64(ACT + A_X, VEC + V_LN0S, VEC + V_LN0B, ACT + A_XN, lane);
-      __syncwarp();
+      // action token: LayerNorm by warp 8, then q / k / v on warps 8 / 9 / 10
+      if (warp == 8) warp_ln64(ACT + A_X, VEC + V_LN0S, VEC + V_LN0B, ACT + A_XN, lane);
+      act_bar();
+      if (warp < 11) {
+        const int j = warp - 8;
+        const bf16* Wj = reinterpret_cast<const bf16*>(smem + (j == 0 ? OFF_WQ : (j == 1 ? OFF_WK : OFF_WV)));
+        const float* bj = VEC + (j == 0 ? V_BQ : (j == 1 ? V_BK : V_BV));
+        float* dst = ACT + (j == 0 ? A_Q : (j == 1 ? A_K : A_V));
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        const int n = lane + 32 * h2;
-        ACT[A_Q + n] = (gemv_col<64>(ACT + A_XN, reinterpret_cast<const bf16*>(smem + OFF_WQ), KLD, n) + VEC[V_BQ + n]) * 0.25f;
-        ACT[A_K + n] = gemv_col<64>(ACT + A_XN, reinterpret_cast<const bf16*>(smem + OFF_WK), KLD, n) + VEC[V_BK + n];
-        ACT[A_V + n] = gemv_col<64>(ACT + A_XN, reinterpret_cast<const bf16*>(smem + OFF_WV), KLD, n) + VEC[V_BV + n];
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int n = lane + 32 * h2;
+          const float v = gemv_col<64>(ACT + A_XN, Wj, KLD, n) + bj[n];
+          dst[n] = j == 0 ? v * 0.25f : v;                    // q / sqrt(16)
+        }
       }
     }
     if (C > 1) cluster_sync_after_cta(); else __syncthreads();      // all 256 K/V rows are in place (in every CTA)
@@ -523,9 +542,9 @@ base_fused_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ weights
 #ifdef HVLA_BASE_TS
       const long long tb0_ = clock64();
 #endif
-      float* P = ACT + A_P;
-#pragma unroll 1
-      for (int h = 0; h < BH; ++h) {
+      const int h = warp - 8;                                 // one head per action warp
+      float* P = ACT + A_P + h * 264;
+      {
         float sc[9];
         float mx = -INFINITY;
 #pragma unroll
@@ -564,32 +583,27 @@ base_fused_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ weights
         for (int j = half * 128; j < half * 128 + 128; ++j) acc = fmaf(P[j], __bfloat162float(vp[j * KLD]), acc);
         acc += __shfl_xor_sync(0xffffffffu, acc, 16);
         if (half == 0) ACT[A_O + h * 16 + d] = acc + pself * inv * ACT[A_V + h * 16 + d];
-        __syncwarp();
       }
-#pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        const int n = lane + 32 * h2;
-        const float v = gemv_col<64>(ACT + A_O, reinterpret_cast<const bf16*>(smem + OFF_WO), KLD, n) + VEC[V_BO + n];
-        ACT[A_X + n] += v;
+      act_bar();                                              // all four heads' outputs are in ACT[A_O..]
+      // out-projection + residual: 16 outputs per warp, the K range split over the two half-warps
+      {
+        const float v = gemv_col_split<64>(ACT + A_O, reinterpret_cast<const bf16*>(smem + OFF_WO), KLD, h * 16, lane);
+        if (lane < 16) ACT[A_X + h * 16 + lane] += v + VEC[V_BO + h * 16 + lane];
       }
-      __syncwarp();
-      warp_ln64(ACT + A_X, VEC + V_LN1S, VEC + V_LN1B, ACT + A_XN, lane);
-      __syncwarp();
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        const int n = lane + 32 * q4;
+      act_bar();
+      if (warp == 8) warp_ln64(ACT + A_X, VEC + V_LN1S, VEC + V_LN1B, ACT + A_XN, lane);
+      act_bar();
+      {                                                        // MLP hidden: 32 of the 128 units per warp
+        const int n = h * 32 + lane;
         ACT[A_H + n] = gelu_tanh_f(gemv_col<64>(ACT + A_XN, reinterpret_cast<const bf16*>(smem + OFF_W0), W0LD, n) + VEC[V_B0 + n]);
       }
-      __syncwarp();
-#pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        const int n = lane + 32 * h2;
-        const float v = gemv_col<128>(ACT + A_H, reinterpret_cast<const bf16*>(smem + OFF_W1), KLD, n) + VEC[V_B1 + n];
-        ACT[A_X + n] += v;
+      act_bar();
+      {
+        const float v = gemv_col_split<128>(ACT + A_H, reinterpret_cast<const bf16*>(smem + OFF_W1), KLD, h * 16, lane);
+        if (lane < 16) ACT[A_X + h * 16 + lane] += v + VEC[V_B1 + h * 16 + lane];
       }
-      __syncwarp();
 #ifdef HVLA_BASE_TS
-      if (blockIdx.x == 0 && lane == 0) printf("base_ts action-token warp, layer %d phase B: %lld cycles\n", l, clock64() - tb0_);
+      if (blockIdx.x == 0 && warp == 8 && lane == 0) printf("base_ts action-token warps, layer %d phase B: %lld cycles\n", l, clock64() - tb0_);
 #endif
     }
     if (C > 1) cluster_sync_after_cta(); else __syncthreads();      // nobody reads this layer's K/V any more
