@@ -35,6 +35,14 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 __device__ __forceinline__ float2 unpack2(const void* p) { return __half22float2(*reinterpret_cast<const __half2*>(p)); }
 
+// tanh-GELU (transformer.py:66) with the MUFU tanh (relative error < 2^-11, below the fp16 rounding of the stored hidden)
+__device__ __forceinline__ float gelu_tanh_approx(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.7978845608028654f * (x + 0.044715f * (x * x * x))));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+
 constexpr int NTH = 256, MT = 3;                         // 8 warps; 3 m-tiles = 48 rows (34 used)
 constexpr int XLD = 132, ALD = 136, QLD = 392, HLD = 520, ELD = 776, WCH = 32;
 constexpr int OFF_X = 0;                                 // fp32 [48][132]
@@ -43,7 +51,8 @@ constexpr int OFF_BIG = OFF_A + 48 * ALD * 2;            // fp16: q|k|v [48][392
 constexpr int BIG_BYTES = 48 * HLD * 2;
 constexpr int NSTG = 4;                                  // weight-chunk ring: 3 chunks in flight while one is consumed
 constexpr int OFF_W = OFF_BIG + BIG_BYTES;               // NSTG x weight chunk [32][<=520] fp16
-constexpr int WBUF_BYTES = WCH * HLD * 2;
+constexpr int WBUF_BYTES = 128 * ALD * 2;               // holds a [32][520] chunk (N = 512) or a [128][136] chunk (N = 128)
+static_assert(WCH * HLD * 2 <= WBUF_BYTES, "ring buffer");
 constexpr int OFF_MISC = OFF_W + NSTG * WBUF_BYTES;      // key-valid flags [34]
 constexpr int SMEM = OFF_MISC + 256;
 static_assert(SMEM <= 232448, "shared memory budget");
@@ -51,11 +60,37 @@ static_assert(32 * ELD * 2 <= BIG_BYTES && 48 * QLD * 2 <= BIG_BYTES, "BIG regio
 
 // C[48 x N] (+)= A[48 x K] (fp16 smem, row stride lda) * W[K x N] (fp16 global, row-major), warp w owns N/8 columns.
 // epi(row, col, v0, v1) is called for column pairs (col, col+1) of rows < 34.
+// The weight-chunk ring is shared by consecutive GEMMs: `g` counts chunks since kernel start (buffer = g % NSTG), and the
+// last NSTG-1 iterations of a GEMM stage the first chunks of the NEXT one (next_W / next_N / next_K), so that its pipeline is
+// already full when it starts instead of paying an L2 round trip per GEMM (26 GEMMs per task).
+struct NextW {
+  const lp* W;
+  int N, K, rows;                                        // rows per chunk of that GEMM (32, or 128 for the 128-wide deep ones)
+};
+// chunk rows: the deep, narrow GEMMs (K >= 512, N = 128) take 128-row chunks -- a quarter of the barrier/stage rounds and
+// four times the bytes in flight (the ring is bound by L2 latency, three chunks in flight)
+template <int N, int K>
+struct ChunkRows { static constexpr int value = (K >= 512 && N == 128) ? 128 : WCH; };
+
+__device__ __forceinline__ void stage_chunk(uint32_t sW, int g, const lp* Wg, int N, int c, int rows) {
+  const uint32_t dst = sW + (uint32_t)((g % NSTG) * WBUF_BYTES);
+  const lp* src = Wg + (int64_t)c * rows * N;
+  const int per_row = N / 8, wld = N + 8;
+  for (int i = threadIdx.x; i < rows * per_row; i += NTH) {
+    const int r = i / per_row, cc = (i - r * per_row) * 8;
+    cp_async16(dst + (uint32_t)((r * wld + cc) * 2), src + (int64_t)r * N + cc);
+  }
+}
+
 template <int N, int K, class Epi>
-__device__ __forceinline__ void cta_gemm(uint8_t* smem, const lp* As, int lda, const lp* __restrict__ Wg, Epi epi) {
+__device__ __forceinline__ void cta_gemm(uint8_t* smem, const lp* As, int lda, const lp* __restrict__ Wg, Epi epi, int& g, bool prefetched,
+                                         NextW next) {
   constexpr int NTW = N / 64;                            // n-tiles (8 columns) per warp
   constexpr int WLD = N + 8;
-  constexpr int NCH = K / WCH;
+  constexpr int CR = ChunkRows<N, K>::value;
+  constexpr int NCH = K / CR;
+  static_assert(NCH >= NSTG - 1, "every GEMM has at least NSTG-1 chunks");
+  static_assert(CR * WLD * 2 <= WBUF_BYTES, "chunk fits a ring buffer");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sW = (uint32_t)__cvta_generic_to_shared(smem + OFF_W);
   const uint32_t sA = (uint32_t)__cvta_generic_to_shared(As);
@@ -64,34 +99,30 @@ __device__ __forceinline__ void cta_gemm(uint8_t* smem, const lp* As, int lda, c
   for (int m = 0; m < MT; ++m)
 #pragma unroll
     for (int n = 0; n < NTW; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
-  // The kernel is bound by L2 round trips (one CTA streams 2.8 MB of weights in 32-row chunks, ~200 of them per task):
-  // a 4-deep cp.async ring keeps three chunks in flight.  One commit group per iteration (empty past the end) keeps
-  // the wait_group arithmetic uniform.
-  auto stage = [&](int c) {
-    if (c < NCH) {
-      const uint32_t dst = sW + (uint32_t)((c % NSTG) * WBUF_BYTES);
-      const lp* src = Wg + (int64_t)c * WCH * N;
-      for (int i = threadIdx.x; i < WCH * (N / 8); i += NTH) {
-        const int r = i / (N / 8), cc = (i % (N / 8)) * 8;
-        cp_async16(dst + (uint32_t)((r * WLD + cc) * 2), src + (int64_t)r * N + cc);
-      }
-    }
-    cp_async_commit();
-  };
+  // One commit group per staged slot (empty when there is nothing to stage) keeps the wait_group arithmetic uniform.
+  const int g0 = g;
+  if (!prefetched) {
 #pragma unroll
-  for (int c = 0; c < NSTG - 1; ++c) stage(c);
+    for (int c = 0; c < NSTG - 1; ++c) { stage_chunk(sW, g0 + c, Wg, N, c, CR); cp_async_commit(); }
+  }
+  const int next_nch = next.W ? next.K / next.rows : 0;
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
     cp_async_wait<NSTG - 2>();                           // chunk c has landed (this thread's copies) ...
-    __syncthreads();                                     // ... and everyone's; everyone is also done with chunk c - 1
-    stage(c + NSTG - 1);                                 // refills the buffer chunk c - 1 was read from
-    const uint32_t wb = sW + (uint32_t)((c % NSTG) * WBUF_BYTES);
+    __syncthreads();                                     // ... and everyone's; everyone is also done with the previous chunk
+    {                                                    // refill the buffer the previous chunk was read from
+      const int cn = c + NSTG - 1;
+      if (cn < NCH) stage_chunk(sW, g0 + cn, Wg, N, cn, CR);
+      else if (cn - NCH < next_nch) stage_chunk(sW, g0 + cn, next.W, next.N, cn - NCH, next.rows);
+      cp_async_commit();
+    }
+    const uint32_t wb = sW + (uint32_t)(((g0 + c) % NSTG) * WBUF_BYTES);
 #pragma unroll
-    for (int ks = 0; ks < WCH / 16; ++ks) {
+    for (int ks = 0; ks < CR / 16; ++ks) {
       uint32_t a[MT][4];
 #pragma unroll
       for (int m = 0; m < MT; ++m)
-        ldsm_x4(sA + (uint32_t)(((m * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * lda + c * WCH + ks * 16 + (lane >> 4) * 8) * 2), a[m][0], a[m][1],
+        ldsm_x4(sA + (uint32_t)(((m * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * lda + c * CR + ks * 16 + (lane >> 4) * 8) * 2), a[m][0], a[m][1],
                 a[m][2], a[m][3]);
 #pragma unroll
       for (int np = 0; np < NTW / 2; ++np) {
@@ -106,8 +137,8 @@ __device__ __forceinline__ void cta_gemm(uint8_t* smem, const lp* As, int lda, c
       }
     }
   }
-  cp_async_wait<0>();
-  __syncthreads();                                       // the ring is free for the next GEMM's prologue
+  g = g0 + NCH;
+  // no trailing barrier: the next refill of the buffer read last happens after the first barrier of the next GEMM
 #pragma unroll
   for (int m = 0; m < MT; ++m)
 #pragma unroll
@@ -140,11 +171,21 @@ __device__ __forceinline__ void ln_rows(const float* X, lp* A, const float* __re
   }
 }
 
+#ifdef HVLA_CTX_TS
+#define CTX_TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (i) < 24) ts_[i] = clock64(); } while (0)
+#else
+#define CTX_TS(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(NTH, 1)
 ctx_fused_kernel(const float* __restrict__ hn, const lp* __restrict__ hnb, const float* __restrict__ tok_emb,
                  const int32_t* __restrict__ tok_mask, const uint8_t* __restrict__ lang_pad, const float* __restrict__ init_cls,
                  float* __restrict__ out_ctx) {
   extern __shared__ __align__(16) uint8_t smem[];
+#ifdef HVLA_CTX_TS
+  long long ts_[24];
+#endif
+  CTX_TS(0);
   typedef HnLayout L;
   const int t = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -169,12 +210,14 @@ ctx_fused_kernel(const float* __restrict__ hn, const lp* __restrict__ hnb, const
   for (int i = threadIdx.x; i < 48 * ALD / 2; i += NTH) reinterpret_cast<uint32_t*>(A)[i] = 0u;
   __syncthreads();
   // ---- K1: task tokens = tok_emb * W + b + task_pos (hypernetwork.py:112-115) --------------------------------------
+  CTX_TS(1);
+  int ring = 0;                                          // chunks staged since kernel start (ring position)
   cta_gemm<CD, LANGD>(smem, BIG, ELD, hnb + L::tok_w, [&](int r, int c, float v0, float v1) {
     if (r < LANG) {
       X[r * XLD + c] = v0 + hn[L::tok_b + c] + hn[L::task_pos + r * CD + c];
       X[r * XLD + c + 1] = v1 + hn[L::tok_b + c + 1] + hn[L::task_pos + r * CD + c + 1];
     }
-  });
+  }, ring, false, NextW{hnb + L::img_w, CD, DD, ChunkRows<CD, DD>::value});
   // initial-image token (row 32): cls * W + b + pos (hypernetwork.py:126-127) as a second small GEMM whose only
   // live row is row 0 of the A operand; layer token (row 33) = 0 + pos (hypernetwork.py:144-145)
   __syncthreads();
@@ -189,23 +232,26 @@ ctx_fused_kernel(const float* __restrict__ hn, const lp* __restrict__ hnb, const
       X[32 * XLD + c] = v0 + hn[L::img_b + c] + hn[L::img_pos + c];
       X[32 * XLD + c + 1] = v1 + hn[L::img_b + c + 1] + hn[L::img_pos + c + 1];
     }
-  });
+  }, ring, true, NextW{hnb + L::layers + L::wqkv, 3 * CD, CD, WCH});
   __syncthreads();
 
+  CTX_TS(2);
   // ---- K2: 6 encoder blocks ----------------------------------------------------------------------------------------
   for (int l = 0; l < CL; ++l) {
     const float* lw = hn + L::layers + (int64_t)l * L::layer_size;
     const lp* lb = hnb + L::layers + (int64_t)l * L::layer_size;
     ln_rows(X, A, lw + L::ln0_s, lw + L::ln0_b);
     __syncthreads();
+    if (l < 2) CTX_TS(3 + 8 * l);
     // q|k|v = LN(x) Wqkv + b; q pre-divided by sqrt(32)
     cta_gemm<3 * CD, CD>(smem, A, ALD, lb + L::wqkv, [&](int r, int c, float v0, float v1) {
       v0 += lw[L::bqkv + c];
       v1 += lw[L::bqkv + c + 1];
       if (c < CD) { v0 *= 0.17677669529663687f; v1 *= 0.17677669529663687f; }
       *reinterpret_cast<uint32_t*>(BIG + r * QLD + c) = pack2(v0, v1);
-    });
+    }, ring, true, NextW{lb + L::wo, CD, CD, WCH});
     __syncthreads();
+    if (l < 2) CTX_TS(4 + 8 * l);
     // attention with warp-level mma: a unit is (head, 16-query m-tile), 12 units over the 8 warps; the 48 key slots
     // (34 live) are one chunk.  Block mask of hypernetwork.py:151-181: keys 0..31 = token mask & language pad, key 32
     // (initial image) always visible, key 33 (layer token) only to query 33.  Rows 34..47 of V are zeroed first: their
@@ -294,25 +340,30 @@ ctx_fused_kernel(const float* __restrict__ hn, const lp* __restrict__ hnb, const
       }
     }
     __syncthreads();
+    if (l < 2) CTX_TS(5 + 8 * l);
     // x += attn Wo + b
     cta_gemm<CD, CD>(smem, A, ALD, lb + L::wo, [&](int r, int c, float v0, float v1) {
       X[r * XLD + c] += v0 + lw[L::bo + c];
       X[r * XLD + c + 1] += v1 + lw[L::bo + c + 1];
-    });
+    }, ring, true, NextW{lb + L::w0, CF, CD, WCH});
     __syncthreads();
+    if (l < 2) CTX_TS(6 + 8 * l);
     ln_rows(X, A, lw + L::ln1_s, lw + L::ln1_b);
     __syncthreads();
+    if (l < 2) CTX_TS(7 + 8 * l);
     // h = gelu_tanh(LN(x) W0 + b0)
     cta_gemm<CF, CD>(smem, A, ALD, lb + L::w0, [&](int r, int c, float v0, float v1) {
-      *reinterpret_cast<uint32_t*>(BIG + r * HLD + c) = pack2(gelu_tanh_f(v0 + lw[L::b0 + c]), gelu_tanh_f(v1 + lw[L::b0 + c + 1]));
-    });
+      *reinterpret_cast<uint32_t*>(BIG + r * HLD + c) = pack2(gelu_tanh_approx(v0 + lw[L::b0 + c]), gelu_tanh_approx(v1 + lw[L::b0 + c + 1]));
+    }, ring, true, NextW{lb + L::w1, CD, CF, ChunkRows<CD, CF>::value});
     __syncthreads();
+    if (l < 2) CTX_TS(8 + 8 * l);
     // x += h W1 + b1
     cta_gemm<CD, CF>(smem, BIG, HLD, lb + L::w1, [&](int r, int c, float v0, float v1) {
       X[r * XLD + c] += v0 + lw[L::b1 + c];
       X[r * XLD + c + 1] += v1 + lw[L::b1 + c + 1];
-    });
+    }, ring, true, l + 1 < CL ? NextW{lb + L::layer_size + L::wqkv, 3 * CD, CD, WCH} : NextW{nullptr, 0, 0, WCH});
     __syncthreads();
+    if (l < 2) CTX_TS(9 + 8 * l);
   }
   // ---- encoder_norm on the layer token, / sqrt(128)  (hypernetwork.py:188-192) --------------------------------------
   if (warp == 0) {
@@ -335,6 +386,13 @@ ctx_fused_kernel(const float* __restrict__ hn, const lp* __restrict__ hnb, const
     o.w = ((v.w - mean) * (rstd * g.w) + b.w) / d;
     *reinterpret_cast<float4*>(out_ctx + (int64_t)t * CD + lane * 4) = o;
   }
+#ifdef HVLA_CTX_TS
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    printf("ctx_ts (in, tok+img proj, | ln0 qkv attn wo ln1 w0 w1 | ...):");
+    for (int i = 1; i < 18; ++i) printf(" %lld", ts_[i] - ts_[i - 1]);
+    printf(" total %lld\n", clock64() - ts_[0]);
+  }
+#endif
 }
 
 inline int ctx_encode_lp(cudaStream_t st, const float* hn, const lp* hnb, const float* tok_emb, const int32_t* tok_mask,
