@@ -373,6 +373,7 @@ template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, EpiP ep, int M, int N, int K) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
@@ -410,6 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();                  // predecessor's outputs are complete and visible
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -553,7 +555,7 @@ inline int launch_one(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap&
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   ProfScope ps(st, "gemm_tc");
-  gemm_tc_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, mo, ep, M, N, K);
+  launch_k(gemm_tc_kernel<EPI>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM_BYTES, st, ma, mb, mo, ep, M, N, K);
   HVLA_LAUNCH_CHECK("gemm_tc");
   return HVLA_OK;
 }

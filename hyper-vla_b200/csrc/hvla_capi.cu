@@ -284,7 +284,10 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
     const int64_t total = (int64_t)B * NPATCH * PATCH_KP;
     {
       ProfScope ps(st, "im2col");
-      launch_k(im2col_norm_bf16_kernel, dim3(cdiv(total / 8, 256 * 4)), dim3(256), 0, st, images, A0, B);
+      {
+        const int blocks = cdiv(total / 8, 256);           // 8 k per thread-item; at most ~4 items per thread
+        launch_k(im2col_norm_bf16_kernel, dim3(blocks < 1184 ? blocks : cdiv(total / 8, 256 * 4)), dim3(256), 0, st, images, A0, B);
+      }
       HVLA_LAUNCH_CHECK("im2col");
     }
     ProfScope ps2(st, "cls_rows");
@@ -448,7 +451,7 @@ static int base_act_impl(cudaStream_t st, const void* emb, const void* weights, 
                          float* out_action, float* out_logit, uint8_t* ws, const Plan& pl, int dtype) {
   if (!task_index && !(T == B || T == 1)) return fail(HVLA_ERR_ARG, "task_index is NULL but T != B and T != 1");
   const int32_t* tidx = task_index;
-  if (!tidx && T == 1) {   // shared weights: materialise an all-zero index
+  if (!tidx && T == 1 && B > 1) {   // shared weights: materialise an all-zero index (B == 1: identity already is)
     int* z = reinterpret_cast<int*>(ws + pl.tidx);
     fill_index_kernel<<<cdiv(B, 256), 256, 0, st>>>(z, B, 0);
     HVLA_LAUNCH_CHECK("fill_index");
