@@ -441,71 +441,97 @@ base_fused_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ weights
           for (int j = 0; j < 8; ++j) { q[j][0] *= 0.25f; q[j][1] *= 0.25f; q[j][2] *= 0.25f; q[j][3] *= 0.25f; }   // / sqrt(16)
           uint32_t qa[4][4];
           c_to_a(q, qa);
-          float o[8][4];
-          zero8(o);
           constexpr float LOG2E = 1.4426950408889634f;
+          // Two heads at a time, stage by stage (scores, max, exp, PV): the warp is latency-bound, two independent
+          // dependency chains roughly double its issue rate.  Head h's normalised output IS k-step h of the
+          // out-projection's A operand, so it is packed straight into `a` (the LayerNorm fragments are dead by now).
 #pragma unroll
-          for (int h = 0; h < BH; ++h) {
-            float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-            float oh[2][4];
-            oh[0][0] = oh[0][1] = oh[0][2] = oh[0][3] = 0.f;
-            oh[1][0] = oh[1][1] = oh[1][2] = oh[1][3] = 0.f;
+          for (int hp = 0; hp < BH / 2; ++hp) {
+            float m0[2], m1[2], l0[2], l1[2], oh[2][2][4];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              m0[u] = m1[u] = -INFINITY; l0[u] = l1[u] = 0.f;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) oh[u][0][e] = oh[u][1][e] = 0.f;
+            }
 #pragma unroll 1
             for (int kc = 0; kc < 4; ++kc) {
               const int key0 = kc * 64;
-              float s[8][4];
+              float s[2][8][4];
               const int i = lane >> 3;
 #pragma unroll
               for (int np = 0; np < 4; ++np) {
-                s[2 * np][0] = s[2 * np][1] = s[2 * np][2] = s[2 * np][3] = 0.f;
-                s[2 * np + 1][0] = s[2 * np + 1][1] = s[2 * np + 1][2] = s[2 * np + 1][3] = 0.f;
-                uint32_t b0, b1, b2, b3;
-                const uint32_t addr = sK + (uint32_t)(((key0 + (np * 2 + (i >> 1)) * 8 + (lane & 7)) * KLD + h * 16 + (i & 1) * 8) * 2);
-                ldsm_x4(addr, b0, b1, b2, b3);
-                mma_bf16(s[2 * np], qa[h], b0, b1);
-                mma_bf16(s[2 * np + 1], qa[h], b2, b3);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const int h = 2 * hp + u;
+                  s[u][2 * np][0] = s[u][2 * np][1] = s[u][2 * np][2] = s[u][2 * np][3] = 0.f;
+                  s[u][2 * np + 1][0] = s[u][2 * np + 1][1] = s[u][2 * np + 1][2] = s[u][2 * np + 1][3] = 0.f;
+                  uint32_t b0, b1, b2, b3;
+                  const uint32_t addr = sK + (uint32_t)(((key0 + (np * 2 + (i >> 1)) * 8 + (lane & 7)) * KLD + h * 16 + (i & 1) * 8) * 2);
+                  ldsm_x4(addr, b0, b1, b2, b3);
+                  mma_bf16(s[u][2 * np], qa[h], b0, b1);
+                  mma_bf16(s[u][2 * np + 1], qa[h], b2, b3);
+                }
               }
-              float mx0 = m0, mx1 = m1;
+              float ms0[2], ms1[2];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                float mx0 = m0[u], mx1 = m1[u];
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                  mx0 = fmaxf(mx0, fmaxf(s[u][nt][0], s[u][nt][1]));
+                  mx1 = fmaxf(mx1, fmaxf(s[u][nt][2], s[u][nt][3]));
+                }
+                mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+                const float c0 = exp2f((m0[u] - mx0) * LOG2E), c1 = exp2f((m1[u] - mx1) * LOG2E);
+                m0[u] = mx0; m1[u] = mx1;
+                l0[u] *= c0; l1[u] *= c1;
+                oh[u][0][0] *= c0; oh[u][0][1] *= c0; oh[u][0][2] *= c1; oh[u][0][3] *= c1;
+                oh[u][1][0] *= c0; oh[u][1][1] *= c0; oh[u][1][2] *= c1; oh[u][1][3] *= c1;
+                ms0[u] = mx0 * LOG2E; ms1[u] = mx1 * LOG2E;
+              }
 #pragma unroll
               for (int nt = 0; nt < 8; ++nt) {
-                mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-                mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-              }
-              mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-              mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-              const float c0 = exp2f((m0 - mx0) * LOG2E), c1 = exp2f((m1 - mx1) * LOG2E);
-              m0 = mx0; m1 = mx1;
-              l0 *= c0; l1 *= c1;
-              oh[0][0] *= c0; oh[0][1] *= c0; oh[0][2] *= c1; oh[0][3] *= c1;
-              oh[1][0] *= c0; oh[1][1] *= c0; oh[1][2] *= c1; oh[1][3] *= c1;
-              const float ms0 = mx0 * LOG2E, ms1 = mx1 * LOG2E;
 #pragma unroll
-              for (int nt = 0; nt < 8; ++nt) {
-                s[nt][0] = exp2f(fmaf(s[nt][0], LOG2E, -ms0)); s[nt][1] = exp2f(fmaf(s[nt][1], LOG2E, -ms0));
-                s[nt][2] = exp2f(fmaf(s[nt][2], LOG2E, -ms1)); s[nt][3] = exp2f(fmaf(s[nt][3], LOG2E, -ms1));
-                l0 += s[nt][0] + s[nt][1];
-                l1 += s[nt][2] + s[nt][3];
+                for (int u = 0; u < 2; ++u) {
+                  s[u][nt][0] = exp2f(fmaf(s[u][nt][0], LOG2E, -ms0[u])); s[u][nt][1] = exp2f(fmaf(s[u][nt][1], LOG2E, -ms0[u]));
+                  s[u][nt][2] = exp2f(fmaf(s[u][nt][2], LOG2E, -ms1[u])); s[u][nt][3] = exp2f(fmaf(s[u][nt][3], LOG2E, -ms1[u]));
+                  l0[u] += s[u][nt][0] + s[u][nt][1];
+                  l1[u] += s[u][nt][2] + s[u][nt][3];
+                }
               }
 #pragma unroll
               for (int kt = 0; kt < 4; ++kt) {
-                uint32_t pa[4];
-                pa[0] = pack2(s[2 * kt][0], s[2 * kt][1]); pa[1] = pack2(s[2 * kt][2], s[2 * kt][3]);
-                pa[2] = pack2(s[2 * kt + 1][0], s[2 * kt + 1][1]); pa[3] = pack2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
-                uint32_t b0, b1, b2, b3;
-                const uint32_t addr = sV + (uint32_t)(((key0 + 16 * kt + (i & 1) * 8 + (lane & 7)) * KLD + h * 16 + (i >> 1) * 8) * 2);
-                ldsm_x4_t(addr, b0, b1, b2, b3);
-                mma_bf16(oh[0], pa, b0, b1);
-                mma_bf16(oh[1], pa, b2, b3);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const int h = 2 * hp + u;
+                  uint32_t pa[4];
+                  pa[0] = pack2(s[u][2 * kt][0], s[u][2 * kt][1]); pa[1] = pack2(s[u][2 * kt][2], s[u][2 * kt][3]);
+                  pa[2] = pack2(s[u][2 * kt + 1][0], s[u][2 * kt + 1][1]); pa[3] = pack2(s[u][2 * kt + 1][2], s[u][2 * kt + 1][3]);
+                  uint32_t b0, b1, b2, b3;
+                  const uint32_t addr = sV + (uint32_t)(((key0 + 16 * kt + (i & 1) * 8 + (lane & 7)) * KLD + h * 16 + (i >> 1) * 8) * 2);
+                  ldsm_x4_t(addr, b0, b1, b2, b3);
+                  mma_bf16(oh[u][0], pa, b0, b1);
+                  mma_bf16(oh[u][1], pa, b2, b3);
+                }
               }
             }
-            l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-            l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-            const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-            o[2 * h][0] = oh[0][0] * i0; o[2 * h][1] = oh[0][1] * i0; o[2 * h][2] = oh[0][2] * i1; o[2 * h][3] = oh[0][3] * i1;
-            o[2 * h + 1][0] = oh[1][0] * i0; o[2 * h + 1][1] = oh[1][1] * i0; o[2 * h + 1][2] = oh[1][2] * i1; o[2 * h + 1][3] = oh[1][3] * i1;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int h = 2 * hp + u;
+              float t0 = l0[u], t1 = l1[u];
+              t0 += __shfl_xor_sync(0xffffffffu, t0, 1); t0 += __shfl_xor_sync(0xffffffffu, t0, 2);
+              t1 += __shfl_xor_sync(0xffffffffu, t1, 1); t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+              const float i0 = 1.0f / t0, i1 = 1.0f / t1;
+              a[h][0] = pack2(oh[u][0][0] * i0, oh[u][0][1] * i0);
+              a[h][1] = pack2(oh[u][0][2] * i1, oh[u][0][3] * i1);
+              a[h][2] = pack2(oh[u][1][0] * i0, oh[u][1][1] * i0);
+              a[h][3] = pack2(oh[u][1][2] * i1, oh[u][1][3] * i1);
+            }
           }
           // out-projection + residual
-          c_to_a(o, a);
+          float o[8][4];
           zero8(o);
           gemm_tile<8, 4>(o, a, sbase + OFF_WO, KLD, 0, 0, lane);
           add_bias(o, VEC + V_BO, lane);
