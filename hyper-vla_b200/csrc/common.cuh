@@ -67,7 +67,10 @@ static_assert(GenLayout::total == NG, "generated row size");
 struct DvecLayout {
   static constexpr int64_t patch_b = 0, cls = DD, pos = 2 * DD, layers = pos + (int64_t)DTOK * DD;
   static constexpr int64_t ln1_s = 0, ln1_b = DD, bqkv = 2 * DD, bo = bqkv + 3 * DD, ls1 = bo + DD, ln2_s = ls1 + DD,
-                           ln2_b = ln2_s + DD, b1 = ln2_b + DD, b2 = b1 + DF, ls2 = b2 + DD, layer_size = ls2 + DD;
+                           ln2_b = ln2_s + DD, b1 = ln2_b + DD, b2 = b1 + DF, ls2 = b2 + DD,
+                           // LayerNorm folded into the next linear (tensor-core path): folded biases and column sums of gamma*W
+                           bqkv_f = ls2 + DD, cs_qkv = bqkv_f + 3 * DD, b1_f = cs_qkv + 3 * DD, cs_1 = b1_f + DF,
+                           layer_size = cs_1 + DF;
   static constexpr int64_t lnf_s = layers + DL * layer_size, lnf_b = lnf_s + DD, total = lnf_b + DD;
 };
 

@@ -322,12 +322,13 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
     const float* v = dv + V::layers + (int64_t)l * V::layer_size;
     const bf16* m = dm + Mx::layers + (int64_t)l * Mx::layer_size;
     LnP ln; memset(&ln, 0, sizeof ln);
-    ln.x = X; ln.ldx = DD; ln.y = Y; ln.ldy = DD; ln.scale = v + V::ln1_s; ln.bias = v + V::ln1_b; ln.rows = M; ln.rows_per_batch = 1;
+    // gamma / beta of both LayerNorms are folded into wqkv / w1 and their biases (params.py: pack_dino_tree): plain (x-mean)*rstd here
+    ln.x = X; ln.ldx = DD; ln.y = Y; ln.ldy = DD; ln.scale = nullptr; ln.bias = nullptr; ln.rows = M; ln.rows_per_batch = 1;
     ln.part = PART; ln.part_stride = part_stride; ln.nsplit = splits - 1;   // partial products of the previous layer's fc2
     HVLA_TRY((layernorm<float, bf16>(st, ln, DD)));
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
-      ep.bias = v + V::bqkv; ep.out = QKV; ep.ldo = 3 * DD; ep.qscale = 0.125f; ep.qcols = DD;   // q / sqrt(64)
+      ep.bias = v + V::bqkv_f; ep.out = QKV; ep.ldo = 3 * DD; ep.qscale = 0.125f; ep.qcols = DD;   // q / sqrt(64)
       HVLA_TRY(gemm(Y, m + Mx::wqkv, M, 3 * DD, DD, tc::EPI_BIAS_BF16, ep));
     }
     if (simt_attn) {
@@ -345,12 +346,11 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
       ep.part = PART; ep.part_bytes = PART_BYTES; ep.splits_used = &splits;
       HVLA_TRY(gemm(ATT, m + Mx::wo, M, DD, DD, tc::EPI_RESIDUAL_F32, ep));
     }
-    ln.scale = v + V::ln2_s; ln.bias = v + V::ln2_b;
     ln.nsplit = splits - 1;      // this LayerNorm first folds the split-K partial products into the stream
     HVLA_TRY((layernorm<float, bf16>(st, ln, DD)));
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
-      ep.bias = v + V::b1; ep.out = HID; ep.ldo = DF;
+      ep.bias = v + V::b1_f; ep.out = HID; ep.ldo = DF;
       HVLA_TRY(gemm(Y, m + Mx::w1, M, DF, DD, tc::EPI_BIAS_GELU_BF16, ep));
     }
     {
@@ -532,6 +532,7 @@ int64_t hvla_layout_offset(const char* name) {
       if (layer < 0 || layer >= DL) return -1;
       FL(DvecLayout, ln1_s) FL(DvecLayout, ln1_b) FL(DvecLayout, bqkv) FL(DvecLayout, bo) FL(DvecLayout, ls1)
       FL(DvecLayout, ln2_s) FL(DvecLayout, ln2_b) FL(DvecLayout, b1) FL(DvecLayout, b2) FL(DvecLayout, ls2)
+      FL(DvecLayout, bqkv_f) FL(DvecLayout, cs_qkv) FL(DvecLayout, b1_f) FL(DvecLayout, cs_1)
       return -1;
     }
     F(DvecLayout, patch_b) F(DvecLayout, cls) F(DvecLayout, pos) F(DvecLayout, lnf_s) F(DvecLayout, lnf_b) F(DvecLayout, total)

@@ -244,8 +244,8 @@ __global__ void __launch_bounds__(256) layernorm768_kernel(float* __restrict__ x
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     const int c = (lane + 32 * i) * 4;
-    const float4 g = __ldg(reinterpret_cast<const float4*>(scale + c));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c));
+    const float4 g = scale ? __ldg(reinterpret_cast<const float4*>(scale + c)) : make_float4(1.f, 1.f, 1.f, 1.f);   // null: unit scale,
+    const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);     // zero bias
     float o[4];
     o[0] = (v[i].x - mean) * (rstd * g.x) + b.x;
     o[1] = (v[i].y - mean) * (rstd * g.y) + b.y;

@@ -281,7 +281,9 @@ def dino_vec_layout() -> Dict[str, Tuple[int, int]]:
     add("pos", C.DINO_TOKENS * D)
     for l in range(C.DINO_LAYERS):
         for nm, n in (("ln1_s", D), ("ln1_b", D), ("bqkv", 3 * D), ("bo", D), ("ls1", D),
-                      ("ln2_s", D), ("ln2_b", D), ("b1", Fm), ("b2", D), ("ls2", D)):
+                      ("ln2_s", D), ("ln2_b", D), ("b1", Fm), ("b2", D), ("ls2", D),
+                      # LayerNorm folded into the following linear layer (bf16 tensor-core path, see pack_dino_tree)
+                      ("bqkv_f", 3 * D), ("cs_qkv", 3 * D), ("b1_f", Fm), ("cs_1", Fm)):
             add(f"l{l}.{nm}", n)
     add("lnf_s", D)
     add("lnf_b", D)
@@ -318,9 +320,21 @@ def pack_dino(params: dict, transposed: bool) -> Tuple[np.ndarray, np.ndarray]:
     return pack_dino_tree(dino_tree_from_params(params), transposed)
 
 
+def bf16_round(x: np.ndarray) -> np.ndarray:
+    """float32 -> nearest bfloat16 (ties to even), returned as float32: what the tensor cores will multiply."""
+    u = np.ascontiguousarray(x, F32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(F32).reshape(np.shape(x))
+
+
 def pack_dino_tree(t: dict, transposed: bool) -> Tuple[np.ndarray, np.ndarray]:
     """(vec blob fp32, matrix blob fp32) of a HF DINOv2-base param tree.  The caller casts the matrix blob to
-    bf16 for the tensor-core path.  The position table is interpolated here, once."""
+    bf16 for the tensor-core path.  The position table is interpolated here, once.
+
+    Tensor-core layout (``transposed``): the LayerNorm in front of the q|k|v and fc1 linears is folded into them,
+    ``LN(x) W + b = xhat (gamma*W) + (beta W + b)`` with ``xhat = (x - mean) rstd``: the matrix blob holds ``gamma*W``, the
+    vector blob the folded biases ``bqkv_f`` / ``b1_f`` and the column sums ``cs_*`` of the bf16-rounded ``gamma*W`` (for
+    kernels that apply mean / rstd after the matrix product: ``rstd (x W' - mean cs) + b_f``)."""
     D = C.DINO_DIM
     vl, ml = dino_vec_layout(), dino_mat_layout(transposed)
     vec = np.zeros((vl["__total__"][0],), F32)
@@ -352,9 +366,18 @@ def pack_dino_tree(t: dict, transposed: bool) -> Tuple[np.ndarray, np.ndarray]:
         putv(f"l{l}.ln2_s", L["norm2"]["scale"]); putv(f"l{l}.ln2_b", L["norm2"]["bias"])
         putv(f"l{l}.b1", L["mlp"]["fc1"]["bias"]); putv(f"l{l}.b2", L["mlp"]["fc2"]["bias"])
         putv(f"l{l}.ls2", L["layer_scale2"]["lambda1"])
-        putm(f"l{l}.wqkv", np.concatenate([a["query"]["kernel"], a["key"]["kernel"], a["value"]["kernel"]], axis=1))
+        wqkv = np.concatenate([a["query"]["kernel"], a["key"]["kernel"], a["value"]["kernel"]], axis=1).astype(F32)
+        w1 = np.asarray(L["mlp"]["fc1"]["kernel"], F32)
+        for nm, w, g, be, b in (("qkv", wqkv, L["norm1"]["scale"], L["norm1"]["bias"], vec[vl[f"l{l}.bqkv"][0]:][:3 * D]),
+                                ("1", w1, L["norm2"]["scale"], L["norm2"]["bias"], np.asarray(L["mlp"]["fc1"]["bias"], F32))):
+            wf = np.asarray(g, F32)[:, None] * w
+            putv(f"l{l}.b{nm}_f", (np.asarray(be, np.float64) @ w.astype(np.float64) + b).astype(F32))
+            putv(f"l{l}.cs_{nm}", bf16_round(wf).astype(np.float64).sum(0).astype(F32))
+            if transposed:
+                putm(f"l{l}.w{nm}", wf)
+            else:
+                putm(f"l{l}.w{nm}", w)
         putm(f"l{l}.wo", L["attention"]["output"]["dense"]["kernel"])
-        putm(f"l{l}.w1", L["mlp"]["fc1"]["kernel"])
         putm(f"l{l}.w2", L["mlp"]["fc2"]["kernel"])
     putv("lnf_s", t["layernorm"]["scale"]); putv("lnf_b", t["layernorm"]["bias"])
     return vec, mat

@@ -53,13 +53,26 @@ def test_dino_packing_layouts(params_p1):
     o, (r, c) = lt["l3.w1"]
     o2, (r2, c2) = ln["l3.w1"]
     assert (r, c) == (3072, 768) and (r2, c2) == (768, 3072) and o == o2
-    assert np.array_equal(mat_t[o:o + r * c].reshape(r, c).T, mat[o2:o2 + r2 * c2].reshape(r2, c2))
+    dino = P.dino_tree_from_params(params_p1)
+    L3 = dino["encoder"]["layer"]["3"]
+    # tensor-core layout: transposed, with LayerNorm-2's gamma folded into fc1 (LN(x) W + b = xhat (gamma*W) + (beta W + b))
+    assert np.array_equal(mat_t[o:o + r * c].reshape(r, c).T, L3["norm2"]["scale"].astype(np.float32)[:, None] * mat[o2:o2 + r2 * c2].reshape(r2, c2))
+    vl = P.dino_vec_layout()
+    b1f = vec[vl["l3.b1_f"][0]:][:3072]
+    ref = L3["norm2"]["bias"].astype(np.float64) @ L3["mlp"]["fc1"]["kernel"].astype(np.float64) + L3["mlp"]["fc1"]["bias"]
+    assert np.allclose(b1f, ref, rtol=1e-6, atol=1e-7)
+    cs = vec[vl["l3.cs_1"][0]:][:3072]
+    assert np.allclose(cs, P.bf16_round(L3["norm2"]["scale"].astype(np.float32)[:, None] * L3["mlp"]["fc1"]["kernel"]).sum(0), rtol=1e-5, atol=1e-5)
+    o, (r, c) = lt["l3.w2"]
+    assert np.array_equal(mat_t[o:o + r * c].reshape(r, c).T, mat[o:o + r * c].reshape(c, r))        # fc2 / wo are not folded
     o, (r, c) = ln["patch_w"]
     assert not mat[o:o + r * c].reshape(r, c)[588:].any()          # K padding rows are zero
     vo, vn = P.dino_vec_layout()["pos"]
     pos = vec[vo:vo + vn].reshape(257, 768)
-    dino = P.dino_tree_from_params(params_p1)
     assert np.array_equal(pos[0], dino["embeddings"]["position_embeddings"][0, 0])   # CLS position is copied
+    x = np.array([1.0, 1.00390625, 1.005859375, -3.1415927, 65504.0], np.float32)
+    import torch
+    assert np.array_equal(P.bf16_round(x), torch.from_numpy(x).to(torch.bfloat16).float().numpy())
 
 
 def test_pos_table_interpolation_agrees_with_oracle_and_is_a_partition_of_unity(params_p1):
