@@ -36,6 +36,12 @@ struct EpiP {
   size_t part_bytes;   //        its size
   int* splits_used;    //        host out: number of K splits of this launch (1 = none)
   int patch_rows;      // EPI 2 used for the patch embedding: GEMM row b*256+p lands in stream row b*257+1+p; ls == null means 1
+  // ---- LayerNorm fused away (see "stream LayerNorm without a LayerNorm kernel" below) ----
+  int rows;            // M (valid rows), for the per-row loads of the two modes below
+  const float* stats;  // EPI 0/1 consumer: [M][6][2] partial (sum, sum of squares) of the A rows; A is the UN-normalised bf16 shadow
+  const float* cs;     //                   [N] column sums of the (gamma-folded, bf16-rounded) weight; bias = folded bias
+  bf16* shadow;        // EPI 2 producer: bf16 copy of the updated stream [M,768] (null: classic reduce-add epilogue)
+  float* stats_out;    //                 [M][6][2] partial row statistics of the updated stream
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -89,6 +95,16 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- stream LayerNorm without a LayerNorm kernel ------------------------------------------------------------------------
+// The 24 LayerNorms between the residual GEMMs and the q|k|v / fc1 GEMMs cost 13 % of a step as a separate HBM pass
+// (50 MB fp32 in, 25 MB bf16 out each).  Instead:
+//  * producer (proj / fc2 epilogue): x_new = x_old + ls*(acc+bias) is formed in registers (x_old read straight from the
+//    stream), stored as fp32 (plain TMA store instead of a reduce-add) AND as a bf16 shadow, and each thread -- it owns one
+//    row and 128 columns of the tile -- writes its partial (sum, sum of squares): 6 partials per row (3 n-tiles x 2 halves);
+//  * consumer (q|k|v / fc1 epilogue): A is the un-normalised shadow, gamma/beta are folded into W and the bias
+//    (params.py), and the row statistics enter after the matrix product:  rstd*(x W' - mean*colsum(W')) + b_f.
+// Small batches (split-K) and the first layer produce shadow + statistics with stream_shadow_kernel instead.
+//
 // ---- split-K partial products -------------------------------------------------------------------------------
 // At small batch the residual GEMMs (N = 768) have only a handful of output tiles; their K range is then split
 // over several CTA pairs.  Split 0 reduce-adds ls*(acc+bias) into the fp32 residual stream as usual; split s > 0
@@ -274,7 +290,7 @@ template <int EPI, int NSLAB = 1>
 __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensorMap* tmO, float* sepi, uint32_t sstage,
                                                   uint32_t tfull_bar_addr, uint32_t aph, int as, uint32_t tmem_base, int m0,
                                                   int n0, int warp, int lane, int split = 0, const CUtensorMap* tmP = nullptr,
-                                                  int part_row0 = 0) {
+                                                  int part_row0 = 0, const CUtensorMap* tmX = nullptr) {
   const bool add_bias = split == 0;
   const int ew = warp - 2;
   const int quarter = warp & 3;
@@ -284,11 +300,34 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
   float* sl = sb + 256;
   sb[te] = add_bias ? __ldg(ep.bias + n0 + te) : 0.f;      // split-K: only the first K split contributes the bias
   if (EPI == EPI_RESIDUAL_F32) sl[te] = ep.ls ? __ldg(ep.ls + n0 + te) : 1.0f;
+  const bool fold = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) && ep.stats != nullptr;
+  if (fold) sl[te] = __ldg(ep.cs + n0 + te);
   const int row0 = m0 + quarter * 32 + (ep.patch_rows ? m0 / 256 + 1 : 0);
+  const int myrow = row0 + lane;                              // the stream / A row this thread's TMEM lane holds
+  float f_rstd = 1.f, f_nmr = 0.f;                            // consumer: rstd and -mean*rstd of this row
+  if (fold && myrow < ep.rows) {
+    const float4* sp = reinterpret_cast<const float4*>(ep.stats + (int64_t)myrow * 12);
+    const float4 p0 = __ldg(sp), p1 = __ldg(sp + 1), p2 = __ldg(sp + 2);
+    const float sum = ((p0.x + p0.z) + (p1.x + p1.z)) + (p2.x + p2.z), sq = ((p0.y + p0.w) + (p1.y + p1.w)) + (p2.y + p2.w);
+    const float mean = sum * (1.f / 768.f);
+    f_rstd = 1.0f / sqrtf(fmaxf(0.f, sq * (1.f / 768.f) - mean * mean) + 1e-6f);
+    f_nmr = -mean * f_rstd;
+  }
+  const bool produce = EPI == EPI_RESIDUAL_F32 && ep.shadow != nullptr && split == 0;
+  float p_sum = 0.f, p_sq = 0.f;                              // producer: this thread's partial row statistics
   // NSLAB 2 KB slabs per warp: with two, the TMA store of one chunk reads its slab while the next chunk is written
   const uint32_t slab0 = sstage + (uint32_t)ew * (2048u * NSLAB);
   const uint32_t my0 = slab0 + (uint32_t)lane * 64u;
   const uint32_t sw = (uint32_t)((lane >> 1) & 3);          // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+  // producer: the old stream values do not depend on the MMAs -- chunk 0 is requested while the mainloop is still running,
+  // chunk c+1 while chunk c is processed (row-per-thread 128-byte reads straight from the stream)
+  float4 xo[2][8];
+  const bool xok = produce && myrow < ep.rows;
+  const float4* xrow = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.out) + (int64_t)(xok ? myrow : 0) * ep.ldo + n0 + half * 128);
+  if (produce) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xo[0][j] = xok ? __ldcg(xrow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   epi_bar_sync();
   mbar_wait(tfull_bar_addr, aph);
   tc_fence_after();
@@ -304,12 +343,26 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
     const int cl = half * 128 + c * 32;
     const int col = n0 + cl;
     float v[32];
+    if (fold) {                                               // rstd*acc + (-mean*rstd)*cs + b_f
+      const float2 rs2 = make_float2(f_rstd, f_rstd), nm2 = make_float2(f_nmr, f_nmr);
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(sb + cl + j);
-      const float2 lo = __fadd2_rn(make_float2(__uint_as_float(rc[j]), __uint_as_float(rc[j + 1])), make_float2(b4.x, b4.y));
-      const float2 hi = __fadd2_rn(make_float2(__uint_as_float(rc[j + 2]), __uint_as_float(rc[j + 3])), make_float2(b4.z, b4.w));
-      v[j] = lo.x; v[j + 1] = lo.y; v[j + 2] = hi.x; v[j + 3] = hi.y;
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sb + cl + j);
+        const float4 c4 = *reinterpret_cast<const float4*>(sl + cl + j);
+        const float2 lo = __ffma2_rn(rs2, make_float2(__uint_as_float(rc[j]), __uint_as_float(rc[j + 1])),
+                                     __ffma2_rn(nm2, make_float2(c4.x, c4.y), make_float2(b4.x, b4.y)));
+        const float2 hi = __ffma2_rn(rs2, make_float2(__uint_as_float(rc[j + 2]), __uint_as_float(rc[j + 3])),
+                                     __ffma2_rn(nm2, make_float2(c4.z, c4.w), make_float2(b4.z, b4.w)));
+        v[j] = lo.x; v[j + 1] = lo.y; v[j + 2] = hi.x; v[j + 3] = hi.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sb + cl + j);
+        const float2 lo = __fadd2_rn(make_float2(__uint_as_float(rc[j]), __uint_as_float(rc[j + 1])), make_float2(b4.x, b4.y));
+        const float2 hi = __fadd2_rn(make_float2(__uint_as_float(rc[j + 2]), __uint_as_float(rc[j + 3])), make_float2(b4.z, b4.w));
+        v[j] = lo.x; v[j + 1] = lo.y; v[j + 2] = hi.x; v[j + 3] = hi.y;
+      }
     }
     if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
       if (EPI == EPI_BIAS_GELU_BF16) {
@@ -339,6 +392,60 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
         tma_store_2d(tmO, slab, col, row0);
         bulk_commit();
       }
+    } else if (produce) {   // EPI_RESIDUAL_F32, LayerNorm-free flow: x_new = x_old + ls*v -> fp32 store, bf16 shadow, row statistics
+      float xn[32];
+      {
+        if (c < 3) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xo[(c + 1) & 1][j] = xok ? __ldcg(xrow + (c + 1) * 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 x4 = xo[c & 1][j];
+          const float4 l4 = *reinterpret_cast<const float4*>(sl + cl + 4 * j);
+          xn[4 * j] = fmaf(v[4 * j], l4.x, x4.x); xn[4 * j + 1] = fmaf(v[4 * j + 1], l4.y, x4.y);
+          xn[4 * j + 2] = fmaf(v[4 * j + 2], l4.z, x4.z); xn[4 * j + 3] = fmaf(v[4 * j + 3], l4.w, x4.w);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { p_sum += xn[j]; p_sq = fmaf(xn[j], xn[j], p_sq); }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const uint32_t slab = slab0, my = my0;
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int e = u * 16 + j * 4;
+          const uint32_t a = my + ((((uint32_t)j) ^ sw) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(xn[e]), "f"(xn[e + 1]), "f"(xn[e + 2]), "f"(xn[e + 3]) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tmO, slab, col + u * 16, row0);
+          bulk_commit();
+        }
+      }
+      {                                                       // the same 32 columns as bf16 into the shadow
+        const uint32_t slab = slab0, my = my0;
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t a = my + ((((uint32_t)j) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16(xn[8 * j], xn[8 * j + 1])),
+                       "r"(pack_bf16(xn[8 * j + 2], xn[8 * j + 3])), "r"(pack_bf16(xn[8 * j + 4], xn[8 * j + 5])),
+                       "r"(pack_bf16(xn[8 * j + 6], xn[8 * j + 7]))
+                       : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tmX, slab, col, row0);
+          bulk_commit();
+        }
+      }
     } else {   // EPI_RESIDUAL_F32: two units of 16 fp32 columns, reduce-added into the residual stream
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -364,6 +471,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
       }
     }
   }
+  if (produce && myrow < ep.rows)                              // partial (sum, sumsq) of this row over this tile's 128-column half
+    *reinterpret_cast<float2*>(ep.stats_out + (int64_t)myrow * 12 + ((n0 / BN) * 2 + half) * 2) = make_float2(p_sum, p_sq);
   tc_fence_before();
   __syncwarp();
 }

@@ -76,8 +76,8 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP, EpiP ep, int M, int N, int K,
-                int splits) {
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmP,
+                const __grid_constant__ CUtensorMap tmX, EpiP ep, int M, int N, int K, int splits) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -104,6 +104,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
     if (splits > 1) tma_prefetch_desc(&tmP);
+    if (EPI == EPI_RESIDUAL_F32 && ep.shadow != nullptr) tma_prefetch_desc(&tmX);
     for (int s = 0; s < STAGES2; ++s) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
@@ -180,7 +181,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       else {
         const int split = unit % splits;          // split s > 0 stores to block s-1 of the partial-product scratch
         epilogue_tile_tma<EPI, NSLAB2>(ep, &tmO, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane, split, &tmP,
-                               (split - 1) * n_tiles_m * BM2 + m0);
+                               (split - 1) * n_tiles_m * BM2 + m0, &tmX);
       }
       if (lane == 0) mbar_arrive_remote(tempty_bar + 8 * as, 0);
     }
@@ -219,11 +220,16 @@ inline int launch_one2(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap
     if (splits > 1) HVLA_TRY(make_map_out(&mp, ep.part, (int64_t)(splits - 1) * ((M + BM2 - 1) / BM2) * BM2, N, true));
   }
   if (ep.splits_used) *ep.splits_used = splits;
+  EpiP ep2 = ep;
+  ep2.rows = M;
+  CUtensorMap mx = mo;
+  if (EPI == EPI_RESIDUAL_F32 && ep.shadow != nullptr && splits == 1) HVLA_TRY(make_map_out(&mx, ep.shadow, M, N, false));
+  else ep2.shadow = nullptr;                 // split K: classic reduce-add + partials, the caller rebuilds shadow / statistics
   const int tiles = tiles0 * splits;
   if (const char* e = getenv("HVLA_GEMM_MAX_PAIRS")) { const int v = atoi(e); if (v > 0 && v < pairs) pairs = v; }   // experiment knob
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
   ProfScope ps(st, "gemm_tc");
-  launch_k(gemm_tc2_kernel<EPI>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM2_BYTES, st, ma, mb, mo, mp, ep, M, N, K, splits);
+  launch_k(gemm_tc2_kernel<EPI>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM2_BYTES, st, ma, mb, mo, mp, mx, ep2, M, N, K, splits);
   HVLA_LAUNCH_CHECK("gemm_tc2");
   return HVLA_OK;
 }

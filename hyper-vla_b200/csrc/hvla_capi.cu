@@ -29,7 +29,7 @@ struct Plan {
   // generate region (fp32)
   size_t tp, ip, xc, yc, qkvc, cc, hc, e;
   // DINO region
-  size_t x, y, qkv, att, hid, emb, part;
+  size_t x, y, qkv, att, hid, emb, part, st;
   // base region (fp32)
   size_t pt, xb, yb, qkvb, cb, hb;
   // host staging (hvla_act_host)
@@ -62,6 +62,7 @@ static Plan make_plan(int B, int T, int dtype) {
   p.hid = take(M * DF * es);
   p.emb = take(M * DD * es);
   p.part = take(dtype == HVLA_BF16 ? PART_BYTES : 0);   // split-K partial products (small batches)
+  p.st = take(dtype == HVLA_BF16 ? M * 12 * 4 : 0);      // partial row statistics of the stream (LayerNorm-free flow)
   p.pt = take(Bb * NPATCH * BD * 4);
   p.xb = take(Bb * BTOK * BD * 4);
   p.yb = take(Bb * BTOK * BD * 4);
@@ -318,6 +319,15 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
     ep.patch_rows = one_cta ? 0 : 1;     // 2-CTA path: the stream already holds cls/pos, the GEMM reduce-adds onto it
     HVLA_TRY(gemm(A0, dm + Mx::patch_w, B * NPATCH, DD, PATCH_KP, tc::EPI_PATCH_F32, ep));
   }
+  // LayerNorm-free flow (gemm_tc.cuh), EXPERIMENTAL and off by default (HVLA_FUSED_LN=1): the q|k|v / fc1 GEMMs read the
+  // un-normalised bf16 shadow of the stream (kept in Y) and apply the row statistics in their epilogue; shadow + statistics
+  // come from the preceding residual GEMM's epilogue, or from stream_shadow_kernel in front of layer 0 and after a split-K
+  // GEMM.  Correct (all parity tests pass with it on) but slower: the 25 LayerNorm launches disappear (0.41 -> 0.03 ms per
+  // 64-env step) while the residual GEMMs pay more than that for reading the old stream row-per-thread (TMEM lane = row):
+  // proj 27.7 -> 71.8 us, fc2 61.6 -> 90.6 us, step 3.24 -> 3.86 ms.  See DESIGN.md section 6c.
+  const bool fused_ln = !one_cta && !simt_gemm && env_flag("HVLA_FUSED_LN");
+  float* ST = reinterpret_cast<float*>(ws + pl.st);
+  bool shadow_ready = false;                 // Y / ST describe the current stream
   for (int l = 0; l < DL; ++l) {
     const float* v = dv + V::layers + (int64_t)l * V::layer_size;
     const bf16* m = dm + Mx::layers + (int64_t)l * Mx::layer_size;
@@ -325,10 +335,12 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
     // gamma / beta of both LayerNorms are folded into wqkv / w1 and their biases (params.py: pack_dino_tree): plain (x-mean)*rstd here
     ln.x = X; ln.ldx = DD; ln.y = Y; ln.ldy = DD; ln.scale = nullptr; ln.bias = nullptr; ln.rows = M; ln.rows_per_batch = 1;
     ln.part = PART; ln.part_stride = part_stride; ln.nsplit = splits - 1;   // partial products of the previous layer's fc2
-    HVLA_TRY((layernorm<float, bf16>(st, ln, DD)));
+    if (!fused_ln) HVLA_TRY((layernorm<float, bf16>(st, ln, DD)));
+    else if (!shadow_ready) HVLA_TRY(stream_shadow(st, X, Y, ST, M, PART, splits - 1, part_stride));
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
       ep.bias = v + V::bqkv_f; ep.out = QKV; ep.ldo = 3 * DD; ep.qscale = 0.125f; ep.qcols = DD;   // q / sqrt(64)
+      if (fused_ln) { ep.stats = ST; ep.cs = v + V::cs_qkv; }
       HVLA_TRY(gemm(Y, m + Mx::wqkv, M, 3 * DD, DD, tc::EPI_BIAS_BF16, ep));
     }
     if (simt_attn) {
@@ -344,21 +356,26 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
       ep.bias = v + V::bo; ep.out = X; ep.ldo = DD; ep.ls = v + V::ls1;
       ep.part = PART; ep.part_bytes = PART_BYTES; ep.splits_used = &splits;
+      if (fused_ln) { ep.shadow = Y; ep.stats_out = ST; }
       HVLA_TRY(gemm(ATT, m + Mx::wo, M, DD, DD, tc::EPI_RESIDUAL_F32, ep));
     }
     ln.nsplit = splits - 1;      // this LayerNorm first folds the split-K partial products into the stream
-    HVLA_TRY((layernorm<float, bf16>(st, ln, DD)));
+    if (!fused_ln) HVLA_TRY((layernorm<float, bf16>(st, ln, DD)));
+    else if (splits > 1) HVLA_TRY(stream_shadow(st, X, Y, ST, M, PART, splits - 1, part_stride));
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
       ep.bias = v + V::b1_f; ep.out = HID; ep.ldo = DF;
+      if (fused_ln) { ep.stats = ST; ep.cs = v + V::cs_1; }
       HVLA_TRY(gemm(Y, m + Mx::w1, M, DF, DD, tc::EPI_BIAS_GELU_BF16, ep));
     }
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
       ep.bias = v + V::b2; ep.out = X; ep.ldo = DD; ep.ls = v + V::ls2;
       ep.part = PART; ep.part_bytes = PART_BYTES; ep.splits_used = &splits;
+      if (fused_ln) { ep.shadow = Y; ep.stats_out = ST; }
       HVLA_TRY(gemm(HID, m + Mx::w2, M, DD, DF, tc::EPI_RESIDUAL_F32, ep));
     }
+    shadow_ready = fused_ln && splits == 1;   // fc2's epilogue left shadow + statistics of the new stream
   }
   LnP ln; memset(&ln, 0, sizeof ln);
   ln.x = X; ln.ldx = DD; ln.y = out_emb; ln.ldy = DD; ln.scale = dv + V::lnf_s; ln.bias = dv + V::lnf_b; ln.rows = M; ln.rows_per_batch = 1;

@@ -255,6 +255,68 @@ __global__ void __launch_bounds__(256) layernorm768_kernel(float* __restrict__ x
   }
 }
 
+// Shadow + row statistics of the fp32 stream for the LayerNorm-free flow (gemm_tc.cuh): xb = bf16(x) (UN-normalised),
+// stats[row] = {(sum, sumsq), 0 x 5}.  Used where no residual-GEMM epilogue produced them: in front of the first layer and
+// after a split-K GEMM, whose NS partial-product blocks it folds into the stream first (like layernorm768_kernel).
+template <int NS>
+__global__ void __launch_bounds__(256) stream_shadow_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ xb, float* __restrict__ stats,
+                                                            int rows, const float* __restrict__ part, int64_t part_stride) {
+  pdl_trigger();
+  pdl_wait();
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float4* xr = reinterpret_cast<float4*>(x + (int64_t)row * 768);
+  float4 v[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) v[i] = xr[lane + 32 * i];
+  if (NS > 0) {
+    float4 q[NS > 0 ? NS : 1][6];
+#pragma unroll
+    for (int sp = 0; sp < NS; ++sp) {
+      const float4* pr = reinterpret_cast<const float4*>(part + sp * part_stride + (int64_t)row * 768);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) q[sp][i] = pr[lane + 32 * i];
+    }
+#pragma unroll
+    for (int sp = 0; sp < NS; ++sp) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { v[i].x += q[sp][i].x; v[i].y += q[sp][i].y; v[i].z += q[sp][i].z; v[i].w += q[sp][i].w; }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xr[lane + 32 * i] = v[i];
+  }
+  float s = 0.f, s2 = 0.f;
+  __nv_bfloat16* br = xb + (int64_t)row * 768;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    s2 = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, fmaf(v[i].w, v[i].w, s2))));
+    float o[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+    Vec4<__nv_bfloat16>::store(br + (lane + 32 * i) * 4, o);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane < 12) stats[(int64_t)row * 12 + lane] = lane == 0 ? s : (lane == 1 ? s2 : 0.f);
+}
+
+inline int stream_shadow(cudaStream_t st, float* x, __nv_bfloat16* xb, float* stats, int rows, const float* part, int nsplit, int64_t part_stride) {
+  ProfScope ps(st, "layernorm");
+  const dim3 grid(cdiv(rows, 8)), block(256);
+  switch (nsplit) {
+    case 0: launch_k(stream_shadow_kernel<0>, grid, block, 0, st, x, xb, stats, rows, part, part_stride); break;
+    case 1: launch_k(stream_shadow_kernel<1>, grid, block, 0, st, x, xb, stats, rows, part, part_stride); break;
+    case 3: launch_k(stream_shadow_kernel<3>, grid, block, 0, st, x, xb, stats, rows, part, part_stride); break;
+    case 7: launch_k(stream_shadow_kernel<7>, grid, block, 0, st, x, xb, stats, rows, part, part_stride); break;
+    default: return fail(HVLA_ERR_ARG, "stream_shadow: unsupported number of split-K partial blocks");
+  }
+  HVLA_LAUNCH_CHECK("stream_shadow");
+  return HVLA_OK;
+}
+
 template <typename TS, typename TO>
 inline int layernorm(cudaStream_t st, const LnP& p, int D) {
   if (p.nsplit > 0 && !(D == 768 && std::is_same<TS, float>::value && p.sS == 0 && p.ldx == 768 && p.ldy == 768 && p.post_div == 0.f))
