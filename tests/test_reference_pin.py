@@ -142,3 +142,26 @@ def test_reference_metadata_equals_ours(reference_model):
         for k in path:
             node = node[k]
         assert tuple(int(v) for v in node) == tuple(shape), path
+
+
+@needs_reference
+def test_reference_initialised_params_degenerate_case(reference_model):
+    """with the reference's own from_config initialisation (BIAS_INIT) every head kernel is zero, so the weights
+    the reference generates are its head biases whatever the context -- executed with the reference's code and parameters,
+    and reproduced by the oracle on the same parameters."""
+    from hvla import metadata as M, synthetic as S
+    from oracle import hypervla_oracle as O
+    mod, model_init, _, RM = reference_model
+    inp = S.make_inputs(7, 1, 1)
+    idict, istate = mod.f64(inp["instruction_dict"]), mod.f64(inp["initial_state"])
+    base_params, _, _ = model_init.create_tasks(instruction_dict=idict, initial_state=istate)
+    lang = inp["instruction_dict"]["language_instruction"]
+    gen, _ = O.generate(model_init.params, lang["token_embedding"], lang["attention_mask"], inp["initial_state"]["patch_embeddings"][:, 0],
+                        dtype=np.float64, generated_paths=M.generated_leaves_canonical())
+    for path, shape in M.generated_leaves_canonical():
+        leaf = base_params
+        for k in path:
+            leaf = leaf[k]
+        bias = np.asarray(model_init.params["output_head_" + "_".join(path)]["bias"], np.float64).reshape(shape)
+        assert np.array_equal(np.asarray(leaf), bias), path                 # reference: generated leaf == head bias, exactly
+        assert np.abs(gen[path][0] - bias).max() < 1e-15, path              # oracle on the same parameters
