@@ -4,16 +4,16 @@
 //   reference: hypervla/components/base_vit.py:130-226, transformer.py:127-262,
 //              action_heads.py:455-470, 536-537; batching = jax.vmap of scripts/train.py:559-579.
 //
-// One CTA per environment, 9 warps.  Everything stays on chip between the embedding read and the
-// 28 output floats: the fp32 residual stream (256 patch tokens) and the layer's K/V live in shared
-// memory, the layer's weights are staged there once, GEMMs are warp-level mma.sync m16n8k16 (bf16
-// operands, fp32 accumulation) -- the problem is 64-wide and per-sample, far below a tcgen05 tile.
+// A thread-block cluster of two CTAs per environment (C = 2; C = 1 kept as an A/B switch), 12 warps each.  Everything stays
+// on chip between the embedding read and the 28 output floats: the fp32 residual stream (128 patch tokens per CTA) and the
+// layer's K/V (all 256 rows, broadcast between the CTAs through distributed shared memory) live in shared memory, the layer's
+// weights are staged there once (cp.async), GEMMs are warp-level mma.sync m16n8k16 (bf16 operands, fp32 accumulation) --
+// the problem is 64-wide and per-sample, far below a tcgen05 tile.
 //
-// Structure exploited (base_vit.py:209-214): patch tokens cannot attend to the action token, so the
-// 256 patch rows form an unmasked 256-token transformer (16 m-tiles, warps 0..7 own two each); the
-// action token is a single query row over 256 patch keys + itself, handled by warp 8 in fp32 on CUDA
-// cores.  Only the action token is needed from the last block, so patch rows stop after writing that
-// block's K/V.
+// Structure exploited (base_vit.py:209-214): patch tokens cannot attend to the action token, so the 256 patch rows form an
+// unmasked 256-token transformer (16 m-tiles: warps 0..7 of each CTA own one each); the action token is a single query
+// row over 256 patch keys + itself, handled in fp32 on CUDA cores by warps 8..11 of rank 0 (one head each).  Only the
+// action token is needed from the last block, so patch rows stop after writing that block's K/V.
 #pragma once
 #include "common.cuh"
 #include "attn_mma.cuh"

@@ -4,9 +4,10 @@
 //   reference: hypervla/components/hypernetwork.py:99-197, transformer.py:127-262.
 //
 // One CTA per task, 8 warps.  The fp32 residual stream (34 x 128), the fp16 A operands and q|k|v / the MLP
-// hidden stay in shared memory for the whole network; the (task-shared) weights are streamed from L2 in
-// 32-row K chunks with double-buffered cp.async and consumed by warp-level mma.sync m16n8k16 (M = 34 rows is far
-// below a tcgen05 tile; the kernel is latency-bound, the 2.8 MB of fp16 weights per task come from L2).
+// hidden stay in shared memory for the whole network; the (task-shared) weights are streamed from L2 in K chunks through a
+// 4-deep cp.async ring shared by consecutive GEMMs and consumed by warp-level mma.sync m16n8k16 (M = 34 rows is far below a
+// tcgen05 tile; the kernel is latency-bound, the 2.8 MB of fp16 weights per task come from L2); the block-masked attention
+// runs as 12 (head, m-tile) mma.sync units.
 #pragma once
 #include "common.cuh"
 #include "attn_mma.cuh"

@@ -1,7 +1,8 @@
 // Generation heads on bf16 tensor cores: out[T, NGP] = E[T,128] * W[128, NGP] + b   (hypernetwork.py:205-217).
 // The 73 Dense heads are ONE skinny GEMM whose cost is streaming W (51.6 MB bf16) from HBM exactly once and
-// writing the per-task weight rows; each CTA owns a 128-column slab of W in shared memory and loops over the
-// tasks 64 at a time (warp-level mma.sync m16n8k16; the problem is K=128 deep and HBM-bound, not a tcgen05 shape).
+// writing the per-task weight rows; persistent CTAs (two per SM) walk the 128-column slabs of W through a double-buffered
+// cp.async ring and loop over the tasks 64 at a time (warp-level mma.sync m16n8k16; the problem is K=128 deep and
+// HBM-bound, not a tcgen05 shape).
 #pragma once
 #include "common.cuh"
 #include "attn_mma.cuh"
