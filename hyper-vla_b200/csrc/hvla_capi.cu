@@ -339,7 +339,7 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
     else if (!shadow_ready) HVLA_TRY(stream_shadow(st, X, Y, ST, M, PART, splits - 1, part_stride));
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
-      ep.bias = v + V::bqkv_f; ep.out = QKV; ep.ldo = 3 * DD; ep.qscale = 0.125f; ep.qcols = DD;   // q / sqrt(64)
+      ep.bias = v + V::bqkv_f; ep.out = QKV; ep.ldo = 3 * DD;   // q / sqrt(64) is folded into the packed weights and bias
       if (fused_ln) { ep.stats = ST; ep.cs = v + V::cs_qkv; }
       HVLA_TRY(gemm(Y, m + Mx::wqkv, M, 3 * DD, DD, tc::EPI_BIAS_BF16, ep));
     }

@@ -334,7 +334,8 @@ def pack_dino_tree(t: dict, transposed: bool) -> Tuple[np.ndarray, np.ndarray]:
     Tensor-core layout (``transposed``): the LayerNorm in front of the q|k|v and fc1 linears is folded into them,
     ``LN(x) W + b = xhat (gamma*W) + (beta W + b)`` with ``xhat = (x - mean) rstd``: the matrix blob holds ``gamma*W``, the
     vector blob the folded biases ``bqkv_f`` / ``b1_f`` and the column sums ``cs_*`` of the bf16-rounded ``gamma*W`` (for
-    kernels that apply mean / rstd after the matrix product: ``rstd (x W' - mean cs) + b_f``)."""
+    kernels that apply mean / rstd after the matrix product: ``rstd (x W' - mean cs) + b_f``).  The query third of
+    ``gamma*Wqkv`` and ``bqkv_f`` also carries the 1/sqrt(64) query scaling."""
     D = C.DINO_DIM
     vl, ml = dino_vec_layout(), dino_mat_layout(transposed)
     vec = np.zeros((vl["__total__"][0],), F32)
@@ -371,7 +372,11 @@ def pack_dino_tree(t: dict, transposed: bool) -> Tuple[np.ndarray, np.ndarray]:
         for nm, w, g, be, b in (("qkv", wqkv, L["norm1"]["scale"], L["norm1"]["bias"], vec[vl[f"l{l}.bqkv"][0]:][:3 * D]),
                                 ("1", w1, L["norm2"]["scale"], L["norm2"]["bias"], np.asarray(L["mlp"]["fc1"]["bias"], F32))):
             wf = np.asarray(g, F32)[:, None] * w
-            putv(f"l{l}.b{nm}_f", (np.asarray(be, np.float64) @ w.astype(np.float64) + b).astype(F32))
+            bf = (np.asarray(be, np.float64) @ w.astype(np.float64) + b).astype(F32)
+            if nm == "qkv":                # q / sqrt(64) (flax scales the query before QK^T): a power of two, exact in bf16
+                wf[:, :D] *= F32(0.125)
+                bf[:D] *= F32(0.125)
+            putv(f"l{l}.b{nm}_f", bf)
             putv(f"l{l}.cs_{nm}", bf16_round(wf).astype(np.float64).sum(0).astype(F32))
             if transposed:
                 putm(f"l{l}.w{nm}", wf)
