@@ -104,6 +104,13 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 //  * consumer (q|k|v / fc1 epilogue): A is the un-normalised shadow, gamma/beta are folded into W and the bias
 //    (params.py), and the row statistics enter after the matrix product:  rstd*(x W' - mean*colsum(W')) + b_f.
 // Small batches (split-K) and the first layer produce shadow + statistics with stream_shadow_kernel instead.
+// Compiled in only with -DHVLA_WITH_FUSED_LN (HVLA_NVCC_EXTRA): it is slower today, and the extra epilogue
+// code costs every GEMM launch ~1 us of instruction fetch at batch 1 (49 launches per step) even when it is not taken.
+#ifdef HVLA_WITH_FUSED_LN
+constexpr bool kFusedLn = true;
+#else
+constexpr bool kFusedLn = false;
+#endif
 //
 // ---- split-K partial products -------------------------------------------------------------------------------
 // At small batch the residual GEMMs (N = 768) have only a handful of output tiles; their K range is then split
@@ -300,7 +307,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
   float* sl = sb + 256;
   sb[te] = add_bias ? __ldg(ep.bias + n0 + te) : 0.f;      // split-K: only the first K split contributes the bias
   if (EPI == EPI_RESIDUAL_F32) sl[te] = ep.ls ? __ldg(ep.ls + n0 + te) : 1.0f;
-  const bool fold = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) && ep.stats != nullptr;
+  const bool fold = kFusedLn && (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) && ep.stats != nullptr;
   if (fold) sl[te] = __ldg(ep.cs + n0 + te);
   const int row0 = m0 + quarter * 32 + (ep.patch_rows ? m0 / 256 + 1 : 0);
   const int myrow = row0 + lane;                              // the stream / A row this thread's TMEM lane holds
@@ -313,7 +320,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
     f_rstd = 1.0f / sqrtf(fmaxf(0.f, sq * (1.f / 768.f) - mean * mean) + 1e-6f);
     f_nmr = -mean * f_rstd;
   }
-  const bool produce = EPI == EPI_RESIDUAL_F32 && ep.shadow != nullptr && split == 0;
+  const bool produce = kFusedLn && EPI == EPI_RESIDUAL_F32 && ep.shadow != nullptr && split == 0;
   float p_sum = 0.f, p_sq = 0.f;                              // producer: this thread's partial row statistics
   // NSLAB 2 KB slabs per warp: with two, the TMA store of one chunk reads its slab while the next chunk is written
   const uint32_t slab0 = sstage + (uint32_t)ew * (2048u * NSLAB);

@@ -282,13 +282,9 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
   const bool mma_attn = env_flag("HVLA_ATTN_MMA");           // A/B switch: warp-level mma.sync attention instead of tcgen05
   const bool one_cta = env_flag("HVLA_GEMM_1CTA");           // A/B switch: single-CTA 128x256 tiles instead of CTA pairs
   {
-    const int64_t total = (int64_t)B * NPATCH * PATCH_KP;
     {
       ProfScope ps(st, "im2col");
-      {
-        const int blocks = cdiv(total / 8, 256);           // 8 k per thread-item; at most ~4 items per thread
-        launch_k(im2col_norm_bf16_kernel, dim3(blocks < 1184 ? blocks : cdiv(total / 8, 256 * 4)), dim3(256), 0, st, images, A0, B);
-      }
+      launch_k(im2col_norm_bf16_kernel, dim3(B * GRID), dim3(256), 0, st, images, A0, B);   // one CTA per row of 16 patches
       HVLA_LAUNCH_CHECK("im2col");
     }
     ProfScope ps2(st, "cls_rows");
@@ -319,13 +315,13 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
     ep.patch_rows = one_cta ? 0 : 1;     // 2-CTA path: the stream already holds cls/pos, the GEMM reduce-adds onto it
     HVLA_TRY(gemm(A0, dm + Mx::patch_w, B * NPATCH, DD, PATCH_KP, tc::EPI_PATCH_F32, ep));
   }
-  // LayerNorm-free flow (gemm_tc.cuh), EXPERIMENTAL and off by default (HVLA_FUSED_LN=1): the q|k|v / fc1 GEMMs read the
+  // LayerNorm-free flow (gemm_tc.cuh), EXPERIMENTAL: compiled in with -DHVLA_WITH_FUSED_LN and then enabled by HVLA_FUSED_LN=1: the q|k|v / fc1 GEMMs read the
   // un-normalised bf16 shadow of the stream (kept in Y) and apply the row statistics in their epilogue; shadow + statistics
   // come from the preceding residual GEMM's epilogue, or from stream_shadow_kernel in front of layer 0 and after a split-K
   // GEMM.  Correct (all parity tests pass with it on) but slower: the 25 LayerNorm launches disappear (0.41 -> 0.03 ms per
   // 64-env step) while the residual GEMMs pay more than that for reading the old stream row-per-thread (TMEM lane = row):
   // proj 27.7 -> 71.8 us, fc2 61.6 -> 90.6 us, step 3.24 -> 3.86 ms.  See DESIGN.md section 6c.
-  const bool fused_ln = !one_cta && !simt_gemm && env_flag("HVLA_FUSED_LN");
+  const bool fused_ln = tc::kFusedLn && !one_cta && !simt_gemm && env_flag("HVLA_FUSED_LN");
   float* ST = reinterpret_cast<float*>(ws + pl.st);
   bool shadow_ready = false;                 // Y / ST describe the current stream
   for (int l = 0; l < DL; ++l) {

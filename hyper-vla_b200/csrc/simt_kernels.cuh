@@ -470,27 +470,31 @@ __global__ void im2col_norm_kernel(const uint8_t* __restrict__ img, TO* __restri
   from_f(out[idx], v);
 }
 
-// The same for the bf16 tensor-core path, as a gather: the 3 x 256 possible outputs (channel, byte) are tabulated per
-// CTA with the expression above, a thread then produces 8 consecutive k (one 16-byte store) from 8 byte loads.
+// The same for the bf16 tensor-core path, as a gather: a CTA owns one row of 16 patches of one image = 14 image rows =
+// one contiguous 9,408-byte block, which it stages in shared memory with 16-byte loads; the 3 x 256 possible outputs
+// (channel, byte) are tabulated per CTA with the expression above; a thread then produces 8 consecutive k (one 16-byte
+// store into the 20,480 contiguous output bytes of the 16 patches) from 8 shared-memory bytes.
 __global__ void __launch_bounds__(256) im2col_norm_bf16_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ out, int B) {
   pdl_trigger();
+  constexpr int ROWB = IMG * 3;                              // 672 bytes per image row
+  constexpr int BLK = PATCH * ROWB;                          // 9,408 bytes: the 14 image rows of this patch row
   __shared__ bf16 lut[3][256];
+  __shared__ __align__(16) uint8_t pix[BLK];
   for (int i = threadIdx.x; i < 768; i += blockDim.x) {
-    const int c = i >> 8, pix = i & 255;
+    const int c = i >> 8, p = i & 255;
     const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
     const float sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
-    lut[c][pix] = __float2bfloat16_rn(((float)pix / 255.0f - mean) / sd);
+    lut[c][p] = __float2bfloat16_rn(((float)p / 255.0f - mean) / sd);
   }
-  __syncthreads();
   pdl_wait();
-  constexpr int GROUPS = PATCH_KP / 8;                       // 80 groups of 8 k per patch row
-  const int64_t total = (int64_t)B * NPATCH * GROUPS;
-  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(it % GROUPS);
-    const int64_t row = it / GROUPS;
-    const int pidx = (int)(row % NPATCH), b = (int)(row / NPATCH);
-    const int py = pidx / GRID, px = pidx % GRID;
-    const uint8_t* base = img + (((int64_t)b * IMG + py * PATCH) * IMG + px * PATCH) * 3;
+  const int py = blockIdx.x % GRID, b = blockIdx.x / GRID;
+  const uint4* src = reinterpret_cast<const uint4*>(img + ((int64_t)b * IMG + py * PATCH) * ROWB);
+  for (int i = threadIdx.x; i < BLK / 16; i += blockDim.x) reinterpret_cast<uint4*>(pix)[i] = __ldg(src + i);
+  __syncthreads();
+  constexpr int GROUPS = PATCH_KP / 8;                       // 80 groups of 8 k per patch
+  bf16* dst = out + ((int64_t)b * NPATCH + py * GRID) * PATCH_KP;
+  for (int it = threadIdx.x; it < GRID * GROUPS; it += blockDim.x) {
+    const int g = it % GROUPS, px = it / GROUPS;
     uint32_t w[4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -498,12 +502,11 @@ __global__ void __launch_bounds__(256) im2col_norm_bf16_kernel(const uint8_t* __
       uint32_t bits = 0;
       if (k < PATCH_K) {
         const int kh = k / 42, rem = k - kh * 42;              // rem = kw * 3 + c
-        const int c = rem % 3;
-        bits = __bfloat16_as_ushort(lut[c][__ldg(base + (int64_t)kh * IMG * 3 + rem)]);
+        bits = __bfloat16_as_ushort(lut[rem % 3][pix[kh * ROWB + px * 42 + rem]]);
       }
       if (j & 1) w[j >> 1] |= bits << 16; else w[j >> 1] = bits;
     }
-    *reinterpret_cast<uint4*>(out + row * PATCH_KP + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(dst + (int64_t)px * PATCH_KP + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
