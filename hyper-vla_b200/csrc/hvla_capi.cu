@@ -11,6 +11,7 @@
 #include "ctx_fused.cuh"
 #include "postprocess.cuh"
 #include "preprocess.cuh"
+#include "t5_embed.cuh"
 
 #include <stdlib.h>
 #include <type_traits>
@@ -751,6 +752,19 @@ int hvla_resize_lanczos3(hvla_stream_t stream, const uint8_t* images, int B, int
     HVLA_LAUNCH_CHECK("crop_bilinear");
   }
   return HVLA_OK;
+}
+
+int64_t hvla_t5_blob_elems(void) { return t5::Layout::total; }
+size_t hvla_t5_workspace_bytes(int T, int S) { return (T > 0 && S > 0) ? t5::workspace_bytes(T, S) : 0; }
+
+int hvla_t5_encode(hvla_stream_t stream, const float* t5_blob, const float* pos_bias, const int32_t* input_ids, const int32_t* attention_mask,
+                   int T, int S, float* out_emb, void* workspace, size_t workspace_bytes) {
+  if (T < 0 || S <= 0 || S > t5::SMAX) return fail(HVLA_ERR_ARG, "hvla_t5_encode: need T >= 0 and 1 <= S <= 32");
+  if (T == 0) return HVLA_OK;
+  if (!t5_blob || !pos_bias || !input_ids || !attention_mask || !out_emb || !workspace) return fail(HVLA_ERR_ARG, "hvla_t5_encode: null argument");
+  if (workspace_bytes < t5::workspace_bytes(T, S)) return fail(HVLA_ERR_WORKSPACE, "hvla_t5_encode: workspace too small");
+  return t5::encode(reinterpret_cast<cudaStream_t>(stream), t5_blob, pos_bias, input_ids, attention_mask, T, S, out_emb,
+                    reinterpret_cast<uint8_t*>(workspace));
 }
 
 // ---- legacy XLA custom-call wrappers (no status channel in this ABI revision: errors are logged) ---------

@@ -23,7 +23,7 @@ struct GemmP {
   const int* widx;
   int M, N, K;
   float out_scale;
-  int act;  // 0 none, 1 tanh-GELU, 2 erf-GELU
+  int act;  // 0 none, 1 tanh-GELU, 2 erf-GELU, 3 ReLU
   int wt;   // W is stored transposed: element (k,n) at W[n*ldw + k]
 };
 
@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmP p) {
       if (p.out_scale != 1.0f) v *= p.out_scale;
       if (p.act == 1) v = gelu_tanh_f(v);
       else if (p.act == 2) v = gelu_erf_f(v);
+      else if (p.act == 3) v = fmaxf(v, 0.f);
       if (p.ls) v *= p.ls[n];
       if (R) v = R[(int64_t)m * p.ldr + n] + v;
       from_f(C[(int64_t)m * p.ldc + n], v);

@@ -139,6 +139,17 @@ size_t hvla_resize_workspace_bytes(int B, int H, int W, int S, int crop);
 int hvla_resize_lanczos3(hvla_stream_t stream, const uint8_t* images, int B, int H, int W, int S, const int32_t* starts_y,
                          const float* weights_y, int span_y, const int32_t* starts_x, const float* weights_x, int span_x, int crop,
                          const float* crop_params, uint8_t* out, void* workspace, size_t workspace_bytes);
+/* ---- T5-base token embedder: replaces FlaxT5EncoderModel('t5-base')(input_ids, attention_mask)
+ * .last_hidden_state, the `token_embedding` the hypernetwork consumes (octo/model/components/tokenizers.py:186-211,
+ * data/utils/language_tokenizer.py:9-28).  fp32.
+ *   t5_blob (device, hvla_t5_blob_elems() floats, HF torch [out,in] weight layout, packed by hvla/t5.py):
+ *     shared[32128,768] | 12 x { ln0[768] wq|wk|wv[2304,768] wo[768,768] ln1[768] wi[3072,768] wo2[768,3072] } | final_ln[768]
+ *   pos_bias (device) [12,S,S]: relative-position bias per head, query, key (block 0's bucket table expanded by the caller)
+ *   input_ids, attention_mask (device) [T,S] i32, S <= 32      out_emb (device) [T,S,768] f32 */
+int64_t hvla_t5_blob_elems(void);
+size_t hvla_t5_workspace_bytes(int T, int S);
+int hvla_t5_encode(hvla_stream_t stream, const float* t5_blob, const float* pos_bias, const int32_t* input_ids, const int32_t* attention_mask,
+                   int T, int S, float* out_emb, void* workspace, size_t workspace_bytes);
 /* number of kernels launched by this library since load (for bench.py's gpu_launches) */
 int64_t hvla_launch_count(void);
 /* per-kernel-class CUDA-event timing on the launching stream (bench.py's live roofline numbers).

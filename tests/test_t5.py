@@ -1,0 +1,98 @@
+"""SURVEY.md 8(f) row 5 — the T5-base token embedder upstream of generate (octo/model/components/tokenizers.py:186-211,
+data/utils/language_tokenizer.py:9-28).  The reference runs HF's *Flax* T5 encoder (un-vendored transformers==4.50.0);
+the oracle's restatement is pinned against HF's *torch* `T5EncoderModel` of the local transformers (random t5-base-shaped
+weights, ragged attention masks); the CUDA path is checked against the oracle to the fp32 bar (1e-5)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+transformers = pytest.importorskip("transformers")
+
+
+@pytest.fixture(scope="module")
+def t5_case():
+    cfg = transformers.T5Config(vocab_size=32128, d_model=768, d_kv=64, d_ff=3072, num_layers=12, num_heads=12,
+                                relative_attention_num_buckets=32, relative_attention_max_distance=128, dropout_rate=0.1,
+                                layer_norm_epsilon=1e-6, feed_forward_proj="relu")
+    torch.manual_seed(0)
+    m = transformers.T5EncoderModel(cfg).eval()
+    with torch.no_grad():
+        for k, v in m.state_dict().items():
+            if "layer_norm" in k:
+                v.copy_(1 + 0.1 * torch.randn_like(v))
+            elif "relative_attention_bias" in k or "shared" in k or "embed_tokens" in k:
+                v.copy_(torch.randn_like(v))
+            else:
+                v.copy_(torch.randn_like(v) * 0.03)
+    sd = {k: v.numpy().copy() for k, v in m.state_dict().items()}
+    rng = np.random.default_rng(0)
+    n = np.array([5, 32, 17, 1])
+    am = (np.arange(32)[None, :] < n[:, None]).astype(np.int64)
+    ids = rng.integers(1, 32000, (4, 32)) * am
+    with torch.no_grad():
+        ref = m(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(am)).last_hidden_state.numpy()
+    return sd, ids, am, ref
+
+
+def test_t5_oracle_matches_hf_torch_encoder(t5_case):
+    from oracle import t5_oracle as TO
+    sd, ids, am, ref = t5_case
+    out = TO.encode(sd, ids, am, np.float32)
+    assert out.shape == (4, 32, 768)
+    assert np.abs(out - ref).max() / np.abs(ref).max() < 2e-5
+    out64 = TO.encode(sd, ids, am, np.float64)
+    assert np.abs(out64 - ref).max() / np.abs(ref).max() < 2e-5
+    # bucket function: small distances exact, sign selects the half, far distances saturate
+    b = TO.relative_bucket(np.array([0, 1, 7, 8, 16, 31, -1, -7, -31, 200]))
+    assert b.tolist()[:4] == [0, 17, 23, 24] and b[6] == 1 and b[7] == 7 and b[9] == 31 and b[8] == b[5] - 16
+
+
+def test_t5_host_packing_and_flax_names(t5_case):
+    from hvla import t5 as T
+    from oracle import t5_oracle as TO
+    sd, ids, am, _ = t5_case
+    blob = T.pack_t5(sd)
+    assert blob.dtype == np.float32 and blob.size == 32128 * 768 + 12 * (768 + 4 * 768 * 768 + 768 + 2 * 768 * 3072) + 768
+    assert np.array_equal(T.relative_bucket(np.arange(-31, 32)), TO.relative_bucket(np.arange(-31, 32)))
+    # the Flax tree of the reference ([in,out] kernels) maps onto the same state dict
+    tree = {"shared": {"embedding": sd["shared.weight"]}, "encoder": {"block": {}, "final_layer_norm": {"weight": sd["encoder.final_layer_norm.weight"]}}}
+    for l in range(12):
+        p = f"encoder.block.{l}.layer."
+        att = {n: {"kernel": sd[p + f"0.SelfAttention.{n}.weight"].T} for n in ("q", "k", "v", "o")}
+        if l == 0:
+            att["relative_attention_bias"] = {"embedding": sd[p + "0.SelfAttention.relative_attention_bias.weight"]}
+        tree["encoder"]["block"][str(l)] = {"layer": {
+            "0": {"SelfAttention": att, "layer_norm": {"weight": sd[p + "0.layer_norm.weight"]}},
+            "1": {"DenseReluDense": {"wi": {"kernel": sd[p + "1.DenseReluDense.wi.weight"].T}, "wo": {"kernel": sd[p + "1.DenseReluDense.wo.weight"].T}},
+                  "layer_norm": {"weight": sd[p + "1.layer_norm.weight"]}}}}
+    assert np.array_equal(T.pack_t5(T.flax_tree_to_state_dict(tree)), blob)
+
+
+@pytest.mark.gpu
+def test_gpu_t5_embedder_matches_oracle_and_feeds_generate(t5_case, params_p1):
+    assert torch.cuda.is_available()
+    from hvla import config as C, synthetic as S, t5 as T
+    from hvla.model import HyperVLA
+    from oracle import t5_oracle as TO
+    sd, ids, am, ref = t5_case
+    emb = T.T5TokenEmbedder(sd)
+    out = emb(ids, am)
+    assert out.is_cuda and tuple(out.shape) == (4, 32, 768)
+    got = out.cpu().numpy()
+    ora = TO.encode(sd, ids, am, np.float64)
+    err = np.abs(got - ora).max() / np.abs(ora).max()
+    print(f"t5 embedder vs fp64 oracle: {err:.2e}; vs HF torch: {np.abs(got - ref).max() / np.abs(ref).max():.2e}")
+    assert err < 1e-5
+    assert tuple(emb(ids[:0], am[:0]).shape) == (0, 32, 768) and tuple(emb(ids[:1, :7], am[:1, :7]).shape) == (1, 7, 768)
+    short = emb(ids[:2, :9], np.ones((2, 9), np.int64)).cpu().numpy()
+    assert np.abs(short - TO.encode(sd, ids[:2, :9], np.ones((2, 9), np.int64), np.float64)).max() < 1e-4
+    with pytest.raises(ValueError):
+        emb(np.zeros((1, 40), np.int64), np.ones((1, 40), np.int64))
+    # embeddings stay on the device and feed create_tasks: tokenise -> embed -> generate without a host round trip
+    model = HyperVLA.from_config(C.default_config(), precision="fp32", params=params_p1)
+    inp = S.make_inputs(9, 4, 4)
+    instr = {"language_instruction": {"input_ids": ids, "attention_mask": am, "token_embedding": out}}
+    bp, _, _ = model.create_tasks(instruction_dict=instr, initial_state=inp["initial_state"])
+    instr_h = {"language_instruction": {"input_ids": ids, "attention_mask": am, "token_embedding": got}}
+    bp_h, _, _ = model.create_tasks(instruction_dict=instr_h, initial_state=inp["initial_state"])
+    assert np.array_equal(bp.packed_numpy(), bp_h.packed_numpy())
