@@ -45,6 +45,48 @@ def workload_config(B: int, world: int) -> dict:
     }
 
 
+def kernel_roofline_table(act_prof: dict, gen_prof: dict, B: int, T: int, peaks: dict, precision: str) -> dict:
+    """Every kernel class of one act step and one generate, against the roofline DESIGN.md section 3 names for it:
+    ALGORITHMIC bytes or FLOP (SURVEY.md 8(d) figures x the units of this run) / the class's live CUDA-event time.
+    HBM peak = MEASURED_PEAKS.json hbm_gbs (burst copy figure; no sustained HBM figure is published), tensor peak =
+    bf16_tflops_sustained; the recipe's fallbacks (6650 GB/s, 1400 TFLOP/s) when the file is absent."""
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    tens = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    e = 2 if precision == "bf16" else 4          # activation / weight element size of the compute path
+    M = B * 257
+    work = {   # class -> (bound, algorithmic work of one step or one generate, in bytes or FLOP)
+        "gemm_tc": ("tensor", FLOP_DINO_GEMM_IMG * B),
+        "dino_attention": ("tensor", FLOP_DINO_ATTN_IMG * B),
+        "layernorm": ("hbm", 25 * M * 768 * (4 + e)),                      # 25 launches: fp32 stream in, normalised rows out
+        "im2col": ("hbm", B * (150_528 + 256 * 640 * e)),                  # u8 image in, K-padded patch matrix out
+        "cls_rows": ("hbm", M * 768 * 4),                                  # stream rows pre-set to cls/pos
+        "base_fused": ("hbm", B * (256 * 768 * e + 112) + T * 201_500 * e),
+        "ctx_fused": ("hbm", 1_386_752 * e + T * (33 * 768 + 768) * 4 + T * 128 * 4),
+        "heads_gemm": ("hbm", 128 * 201_504 * e + 201_504 * 4 + T * 201_504 * e),
+    }
+    notes = {
+        "cls_rows": "write-only, absorbed by the 126 MB L2 at this batch: can exceed the HBM copy peak",
+        "dino_attention": "bound by MUFU.EX2 (16/clk/SM) and instruction issue before the tensor pipe (DESIGN.md section 3)",
+        "base_fused": "latency-bound (dependent mma.sync chains per env), not bandwidth-bound at this batch (DESIGN.md section 3)",
+        "ctx_fused": "latency-bound: one CTA per task, weights streamed from L2 (DESIGN.md section 3)",
+    }
+    out = {}
+    for src in (act_prof, gen_prof):
+        for name, (n, ms) in src.items():
+            if name not in work or ms <= 0:
+                continue
+            bound, w = work[name]
+            if bound == "tensor":
+                a, pk, unit = w / (ms / 1e3) / 1e12, tens, "TFLOP/s"
+            else:
+                a, pk, unit = w / (ms / 1e3) / 1e9, hbm, "GB/s"
+            out[name] = {"bound": bound, "launches": n, "ms": round(ms, 4), "achieved": round(a, 2), "peak": pk, "unit": unit,
+                         "frac": round(a / pk, 4)}
+            if name in notes:
+                out[name]["note"] = notes[name]
+    return out
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -337,6 +379,7 @@ def run_ours(args):
     kernel_ms = {k: round(v[1], 4) for k, v in prof.items()}
     gen_prof = rt.profile(lambda: model.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"]), repeats=2)
     gen_kernel_ms = {k: [v[0], round(v[1], 4)] for k, v in gen_prof.items()}
+    kernel_rooflines = kernel_roofline_table(prof, gen_prof, B, B, peaks, args.precision)
 
     # ---- batch-1 latency (configs[0] shape on the GPU) ----------------------------------------------------
     inp1 = S.make_inputs(1, 1, 1)
@@ -380,6 +423,7 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "kernel_ms_per_step": kernel_ms,
+            "kernel_rooflines": kernel_rooflines,
             "p50_step_ms": float(np.median(lat)), "p95_step_ms": float(np.percentile(lat, 95)),
             "batch1_p50_latency_ms": float(np.median(l1)), "batch1_e2e_p50_latency_ms": float(np.median(l1h)),
             "hypernet_gen_ms": {"tasks": B, "p50": float(np.median(gen_dev_ms)), "p50_host_inputs": float(np.median(gen_ms)),
