@@ -8,6 +8,7 @@
 #pragma once
 #include "common.cuh"
 #include "simt_kernels.cuh"
+#include "gemm_tc2.cuh"
 #include <cfloat>
 
 namespace hvla {
@@ -137,6 +138,136 @@ inline int encode(cudaStream_t st, const float* blob, const float* pos_bias, con
       g.R = X; g.ldr = TD;
       HVLA_TRY((gemm_simt<float, float, float, float>(st, g, 1)));
     }
+  }
+  rmsnorm768_kernel<<<cdiv(M, 8), 256, 0, st>>>(X, blob + L::lnf, out, M);
+  HVLA_LAUNCH_CHECK("t5_rmsnorm");
+  return HVLA_OK;
+}
+
+// ---- tensor-core path ("bf16x3") ---------------------------------------------------------------------------------
+// The fp32 path above is exact but runs its GEMMs on CUDA cores (6.7 ms for one instruction, 21 ms for 64: the skinny
+// M = 32..2048 GEMMs reach a few % of anything).  Here every GEMM runs on the tcgen05 kernel of the DINOv2 blocks with
+// fp32-like accuracy: activations and weights are split into two bf16 numbers (x = hi + lo, hi = bf16(x), lo = bf16(x - hi),
+// 16 mantissa bits together) and  A W^T ~= Ahi Whi^T + Alo Whi^T + Ahi Wlo^T  (the dropped Alo Wlo^T term is 2^-18 relative),
+// three launches that accumulate into the same fp32 output through the TMA reduce-add epilogue (EPI_RESIDUAL_F32, LayerScale
+// 1, zero bias; one add per element and launch, so run-to-run deterministic).  terms = 1 keeps only Ahi Whi^T (plain bf16).
+// Rows are padded to a multiple of 256 (one CTA-pair tile); padding rows are zero / never read back.
+struct MatLayout {   // bf16 elements per layer: [hi: wqkv | wo | wi | wo2][lo: the same], HF torch [out,in] layout
+  static constexpr int64_t wqkv = 0, wo = wqkv + (int64_t)3 * TD * TD, wi = wo + (int64_t)TD * TD, wo2 = wi + (int64_t)TFF * TD,
+                           half = wo2 + (int64_t)TD * TFF, layer_size = 2 * half;
+  static constexpr int64_t total = TL * layer_size;
+};
+
+__device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// T5LayerNorm straight into the split operand: one warp per row
+__global__ void __launch_bounds__(256) rmsnorm768_split_kernel(const float* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ yhi,
+                                                               bf16* __restrict__ ylo, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * TD);
+  float4 v[6];
+  float s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s2 = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, fmaf(v[i].w, v[i].w, s2))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  const float r = 1.0f / sqrtf(s2 / (float)TD + 1e-6f);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * i);
+    const float y[4] = {v[i].x * r * g.x, v[i].y * r * g.y, v[i].z * r * g.z, v[i].w * r * g.w};
+    __align__(8) bf16 h[4];
+    __align__(8) bf16 l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_bf16(y[j], h[j], l[j]);
+    const int64_t o4 = (int64_t)row * TD + (lane + 32 * i) * 4;
+    *reinterpret_cast<uint2*>(yhi + o4) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(ylo + o4) = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
+// fp32 [n] -> (hi, lo) bf16, optionally through ReLU; n % 4 == 0
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ in, bf16* __restrict__ hi, bf16* __restrict__ lo, int64_t n4, int relu) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 a = reinterpret_cast<const float4*>(in)[i];
+  float y[4] = {a.x, a.y, a.z, a.w};
+  __align__(8) bf16 h[4];
+  __align__(8) bf16 l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (relu) y[j] = fmaxf(y[j], 0.f);
+    split_bf16(y[j], h[j], l[j]);
+  }
+  reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<const uint2*>(h);
+  reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<const uint2*>(l);
+}
+
+inline int padded_rows(int M) { return (M + 255) / 256 * 256; }
+inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+inline size_t workspace_bytes_tc(int T, int S) {
+  const size_t Mp = (size_t)padded_rows(T * S);
+  return 2 * al256(Mp * TD * 4) + al256(Mp * 3 * TD * 4) + al256(Mp * TFF * 4) + 2 * al256(Mp * TFF * 2) + al256((size_t)TFF * 4);
+}
+
+// OUT[Mp,N] (fp32) += A W^T with split operands
+inline int gemm_split(cudaStream_t st, const bf16* Ahi, const bf16* Alo, const bf16* Whi, const bf16* Wlo, float* OUT, int Mp, int N, int K,
+                      const float* zero_bias, int terms) {
+  tc::EpiP ep;
+  memset(&ep, 0, sizeof ep);
+  ep.bias = zero_bias; ep.out = OUT; ep.ldo = N;            // ls == null: LayerScale 1; part == null: K is never split
+  HVLA_TRY(tc2::gemm_tc2(st, Ahi, Whi, Mp, N, K, tc::EPI_RESIDUAL_F32, ep));
+  if (terms >= 3) {
+    HVLA_TRY(tc2::gemm_tc2(st, Alo, Whi, Mp, N, K, tc::EPI_RESIDUAL_F32, ep));
+    HVLA_TRY(tc2::gemm_tc2(st, Ahi, Wlo, Mp, N, K, tc::EPI_RESIDUAL_F32, ep));
+  }
+  return HVLA_OK;
+}
+
+inline int encode_tc(cudaStream_t st, const float* blob, const bf16* mat, const float* pos_bias, const int32_t* ids, const int32_t* mask, int T,
+                     int S, float* out, uint8_t* ws, int terms) {
+  typedef Layout L;
+  typedef MatLayout W;
+  const int M = T * S, Mp = padded_rows(M);
+  uint8_t* p = ws;
+  float* X = reinterpret_cast<float*>(p);   p += al256((size_t)Mp * TD * 4);
+  float* ATT = reinterpret_cast<float*>(p); p += al256((size_t)Mp * TD * 4);
+  float* QKV = reinterpret_cast<float*>(p); p += al256((size_t)Mp * 3 * TD * 4);
+  float* HID = reinterpret_cast<float*>(p); p += al256((size_t)Mp * TFF * 4);
+  bf16* AH = reinterpret_cast<bf16*>(p);    p += al256((size_t)Mp * TFF * 2);
+  bf16* AL = reinterpret_cast<bf16*>(p);    p += al256((size_t)Mp * TFF * 2);
+  float* ZERO = reinterpret_cast<float*>(p);
+  ProfScope ps(st, "t5_encode");
+  HVLA_CUDA(cudaMemsetAsync(ws, 0, workspace_bytes_tc(T, S), st));     // padding rows, zero bias
+  gather_kernel<<<M, 192, 0, st>>>(ids, blob + L::embed, X, M);
+  HVLA_LAUNCH_CHECK("t5_gather");
+  for (int l = 0; l < TL; ++l) {
+    const float* w = blob + L::layers + (int64_t)l * L::layer_size;
+    const bf16* hi = mat + (int64_t)l * W::layer_size;
+    const bf16* lo = hi + W::half;
+    rmsnorm768_split_kernel<<<cdiv(M, 8), 256, 0, st>>>(X, w + L::ln0, AH, AL, M);
+    HVLA_LAUNCH_CHECK("t5_rmsnorm_split");
+    HVLA_CUDA(cudaMemsetAsync(QKV, 0, (size_t)Mp * 3 * TD * 4, st));
+    HVLA_TRY(gemm_split(st, AH, AL, hi + W::wqkv, lo + W::wqkv, QKV, Mp, 3 * TD, TD, ZERO, terms));
+    attention_kernel<<<dim3(S, TH, T), 32, 0, st>>>(QKV, mask, pos_bias, ATT, S);
+    HVLA_LAUNCH_CHECK("t5_attention");
+    split_kernel<<<cdiv((int64_t)M * TD / 4, 256), 256, 0, st>>>(ATT, AH, AL, (int64_t)M * TD / 4, 0);
+    HVLA_LAUNCH_CHECK("t5_split");
+    HVLA_TRY(gemm_split(st, AH, AL, hi + W::wo, lo + W::wo, X, Mp, TD, TD, ZERO, terms));            // x += att Wo^T
+    rmsnorm768_split_kernel<<<cdiv(M, 8), 256, 0, st>>>(X, w + L::ln1, AH, AL, M);
+    HVLA_LAUNCH_CHECK("t5_rmsnorm_split");
+    HVLA_CUDA(cudaMemsetAsync(HID, 0, (size_t)Mp * TFF * 4, st));
+    HVLA_TRY(gemm_split(st, AH, AL, hi + W::wi, lo + W::wi, HID, Mp, TFF, TD, ZERO, terms));
+    split_kernel<<<cdiv((int64_t)M * TFF / 4, 256), 256, 0, st>>>(HID, AH, AL, (int64_t)M * TFF / 4, 1);   // ReLU, then split
+    HVLA_LAUNCH_CHECK("t5_split");
+    HVLA_TRY(gemm_split(st, AH, AL, hi + W::wo2, lo + W::wo2, X, Mp, TD, TFF, ZERO, terms));         // x += relu(.) Wo2^T
   }
   rmsnorm768_kernel<<<cdiv(M, 8), 256, 0, st>>>(X, blob + L::lnf, out, M);
   HVLA_LAUNCH_CHECK("t5_rmsnorm");

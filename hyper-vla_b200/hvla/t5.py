@@ -62,9 +62,32 @@ def pack_t5(sd: dict) -> np.ndarray:
     return blob
 
 
+def split_matrices(blob):
+    """The GEMM weights of the packed fp32 blob (torch tensor, any device) as two bf16 numbers each: hi = bf16(w),
+    lo = bf16(w - hi), laid out per layer as [hi: wqkv | wo | wi | wo2][lo: the same] (include/hvla.h, hvla_t5_encode_tc)."""
+    import torch
+    layer = D + 3 * D * D + D * D + D + FF * D + D * FF
+    out = []
+    for l in range(LAYERS):
+        base = VOCAB * D + l * layer
+        qkv_o = blob[base + D: base + D + 4 * D * D]                       # wq|wk|wv then wo, contiguous
+        ffn = blob[base + D + 4 * D * D + D: base + layer]                 # wi then wo2, contiguous
+        w = torch.cat([qkv_o, ffn])
+        hi = w.to(torch.bfloat16)
+        lo = (w - hi.float()).to(torch.bfloat16)
+        out += [hi, lo]
+    return torch.cat(out)
+
+
 class T5TokenEmbedder:
-    def __init__(self, weights: dict, device=None):
+    """precision: "bf16x3" (default; tcgen05 GEMMs on split operands, ~3e-5 of the fp64 result), "bf16" (one term, ~2e-2)
+    or "fp32" (CUDA-core GEMMs in the reference's operation order, 1e-5; ~10x slower)."""
+
+    def __init__(self, weights: dict, device=None, precision: str = "bf16x3"):
         import torch
+        if precision not in ("bf16x3", "bf16", "fp32"):
+            raise ValueError("precision must be 'bf16x3', 'bf16' or 'fp32'")
+        self.precision = precision
         if not torch.cuda.is_available():
             raise N.HvlaError("no CUDA device: the hvla T5 embedder is CUDA-only")
         self.lib = N.lib()
@@ -74,6 +97,11 @@ class T5TokenEmbedder:
         if blob.size != int(self.lib.hvla_t5_blob_elems()):
             raise ValueError("T5 weights do not have the t5-base encoder shapes")
         self.blob = torch.from_numpy(blob).to(self.device)
+        self.mat = None
+        if precision != "fp32":
+            self.mat = split_matrices(self.blob).contiguous()
+            if self.mat.numel() != int(self.lib.hvla_t5_mat_elems()):
+                raise ValueError("T5 split-weight blob does not match hvla_t5_mat_elems()")
         rb = sd["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"]
         self._rel = np.asarray(rb.detach().cpu().numpy() if hasattr(rb, "detach") else rb, np.float32)      # [32 buckets, 12 heads]
         self._bias, self._ws = {}, None
@@ -99,10 +127,17 @@ class T5TokenEmbedder:
         out = torch.empty((T, S, D), dtype=torch.float32, device=self.device)
         if T == 0:
             return out
-        need = int(self.lib.hvla_t5_workspace_bytes(T, S))
+        tc = self.precision != "fp32"
+        need = int(self.lib.hvla_t5_tc_workspace_bytes(T, S) if tc else self.lib.hvla_t5_workspace_bytes(T, S))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
-        st = self.lib.hvla_t5_encode(int(torch.cuda.current_stream(self.device).cuda_stream), self.blob.data_ptr(), self._pos_bias(S).data_ptr(),
-                                     ids.data_ptr(), am.data_ptr(), T, S, out.data_ptr(), self._ws.data_ptr(), need)
-        N.check(st, "hvla_t5_encode")
+        stream = int(torch.cuda.current_stream(self.device).cuda_stream)
+        if tc:
+            st = self.lib.hvla_t5_encode_tc(stream, self.blob.data_ptr(), self.mat.data_ptr(), self._pos_bias(S).data_ptr(), ids.data_ptr(),
+                                            am.data_ptr(), T, S, out.data_ptr(), self._ws.data_ptr(), need, 3 if self.precision == "bf16x3" else 1)
+            N.check(st, "hvla_t5_encode_tc")
+        else:
+            st = self.lib.hvla_t5_encode(stream, self.blob.data_ptr(), self._pos_bias(S).data_ptr(), ids.data_ptr(), am.data_ptr(), T, S,
+                                         out.data_ptr(), self._ws.data_ptr(), need)
+            N.check(st, "hvla_t5_encode")
         return out
