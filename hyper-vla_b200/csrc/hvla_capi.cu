@@ -759,7 +759,7 @@ size_t hvla_t5_workspace_bytes(int T, int S) { return (T > 0 && S > 0) ? t5::wor
 
 int hvla_t5_encode(hvla_stream_t stream, const float* t5_blob, const float* pos_bias, const int32_t* input_ids, const int32_t* attention_mask,
                    int T, int S, float* out_emb, void* workspace, size_t workspace_bytes) {
-  if (T < 0 || S <= 0 || S > t5::SMAX) return fail(HVLA_ERR_ARG, "hvla_t5_encode: need T >= 0 and 1 <= S <= 32");
+  if (T < 0 || T > 65535 || S <= 0 || S > t5::SMAX) return fail(HVLA_ERR_ARG, "hvla_t5_encode: need 0 <= T <= 65535 and 1 <= S <= 32");
   if (T == 0) return HVLA_OK;
   if (!t5_blob || !pos_bias || !input_ids || !attention_mask || !out_emb || !workspace) return fail(HVLA_ERR_ARG, "hvla_t5_encode: null argument");
   if (workspace_bytes < t5::workspace_bytes(T, S)) return fail(HVLA_ERR_WORKSPACE, "hvla_t5_encode: workspace too small");
@@ -771,15 +771,14 @@ int64_t hvla_t5_mat_elems(void) { return t5::MatLayout::total; }
 size_t hvla_t5_tc_workspace_bytes(int T, int S) { return (T > 0 && S > 0) ? t5::workspace_bytes_tc(T, S) : 0; }
 
 int hvla_t5_encode_tc(hvla_stream_t stream, const float* t5_blob, const void* t5_mat, const float* pos_bias, const int32_t* input_ids,
-                      const int32_t* attention_mask, int T, int S, float* out_emb, void* workspace, size_t workspace_bytes, int terms) {
-  if (T < 0 || S <= 0 || S > t5::SMAX) return fail(HVLA_ERR_ARG, "hvla_t5_encode_tc: need T >= 0 and 1 <= S <= 32");
-  if (terms != 1 && terms != 3) return fail(HVLA_ERR_ARG, "hvla_t5_encode_tc: terms must be 1 (bf16) or 3 (bf16x3)");
+                      const int32_t* attention_mask, int T, int S, float* out_emb, void* workspace, size_t workspace_bytes) {
+  if (T < 0 || T > 65535 || S <= 0 || S > t5::SMAX) return fail(HVLA_ERR_ARG, "hvla_t5_encode_tc: need 0 <= T <= 65535 and 1 <= S <= 32");
   if (T == 0) return HVLA_OK;
   if (!t5_blob || !t5_mat || !pos_bias || !input_ids || !attention_mask || !out_emb || !workspace)
     return fail(HVLA_ERR_ARG, "hvla_t5_encode_tc: null argument");
   if (workspace_bytes < t5::workspace_bytes_tc(T, S)) return fail(HVLA_ERR_WORKSPACE, "hvla_t5_encode_tc: workspace too small");
   return t5::encode_tc(reinterpret_cast<cudaStream_t>(stream), t5_blob, reinterpret_cast<const bf16*>(t5_mat), pos_bias, input_ids,
-                       attention_mask, T, S, out_emb, reinterpret_cast<uint8_t*>(workspace), terms);
+                       attention_mask, T, S, out_emb, reinterpret_cast<uint8_t*>(workspace));
 }
 
 // ---- legacy XLA custom-call wrappers (no status channel in this ABI revision: errors are logged) ---------

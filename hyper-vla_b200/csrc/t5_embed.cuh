@@ -56,37 +56,53 @@ __global__ void __launch_bounds__(256) rmsnorm768_kernel(const float* __restrict
   }
 }
 
-// one warp per (query i, head h, task t); lane = key.  s = q.k (no 1/sqrt(d)) + pos_bias[h,i,j] + (1-mask_j)*finfo.min
-__global__ void __launch_bounds__(32) attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ mask,
-                                                       const float* __restrict__ pos_bias, float* __restrict__ out, int S) {
-  const int i = blockIdx.x, h = blockIdx.y, t = blockIdx.z, lane = threadIdx.x;
-  const float* q = qkv + ((int64_t)t * S + i) * (3 * TD) + h * THD;
-  float s = -INFINITY;
-  if (lane < S) {
-    const float* k = qkv + ((int64_t)t * S + lane) * (3 * TD) + TD + h * THD;
-    float a = 0.f;
-#pragma unroll 8
-    for (int d = 0; d < THD; ++d) a = fmaf(__ldg(q + d), __ldg(k + d), a);
-    s = a + pos_bias[((int64_t)h * S + i) * S + lane] + (mask[t * S + lane] != 0 ? 0.f : -FLT_MAX);
+// one CTA (4 warps) per (head h, task t): q, k, v of the head staged in shared memory (k rows padded to 65 floats: lane = key
+// reads a column conflict-free), a warp owns every 4th query.  s = q.k (no 1/sqrt(d)) + pos_bias[h,i,j] + (1-mask_j)*finfo.min;
+// the dot product runs over d ascending and the output over keys ascending (the summation order of the oracle's einsum is not
+// defined; this one is fixed).  The first version ran one single-warp CTA per (query, head, task) straight from global memory:
+// 211 us per layer for 64 instructions, half of the whole encoder.
+__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ mask,
+                                                        const float* __restrict__ pos_bias, float* __restrict__ out, int S) {
+  __shared__ __align__(16) float sq[SMAX][THD];
+  __shared__ float sk[SMAX][THD + 1];
+  __shared__ __align__(16) float sv[SMAX][THD];
+  const int h = blockIdx.x, t = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int e = threadIdx.x; e < S * (THD / 4); e += blockDim.x) {
+    const int r = e / (THD / 4), c4 = e % (THD / 4);
+    const float4* src = reinterpret_cast<const float4*>(qkv + ((int64_t)t * S + r) * (3 * TD) + h * THD) + c4;
+    const float4 q4 = __ldg(src), k4 = __ldg(src + TD / 4), v4 = __ldg(src + 2 * TD / 4);
+    *reinterpret_cast<float4*>(&sq[r][c4 * 4]) = q4;
+    *reinterpret_cast<float4*>(&sv[r][c4 * 4]) = v4;
+    sk[r][c4 * 4] = k4.x; sk[r][c4 * 4 + 1] = k4.y; sk[r][c4 * 4 + 2] = k4.z; sk[r][c4 * 4 + 3] = k4.w;
   }
-  float mx = s;
+  __syncthreads();
+  const float neg = (lane < S && mask[t * S + lane] != 0) ? 0.f : -FLT_MAX;
+  for (int i = warp; i < S; i += 4) {
+    float s = -INFINITY;
+    if (lane < S) {
+      float a = 0.f;
+#pragma unroll 16
+      for (int d = 0; d < THD; ++d) a = fmaf(sq[i][d], sk[lane][d], a);
+      s = a + __ldg(pos_bias + ((int64_t)h * S + i) * S + lane) + neg;
+    }
+    float mx = s;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  const float e = lane < S ? expf(s - mx) : 0.f;
-  float sum = e;
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e = lane < S ? expf(s - mx) : 0.f;
+    float sum = e;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float p = e / sum;
-  float o0 = 0.f, o1 = 0.f;
-  for (int j = 0; j < S; ++j) {
-    const float pj = __shfl_sync(0xffffffffu, p, j);
-    const float* v = qkv + ((int64_t)t * S + j) * (3 * TD) + 2 * TD + h * THD;
-    o0 = fmaf(pj, __ldg(v + lane), o0);
-    o1 = fmaf(pj, __ldg(v + lane + 32), o1);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float p = e / sum;
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < S; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, p, j);
+      o0 = fmaf(pj, sv[j][lane], o0);
+      o1 = fmaf(pj, sv[j][lane + 32], o1);
+    }
+    float* o = out + ((int64_t)t * S + i) * TD + h * THD;
+    o[lane] = o0;
+    o[lane + 32] = o1;
   }
-  float* o = out + ((int64_t)t * S + i) * TD + h * THD;
-  o[lane] = o0;
-  o[lane + 32] = o1;
 }
 
 inline size_t workspace_bytes(int T, int S) {
@@ -119,7 +135,7 @@ inline int encode(cudaStream_t st, const float* blob, const float* pos_bias, con
     rmsnorm768_kernel<<<cdiv(M, 8), 256, 0, st>>>(X, w + L::ln0, Y, M);
     HVLA_LAUNCH_CHECK("t5_rmsnorm");
     HVLA_TRY((gemm_simt<float, float, float, float>(st, gp(Y, TD, w + L::wqkv, TD, QKV, 3 * TD, M, 3 * TD, TD), 1)));
-    attention_kernel<<<dim3(S, TH, T), 32, 0, st>>>(QKV, mask, pos_bias, ATT, S);
+    attention_kernel<<<dim3(TH, T), 128, 0, st>>>(QKV, mask, pos_bias, ATT, S);
     HVLA_LAUNCH_CHECK("t5_attention");
     {
       GemmP g = gp(ATT, TD, w + L::wo, TD, X, TD, M, TD, TD);
@@ -148,13 +164,16 @@ inline int encode(cudaStream_t st, const float* blob, const float* pos_bias, con
 // The fp32 path above is exact but runs its GEMMs on CUDA cores (6.7 ms for one instruction, 21 ms for 64: the skinny
 // M = 32..2048 GEMMs reach a few % of anything).  Here every GEMM runs on the tcgen05 kernel of the DINOv2 blocks with
 // fp32-like accuracy: activations and weights are split into two bf16 numbers (x = hi + lo, hi = bf16(x), lo = bf16(x - hi),
-// 16 mantissa bits together) and  A W^T ~= Ahi Whi^T + Alo Whi^T + Ahi Wlo^T  (the dropped Alo Wlo^T term is 2^-18 relative),
-// three launches that accumulate into the same fp32 output through the TMA reduce-add epilogue (EPI_RESIDUAL_F32, LayerScale
-// 1, zero bias; one add per element and launch, so run-to-run deterministic).  terms = 1 keeps only Ahi Whi^T (plain bf16).
+// 16 mantissa bits together) and  A W^T ~= Ahi Whi^T + Alo Whi^T + Ahi Wlo^T  (the dropped Alo Wlo^T term is 2^-18 relative).
+// The three products are ONE launch: the operands are concatenated along K,  A' = [Ahi | Alo | Ahi]  (M x 3K, written by the
+// producing kernel) and  W' = [Whi | Whi | Wlo]  (N x 3K, packed once by hvla/t5.py), so the large hi.hi part is accumulated
+// first and the corrections after it, in the fp32 TMEM accumulator.  Outputs go through the TMA reduce-add epilogue
+// (EPI_RESIDUAL_F32, LayerScale 1, zero bias) into the fp32 stream, or into a zeroed fp32 buffer for q|k|v and the MLP hidden
+// layer; K is never split, so results are run-to-run deterministic and independent of the batch.
 // Rows are padded to a multiple of 256 (one CTA-pair tile); padding rows are zero / never read back.
-struct MatLayout {   // bf16 elements per layer: [hi: wqkv | wo | wi | wo2][lo: the same], HF torch [out,in] layout
-  static constexpr int64_t wqkv = 0, wo = wqkv + (int64_t)3 * TD * TD, wi = wo + (int64_t)TD * TD, wo2 = wi + (int64_t)TFF * TD,
-                           half = wo2 + (int64_t)TD * TFF, layer_size = 2 * half;
+struct MatLayout {   // bf16 elements per layer, each matrix [N, 3K] = [hi | hi | lo] per row (HF torch [out,in] orientation)
+  static constexpr int64_t wqkv = 0, wo = wqkv + (int64_t)3 * TD * 3 * TD, wi = wo + (int64_t)TD * 3 * TD, wo2 = wi + (int64_t)TFF * 3 * TD,
+                           layer_size = wo2 + (int64_t)TD * 3 * TFF;
   static constexpr int64_t total = TL * layer_size;
 };
 
@@ -162,10 +181,21 @@ __device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
   hi = __float2bfloat16_rn(v);
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
+// four consecutive columns c..c+3 of row `row` of A' [*, 3K]: hi at c and 2K + c, lo at K + c
+__device__ __forceinline__ void store_split4(bf16* __restrict__ a, int64_t row, int c, int K, const float y[4]) {
+  __align__(8) bf16 h[4];
+  __align__(8) bf16 l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_bf16(y[j], h[j], l[j]);
+  bf16* r = a + row * (3 * (int64_t)K) + c;
+  *reinterpret_cast<uint2*>(r) = *reinterpret_cast<const uint2*>(h);
+  *reinterpret_cast<uint2*>(r + K) = *reinterpret_cast<const uint2*>(l);
+  *reinterpret_cast<uint2*>(r + 2 * K) = *reinterpret_cast<const uint2*>(h);
+}
 
 // T5LayerNorm straight into the split operand: one warp per row
-__global__ void __launch_bounds__(256) rmsnorm768_split_kernel(const float* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ yhi,
-                                                               bf16* __restrict__ ylo, int rows) {
+__global__ void __launch_bounds__(256) rmsnorm768_split_kernel(const float* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ a,
+                                                               int rows) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * TD);
@@ -183,56 +213,41 @@ __global__ void __launch_bounds__(256) rmsnorm768_split_kernel(const float* __re
   for (int i = 0; i < 6; ++i) {
     const float4 g = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * i);
     const float y[4] = {v[i].x * r * g.x, v[i].y * r * g.y, v[i].z * r * g.z, v[i].w * r * g.w};
-    __align__(8) bf16 h[4];
-    __align__(8) bf16 l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) split_bf16(y[j], h[j], l[j]);
-    const int64_t o4 = (int64_t)row * TD + (lane + 32 * i) * 4;
-    *reinterpret_cast<uint2*>(yhi + o4) = *reinterpret_cast<const uint2*>(h);
-    *reinterpret_cast<uint2*>(ylo + o4) = *reinterpret_cast<const uint2*>(l);
+    store_split4(a, row, (lane + 32 * i) * 4, TD, y);
   }
 }
 
-// fp32 [n] -> (hi, lo) bf16, optionally through ReLU; n % 4 == 0
-__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ in, bf16* __restrict__ hi, bf16* __restrict__ lo, int64_t n4, int relu) {
+// fp32 [rows, K] -> A' [rows, 3K], optionally through ReLU; K % 4 == 0
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ in, bf16* __restrict__ a, int64_t n4, int K, int relu) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
-  const float4 a = reinterpret_cast<const float4*>(in)[i];
-  float y[4] = {a.x, a.y, a.z, a.w};
-  __align__(8) bf16 h[4];
-  __align__(8) bf16 l[4];
+  const float4 v = reinterpret_cast<const float4*>(in)[i];
+  float y[4] = {v.x, v.y, v.z, v.w};
+  if (relu) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (relu) y[j] = fmaxf(y[j], 0.f);
-    split_bf16(y[j], h[j], l[j]);
+    for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
   }
-  reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<const uint2*>(h);
-  reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<const uint2*>(l);
+  const int k4 = K / 4;
+  store_split4(a, i / k4, (int)(i % k4) * 4, K, y);
 }
 
 inline int padded_rows(int M) { return (M + 255) / 256 * 256; }
 inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 inline size_t workspace_bytes_tc(int T, int S) {
   const size_t Mp = (size_t)padded_rows(T * S);
-  return 2 * al256(Mp * TD * 4) + al256(Mp * 3 * TD * 4) + al256(Mp * TFF * 4) + 2 * al256(Mp * TFF * 2) + al256((size_t)TFF * 4);
+  return 2 * al256(Mp * TD * 4) + al256(Mp * 3 * TD * 4) + al256(Mp * TFF * 4) + al256(Mp * 3 * TFF * 2) + al256((size_t)TFF * 4);
 }
 
-// OUT[Mp,N] (fp32) += A W^T with split operands
-inline int gemm_split(cudaStream_t st, const bf16* Ahi, const bf16* Alo, const bf16* Whi, const bf16* Wlo, float* OUT, int Mp, int N, int K,
-                      const float* zero_bias, int terms) {
+// OUT[Mp,N] (fp32) += A'[Mp,3K] W'[N,3K]^T
+inline int gemm_split(cudaStream_t st, const bf16* A3, const bf16* W3, float* OUT, int Mp, int N, int K, const float* zero_bias) {
   tc::EpiP ep;
   memset(&ep, 0, sizeof ep);
   ep.bias = zero_bias; ep.out = OUT; ep.ldo = N;            // ls == null: LayerScale 1; part == null: K is never split
-  HVLA_TRY(tc2::gemm_tc2(st, Ahi, Whi, Mp, N, K, tc::EPI_RESIDUAL_F32, ep));
-  if (terms >= 3) {
-    HVLA_TRY(tc2::gemm_tc2(st, Alo, Whi, Mp, N, K, tc::EPI_RESIDUAL_F32, ep));
-    HVLA_TRY(tc2::gemm_tc2(st, Ahi, Wlo, Mp, N, K, tc::EPI_RESIDUAL_F32, ep));
-  }
-  return HVLA_OK;
+  return tc2::gemm_tc2(st, A3, W3, Mp, N, 3 * K, tc::EPI_RESIDUAL_F32, ep);
 }
 
 inline int encode_tc(cudaStream_t st, const float* blob, const bf16* mat, const float* pos_bias, const int32_t* ids, const int32_t* mask, int T,
-                     int S, float* out, uint8_t* ws, int terms) {
+                     int S, float* out, uint8_t* ws) {
   typedef Layout L;
   typedef MatLayout W;
   const int M = T * S, Mp = padded_rows(M);
@@ -241,8 +256,7 @@ inline int encode_tc(cudaStream_t st, const float* blob, const bf16* mat, const 
   float* ATT = reinterpret_cast<float*>(p); p += al256((size_t)Mp * TD * 4);
   float* QKV = reinterpret_cast<float*>(p); p += al256((size_t)Mp * 3 * TD * 4);
   float* HID = reinterpret_cast<float*>(p); p += al256((size_t)Mp * TFF * 4);
-  bf16* AH = reinterpret_cast<bf16*>(p);    p += al256((size_t)Mp * TFF * 2);
-  bf16* AL = reinterpret_cast<bf16*>(p);    p += al256((size_t)Mp * TFF * 2);
+  bf16* A3 = reinterpret_cast<bf16*>(p);    p += al256((size_t)Mp * 3 * TFF * 2);
   float* ZERO = reinterpret_cast<float*>(p);
   ProfScope ps(st, "t5_encode");
   HVLA_CUDA(cudaMemsetAsync(ws, 0, workspace_bytes_tc(T, S), st));     // padding rows, zero bias
@@ -250,24 +264,23 @@ inline int encode_tc(cudaStream_t st, const float* blob, const bf16* mat, const 
   HVLA_LAUNCH_CHECK("t5_gather");
   for (int l = 0; l < TL; ++l) {
     const float* w = blob + L::layers + (int64_t)l * L::layer_size;
-    const bf16* hi = mat + (int64_t)l * W::layer_size;
-    const bf16* lo = hi + W::half;
-    rmsnorm768_split_kernel<<<cdiv(M, 8), 256, 0, st>>>(X, w + L::ln0, AH, AL, M);
+    const bf16* m = mat + (int64_t)l * W::layer_size;
+    rmsnorm768_split_kernel<<<cdiv(M, 8), 256, 0, st>>>(X, w + L::ln0, A3, M);
     HVLA_LAUNCH_CHECK("t5_rmsnorm_split");
-    HVLA_CUDA(cudaMemsetAsync(QKV, 0, (size_t)Mp * 3 * TD * 4, st));
-    HVLA_TRY(gemm_split(st, AH, AL, hi + W::wqkv, lo + W::wqkv, QKV, Mp, 3 * TD, TD, ZERO, terms));
-    attention_kernel<<<dim3(S, TH, T), 32, 0, st>>>(QKV, mask, pos_bias, ATT, S);
+    if (l) HVLA_CUDA(cudaMemsetAsync(QKV, 0, (size_t)Mp * 3 * TD * 4, st));
+    HVLA_TRY(gemm_split(st, A3, m + W::wqkv, QKV, Mp, 3 * TD, TD, ZERO));
+    attention_kernel<<<dim3(TH, T), 128, 0, st>>>(QKV, mask, pos_bias, ATT, S);
     HVLA_LAUNCH_CHECK("t5_attention");
-    split_kernel<<<cdiv((int64_t)M * TD / 4, 256), 256, 0, st>>>(ATT, AH, AL, (int64_t)M * TD / 4, 0);
+    split_kernel<<<cdiv((int64_t)M * TD / 4, 256), 256, 0, st>>>(ATT, A3, (int64_t)M * TD / 4, TD, 0);
     HVLA_LAUNCH_CHECK("t5_split");
-    HVLA_TRY(gemm_split(st, AH, AL, hi + W::wo, lo + W::wo, X, Mp, TD, TD, ZERO, terms));            // x += att Wo^T
-    rmsnorm768_split_kernel<<<cdiv(M, 8), 256, 0, st>>>(X, w + L::ln1, AH, AL, M);
+    HVLA_TRY(gemm_split(st, A3, m + W::wo, X, Mp, TD, TD, ZERO));                 // x += att Wo^T
+    rmsnorm768_split_kernel<<<cdiv(M, 8), 256, 0, st>>>(X, w + L::ln1, A3, M);
     HVLA_LAUNCH_CHECK("t5_rmsnorm_split");
-    HVLA_CUDA(cudaMemsetAsync(HID, 0, (size_t)Mp * TFF * 4, st));
-    HVLA_TRY(gemm_split(st, AH, AL, hi + W::wi, lo + W::wi, HID, Mp, TFF, TD, ZERO, terms));
-    split_kernel<<<cdiv((int64_t)M * TFF / 4, 256), 256, 0, st>>>(HID, AH, AL, (int64_t)M * TFF / 4, 1);   // ReLU, then split
+    if (l) HVLA_CUDA(cudaMemsetAsync(HID, 0, (size_t)Mp * TFF * 4, st));
+    HVLA_TRY(gemm_split(st, A3, m + W::wi, HID, Mp, TFF, TD, ZERO));
+    split_kernel<<<cdiv((int64_t)M * TFF / 4, 256), 256, 0, st>>>(HID, A3, (int64_t)M * TFF / 4, TFF, 1);   // ReLU, then split
     HVLA_LAUNCH_CHECK("t5_split");
-    HVLA_TRY(gemm_split(st, AH, AL, hi + W::wo2, lo + W::wo2, X, Mp, TD, TFF, ZERO, terms));         // x += relu(.) Wo2^T
+    HVLA_TRY(gemm_split(st, A3, m + W::wo2, X, Mp, TD, TFF, ZERO));               // x += relu(.) Wo2^T
   }
   rmsnorm768_kernel<<<cdiv(M, 8), 256, 0, st>>>(X, blob + L::lnf, out, M);
   HVLA_LAUNCH_CHECK("t5_rmsnorm");

@@ -42,7 +42,7 @@ SIGNATURES = {
     "hvla_t5_encode": (c_int, [c_void_p] * 5 + [c_int, c_int, c_void_p, c_void_p, c_size_t]),
     "hvla_t5_mat_elems": (c_i64, []),
     "hvla_t5_tc_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "hvla_t5_encode_tc": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_size_t, c_int]),
+    "hvla_t5_encode_tc": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_size_t]),
     "hvla_launch_count": (c_i64, []),
     "hvla_profile_enable": (c_int, [c_int]),
     "hvla_profile_report": (c_int, [C.c_char_p, c_size_t]),

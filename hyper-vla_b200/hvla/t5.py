@@ -63,30 +63,34 @@ def pack_t5(sd: dict) -> np.ndarray:
 
 
 def split_matrices(blob):
-    """The GEMM weights of the packed fp32 blob (torch tensor, any device) as two bf16 numbers each: hi = bf16(w),
-    lo = bf16(w - hi), laid out per layer as [hi: wqkv | wo | wi | wo2][lo: the same] (include/hvla.h, hvla_t5_encode_tc)."""
+    """The GEMM weights of the packed fp32 blob (torch tensor, any device) as split bf16 operands: every [N,K] matrix becomes
+    [N,3K] with rows [hi | hi | lo], hi = bf16(w), lo = bf16(w - hi); per layer wqkv | wo | wi | wo2 (include/hvla.h,
+    hvla_t5_encode_tc: the activations are laid out [hi | lo | hi], so one GEMM adds hi.hi + lo.hi + hi.lo)."""
     import torch
     layer = D + 3 * D * D + D * D + D + FF * D + D * FF
     out = []
     for l in range(LAYERS):
         base = VOCAB * D + l * layer
-        qkv_o = blob[base + D: base + D + 4 * D * D]                       # wq|wk|wv then wo, contiguous
-        ffn = blob[base + D + 4 * D * D + D: base + layer]                 # wi then wo2, contiguous
-        w = torch.cat([qkv_o, ffn])
-        hi = w.to(torch.bfloat16)
-        lo = (w - hi.float()).to(torch.bfloat16)
-        out += [hi, lo]
+        o = base + D
+        mats = [(blob[o: o + 3 * D * D], D), (blob[o + 3 * D * D: o + 4 * D * D], D)]
+        o += 4 * D * D + D
+        mats += [(blob[o: o + FF * D], D), (blob[o + FF * D: o + 2 * FF * D], FF)]
+        for w, k in mats:
+            w = w.reshape(-1, k)
+            hi = w.to(torch.bfloat16)
+            lo = (w - hi.float()).to(torch.bfloat16)
+            out.append(torch.cat([hi, hi, lo], dim=1).reshape(-1))
     return torch.cat(out)
 
 
 class T5TokenEmbedder:
-    """precision: "bf16x3" (default; tcgen05 GEMMs on split operands, ~3e-5 of the fp64 result), "bf16" (one term, ~2e-2)
-    or "fp32" (CUDA-core GEMMs in the reference's operation order, 1e-5; ~10x slower)."""
+    """precision: "bf16x3" (default; tcgen05 GEMMs on split operands, 3e-5 of the fp64 result) or "fp32" (CUDA-core GEMMs in
+    the reference's operation order, 4e-6; several times slower)."""
 
     def __init__(self, weights: dict, device=None, precision: str = "bf16x3"):
         import torch
-        if precision not in ("bf16x3", "bf16", "fp32"):
-            raise ValueError("precision must be 'bf16x3', 'bf16' or 'fp32'")
+        if precision not in ("bf16x3", "fp32"):
+            raise ValueError("precision must be 'bf16x3' or 'fp32'")
         self.precision = precision
         if not torch.cuda.is_available():
             raise N.HvlaError("no CUDA device: the hvla T5 embedder is CUDA-only")
@@ -134,7 +138,7 @@ class T5TokenEmbedder:
         stream = int(torch.cuda.current_stream(self.device).cuda_stream)
         if tc:
             st = self.lib.hvla_t5_encode_tc(stream, self.blob.data_ptr(), self.mat.data_ptr(), self._pos_bias(S).data_ptr(), ids.data_ptr(),
-                                            am.data_ptr(), T, S, out.data_ptr(), self._ws.data_ptr(), need, 3 if self.precision == "bf16x3" else 1)
+                                            am.data_ptr(), T, S, out.data_ptr(), self._ws.data_ptr(), need)
             N.check(st, "hvla_t5_encode_tc")
         else:
             st = self.lib.hvla_t5_encode(stream, self.blob.data_ptr(), self._pos_bias(S).data_ptr(), ids.data_ptr(), am.data_ptr(), T, S,

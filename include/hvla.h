@@ -152,13 +152,14 @@ int hvla_t5_encode(hvla_stream_t stream, const float* t5_blob, const float* pos_
                    int T, int S, float* out_emb, void* workspace, size_t workspace_bytes);
 /* The same encoder with every GEMM on the tcgen05 kernel (the fp32 entry above runs them on CUDA cores: exact, but 6.7 ms for
  * one instruction and 21 ms for 64).  Operands are split into two bf16 numbers (hi + lo) and A W^T is accumulated in fp32 as
- * Ahi Whi^T + Alo Whi^T + Ahi Wlo^T (terms = 3, "bf16x3": ~3e-5 of the fp64 result after 12 blocks) or Ahi Whi^T alone
- * (terms = 1, plain bf16: ~2e-2).  LayerNorm weights and the embedding table still come from t5_blob;
- *   t5_mat (device, hvla_t5_mat_elems() bf16): 12 x { hi: wq|wk|wv[2304,768] wo[768,768] wi[3072,768] wo2[768,3072] | lo: the same } */
+ * Ahi Whi^T + Alo Whi^T + Ahi Wlo^T ("bf16x3": 3e-5 of the fp64 result after 12 blocks) in ONE launch per matrix, the three
+ * products concatenated along K.  LayerNorm weights and the embedding table still come from t5_blob;
+ *   t5_mat (device, hvla_t5_mat_elems() bf16, packed by hvla/t5.py: split_matrices): 12 x { wq|wk|wv[2304,3*768] wo[768,3*768]
+ *   wi[3072,3*768] wo2[768,3*3072] }, every row = [hi | hi | lo] of the HF torch [out,in] weight row. */
 int64_t hvla_t5_mat_elems(void);
 size_t hvla_t5_tc_workspace_bytes(int T, int S);
 int hvla_t5_encode_tc(hvla_stream_t stream, const float* t5_blob, const void* t5_mat, const float* pos_bias, const int32_t* input_ids,
-                      const int32_t* attention_mask, int T, int S, float* out_emb, void* workspace, size_t workspace_bytes, int terms);
+                      const int32_t* attention_mask, int T, int S, float* out_emb, void* workspace, size_t workspace_bytes);
 /* number of kernels launched by this library since load (for bench.py's gpu_launches) */
 int64_t hvla_launch_count(void);
 /* per-kernel-class CUDA-event timing on the launching stream (bench.py's live roofline numbers).
