@@ -171,7 +171,8 @@ int hvla_profile_report(char* buf, size_t cap);
 /* ---- legacy XLA GPU custom-call wrappers (jax<=0.4.30: xla_client.register_custom_call_target;
  * signature void(cudaStream_t, void** buffers, const char* opaque, size_t opaque_len)).
  * `opaque` = struct hvla_xla_opaque.  Buffer order = the argument order above (inputs, then
- * outputs, then workspace).  Untestable in this image (no jax); see INTEGRATION.md. */
+ * outputs, then workspace).  jax is absent from this image, so tests/test_gpu_parity.py drives both targets through
+ * ctypes exactly as XLA would (pointer array + packed opaque) and checks them bit-for-bit against the direct calls. */
 struct hvla_xla_opaque { int32_t B, T, dtype, reserved; uint64_t workspace_bytes; };
 void hvla_xla_generate(void* stream, void** buffers, const char* opaque, size_t opaque_len);
 void hvla_xla_act(void* stream, void** buffers, const char* opaque, size_t opaque_len);

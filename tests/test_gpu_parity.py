@@ -250,6 +250,67 @@ def test_grouped_equals_per_sample_and_is_deterministic(models, torch_cuda):
     assert np.isfinite(a1).all() and np.abs(a1[..., :6]).max() <= 5.0
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_xla_custom_call_wrappers_equal_the_direct_calls(models, torch_cuda, prec):
+    """The legacy XLA GPU custom-call targets (void f(stream, void** buffers, const char* opaque, size_t opaque_len), what
+    jax's xla_client.register_custom_call_target binds; include/hvla.h) are driven here exactly as XLA would:
+    an array of device pointers in argument order plus the packed hvla_xla_opaque.  Results must be bit-identical to the
+    public path (hvla_generate / hvla_act through HyperVLA.create_tasks / sample_actions)."""
+    import ctypes as C
+    from hvla import config as Cfg, metadata as M, synthetic as S
+    torch = torch_cuda
+    m = models[prec]
+    rt = m.runtime
+    B = T = 3
+    inp = S.make_inputs(4, B, T)
+    bp, tasks, _ = m.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"])
+    rt.use_graphs = False
+    rt._graphs.clear()
+    try:
+        act_ref, inter_ref = m.sample_actions(inp["images"], None, tasks, None, bp)
+    finally:
+        rt.use_graphs = True
+    dev = rt.device
+    lang = inp["instruction_dict"]["language_instruction"]
+    tok = torch.from_numpy(np.ascontiguousarray(lang["token_embedding"], np.float32)).to(dev)
+    am = torch.from_numpy(np.ascontiguousarray(lang["attention_mask"]).astype(np.int32)).to(dev)
+    pad = torch.ones((T,), dtype=torch.uint8, device=dev)
+    cls = torch.from_numpy(np.ascontiguousarray(inp["initial_state"]["patch_embeddings"][:, 0], np.float32)).to(dev)
+    out_w = torch.zeros((T, M.N_GENERATED_PADDED), dtype=rt.tdtype, device=dev)
+    out_ctx = torch.zeros((T, Cfg.CTX_DIM), dtype=torch.float32, device=dev)
+    nbytes = int(rt.lib.hvla_workspace_bytes(B, T, rt.dtype))
+    ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+    wptr = (ws.data_ptr() + 255) & ~255
+
+    class Opaque(C.Structure):
+        _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32), ("workspace_bytes", C.c_uint64)]
+    op = Opaque(B, T, rt.dtype, 0, nbytes)
+    raw = C.string_at(C.addressof(op), C.sizeof(op))
+    f16 = rt.hn_blob_f16.data_ptr() if rt.hn_blob_f16 is not None else None
+    bufs = (C.c_void_p * 11)(rt.hn_blob.data_ptr(), f16, rt.heads_w.data_ptr(), rt.heads_b.data_ptr(), tok.data_ptr(), am.data_ptr(),
+                             pad.data_ptr(), cls.data_ptr(), out_w.data_ptr(), out_ctx.data_ptr(), wptr)
+    stream = rt.stream()
+    rt.lib.hvla_xla_generate(stream, bufs, raw, len(raw))
+    torch.cuda.synchronize()
+    assert torch.equal(out_w[:, :M.N_GENERATED], bp.weights[:, :M.N_GENERATED])
+    img = torch.from_numpy(np.ascontiguousarray(inp["images"][:, 0])).to(dev)
+    tidx = torch.arange(B, dtype=torch.int32, device=dev)
+    act = torch.zeros((B, 4, 7), dtype=torch.float32, device=dev)
+    logit = torch.zeros((B, 4), dtype=torch.float32, device=dev)
+    bufs2 = (C.c_void_p * 8)(rt.dino_vec.data_ptr(), rt.dino_mat.data_ptr(), img.data_ptr(), out_w.data_ptr(), tidx.data_ptr(),
+                             act.data_ptr(), logit.data_ptr(), wptr)
+    rt.lib.hvla_xla_act(stream, bufs2, raw, len(raw))
+    torch.cuda.synchronize()
+    assert np.array_equal(act.cpu().numpy(), np.asarray(act_ref).reshape(B, 4, 7))
+    assert np.array_equal(logit.cpu().numpy(), np.asarray(inter_ref["gripper_logits"]).reshape(B, 4))
+    # a short opaque (an older caller) is ignored instead of read out of bounds
+    act.zero_()
+    rt.lib.hvla_xla_act(stream, bufs2, raw[:8], 8)
+    torch.cuda.synchronize()
+    assert float(act.abs().max()) == 0.0
+
+
 def test_cuda_graph_replay_equals_eager_launches(models, torch_cuda):
     """The act step is replayed from a captured CUDA graph; results must be bit-identical to eager launches through
     the C ABI, also after the weights (task switch), the task map or the batch size change."""
