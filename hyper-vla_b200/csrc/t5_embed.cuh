@@ -169,7 +169,7 @@ inline int encode(cudaStream_t st, const float* blob, const float* pos_bias, con
 // producing kernel) and  W' = [Whi | Whi | Wlo]  (N x 3K, packed once by hvla/t5.py), so the large hi.hi part is accumulated
 // first and the corrections after it, in the fp32 TMEM accumulator.  Outputs go through the TMA reduce-add epilogue
 // (EPI_RESIDUAL_F32, LayerScale 1, zero bias) into the fp32 stream, or into a zeroed fp32 buffer for q|k|v and the MLP hidden
-// layer; K is never split, so results are run-to-run deterministic and independent of the batch.
+// layer.  Results are run-to-run deterministic (K splits at small row counts are folded in a fixed order).
 // Rows are padded to a multiple of 256 (one CTA-pair tile); padding rows are zero / never read back.
 struct MatLayout {   // bf16 elements per layer, each matrix [N, 3K] = [hi | hi | lo] per row (HF torch [out,in] orientation)
   static constexpr int64_t wqkv = 0, wo = wqkv + (int64_t)3 * TD * 3 * TD, wi = wo + (int64_t)TD * 3 * TD, wo2 = wi + (int64_t)TFF * 3 * TD,
@@ -231,19 +231,45 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ in
   store_split4(a, i / k4, (int)(i % k4) * 4, K, y);
 }
 
+constexpr size_t PART_BYTES_TC = (size_t)24 << 20;   // split-K scratch: covers every (rows, N, splits) the launcher can choose (<= 16.5 MB)
 inline int padded_rows(int M) { return (M + 255) / 256 * 256; }
 inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 inline size_t workspace_bytes_tc(int T, int S) {
   const size_t Mp = (size_t)padded_rows(T * S);
-  return 2 * al256(Mp * TD * 4) + al256(Mp * 3 * TD * 4) + al256(Mp * TFF * 4) + al256(Mp * 3 * TFF * 2) + al256((size_t)TFF * 4);
+  return 2 * al256(Mp * TD * 4) + al256(Mp * 3 * TD * 4) + al256(Mp * TFF * 4) + al256(Mp * 3 * TFF * 2) + al256((size_t)TFF * 4) + PART_BYTES_TC;
 }
 
-// OUT[Mp,N] (fp32) += A'[Mp,3K] W'[N,3K]^T
-inline int gemm_split(cudaStream_t st, const bf16* A3, const bf16* W3, float* OUT, int Mp, int N, int K, const float* zero_bias) {
+// out[i] += part[0][i] + part[1][i] + ... in a fixed order (the K splits of the preceding GEMM); real rows only
+__global__ void __launch_bounds__(256) fold_kernel(float* __restrict__ out, const float* __restrict__ part, int64_t stride4, int ns, int64_t n4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = reinterpret_cast<float4*>(out)[i];
+  for (int s = 0; s < ns; ++s) {
+    const float4 p = __ldg(reinterpret_cast<const float4*>(part) + s * stride4 + i);
+    a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+  }
+  reinterpret_cast<float4*>(out)[i] = a;
+}
+
+
+// OUT[Mp,N] (fp32) += A'[Mp,3K] W'[N,3K]^T.  With few instructions the N = 768 GEMMs have 3 output tiles and 3 CTA pairs would
+// stream a whole 14 MB matrix (45 us at one instruction): the launcher then splits K over up to 8 CTA pairs (the mechanism of
+// the DINOv2 residual GEMMs at batch 1: split 0 reduce-adds into OUT, the others store partial products) and fold_kernel adds
+// the partial products in a fixed order -- still deterministic.  HVLA_GEMM_SPLITK=0 turns it off.
+inline int gemm_split(cudaStream_t st, const bf16* A3, const bf16* W3, float* OUT, int Mp, int M, int N, int K, const float* zero_bias,
+                      float* part) {
   tc::EpiP ep;
   memset(&ep, 0, sizeof ep);
-  ep.bias = zero_bias; ep.out = OUT; ep.ldo = N;            // ls == null: LayerScale 1; part == null: K is never split
-  return tc2::gemm_tc2(st, A3, W3, Mp, N, 3 * K, tc::EPI_RESIDUAL_F32, ep);
+  int splits = 1;
+  ep.bias = zero_bias; ep.out = OUT; ep.ldo = N;            // ls == null: LayerScale 1
+  ep.part = part; ep.part_bytes = PART_BYTES_TC; ep.splits_used = &splits;
+  HVLA_TRY(tc2::gemm_tc2(st, A3, W3, Mp, N, 3 * K, tc::EPI_RESIDUAL_F32, ep));
+  if (splits > 1) {
+    const int64_t n4 = (int64_t)M * N / 4;
+    fold_kernel<<<cdiv(n4, 256), 256, 0, st>>>(OUT, part, (int64_t)Mp * N / 4, splits - 1, n4);
+    HVLA_LAUNCH_CHECK("t5_fold");
+  }
+  return HVLA_OK;
 }
 
 inline int encode_tc(cudaStream_t st, const float* blob, const bf16* mat, const float* pos_bias, const int32_t* ids, const int32_t* mask, int T,
@@ -257,9 +283,10 @@ inline int encode_tc(cudaStream_t st, const float* blob, const bf16* mat, const 
   float* QKV = reinterpret_cast<float*>(p); p += al256((size_t)Mp * 3 * TD * 4);
   float* HID = reinterpret_cast<float*>(p); p += al256((size_t)Mp * TFF * 4);
   bf16* A3 = reinterpret_cast<bf16*>(p);    p += al256((size_t)Mp * 3 * TFF * 2);
-  float* ZERO = reinterpret_cast<float*>(p);
+  float* ZERO = reinterpret_cast<float*>(p); p += al256((size_t)TFF * 4);
+  float* PART = reinterpret_cast<float*>(p);
   ProfScope ps(st, "t5_encode");
-  HVLA_CUDA(cudaMemsetAsync(ws, 0, workspace_bytes_tc(T, S), st));     // padding rows, zero bias
+  HVLA_CUDA(cudaMemsetAsync(ws, 0, workspace_bytes_tc(T, S) - PART_BYTES_TC, st));     // padding rows, zero bias
   gather_kernel<<<M, 192, 0, st>>>(ids, blob + L::embed, X, M);
   HVLA_LAUNCH_CHECK("t5_gather");
   for (int l = 0; l < TL; ++l) {
@@ -268,19 +295,19 @@ inline int encode_tc(cudaStream_t st, const float* blob, const bf16* mat, const 
     rmsnorm768_split_kernel<<<cdiv(M, 8), 256, 0, st>>>(X, w + L::ln0, A3, M);
     HVLA_LAUNCH_CHECK("t5_rmsnorm_split");
     if (l) HVLA_CUDA(cudaMemsetAsync(QKV, 0, (size_t)Mp * 3 * TD * 4, st));
-    HVLA_TRY(gemm_split(st, A3, m + W::wqkv, QKV, Mp, 3 * TD, TD, ZERO));
+    HVLA_TRY(gemm_split(st, A3, m + W::wqkv, QKV, Mp, M, 3 * TD, TD, ZERO, PART));
     attention_kernel<<<dim3(TH, T), 128, 0, st>>>(QKV, mask, pos_bias, ATT, S);
     HVLA_LAUNCH_CHECK("t5_attention");
     split_kernel<<<cdiv((int64_t)M * TD / 4, 256), 256, 0, st>>>(ATT, A3, (int64_t)M * TD / 4, TD, 0);
     HVLA_LAUNCH_CHECK("t5_split");
-    HVLA_TRY(gemm_split(st, A3, m + W::wo, X, Mp, TD, TD, ZERO));                 // x += att Wo^T
+    HVLA_TRY(gemm_split(st, A3, m + W::wo, X, Mp, M, TD, TD, ZERO, PART));                 // x += att Wo^T
     rmsnorm768_split_kernel<<<cdiv(M, 8), 256, 0, st>>>(X, w + L::ln1, A3, M);
     HVLA_LAUNCH_CHECK("t5_rmsnorm_split");
     if (l) HVLA_CUDA(cudaMemsetAsync(HID, 0, (size_t)Mp * TFF * 4, st));
-    HVLA_TRY(gemm_split(st, A3, m + W::wi, HID, Mp, TFF, TD, ZERO));
+    HVLA_TRY(gemm_split(st, A3, m + W::wi, HID, Mp, M, TFF, TD, ZERO, PART));
     split_kernel<<<cdiv((int64_t)M * TFF / 4, 256), 256, 0, st>>>(HID, A3, (int64_t)M * TFF / 4, TFF, 1);   // ReLU, then split
     HVLA_LAUNCH_CHECK("t5_split");
-    HVLA_TRY(gemm_split(st, A3, m + W::wo2, X, Mp, TD, TFF, ZERO));               // x += relu(.) Wo2^T
+    HVLA_TRY(gemm_split(st, A3, m + W::wo2, X, Mp, M, TD, TFF, ZERO, PART));               // x += relu(.) Wo2^T
   }
   rmsnorm768_kernel<<<cdiv(M, 8), 256, 0, st>>>(X, blob + L::lnf, out, M);
   HVLA_LAUNCH_CHECK("t5_rmsnorm");

@@ -112,7 +112,7 @@ def test_gpu_t5_embedder_matches_oracle_and_feeds_generate(t5_case, params_p1):
     print(f"t5 embedder vs fp64 oracle: {err:.2e}; vs HF torch: {np.abs(got - ref).max() / np.abs(ref).max():.2e}")
     assert err < 1e-5
     # tensor-core path: split-operand GEMMs (bf16x3, the default) to 1e-4 (the CPU emulation of the same rounding points gives
-    # 2.9e-5 on this case; plain bf16 operands would give 2e-2); deterministic run to run and independent of the batch
+    # 2.9e-5 on this case; plain bf16 operands would give 2e-2); deterministic run to run; the batch only changes the fp32 summation order
     for prec, tol in (("bf16x3", 1e-4),):
         e2 = T.T5TokenEmbedder(sd, precision=prec)
         o2 = e2(ids, am)
@@ -126,7 +126,12 @@ def test_gpu_t5_embedder_matches_oracle_and_feeds_generate(t5_case, params_p1):
         assert np.abs(s2 - o9).max() / np.abs(o9).max() < tol
         big = np.tile(ids, (17, 1)), np.tile(am, (17, 1))                     # 68 instructions: more than one 256-row tile, ragged tail
         b2 = e2(*big).cpu().numpy()
-        assert np.abs(b2[64:68] - g2).max() / np.abs(ora).max() < 1e-6
+        assert np.abs(b2 - np.tile(ora, (17, 1, 1))).max() / np.abs(ora).max() < tol
+        # the number of K splits (fp32 summation order) depends on the row count, and 12 blocks of un-scaled softmax amplify it:
+        # the same instruction inside a large batch agrees with the small batch to the accuracy of the path, not bit for bit
+        dif = np.abs(b2[64:68] - g2).max() / np.abs(ora).max()
+        print(f"t5 embedder [{prec}] same instructions in a batch of 68 vs 4: {dif:.2e}")
+        assert dif < tol and np.array_equal(b2[:4], b2[64:68])
         del e2
     emb = T.T5TokenEmbedder(sd)
     assert emb.precision == "bf16x3"
