@@ -403,6 +403,62 @@ def test_batched_postprocessing_matches_per_env_oracle(torch_cuda, policy, norm)
     assert worst < 2e-6
 
 
+def test_full_size_configs_through_replication_properties(models, params_p1, torch_cuda):
+    """BASELINE.json configs 3 (1024 envs, 1024 weight sets) and 5 (1000 envs x 10 tasks, shuffled task map) at FULL size.
+    The oracle needs ~0.2 s per image, so the full batches are built by replicating 8 images x 10 tasks and checked through
+    properties that do not depend on the size: every copy of an (image, task) pair is bit-identical wherever it sits in
+    the batch, the distinct pairs agree with the same pairs run as their own small batch, and a handful of pairs is
+    checked against the CPU oracle."""
+    from hvla import metadata as M, params as P, synthetic as S
+    from oracle import hypervla_oracle as O
+    m = models["bf16"]
+    small = S.make_inputs(5, 8, 10)
+    lang = small["instruction_dict"]["language_instruction"]
+    small["initial_state"] = {"patch_embeddings": small["initial_state"]["patch_embeddings"][:, :1]}    # only [:, 0] is read (hypernetwork.py:126)
+    rng = np.random.default_rng(7)
+    # ---- config 5: 1000 envs, 10 tasks, grouped weights -------------------------------------------------------------
+    img_id = rng.integers(0, 8, 1000)
+    task_id = rng.permutation(np.repeat(np.arange(10), 100)).astype(np.int32)
+    bp, tasks, _ = m.create_tasks(instruction_dict=small["instruction_dict"], initial_state=small["initial_state"])
+    act, inter = m.sample_actions(small["images"][img_id], None, tasks, None, bp, task_index=task_id)
+    logit = inter["gripper_logits"]
+    assert act.shape == (1000, 4, 7) and np.isfinite(act).all()
+    key = img_id * 10 + task_id
+    pairs, first = np.unique(key, return_index=True)
+    rep = first[np.searchsorted(pairs, key)]
+    assert np.array_equal(act, act[rep]) and np.array_equal(logit, logit[rep])
+    a_s, i_s = m.sample_actions(small["images"][pairs // 10], None, tasks, None, bp, task_index=(pairs % 10).astype(np.int32))
+    assert rel_err(act[first][..., :6], a_s[..., :6]) < 1e-6 and rel_err(logit[first], i_s["gripper_logits"]) < 1e-6
+    # oracle on three of the pairs
+    gen, _ = O.generate(params_p1, lang["token_embedding"], lang["attention_mask"], small["initial_state"]["patch_embeddings"][:, 0],
+                        generated_paths=M.generated_leaves_canonical())
+    sel = np.array([0, len(pairs) // 2, len(pairs) - 1])
+    ref_act, ref_logit = O.sample_actions(P.dino_tree_from_params(params_p1), O.to_tree({p: v[pairs[sel] % 10] for p, v in gen.items()}),
+                                          small["images"][pairs[sel] // 10, 0])
+    assert rel_err(act[first[sel]][..., :6], ref_act[..., :6]) <= TOL["bf16"]
+    sure = np.abs(ref_logit) > 2e-2 * np.abs(ref_logit).max()
+    assert np.array_equal(act[first[sel]][..., 6][sure], ref_act[..., 6][sure])
+    # ---- config 3: 1024 envs, one weight set per env (1024 rows generated in one call) ---------------------------------
+    t_of = np.arange(1024) % 10
+    i_of = np.arange(1024) % 8
+    big_instr = {"language_instruction": {k: np.ascontiguousarray(v[t_of]) for k, v in lang.items()}}
+    big_state = {"patch_embeddings": np.ascontiguousarray(small["initial_state"]["patch_embeddings"][t_of])}
+    bp3, tasks3, _ = m.create_tasks(instruction_dict=big_instr, initial_state=big_state)
+    w3, w10 = bp3.weights[:, :M.N_GENERATED], bp.weights[:, :M.N_GENERATED]
+    assert tuple(w3.shape) == (1024, M.N_GENERATED)
+    assert torch_cuda.equal(w3, w3[:10].repeat(103, 1)[:1024])                       # copies of a task: identical rows
+    assert rel_err(w3[:10].float().cpu().numpy(), w10.float().cpu().numpy()) < 1e-6   # and equal to the 10-task generate
+    act3, inter3 = m.sample_actions(small["images"][i_of], None, tasks3, None, bp3)
+    assert act3.shape == (1024, 4, 7)
+    idx40 = np.arange(1024) % 40                                                      # (image, task) repeats with period lcm(8,10)
+    assert np.array_equal(act3, act3[idx40]) and np.array_equal(inter3["gripper_logits"], inter3["gripper_logits"][idx40])
+    k40 = i_of[:40] * 10 + t_of[:40]
+    have = np.isin(k40, pairs)
+    assert have.sum() >= 30
+    same = first[np.searchsorted(pairs, k40[have])]
+    assert rel_err(act3[:40][have][..., :6], act[same][..., :6]) < 1e-6               # per-env weights == grouped weights
+
+
 def test_edge_cases(models, torch_cuda):
     from hvla import _native as N
     from hvla import synthetic as S
