@@ -145,3 +145,19 @@ class T5TokenEmbedder:
                                          out.data_ptr(), self._ws.data_ptr(), need)
             N.check(st, "hvla_t5_encode")
         return out
+
+
+def token_to_embedding(model: "T5TokenEmbedder", params, tokens: dict, as_numpy: bool = False):
+    """Same name and argument meaning as the reference helper (data/utils/language_tokenizer.py:25-29, called at
+    data/simpler/evaluate.py:249-252): ``tokens`` is the tokenizer output ``{"input_ids", "attention_mask"}`` of one or more
+    instructions, the result their T5 embeddings (T,S,768).  ``model`` is a :class:`T5TokenEmbedder` (it owns the packed
+    weights, so ``params`` is accepted for signature compatibility and ignored).  The reference returns a host array
+    (``as_numpy=True``); by default the embeddings stay on the device so that
+    ``instruction_dict["language_instruction"]["token_embedding"] = token_to_embedding(...)`` feeds ``create_tasks`` directly."""
+    if not isinstance(tokens, dict) or "input_ids" not in tokens or "attention_mask" not in tokens:
+        raise ValueError("tokens must be the tokenizer output dict with 'input_ids' and 'attention_mask'")
+    ids, am = np.asarray(tokens["input_ids"]), np.asarray(tokens["attention_mask"])
+    if ids.ndim == 1:
+        ids, am = ids[None], am[None]
+    out = model(ids, am)
+    return out.cpu().numpy() if as_numpy else out

@@ -143,6 +143,11 @@ def test_gpu_t5_embedder_matches_oracle_and_feeds_generate(t5_case, params_p1):
     assert np.abs(short - o9).max() / np.abs(o9).max() < 1e-4
     with pytest.raises(ValueError):
         emb(np.zeros((1, 40), np.int64), np.ones((1, 40), np.int64))
+    # the reference's helper name / call shape (data/utils/language_tokenizer.py:25-29)
+    e1 = T.token_to_embedding(emb, None, {"input_ids": ids[2], "attention_mask": am[2]}, as_numpy=True)
+    assert e1.shape == (1, 32, 768) and np.abs(e1[0] - ora[2]).max() / np.abs(ora).max() < 1e-4
+    with pytest.raises(ValueError):
+        T.token_to_embedding(emb, None, {"input_ids": ids})
     # embeddings stay on the device and feed create_tasks: tokenise -> embed -> generate without a host round trip
     model = HyperVLA.from_config(C.default_config(), precision="fp32", params=params_p1)
     inp = S.make_inputs(9, 4, 4)
