@@ -87,6 +87,58 @@ def kernel_roofline_table(act_prof: dict, gen_prof: dict, B: int, T: int, peaks:
     return out
 
 
+def time_task_switch(model, B: int, dev) -> dict:
+    """p50 device time (CUDA events) of a complete task switch for 1 task and for B tasks: hvla.t5.T5TokenEmbedder (bf16x3
+    tensor-core path) -> HyperVLA.encode_initial_image (DINOv2 of the first camera frame) -> HyperVLA.create_tasks."""
+    import torch
+    from hvla import t5 as T5
+    g = torch.Generator(device="cpu").manual_seed(7)
+    rn = lambda *shape, s=1.0: (torch.randn(*shape, generator=g) * s).numpy()
+    sd = {"shared.weight": rn(T5.VOCAB, T5.D), "encoder.final_layer_norm.weight": np.ones(T5.D, np.float32),
+          "encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight": rn(32, 12)}
+    for l in range(T5.LAYERS):
+        p = f"encoder.block.{l}.layer."
+        for n, shp in (("0.SelfAttention.q", (768, 768)), ("0.SelfAttention.k", (768, 768)), ("0.SelfAttention.v", (768, 768)),
+                       ("0.SelfAttention.o", (768, 768)), ("1.DenseReluDense.wi", (3072, 768)), ("1.DenseReluDense.wo", (768, 3072))):
+            sd[p + n + ".weight"] = rn(*shp, s=0.03)
+        sd[p + "0.layer_norm.weight"] = np.ones(768, np.float32)
+        sd[p + "1.layer_norm.weight"] = np.ones(768, np.float32)
+    emb = T5.T5TokenEmbedder(sd, device=dev)
+    del sd
+    rng = np.random.default_rng(11)
+    out = {"api": "T5TokenEmbedder(ids, mask) -> encode_initial_image(frames) -> create_tasks; inputs resident on the GPU, "
+                  "synthetic t5-base-shaped weights, p50 of 10 after 3 warm-ups"}
+    for T in sorted({1, B}):
+        n_tok = rng.integers(3, 21, size=T)
+        am = (np.arange(32)[None, :] < n_tok[:, None]).astype(np.int32)
+        ids = (rng.integers(1, 32000, size=(T, 32)) * am).astype(np.int32)
+        ids_d, am_d = torch.from_numpy(ids).to(dev), torch.from_numpy(am).to(dev)
+        frames = torch.from_numpy(rng.integers(0, 256, size=(T, 224, 224, 3), dtype=np.uint8)).to(dev)
+
+        def switch(ev=None):
+            if ev: ev[0].record()
+            tok = emb(ids_d, am_d)
+            if ev: ev[1].record()
+            state = model.encode_initial_image(frames)
+            if ev: ev[2].record()
+            model.create_tasks(instruction_dict={"language_instruction": {"input_ids": ids, "attention_mask": am_d, "token_embedding": tok}},
+                               initial_state=state)
+            if ev: ev[3].record()
+        for _ in range(3):
+            switch()
+        torch.cuda.synchronize()
+        parts = []
+        for _ in range(10):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            switch(ev)
+            torch.cuda.synchronize()
+            parts.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
+        p50 = np.median(np.asarray(parts), axis=0)
+        out[f"tasks_{T}"] = {"t5_embed": round(float(p50[0]), 4), "initial_image_encode": round(float(p50[1]), 4),
+                             "generate": round(float(p50[2]), 4), "total": round(float(np.median(np.asarray(parts).sum(1))), 4)}
+    return out
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -97,6 +149,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=8, help="images in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-task-switch", action="store_true", help="skip the T5 + initial-image + generate timing leg")
     return ap.parse_args()
 
 
@@ -381,6 +434,15 @@ def run_ours(args):
     gen_kernel_ms = {k: [v[0], round(v[1], 4)] for k, v in gen_prof.items()}
     kernel_rooflines = kernel_roofline_table(prof, gen_prof, B, B, peaks, args.precision)
 
+    # ---- whole task switch on the GPU (BASELINE configs[3] shape: regenerate every task's weights): token ids -> T5-base
+    # embedder -> initial image -> DINOv2 -> generate, nothing leaves the device.  Synthetic t5-base-shaped weights. -------
+    task_switch = None
+    if rank == 0 and world == 1 and not args.no_task_switch:
+        try:
+            task_switch = time_task_switch(model, B, dev)
+        except Exception as exc:  # the headline numbers do not depend on this leg
+            task_switch = {"error": repr(exc)}
+
     # ---- batch-1 latency (configs[0] shape on the GPU) ----------------------------------------------------
     inp1 = S.make_inputs(1, 1, 1)
     bp1, _, _ = model.create_tasks(instruction_dict=inp1["instruction_dict"], initial_state=inp1["initial_state"])
@@ -429,6 +491,7 @@ def run_ours(args):
             "hypernet_gen_ms": {"tasks": B, "p50": float(np.median(gen_dev_ms)), "p50_host_inputs": float(np.median(gen_ms)),
                                 "note": "create_tasks for all tasks of the batch; p50 = embeddings already on the GPU, p50_host_inputs = numpy inputs (pageable H2D inside)",
                                 "kernel_launches_ms": gen_kernel_ms},
+            "task_switch_ms": task_switch,
             "tflops_step": (FLOP_DINO_IMG + FLOP_BASE_IMG) * B / (step_ms / 1e3) / 1e12,
         }
         print(json.dumps(out))
