@@ -109,6 +109,9 @@ class T5TokenEmbedder:
         rb = sd["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"]
         self._rel = np.asarray(rb.detach().cpu().numpy() if hasattr(rb, "detach") else rb, np.float32)      # [32 buckets, 12 heads]
         self._bias, self._ws = {}, None
+        # tensor-core path: ~175 dependent launches per call; captured once per (T,S) in a CUDA graph and replayed (as the act step is)
+        self.use_graphs = True
+        self._graphs = {}
 
     def _pos_bias(self, S: int):
         import torch
@@ -131,21 +134,53 @@ class T5TokenEmbedder:
         out = torch.empty((T, S, D), dtype=torch.float32, device=self.device)
         if T == 0:
             return out
-        tc = self.precision != "fp32"
-        need = int(self.lib.hvla_t5_tc_workspace_bytes(T, S) if tc else self.lib.hvla_t5_workspace_bytes(T, S))
+        if self.precision != "fp32" and self.use_graphs:
+            st = self._graphs.get((T, S))
+            if st is None:
+                st = self._capture(T, S)
+            st["ids"].copy_(ids, non_blocking=True)
+            st["am"].copy_(am, non_blocking=True)
+            st["graph"].replay()
+            return st["out"].clone()
+        need = self._ws_bytes(T, S)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
+        self._encode(ids, am, T, S, out, self._ws)
+        return out
+
+    def _ws_bytes(self, T: int, S: int) -> int:
+        return int(self.lib.hvla_t5_tc_workspace_bytes(T, S) if self.precision != "fp32" else self.lib.hvla_t5_workspace_bytes(T, S))
+
+    def _encode(self, ids, am, T, S, out, ws):
+        import torch
         stream = int(torch.cuda.current_stream(self.device).cuda_stream)
-        if tc:
+        if self.precision != "fp32":
             st = self.lib.hvla_t5_encode_tc(stream, self.blob.data_ptr(), self.mat.data_ptr(), self._pos_bias(S).data_ptr(), ids.data_ptr(),
-                                            am.data_ptr(), T, S, out.data_ptr(), self._ws.data_ptr(), need)
+                                            am.data_ptr(), T, S, out.data_ptr(), ws.data_ptr(), ws.numel())
             N.check(st, "hvla_t5_encode_tc")
         else:
             st = self.lib.hvla_t5_encode(stream, self.blob.data_ptr(), self._pos_bias(S).data_ptr(), ids.data_ptr(), am.data_ptr(), T, S,
-                                         out.data_ptr(), self._ws.data_ptr(), need)
+                                         out.data_ptr(), ws.data_ptr(), ws.numel())
             N.check(st, "hvla_t5_encode")
-        return out
 
+    def _capture(self, T: int, S: int) -> dict:
+        """Static buffers + captured graph of hvla_t5_encode_tc for this (T,S); at most 4 shapes are kept."""
+        import torch
+        if len(self._graphs) >= 4:
+            self._graphs.pop(next(iter(self._graphs)))
+        dev = self.device
+        st = {"ids": torch.zeros((T, S), dtype=torch.int32, device=dev), "am": torch.ones((T, S), dtype=torch.int32, device=dev),
+              "out": torch.empty((T, S, D), dtype=torch.float32, device=dev),
+              "ws": torch.empty((self._ws_bytes(T, S),), dtype=torch.uint8, device=dev)}
+        self._pos_bias(S)
+        self._encode(st["ids"], st["am"], T, S, st["out"], st["ws"])       # one-time kernel setup outside capture
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._encode(st["ids"], st["am"], T, S, st["out"], st["ws"])
+        st["graph"] = graph
+        self._graphs[(T, S)] = st
+        return st
 
 def token_to_embedding(model: "T5TokenEmbedder", params, tokens: dict, as_numpy: bool = False):
     """Same name and argument meaning as the reference helper (data/utils/language_tokenizer.py:25-29, called at

@@ -121,6 +121,9 @@ def test_gpu_t5_embedder_matches_oracle_and_feeds_generate(t5_case, params_p1):
         print(f"t5 embedder [{prec}] vs fp64 oracle: {err2:.2e}")
         assert np.isfinite(g2).all() and err2 < tol, (prec, err2)
         assert torch.equal(e2(ids, am), o2)
+        e2.use_graphs = False                                                 # CUDA-graph replay == eager launches, bit for bit
+        assert torch.equal(e2(ids, am), o2)
+        e2.use_graphs = True
         s2 = e2(ids[:2, :9], np.ones((2, 9), np.int64)).cpu().numpy()
         o9 = TO.encode(sd, ids[:2, :9], np.ones((2, 9), np.int64), np.float64)
         assert np.abs(s2 - o9).max() / np.abs(o9).max() < tol
