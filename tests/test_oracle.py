@@ -135,3 +135,30 @@ def test_postprocess_oracle_euler_matches_scipy_and_ensemble_rule():
     r1, act = env.step(a0 + 100)
     assert np.allclose(r1, 0.5 * (a0[1] + (a0 + 100)[0]))          # oldest prediction contributes its step 1
     assert np.isclose(act[6], 2 * r1[6] - 1)
+
+
+def test_position_table_resize_machinery_against_pil_bicubic():
+    """The 37x37 -> 16x16 position-table interpolation restates jax.image.scale_and_translate(method='bicubic',
+    antialias=False) (un-vendored FlaxDinov2Embeddings.interpolate_pos_encoding; no jax here).  Its machinery -- Keys cubic
+    kernel a=-0.5, half-pixel sample positions, renormalisation over the in-range taps -- is pinned against an independent
+    implementation: Pillow's BICUBIC uses the same kernel and the same border rule, and when UPsampling its support is not
+    widened, i.e. it computes exactly the antialias=False formula.  (The down-scaling call of the path differs from this
+    only through the scale argument; that the reference passes antialias=False and scale (16+0.1)/37 is taken from the
+    transformers 4.50 source as recalled in SURVEY.md Appendix B and stays unpinned.)"""
+    PIL = pytest.importorskip("PIL.Image")
+    from hvla import params as P
+    from oracle import hypervla_oracle as O
+    rng = np.random.default_rng(0)
+    for n_in, n_out in ((16, 37), (10, 23), (37, 37), (7, 8)):
+        a = rng.standard_normal((n_in, n_in)).astype(np.float32)
+        ref = np.asarray(PIL.fromarray(a, mode="F").resize((n_out, n_out), PIL.BICUBIC))
+        w = P._resize_weights(n_in, n_out, np.float32(n_out / n_in))
+        assert w.shape == (n_in, n_out) and np.allclose(w.sum(0), 1.0, atol=1e-6)
+        got = np.einsum("hw,ha,wb->ab", a, w, w)
+        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    # the path's own call: product and oracle restatements agree bit for bit, rows of the weight matrix sum to one, and a
+    # constant table stays constant (partition of unity under the +0.1 scale trick)
+    pe = rng.standard_normal((1, 1370, 768)).astype(np.float32)
+    assert np.array_equal(P.interpolate_pos_table(pe), O.interpolate_pos_table(pe))
+    w = P._resize_weights(37, 16, np.float32(16.1 / 37))
+    assert np.allclose(w.sum(0), 1.0, atol=1e-6) and (np.count_nonzero(w, axis=0) <= 4).all()
