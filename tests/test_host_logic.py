@@ -139,3 +139,29 @@ def test_shard_range_covers_every_env_once():
     ti = np.repeat(np.arange(10), 100)
     uniq, local = PL.local_task_table(ti, 250, 375)
     assert uniq.tolist() == [2, 3] and np.array_equal(uniq[local], ti[250:375])
+
+
+def test_bench_kernel_roofline_table_arithmetic():
+    """bench.py's kernel_rooflines: algorithmic work (SURVEY.md 8(d) figures x units of the run) / live time against the measured
+    peaks; a tensor-bound class is reported in TFLOP/s, an HBM-bound class in GB/s, frac = achieved / peak."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("hvla_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    act = {"im2col": (1, 0.024), "cls_rows": (1, 0.019), "gemm_tc": (49, 2.471), "layernorm": (25, 0.3683),
+           "dino_attention": (12, 0.4245), "base_fused": (1, 0.0947), "unknown_class": (3, 1.0)}
+    gen = {"ctx_fused": (1, 0.1528), "heads_gemm": (1, 0.028), "idle": (1, 0.0)}
+    peaks = {"hbm_gbs": 6542.1, "bf16_tflops_sustained": 1386.3}
+    t = bench.kernel_roofline_table(act, gen, 64, 64, peaks, "bf16")
+    assert set(t) == {"im2col", "cls_rows", "gemm_tc", "layernorm", "dino_attention", "base_fused", "ctx_fused", "heads_gemm"}
+    for name, r in t.items():
+        assert r["unit"] == ("TFLOP/s" if r["bound"] == "tensor" else "GB/s")
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+    assert t["gemm_tc"]["bound"] == "tensor" and abs(t["gemm_tc"]["achieved"] - (46_322_454_528 - 12 * 4 * 257 * 257 * 768) * 64 / 2.471e-3 / 1e12) < 0.5
+    # base net: 796,328 algorithmic bytes per env when every env has its own weights (SURVEY.md 8(d))
+    assert abs(t["base_fused"]["achieved"] - 796_328 * 64 / 0.0947e-3 / 1e9) < 0.5
+    # fallback peaks of the profiling recipe when MEASURED_PEAKS.json is absent
+    t2 = bench.kernel_roofline_table(act, gen, 64, 64, {}, "bf16")
+    assert t2["layernorm"]["peak"] == 6650.0 and t2["gemm_tc"]["peak"] == 1400.0
