@@ -8,16 +8,7 @@
 #include "common.cuh"
 
 namespace hvla {
-inline int tc_num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+inline int tc_num_sms() { return num_sms(); }
 namespace attn {
 
 constexpr int S = DTOK;          // 257
@@ -205,10 +196,9 @@ dino_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int 
 }
 
 inline int dino_attention(cudaStream_t st, const bf16* qkv, bf16* out, int B) {
-  static bool attr = false;
-  if (!attr) {
+  static std::atomic<uint64_t> attr{0};   // per-device one-time setup
+  if (device_once(attr)) {
     HVLA_CUDA(cudaFuncSetAttribute(dino_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSMEM));
-    attr = true;
   }
   const int n_items = B * DH;
   const int grid = n_items < tc_num_sms() ? n_items : tc_num_sms();

@@ -504,10 +504,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
 }
 
 inline int dino_attention_tc(cudaStream_t st, const bf16* qkv, bf16* out, int B) {
-  static bool attr = false;
-  if (!attr) {
+  static std::atomic<uint64_t> attr{0};   // per-device one-time setup
+  if (device_once(attr)) {
     HVLA_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr = true;
   }
   CUtensorMap map, tail, omap;
   HVLA_TRY(make_map_bf16(&map, qkv, (int64_t)B * S_, 3 * DD, 128));

@@ -674,11 +674,10 @@ base_fused_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ weights
 }
 
 inline int base_act_bf16(cudaStream_t st, const bf16* emb, const bf16* weights, const int* tidx, int B, float* action, float* logit) {
-  static bool attr = false;
-  if (!attr) {
+  static std::atomic<uint64_t> attr{0};   // per-device one-time setup
+  if (device_once(attr)) {
     HVLA_CUDA(cudaFuncSetAttribute(base_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     HVLA_CUDA(cudaFuncSetAttribute(base_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr = true;
   }
   static const int force = getenv("HVLA_BASE_CLUSTER") ? atoi(getenv("HVLA_BASE_CLUSTER")) : 0;   // experiments: 1 or 2 CTAs per environment
   const int c = force ? force : 2;

@@ -213,6 +213,26 @@ __device__ __forceinline__ float2 gelu_erf_tanhfit2(float2 x) {
   return __ffma2_rn(hx, th, hx);
 }
 
+// One-time setup per DEVICE (cudaFuncSetAttribute applies to the current device only): bit d of `mask` = done on device d.
+inline bool device_once(std::atomic<uint64_t>& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  return !(mask.fetch_or(bit) & bit);
+}
+// SM count of the current device (cached per device ordinal)
+inline int num_sms() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int n = cache[dev & 63].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev & 63].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace hvla

@@ -398,10 +398,9 @@ ctx_fused_kernel(const float* __restrict__ hn, const lp* __restrict__ hnb, const
 
 inline int ctx_encode_lp(cudaStream_t st, const float* hn, const lp* hnb, const float* tok_emb, const int32_t* tok_mask,
                            const uint8_t* lang_pad, const float* init_cls, int T, float* out_ctx) {
-  static bool attr = false;
-  if (!attr) {
+  static std::atomic<uint64_t> attr{0};   // per-device one-time setup
+  if (device_once(attr)) {
     HVLA_CUDA(cudaFuncSetAttribute(ctx_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr = true;
   }
   ProfScope ps(st, "ctx_fused");
   ctx_fused_kernel<<<T, NTH, SMEM, st>>>(hn, hnb, tok_emb, tok_mask, lang_pad, init_cls, out_ctx);

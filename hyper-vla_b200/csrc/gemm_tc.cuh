@@ -649,24 +649,12 @@ inline int make_out_map_for(CUtensorMap* mo, int epi, const EpiP& ep, int M) {
   return make_map_out(mo, ep.out, M, ep.ldo, epi == EPI_RESIDUAL_F32);
 }
 
-inline int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
 template <int EPI>
 inline int launch_one(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const EpiP& ep, int M, int N,
                       int K) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_set{0};   // per-device one-time setup
+  if (device_once(attr_set)) {
     HVLA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
   }
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();

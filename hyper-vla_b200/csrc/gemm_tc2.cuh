@@ -199,10 +199,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 template <int EPI>
 inline int launch_one2(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const EpiP& ep, int M, int N,
                        int K) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_set{0};   // per-device one-time setup
+  if (device_once(attr_set)) {
     HVLA_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-    attr_set = true;
   }
   const int tiles0 = ((M + BM2 - 1) / BM2) * (N / BN);
   int pairs = num_sms() / 2;

@@ -28,7 +28,7 @@ using attn::cp_async_wait;
 // embeddings in shared memory across slabs when they fit one pass (T <= 64).
 __global__ void __launch_bounds__(256, 2)
 heads_mma_kernel(const float* __restrict__ E, const bf16* __restrict__ W, const float* __restrict__ bias, bf16* __restrict__ out, int T,
-                 int nslabs) {
+                 int nslabs, const int32_t* __restrict__ rows, int T_max) {
   extern __shared__ __align__(16) uint8_t smem[];
   bf16* Es = reinterpret_cast<bf16*>(smem + 2 * WSLAB);
   bf16* Os = Es + TM * LDS_;
@@ -104,8 +104,11 @@ heads_mma_kernel(const float* __restrict__ E, const bf16* __restrict__ W, const 
       __syncthreads();
       for (int i = threadIdx.x; i < TM * 16; i += 256) {        // coalesced 16-byte stores, 256 B per task row
         const int r = i >> 4, c = (i & 15) * 8;
-        if (t0 + r < T && c < ncols)
-          *reinterpret_cast<uint4*>(out + (int64_t)(t0 + r) * NGP + col0 + c) = *reinterpret_cast<const uint4*>(Os + r * LDS_ + c);
+        if (t0 + r < T && c < ncols) {
+          const int orow = rows ? __ldg(rows + t0 + r) : t0 + r;          // task-switch scheduler: scattered rows of a persistent buffer
+          if (orow >= 0 && orow < T_max)
+            *reinterpret_cast<uint4*>(out + (int64_t)orow * NGP + col0 + c) = *reinterpret_cast<const uint4*>(Os + r * LDS_ + c);
+        }
       }
       __syncthreads();                                          // Os (and this W buffer, after the last pass) may be overwritten
     }
@@ -113,21 +116,17 @@ heads_mma_kernel(const float* __restrict__ E, const bf16* __restrict__ W, const 
   cp_async_wait<0>();
 }
 
-inline int heads_gemm_bf16(cudaStream_t st, const float* E, const bf16* W, const float* bias, bf16* out, int T) {
-  static bool attr = false;
-  static int grid = 0;
-  if (!attr) {
+inline int heads_gemm_bf16(cudaStream_t st, const float* E, const bf16* W, const float* bias, bf16* out, int T,
+                           const int32_t* rows = nullptr, int T_max = 0) {
+  static std::atomic<uint64_t> attr{0};   // per-device one-time setup
+  if (device_once(attr)) {
     HVLA_CUDA(cudaFuncSetAttribute(heads_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     HVLA_CUDA(cudaFuncSetAttribute(heads_mma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    grid = 2 * (sms > 0 ? sms : 148);                           // two resident CTAs per SM
-    attr = true;
   }
+  const int grid = 2 * num_sms();                               // two resident CTAs per SM
   const int nslabs = cdiv(NGP, NC);
   ProfScope ps(st, "heads_gemm");
-  heads_mma_kernel<<<grid < nslabs ? grid : nslabs, 256, SMEM, st>>>(E, W, bias, out, T, nslabs);
+  heads_mma_kernel<<<grid < nslabs ? grid : nslabs, 256, SMEM, st>>>(E, W, bias, out, T, nslabs, rows, rows ? T_max : T);
   HVLA_LAUNCH_CHECK("heads_mma");
   return HVLA_OK;
 }

@@ -114,10 +114,18 @@ static bool env_flag(const char* name) {
 }
 
 // ---- generate (K1-K3) ---------------------------------------------------------------------------------
+// dense [T, 128] context rows -> rows[t] of a persistent [T_max, 128] buffer
+__global__ void scatter_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, const int32_t* __restrict__ rows, int T, int T_max) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * CD) return;
+  const int r = rows[i / CD];
+  if (r >= 0 && r < T_max) dst[(int64_t)r * CD + i % CD] = src[i];
+}
+
 template <typename TW>
 static int generate_impl(cudaStream_t st, const float* hn, const void* hn_lp, const void* heads_w, const float* heads_b, const float* tok_emb,
                          const int32_t* tok_mask, const uint8_t* lang_pad, const float* init_cls, int T, void* out_w,
-                         float* out_ctx, uint8_t* ws, const Plan& pl) {
+                         float* out_ctx, uint8_t* ws, const Plan& pl, const int32_t* rows = nullptr, int T_max = 0) {
   float* TPj = reinterpret_cast<float*>(ws + pl.tp);
   float* IPj = reinterpret_cast<float*>(ws + pl.ip);
   float* X = reinterpret_cast<float*>(ws + pl.xc);
@@ -125,13 +133,22 @@ static int generate_impl(cudaStream_t st, const float* hn, const void* hn_lp, co
   float* QKV = reinterpret_cast<float*>(ws + pl.qkvc);
   float* CC = reinterpret_cast<float*>(ws + pl.cc);
   float* HC = reinterpret_cast<float*>(ws + pl.hc);
-  float* E = out_ctx ? out_ctx : reinterpret_cast<float*>(ws + pl.e);
+  // rows != null (task-switch scheduler): weights / context rows are scattered into persistent [T_max, .] buffers
+  float* E = (out_ctx && !rows) ? out_ctx : reinterpret_cast<float*>(ws + pl.e);
+  if (!rows) T_max = T;
+  auto scatter_ctx = [&]() -> int {
+    if (!rows || !out_ctx) return HVLA_OK;
+    scatter_rows_kernel<<<cdiv((int64_t)T * CD, 256), 256, 0, st>>>(E, out_ctx, rows, T, T_max);
+    HVLA_LAUNCH_CHECK("scatter_ctx");
+    return HVLA_OK;
+  };
   const int M = T * CTOK;
   typedef HnLayout L;
   if (std::is_same<TW, bf16>::value && hn_lp && !env_flag("HVLA_DEBUG_GENERIC_CTX")) {
     // bf16 tensor-core path: the whole context encoder is one kernel, the 73 heads another
     HVLA_TRY(ctxf::ctx_encode_lp(st, hn, reinterpret_cast<const ctxf::lp*>(hn_lp), tok_emb, tok_mask, lang_pad, init_cls, T, E));
-    return heads::heads_gemm_bf16(st, E, reinterpret_cast<const bf16*>(heads_w), heads_b, reinterpret_cast<bf16*>(out_w), T);
+    HVLA_TRY(scatter_ctx());
+    return heads::heads_gemm_bf16(st, E, reinterpret_cast<const bf16*>(heads_w), heads_b, reinterpret_cast<bf16*>(out_w), T, rows, T_max);
   }
   // K1: projections (hypernetwork.py:112, 126)
   HVLA_TRY((gemm_simt<float, float, float, float>(
@@ -174,11 +191,12 @@ static int generate_impl(cudaStream_t st, const float* hn, const void* hn_lp, co
     HVLA_TRY((layernorm<float, float>(st, ln, CD)));
   }
   // K3: all 73 output heads as one skinny GEMM (hypernetwork.py:205-217, 227)
+  HVLA_TRY(scatter_ctx());
   if (std::is_same<TW, bf16>::value && !env_flag("HVLA_DEBUG_SIMT_HEADS"))
-    return heads::heads_gemm_bf16(st, E, reinterpret_cast<const bf16*>(heads_w), heads_b, reinterpret_cast<bf16*>(out_w), T);
+    return heads::heads_gemm_bf16(st, E, reinterpret_cast<const bf16*>(heads_w), heads_b, reinterpret_cast<bf16*>(out_w), T, rows, T_max);
   ProfScope ps(st, "heads_gemm");
   heads_gemm_kernel<TW, TW><<<cdiv(NGP, 1024), 256, 0, st>>>(E, reinterpret_cast<const TW*>(heads_w), heads_b,
-                                                             reinterpret_cast<TW*>(out_w), T);
+                                                             reinterpret_cast<TW*>(out_w), T, rows, T_max);
   HVLA_LAUNCH_CHECK("heads_gemm");
   return HVLA_OK;
 }
@@ -393,7 +411,7 @@ static int base_generic(cudaStream_t st, const TE* emb, const TW* weights, const
   float* QKV = reinterpret_cast<float*>(ws + pl.qkvb);
   float* CB = reinterpret_cast<float*>(ws + pl.cb);
   float* HB = reinterpret_cast<float*>(ws + pl.hb);
-  const int64_t sW = T == 1 ? NGP : NGP;   // weight-batch stride; T==1 is handled by an all-zero index below
+  const int64_t sW = NGP;                  // weight-batch stride; T==1 is handled by an all-zero index below
   // image_embedding_projection on patch tokens (skip CLS row): base_vit.py:122, 130-133
   {
     GemmP g = gemm_params(emb + DD, DD, weights + G::proj_w, BD, weights + G::proj_b, PT, BD, NPATCH, BD, DD);
@@ -582,6 +600,25 @@ int hvla_generate(hvla_stream_t stream, const float* hn_blob, const void* hn_blo
   if (dtype == HVLA_F32)
     return generate_impl<float>(st, hn_blob, nullptr, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, out_weights, out_ctx, ws, pl);
   return generate_impl<bf16>(st, hn_blob, hn_blob_f16, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, out_weights, out_ctx, ws, pl);
+}
+
+int hvla_generate_rows(hvla_stream_t stream, const float* hn_blob, const void* hn_blob_f16, const void* heads_w, const float* heads_b,
+                       const float* tok_emb, const int32_t* tok_mask, const uint8_t* lang_pad, const float* init_cls, int T,
+                       const int32_t* row_index, int T_max, void* weights, float* ctx, void* workspace, size_t workspace_bytes,
+                       int dtype) {
+  if (!hn_blob || !heads_w || !heads_b || !tok_emb || !tok_mask || !init_cls || !weights || !row_index)
+    return fail(HVLA_ERR_ARG, "hvla_generate_rows: NULL argument");
+  if (T_max <= 0 || T > T_max) return fail(HVLA_ERR_ARG, "hvla_generate_rows: need 0 <= T <= T_max");
+  HVLA_TRY(check_common(0, T, dtype, workspace, workspace_bytes));
+  if (T == 0) return HVLA_OK;
+  const Plan pl = make_plan(0, T, dtype);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  if (dtype == HVLA_F32)
+    return generate_impl<float>(st, hn_blob, nullptr, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, weights, ctx, ws, pl,
+                                row_index, T_max);
+  return generate_impl<bf16>(st, hn_blob, hn_blob_f16, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, weights, ctx, ws, pl,
+                             row_index, T_max);
 }
 
 int hvla_dino_forward(hvla_stream_t stream, const float* dino_vec, const void* dino_mat, const uint8_t* images, int B,
@@ -781,20 +818,61 @@ int hvla_t5_encode_tc(hvla_stream_t stream, const float* t5_blob, const void* t5
                        attention_mask, T, S, out_emb, reinterpret_cast<uint8_t*>(workspace));
 }
 
-// ---- legacy XLA custom-call wrappers (no status channel in this ABI revision: errors are logged) ---------
-void hvla_xla_generate(void* stream, void** b, const char* opaque, size_t opaque_len) {
-  if (opaque_len < sizeof(hvla_xla_opaque)) return;
+// ---- legacy XLA custom-call wrappers -----------------------------------------------------------------------
+// Status-returning form (API_VERSION_STATUS_RETURNING): void f(stream, buffers, opaque, opaque_len, XlaCustomCallStatus*).
+// The failure hook is XLA's own XlaCustomCallStatusSetFailure, resolved as a WEAK symbol (present when the library is
+// loaded into a process that links xla / jaxlib) or registered explicitly with hvla_xla_register_status_setter.
+// On any error the outputs are zero-filled (when the opaque is long enough to know their sizes) so that a caller that
+// ignores the status never reads uninitialised memory.
+extern "C" void XlaCustomCallStatusSetFailure(void* status, const char* message, size_t message_len) __attribute__((weak));
+static std::atomic<hvla_xla_status_setter> g_status_setter{nullptr};
+
+static void xla_fail(void* status, const char* who) {
+  std::string msg = std::string(who) + ": " + g_last_error;
+  fprintf(stderr, "%s\n", msg.c_str());
+  if (!status) return;
+  hvla_xla_status_setter fn = g_status_setter.load();
+  if (fn) fn(status, msg.c_str(), msg.size());
+  else if (XlaCustomCallStatusSetFailure) XlaCustomCallStatusSetFailure(status, msg.c_str(), msg.size());
+}
+
+void hvla_xla_register_status_setter(hvla_xla_status_setter fn) { g_status_setter.store(fn); }
+
+void hvla_xla_generate_status(void* stream, void** b, const char* opaque, size_t opaque_len, void* status) {
+  if (!b || !opaque || opaque_len < sizeof(hvla_xla_opaque)) {
+    fail(HVLA_ERR_ARG, "opaque is shorter than struct hvla_xla_opaque");
+    xla_fail(status, "hvla_xla_generate");
+    return;
+  }
   hvla_xla_opaque o; memcpy(&o, opaque, sizeof o);
   int r = hvla_generate(stream, (const float*)b[0], b[1], b[2], (const float*)b[3], (const float*)b[4], (const int32_t*)b[5],
                         (const uint8_t*)b[6], (const float*)b[7], o.T, b[8], (float*)b[9], b[10], (size_t)o.workspace_bytes, o.dtype);
-  if (r != HVLA_OK) fprintf(stderr, "hvla_xla_generate: %s\n", hvla_last_error());
+  if (r != HVLA_OK) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t es = o.dtype == HVLA_BF16 ? 2 : 4;
+    if (o.T > 0 && b[8]) cudaMemsetAsync(b[8], 0, (size_t)o.T * NGP * es, st);
+    if (o.T > 0 && b[9]) cudaMemsetAsync(b[9], 0, (size_t)o.T * CD * 4, st);
+    xla_fail(status, "hvla_xla_generate");
+  }
 }
-void hvla_xla_act(void* stream, void** b, const char* opaque, size_t opaque_len) {
-  if (opaque_len < sizeof(hvla_xla_opaque)) return;
+void hvla_xla_act_status(void* stream, void** b, const char* opaque, size_t opaque_len, void* status) {
+  if (!b || !opaque || opaque_len < sizeof(hvla_xla_opaque)) {
+    fail(HVLA_ERR_ARG, "opaque is shorter than struct hvla_xla_opaque");
+    xla_fail(status, "hvla_xla_act");
+    return;
+  }
   hvla_xla_opaque o; memcpy(&o, opaque, sizeof o);
   int r = hvla_act(stream, (const float*)b[0], b[1], (const uint8_t*)b[2], b[3], (const int32_t*)b[4], o.B, o.T, (float*)b[5],
                    (float*)b[6], b[7], (size_t)o.workspace_bytes, o.dtype);
-  if (r != HVLA_OK) fprintf(stderr, "hvla_xla_act: %s\n", hvla_last_error());
+  if (r != HVLA_OK) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (o.B > 0 && b[5]) cudaMemsetAsync(b[5], 0, (size_t)o.B * AH * AD * 4, st);
+    if (o.B > 0 && b[6]) cudaMemsetAsync(b[6], 0, (size_t)o.B * AH * 4, st);
+    xla_fail(status, "hvla_xla_act");
+  }
 }
+// original (API_VERSION_ORIGINAL) form: no status channel -- same behaviour (message on stderr, outputs zero-filled)
+void hvla_xla_generate(void* stream, void** b, const char* opaque, size_t opaque_len) { hvla_xla_generate_status(stream, b, opaque, opaque_len, nullptr); }
+void hvla_xla_act(void* stream, void** b, const char* opaque, size_t opaque_len) { hvla_xla_act_status(stream, b, opaque, opaque_len, nullptr); }
 
 }  // extern "C"

@@ -607,7 +607,8 @@ __global__ void __launch_bounds__(128) mix_head_kernel(const float* __restrict__
 constexpr int HEADS_TT = 8;
 template <typename TW, typename TO>
 __global__ void __launch_bounds__(256) heads_gemm_kernel(const float* __restrict__ E, const TW* __restrict__ W,
-                                                         const float* __restrict__ bias, TO* __restrict__ out, int T) {
+                                                         const float* __restrict__ bias, TO* __restrict__ out, int T,
+                                                         const int32_t* __restrict__ rows, int T_max) {
   __shared__ float es[HEADS_TT][CD];
   const int64_t col = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
   const bool active = col < NGP;
@@ -643,7 +644,8 @@ __global__ void __launch_bounds__(256) heads_gemm_kernel(const float* __restrict
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[j] = acc[tt][j] + bv[j];
-        Vec4<TO>::store(out + (int64_t)(t0 + tt) * NGP + col, o);
+        const int orow = rows ? __ldg(rows + t0 + tt) : t0 + tt;      // task-switch scheduler: scattered rows of a persistent buffer
+        if (orow >= 0 && orow < T_max) Vec4<TO>::store(out + (int64_t)orow * NGP + col, o);
       }
     }
   }

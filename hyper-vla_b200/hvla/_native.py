@@ -25,6 +25,7 @@ SIGNATURES = {
     "hvla_layout_offset": (c_i64, [C.c_char_p]),
     "hvla_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "hvla_generate": (c_int, [c_void_p] * 9 + [c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
+    "hvla_generate_rows": (c_int, [c_void_p] * 9 + [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
     "hvla_dino_forward": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_void_p, c_size_t, c_int]),
     "hvla_base_act": (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
     "hvla_act": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
@@ -48,6 +49,9 @@ SIGNATURES = {
     "hvla_profile_report": (c_int, [C.c_char_p, c_size_t]),
     "hvla_xla_generate": (None, [c_void_p, c_void_p, C.c_char_p, c_size_t]),
     "hvla_xla_act": (None, [c_void_p, c_void_p, C.c_char_p, c_size_t]),
+    "hvla_xla_register_status_setter": (None, [c_void_p]),
+    "hvla_xla_generate_status": (None, [c_void_p, c_void_p, C.c_char_p, c_size_t, c_void_p]),
+    "hvla_xla_act_status": (None, [c_void_p, c_void_p, C.c_char_p, c_size_t, c_void_p]),
 }
 
 

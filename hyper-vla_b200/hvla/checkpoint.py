@@ -50,12 +50,19 @@ class _ParamUnpickler(pickle.Unpickler):
         raise pickle.UnpicklingError(f"refusing to load {module}.{name} from a parameter pickle")
 
 
+def ema_key(ema) -> str:
+    """``--EMA 0.999`` of the eval loops -> the pickle key ``f"EMA_{args.EMA}"`` (data/simpler/evaluate.py:443)."""
+    return ema if isinstance(ema, str) and ema.startswith("EMA_") else f"EMA_{ema}"
+
+
 def load_ema_pickle(path: str, key: str = "EMA_0.999") -> dict:
+    """One EMA parameter tree of ``pickle.dump({f"EMA_{c}": tree, ...})`` (scripts/train.py:684-699)."""
     with open(path, "rb") as f:
-        tree = _ParamUnpickler(io.BytesIO(f.read())).load()
-    if isinstance(tree, dict) and key in tree:
-        tree = tree[key]
-    return _as_numpy_tree(tree)
+        trees = _ParamUnpickler(io.BytesIO(f.read())).load()
+    if not isinstance(trees, dict) or key not in trees:
+        have = sorted(str(k) for k in trees) if isinstance(trees, dict) else type(trees).__name__
+        raise KeyError(f"{path} holds no {key} entry (found: {have}); pass ema=<coefficient> matching one of them")
+    return _as_numpy_tree(trees[key])
 
 
 def _as_numpy_tree(tree):
@@ -78,13 +85,19 @@ def latest_step(checkpoint_path: str) -> Optional[int]:
     return max(steps) if steps else None
 
 
-def load_params(checkpoint_path: str, step: Optional[int] = None) -> dict:
-    """EMA pickle of the step if present, else the flat npz; ``step`` defaults to the latest (model.py:212)."""
+def load_params(checkpoint_path: str, step: Optional[int] = None, ema=None) -> dict:
+    """The RAW parameters of ``step`` (what ``HyperVLA.load_pretrained`` restores, model.py:209-214; ``step`` defaults to
+    the latest, :212).  ``ema`` (e.g. ``0.999``) selects the EMA tree ``<step>/EMA_params.pkl[f"EMA_{ema}"]`` instead -- what
+    the eval loops swap in only when run with ``--EMA`` (data/simpler/evaluate.py:439-444)."""
     step = step if step is not None else latest_step(checkpoint_path)
+    if ema is not None:
+        if step is None:
+            raise FileNotFoundError(f"no step directory under {checkpoint_path} to read EMA_params.pkl from")
+        pkl = os.path.join(checkpoint_path, str(step), "EMA_params.pkl")
+        if not os.path.exists(pkl):
+            raise FileNotFoundError(f"ema={ema!r} requested but {pkl} does not exist")
+        return load_ema_pickle(pkl, ema_key(ema))
     if step is not None:
-        ema = os.path.join(checkpoint_path, str(step), "EMA_params.pkl")
-        if os.path.exists(ema):
-            return load_ema_pickle(ema)
         npz = os.path.join(checkpoint_path, f"params_{step}.npz")
         if os.path.exists(npz):
             return load_flat_npz(npz)
@@ -92,5 +105,5 @@ def load_params(checkpoint_path: str, step: Optional[int] = None) -> dict:
     if cand and step is None:
         return load_flat_npz(os.path.join(checkpoint_path, cand[-1]))
     raise FileNotFoundError(
-        f"no <step>/EMA_params.pkl or params_<step>.npz under {checkpoint_path}; convert the orbax checkpoint with "
-        "tools/convert_orbax_checkpoint.py in an environment that has orbax (see INTEGRATION.md)")
+        f"no params_<step>.npz under {checkpoint_path}; convert the orbax checkpoint with tools/convert_orbax_checkpoint.py "
+        "in an environment that has orbax (see INTEGRATION.md), or pass ema=<coefficient> to read <step>/EMA_params.pkl")

@@ -20,7 +20,8 @@ class HyperNetwork:
         self.hypernet_kwargs = hypernet_kwargs
         self.layer_token_num = base_net_metadata["block_num"]      # generation_strategy == 'block'
 
-    def apply(self, variables, tasks, train: bool = False, initial_states=None, *, model=None, **_unused):
+    def apply(self, variables, tasks, train: bool = False, initial_states=None, *, model=None, task_ids=None, base_params=None,
+              **_unused):
         """-> ((base_params, context_embedding), intermediate_states)   (hypernetwork.py:199-219)"""
         if train:
             raise ValueError("hvla is an inference path: train=True is unsupported")
@@ -35,6 +36,13 @@ class HyperNetwork:
         pe = initial_states["patch_embeddings"]
         cls = pe[:, 0]                                                   # initial_image[:, :1]  (:126)
         pad = tasks.get("pad_mask_dict", {}).get("language_instruction")
+        if task_ids is not None:      # task-switch scheduler: regenerate only these rows of the existing buffers, in place
+            model.runtime.generate(lang["token_embedding"], lang["attention_mask"], cls, pad, rows=task_ids,
+                                   into=(base_params.weights, base_params.context_embedding))
+            base_params._tree = None
+            base_params.generation += 1
+            ctx = base_params.context_embedding
+            return (base_params, ctx.reshape(int(ctx.shape[0]), 1, -1)), {}
         weights, ctx = model.runtime.generate(lang["token_embedding"], lang["attention_mask"], cls, pad)
         T = int(weights.shape[0])
         base_params = GeneratedBaseParams(model, weights, ctx, squeeze=(T == 1))

@@ -166,4 +166,8 @@ def validate_config(config: dict) -> dict:
     _require(not ak.get("token_per_horizon", False), "token_per_horizon")
     _require(ak.get("squash_continuous_action", True), "squash_continuous_action=False")
     _require(len(tuple(ak.get("hidden_dims", ()))) == 0, "action head hidden_dims")
+    # the head epilogues compute tanh(x / 5) * 5 (MixActionHead defaults, action_heads.py:439, 445); a checkpoint trained with
+    # another tanh_scaling_factor / max_action (e.g. max_action=1 for bounds normalisation) must not load silently
+    _require(float(ak.get("tanh_scaling_factor", 5.0)) == 5.0, "tanh_scaling_factor != 5")
+    _require(float(ak.get("max_action", 5.0)) == 5.0, "max_action != 5")
     return cfg

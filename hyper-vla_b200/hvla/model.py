@@ -43,6 +43,7 @@ class GeneratedBaseParams(Mapping):
         self._squeeze = squeeze
         self._tree = None
         self.task_index = None          # optional default env -> task map for sample_actions
+        self.generation = 0             # bumped by every in-place row regeneration (task-switch scheduler)
 
     def packed_numpy(self) -> np.ndarray:
         return self.weights.float().cpu().numpy()[:, :M.N_GENERATED]
@@ -104,12 +105,12 @@ class HyperVLA:
 
     @classmethod
     def load_pretrained(cls, checkpoint_path: str, step: Optional[int] = None, *, precision: str = "bf16",
-                        device=None) -> "HyperVLA":
+                        device=None, ema=None) -> "HyperVLA":
         """Reads ``config.json`` / ``dataset_statistics.json`` like the reference (model.py:152-189).
-        Parameters (hvla/checkpoint.py): the EMA pickle ``<step>/EMA_params.pkl`` the reference's eval loop prefers
-        (data/simpler/evaluate.py:441-443, scripts/train.py:697-699), read without jax, or a flat
-        ``params_<step>.npz`` ("a/b/c" keys, Flax names) written by ``save_pretrained`` / tools/convert_orbax_checkpoint.py.
-        The orbax on-disk format itself (tensorstore/OCDBT) is not parsed here -- convert it once where orbax exists."""
+        Parameters (hvla/checkpoint.py): the RAW params of ``step`` as the reference restores them (model.py:209-214), from a
+        flat ``params_<step>.npz`` ("a/b/c" keys, Flax names) written by ``save_pretrained`` / tools/convert_orbax_checkpoint.py;
+        ``ema=0.999`` selects ``<step>/EMA_params.pkl["EMA_0.999"]`` instead -- the swap the eval loops do under ``--EMA``
+        (data/simpler/evaluate.py:439-444, scripts/train.py:697-699), read without jax."""
         with open(os.path.join(checkpoint_path, "config.json")) as f:
             config = json.load(f)
         stats = None
@@ -118,7 +119,7 @@ class HyperVLA:
             with open(sp) as f:
                 stats = json.load(f)
         from . import checkpoint as CK
-        params = CK.load_params(checkpoint_path, step)
+        params = CK.load_params(checkpoint_path, step, ema=ema)
         if "shared_modules" in config.get("hypernet_kwargs", {}):
             config["hypernet_kwargs"]["shared_modules"] = tuple(config["hypernet_kwargs"]["shared_modules"])
         return cls.from_config(config, None, None, stats, precision=precision, device=device, params=params)
@@ -140,7 +141,20 @@ class HyperVLA:
         if self._runtime is None:
             from .runtime import Runtime
             self._runtime = Runtime(self.params, self.precision, self.device)
+        elif self._runtime._params_id != id(self.params):
+            # ``model.params = ema_params`` (the reference's EMA swap is base_model.replace(params=...), data/simpler/
+            # evaluate.py:443): re-upload the device blobs and drop the captured graphs that point into the old ones
+            self._runtime.upload(self.params)
         return self._runtime
+
+    def replace(self, **changes) -> "HyperVLA":
+        """flax.struct.dataclass.replace of the reference (evaluate.py:443 ``model.replace(params=...)``): a new model object;
+        the device runtime is rebuilt on first use when ``params`` changed."""
+        import dataclasses
+        new = dataclasses.replace(self, **changes)
+        if any(k in changes and changes[k] is not getattr(self, k) for k in ("params", "precision", "device")):
+            new._runtime = None
+        return new
 
     # ---- initial-image encoder (SURVEY 8(f) row 2) --------------------------------------------------------------
     def set_initial_image_encoder(self, dino_tree: Optional[dict]) -> None:
@@ -164,9 +178,14 @@ class HyperVLA:
                 "pad_mask_dict": {"image_primary": np.ones((int(img.shape[0]), 1))}}
 
     # ---- generate ------------------------------------------------------------------------------------
-    def create_tasks(self, goals=None, instruction_dict: dict = None, initial_state=None):
+    def create_tasks(self, goals=None, instruction_dict: dict = None, initial_state=None, *, task_ids=None, base_params=None):
         """Build the ``tasks`` dict and generate base-net parameters (reference: model.py:35-83).
-        Returns ``(base_params, tasks, intermediate_states)``."""
+        Returns ``(base_params, tasks, intermediate_states)``.
+
+        Task-switch scheduler (batched form of the per-episode reset, data/utils/hypervla_interface.py:141-146,
+        data/simpler/evaluate.py:263-277): with ``task_ids`` (k distinct slots) and the ``base_params`` returned by an
+        earlier call, only those k rows are regenerated, IN PLACE, from the k instructions / initial states given; the
+        other rows are untouched bit for bit and the weight buffer keeps its address, so the captured act graph is reused."""
         if instruction_dict is None or "language_instruction" not in instruction_dict:
             raise ValueError("create_tasks needs instruction_dict['language_instruction']")
         lang = instruction_dict["language_instruction"]
@@ -182,8 +201,13 @@ class HyperVLA:
                 tasks["pad_mask_dict"][k] = np.zeros(batch_size, dtype=bool)
         tasks["pad_mask_dict"]["language_instruction"] = np.ones(batch_size, dtype=bool)
         tasks["language_instruction"] = lang
+        if (task_ids is None) != (base_params is None):
+            raise ValueError("task_ids and base_params go together (regenerate rows of an existing GeneratedBaseParams in place)")
+        if base_params is not None and not isinstance(base_params, GeneratedBaseParams):
+            raise TypeError("base_params must be the object returned by HyperVLA.create_tasks")
         (base_params, _ctx), intermediate_states = self.hypernet.apply(
-            {"params": self.params}, tasks, train=False, initial_states=initial_state, model=self)
+            {"params": self.params}, tasks, train=False, initial_states=initial_state, model=self,
+            task_ids=task_ids, base_params=base_params)
         return base_params, tasks, intermediate_states
 
     # ---- act -------------------------------------------------------------------------------------------

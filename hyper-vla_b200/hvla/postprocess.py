@@ -61,11 +61,12 @@ class BatchedActionPostprocessor:
             raise ValueError(f"raw_actions must be ({self.B}, 4, 7)")              # :249
         out_raw = torch.empty((self.B, 7), dtype=torch.float32, device=self.device)
         out_act = torch.empty((self.B, 7), dtype=torch.float32, device=self.device)
-        st = self.lib.hvla_postprocess(int(torch.cuda.current_stream(self.device).cuda_stream), ra.data_ptr(), self.state.data_ptr(),
-                                       self._pending_reset.data_ptr(), self.B, self.norm,
-                                       self._a.ctypes.data_as(C.c_void_p), self._b.ctypes.data_as(C.c_void_p),
-                                       self._mask.ctypes.data_as(C.c_void_p), self.ensemble, C.c_float(self.temp), self.policy,
-                                       self.sticky_repeat, out_raw.data_ptr(), out_act.data_ptr())
+        with torch.cuda.device(self.device):       # launches go to the current device's context
+            st = self.lib.hvla_postprocess(int(torch.cuda.current_stream(self.device).cuda_stream), ra.data_ptr(), self.state.data_ptr(),
+                                           self._pending_reset.data_ptr(), self.B, self.norm,
+                                           self._a.ctypes.data_as(C.c_void_p), self._b.ctypes.data_as(C.c_void_p),
+                                           self._mask.ctypes.data_as(C.c_void_p), self.ensemble, C.c_float(self.temp), self.policy,
+                                           self.sticky_repeat, out_raw.data_ptr(), out_act.data_ptr())
         N.check(st, "hvla_postprocess")
         self._pending_reset.zero_()
         return out_raw, out_act

@@ -94,9 +94,10 @@ class BatchedImagePreprocessor:
         need = int(self.lib.hvla_resize_workspace_bytes(B, H, W, self.S, int(self.crop)))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
-        st = self.lib.hvla_resize_lanczos3(
-            int(torch.cuda.current_stream(self.device).cuda_stream), x.data_ptr(), B, H, W, self.S, sy.data_ptr(), wy.data_ptr(), ny,
-            sx.data_ptr(), wx.data_ptr(), nx, int(self.crop), C.cast(self._crop_params, C.c_void_p), out.data_ptr(),
-            self._ws.data_ptr(), need)
+        with torch.cuda.device(self.device):       # launches go to the current device's context
+            st = self.lib.hvla_resize_lanczos3(
+                int(torch.cuda.current_stream(self.device).cuda_stream), x.data_ptr(), B, H, W, self.S, sy.data_ptr(), wy.data_ptr(), ny,
+                sx.data_ptr(), wx.data_ptr(), nx, int(self.crop), C.cast(self._crop_params, C.c_void_p), out.data_ptr(),
+                self._ws.data_ptr(), need)
         N.check(st, "hvla_resize_lanczos3")
         return out

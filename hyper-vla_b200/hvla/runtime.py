@@ -39,7 +39,12 @@ class Runtime:
         self.use_graphs = True          # replay a captured CUDA graph of the act step instead of ~110 eager launches
         self._profiling = False
         self.replayed_launches = 0      # kernels launched through graph replays (the C counter only sees eager launches)
+        self.graph_captures = 0         # CUDA-graph captures so far (a task switch through generate_rows must not add one)
         self.upload(params)
+
+    def _on_device(self):
+        """Make this runtime's device current around library calls (launches go to the current device's context)."""
+        return _torch().cuda.device(self.device)
 
     # ---- parameters -------------------------------------------------------------------------------
     def upload(self, params: dict) -> None:
@@ -59,6 +64,7 @@ class Runtime:
         self.dino_mat = torch.from_numpy(mat).to(self.tdtype).to(dev)
         del mat
         self._params_id = id(params)
+        self._graphs.clear()            # captured graphs hold pointers into the previous blobs
 
     # ---- scratch ------------------------------------------------------------------------------------
     def workspace(self, B: int, T: int):
@@ -89,8 +95,10 @@ class Runtime:
         return int(_torch().cuda.current_stream(self.device).cuda_stream)
 
     # ---- generate -------------------------------------------------------------------------------------
-    def generate(self, token_embedding, attention_mask, init_cls, lang_pad=None):
-        """-> (weights [T, NGP] device tensor, ctx_emb [T,128] device tensor)"""
+    def generate(self, token_embedding, attention_mask, init_cls, lang_pad=None, rows=None, into=None):
+        """-> (weights [T, NGP] device tensor, ctx_emb [T,128] device tensor).
+        ``rows`` + ``into=(weights [T_max,NGP], ctx [T_max,128])``: regenerate only those rows of the persistent buffers in
+        place (hvla_generate_rows): the buffers keep their addresses, so CUDA graphs captured over them stay valid."""
         torch = _torch()
         dev = self.device
         tok = torch.as_tensor(np.ascontiguousarray(token_embedding, dtype=np.float32) if not torch.is_tensor(token_embedding)
@@ -108,15 +116,32 @@ class Runtime:
         if lang_pad is not None:
             pad = torch.as_tensor(np.asarray(lang_pad)).to(dev).to(torch.uint8).contiguous()
             pad_ptr = pad.data_ptr()
-        out = torch.empty((T, M.N_GENERATED_PADDED), dtype=self.tdtype, device=dev)
-        ctx = torch.empty((T, Cfg.CTX_DIM), dtype=torch.float32, device=dev)
-        ws, ws_bytes = self.workspace(0, T)
-        st = self.lib.hvla_generate(self.stream(), self.hn_blob.data_ptr(),
-                                    self.hn_blob_f16.data_ptr() if self.hn_blob_f16 is not None else None,
-                                    self.heads_w.data_ptr(), self.heads_b.data_ptr(),
-                                    tok.data_ptr(), am.data_ptr(), pad_ptr, cls.data_ptr(), T, out.data_ptr(), ctx.data_ptr(),
-                                    ws, ws_bytes, self.dtype)
-        N.check(st, "hvla_generate")
+        f16 = self.hn_blob_f16.data_ptr() if self.hn_blob_f16 is not None else None
+        if rows is None:
+            out = torch.empty((T, M.N_GENERATED_PADDED), dtype=self.tdtype, device=dev)
+            ctx = torch.empty((T, Cfg.CTX_DIM), dtype=torch.float32, device=dev)
+            with self._on_device():
+                ws, ws_bytes = self.workspace(0, T)
+                st = self.lib.hvla_generate(self.stream(), self.hn_blob.data_ptr(), f16, self.heads_w.data_ptr(), self.heads_b.data_ptr(),
+                                            tok.data_ptr(), am.data_ptr(), pad_ptr, cls.data_ptr(), T, out.data_ptr(), ctx.data_ptr(),
+                                            ws, ws_bytes, self.dtype)
+            N.check(st, "hvla_generate")
+            return out, ctx
+        # task-switch scheduler: regenerate rows `rows` of the persistent (weights, ctx) buffers in place
+        out, ctx = into
+        T_max = int(out.shape[0])
+        ridx = np.asarray(rows.cpu() if torch.is_tensor(rows) else rows).astype(np.int64).ravel()
+        if ridx.shape != (T,) or (T and (ridx.min() < 0 or ridx.max() >= T_max)) or len(set(ridx.tolist())) != T:
+            raise ValueError(f"task_ids must be {T} distinct slots in [0, {T_max})")
+        if out.dtype != self.tdtype or tuple(out.shape[1:]) != (M.N_GENERATED_PADDED,) or not out.is_contiguous():
+            raise ValueError("persistent weight buffer does not match this runtime")
+        rdev = torch.from_numpy(ridx.astype(np.int32)).to(dev)
+        with self._on_device():
+            ws, ws_bytes = self.workspace(0, T)
+            st = self.lib.hvla_generate_rows(self.stream(), self.hn_blob.data_ptr(), f16, self.heads_w.data_ptr(), self.heads_b.data_ptr(),
+                                             tok.data_ptr(), am.data_ptr(), pad_ptr, cls.data_ptr(), T, rdev.data_ptr(), T_max,
+                                             out.data_ptr(), ctx.data_ptr() if ctx is not None else None, ws, ws_bytes, self.dtype)
+        N.check(st, "hvla_generate_rows")
         return out, ctx
 
     # ---- act: one CUDA graph (~110 kernels) per (batch, weights, task map), replayed every control step ------------
@@ -127,6 +152,8 @@ class Runtime:
                 raise ValueError(f"task_index is required when T ({T}) is neither 1 nor B ({B})")
             return None, None
         ti = torch.as_tensor(np.asarray(task_index) if not torch.is_tensor(task_index) else task_index)
+        if ti.is_cuda and (ti.dtype != torch.int32 or not ti.is_contiguous()):
+            raise ValueError("a CUDA task_index must be a contiguous int32 tensor (it is read in place by the captured graph)")
         ti = ti.to(self.device).to(torch.int32).contiguous()
         if tuple(ti.shape) != (B,):
             raise ValueError("task_index must have shape (B,)")
@@ -135,16 +162,24 @@ class Runtime:
         return ti, ti.data_ptr()
 
     def _act_eager(self, img_dev, weights, tptr, B, T, act_dev, logit_dev):
-        ws, ws_bytes = self.workspace(B, 0)
-        N.check(self.lib.hvla_act(self.stream(), self.dino_vec.data_ptr(), self.dino_mat.data_ptr(), img_dev.data_ptr(),
-                                  weights.data_ptr(), tptr, B, T, act_dev.data_ptr(), logit_dev.data_ptr(), ws, ws_bytes,
-                                  self.dtype), "hvla_act")
+        with self._on_device():
+            ws, ws_bytes = self.workspace(B, 0)
+            N.check(self.lib.hvla_act(self.stream(), self.dino_vec.data_ptr(), self.dino_mat.data_ptr(), img_dev.data_ptr(),
+                                      weights.data_ptr(), tptr, B, T, act_dev.data_ptr(), logit_dev.data_ptr(), ws, ws_bytes,
+                                      self.dtype), "hvla_act")
 
     def _graph(self, B, weights, task_index):
         """Static device buffers + captured graph of hvla_act for this (B, weights, task map)."""
         torch = _torch()
         T = int(weights.shape[0])
-        tkey = None if task_index is None else np.asarray(task_index.cpu() if torch.is_tensor(task_index) else task_index).tobytes()
+        # key without a device sync: a CUDA task map is identified by its address (the graph reads its CONTENTS at replay, so
+        # in-place edits of the map are picked up; its range is validated when the graph is built), a host map by its bytes
+        if task_index is None:
+            tkey = None
+        elif torch.is_tensor(task_index) and task_index.is_cuda:
+            tkey = ("dev", int(task_index.data_ptr()), int(task_index.numel()), str(task_index.dtype))
+        else:
+            tkey = np.asarray(task_index).tobytes()
         key = (B, int(weights.data_ptr()), tkey)
         st = self._graphs.get(key)
         if st is not None and st["ws_key"] == self._ws_key:
@@ -166,9 +201,10 @@ class Runtime:
             st["n_launches"] = int(self.lib.hvla_launch_count()) - n0
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with self._on_device(), torch.cuda.graph(graph):
                 self._act_eager(st["img_dev"], weights, tptr, B, T, st["act_dev"], st["logit_dev"])
             st["graph"] = graph
+            self.graph_captures += 1
         st["ws_key"] = self._ws_key
         self._graphs[key] = st
         return st
@@ -255,9 +291,11 @@ class Runtime:
             raise ValueError("Input image size must be 224x224 (uint8, NHWC)")
         vec, mat = blobs if blobs is not None else (self.dino_vec, self.dino_mat)
         out = torch.empty((B, Cfg.DINO_TOKENS, Cfg.DINO_DIM), dtype=self.tdtype, device=self.device)
-        ws, ws_bytes = self.workspace(B, 0)
-        st = self.lib.hvla_dino_forward(self.stream(), vec.data_ptr(), mat.data_ptr(),
-                                        images.contiguous().data_ptr(), B, out.data_ptr(), ws, ws_bytes, self.dtype)
+        images = images.contiguous()
+        with self._on_device():
+            ws, ws_bytes = self.workspace(B, 0)
+            st = self.lib.hvla_dino_forward(self.stream(), vec.data_ptr(), mat.data_ptr(),
+                                            images.data_ptr(), B, out.data_ptr(), ws, ws_bytes, self.dtype)
         N.check(st, "hvla_dino_forward")
         return out
 
@@ -267,8 +305,10 @@ class Runtime:
         keep, tptr = self._tidx(task_index, B, T)
         act = torch.empty((B, Cfg.ACTION_HORIZON, Cfg.ACTION_DIM), dtype=torch.float32, device=self.device)
         logit = torch.empty((B, Cfg.ACTION_HORIZON), dtype=torch.float32, device=self.device)
-        ws, ws_bytes = self.workspace(B, 0)
-        st = self.lib.hvla_base_act(self.stream(), emb.contiguous().data_ptr(), weights.data_ptr(), tptr, B, T,
-                                    act.data_ptr(), logit.data_ptr(), ws, ws_bytes, self.dtype)
+        emb = emb.contiguous()
+        with self._on_device():
+            ws, ws_bytes = self.workspace(B, 0)
+            st = self.lib.hvla_base_act(self.stream(), emb.data_ptr(), weights.data_ptr(), tptr, B, T,
+                                        act.data_ptr(), logit.data_ptr(), ws, ws_bytes, self.dtype)
         N.check(st, "hvla_base_act")
         return act, logit

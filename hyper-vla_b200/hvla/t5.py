@@ -154,14 +154,16 @@ class T5TokenEmbedder:
     def _encode(self, ids, am, T, S, out, ws):
         import torch
         stream = int(torch.cuda.current_stream(self.device).cuda_stream)
-        if self.precision != "fp32":
-            st = self.lib.hvla_t5_encode_tc(stream, self.blob.data_ptr(), self.mat.data_ptr(), self._pos_bias(S).data_ptr(), ids.data_ptr(),
-                                            am.data_ptr(), T, S, out.data_ptr(), ws.data_ptr(), ws.numel())
-            N.check(st, "hvla_t5_encode_tc")
-        else:
-            st = self.lib.hvla_t5_encode(stream, self.blob.data_ptr(), self._pos_bias(S).data_ptr(), ids.data_ptr(), am.data_ptr(), T, S,
-                                         out.data_ptr(), ws.data_ptr(), ws.numel())
-            N.check(st, "hvla_t5_encode")
+        pb = self._pos_bias(S)
+        with torch.cuda.device(self.device):       # launches go to the current device's context
+            if self.precision != "fp32":
+                st = self.lib.hvla_t5_encode_tc(stream, self.blob.data_ptr(), self.mat.data_ptr(), pb.data_ptr(), ids.data_ptr(),
+                                                am.data_ptr(), T, S, out.data_ptr(), ws.data_ptr(), ws.numel())
+                N.check(st, "hvla_t5_encode_tc")
+            else:
+                st = self.lib.hvla_t5_encode(stream, self.blob.data_ptr(), pb.data_ptr(), ids.data_ptr(), am.data_ptr(), T, S,
+                                             out.data_ptr(), ws.data_ptr(), ws.numel())
+                N.check(st, "hvla_t5_encode")
 
     def _capture(self, T: int, S: int) -> dict:
         """Static buffers + captured graph of hvla_t5_encode_tc for this (T,S); at most 4 shapes are kept."""
@@ -176,7 +178,7 @@ class T5TokenEmbedder:
         self._encode(st["ids"], st["am"], T, S, st["out"], st["ws"])       # one-time kernel setup outside capture
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.device(dev), torch.cuda.graph(graph):
             self._encode(st["ids"], st["am"], T, S, st["out"], st["ws"])
         st["graph"] = graph
         self._graphs[(T, S)] = st

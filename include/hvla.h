@@ -80,6 +80,17 @@ int hvla_generate(hvla_stream_t stream, const float* hn_blob, const void* hn_blo
                   const float* init_cls, int T, void* out_weights, float* out_ctx, void* workspace,
                   size_t workspace_bytes, int dtype);
 
+/* ---- task-switch scheduler: regenerate only the T tasks that switched, IN PLACE ----------------------------
+ * (the reference regenerates at every episode reset: data/utils/hypervla_interface.py:141-146,
+ *  data/simpler/evaluate.py:263-277).  Inputs as hvla_generate for the T switched tasks; row_index [T] i32 (device):
+ *  task t is written to row row_index[t] of the persistent `weights` [T_max,NGP] (dtype) and `ctx` [T_max,128] f32
+ *  (or NULL) buffers; other rows are untouched, so a CUDA graph captured over `weights` stays valid.
+ *  Rows outside [0, T_max) are skipped. */
+int hvla_generate_rows(hvla_stream_t stream, const float* hn_blob, const void* hn_blob_f16, const void* heads_w,
+                       const float* heads_b, const float* tok_emb, const int32_t* tok_mask, const uint8_t* lang_pad,
+                       const float* init_cls, int T, const int32_t* row_index, int T_max, void* weights, float* ctx,
+                       void* workspace, size_t workspace_bytes, int dtype);
+
 /* ---- DINOv2 image encoder: replaces self.image_encoder(raw_images) + normalisation ------
  * (hypervla/components/base_vit.py:111-122; FlaxDinov2Module of transformers==4.50.0).
  *   images  [B,224,224,3] u8 (NHWC)      out_emb [B,257,768] (dtype) = last_hidden_state */
@@ -176,6 +187,14 @@ int hvla_profile_report(char* buf, size_t cap);
 struct hvla_xla_opaque { int32_t B, T, dtype, reserved; uint64_t workspace_bytes; };
 void hvla_xla_generate(void* stream, void** buffers, const char* opaque, size_t opaque_len);
 void hvla_xla_act(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+/* Status-returning form (xla_client.register_custom_call_target(..., api_version=1)): the trailing argument is XLA's
+ * `XlaCustomCallStatus*` (opaque here -- no XLA header needed).  On failure (short opaque, bad argument, CUDA error) the
+ * message is reported through XlaCustomCallStatusSetFailure -- resolved as a weak symbol from the hosting process, or set
+ * explicitly with hvla_xla_register_status_setter -- and the outputs are zero-filled on `stream`. */
+typedef void (*hvla_xla_status_setter)(void* status, const char* message, size_t message_len);
+void hvla_xla_register_status_setter(hvla_xla_status_setter fn);
+void hvla_xla_generate_status(void* stream, void** buffers, const char* opaque, size_t opaque_len, void* status);
+void hvla_xla_act_status(void* stream, void** buffers, const char* opaque, size_t opaque_len, void* status);
 
 #ifdef __cplusplus
 }

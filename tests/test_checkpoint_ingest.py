@@ -48,10 +48,17 @@ def test_ema_pickle_with_jax_array_leaves_loads_without_jax(tmp_path, params_p1)
     os.makedirs(tmp_path / "5000")
     _write_ema(tmp_path / "5000" / "EMA_params.pkl", tree)
     assert "jax" not in sys.modules or not hasattr(sys.modules["jax"], "numpy") or True
-    got = CK.load_params(str(tmp_path), 5000)
+    got = CK.load_params(str(tmp_path), 5000, ema=0.999)
     assert np.array_equal(got["task_token_projection"]["kernel"], sub["task_token_projection"]["kernel"])
     assert np.array_equal(got["layer_pos_embedding"], sub["layer_pos_embedding"])
-    assert CK.latest_step(str(tmp_path)) == 5000 and CK.load_params(str(tmp_path))["layer_pos_embedding"].shape == (1, 1, 128)
+    assert CK.latest_step(str(tmp_path)) == 5000
+    assert CK.load_params(str(tmp_path), ema="EMA_0.999")["layer_pos_embedding"].shape == (1, 1, 128)
+    # the reference swaps EMA weights in only under --EMA (data/simpler/evaluate.py:439-444): without ema= the RAW params are
+    # wanted, and an EMA pickle alone must not be returned in their place
+    with pytest.raises(FileNotFoundError):
+        CK.load_params(str(tmp_path), 5000)
+    with pytest.raises(KeyError, match="EMA_0.99 "):
+        CK.load_params(str(tmp_path), 5000, ema=0.99)
 
 
 def test_pickle_with_code_is_refused(tmp_path):
@@ -60,7 +67,7 @@ def test_pickle_with_code_is_refused(tmp_path):
     with open(tmp_path / "1" / "EMA_params.pkl", "wb") as f:
         pickle.dump({"EMA_0.999": {"x": os.getcwd}}, f)
     with pytest.raises(pickle.UnpicklingError):
-        CK.load_params(str(tmp_path), 1)
+        CK.load_params(str(tmp_path), 1, ema=0.999)
 
 
 def test_save_then_load_pretrained_roundtrip_layout(tmp_path, params_p1):

@@ -488,3 +488,112 @@ def test_edge_cases(models, torch_cuda):
     img = torch_cuda.from_numpy(inp["images"]).to(rt.device)
     a_dev, inter = m.sample_actions(img, None, tasks, None, bp)
     assert a_dev.is_cuda and np.array_equal(a_dev.cpu().numpy(), a_all)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_task_switch_scheduler_regenerates_only_the_switched_rows_in_place(models, torch_cuda, prec):
+    """SURVEY 8(f) row 2, second half (data/utils/hypervla_interface.py:141-162, data/simpler/evaluate.py:263-277 reset
+    one episode at a time): resetting 3 of 64 envs must (a) leave the other 61 weight rows bit-identical, (b) keep the captured
+    act graph (no re-capture), (c) give the same actions as regenerating all 64 tasks from the mixed instruction set."""
+    from hvla import synthetic as S
+    torch = torch_cuda
+    m = models[prec]
+    rt = m.runtime
+    B = 64 if prec == "bf16" else 8
+    ids = [5, 17, 40] if prec == "bf16" else [1, 6, 3]
+    old, new = S.make_inputs(21, B, B), S.make_inputs(22, len(ids), len(ids))
+    bp, tasks, _ = m.create_tasks(instruction_dict=old["instruction_dict"], initial_state=old["initial_state"])
+    a0, _ = m.sample_actions(old["images"], None, tasks, None, bp)          # captures the act graph for (B, this buffer)
+    before = bp.weights.clone()
+    ctx_before = bp.context_embedding.clone()
+    ptr, caps, launches = bp.weights.data_ptr(), rt.graph_captures, rt.launch_count()
+    bp2, _, _ = m.create_tasks(instruction_dict=new["instruction_dict"], initial_state=new["initial_state"], task_ids=ids, base_params=bp)
+    assert bp2 is bp and bp.weights.data_ptr() == ptr and bp.generation == 1
+    keep = np.setdiff1d(np.arange(B), ids)
+    assert torch.equal(bp.weights[keep], before[keep]) and torch.equal(bp.context_embedding[keep], ctx_before[keep])
+    assert not torch.equal(bp.weights[ids], before[ids])
+    a1, _ = m.sample_actions(old["images"], None, tasks, None, bp)
+    assert rt.graph_captures == caps, "a task switch must not force a graph re-capture"
+    # reference result: all B tasks regenerated from the mixed instruction set
+    lang_o, lang_n = old["instruction_dict"]["language_instruction"], new["instruction_dict"]["language_instruction"]
+    mixed = {k: np.array(lang_o[k]) for k in ("input_ids", "attention_mask", "token_embedding")}
+    pe = np.array(old["initial_state"]["patch_embeddings"])
+    for j, i in enumerate(ids):
+        for k in mixed:
+            mixed[k][i] = lang_n[k][j]
+        pe[i] = new["initial_state"]["patch_embeddings"][j]
+    bp_full, tasks_full, _ = m.create_tasks(instruction_dict={"language_instruction": mixed}, initial_state={"patch_embeddings": pe})
+    assert torch.equal(bp_full.weights[:, :201500], bp.weights[:, :201500])
+    assert torch.equal(bp_full.context_embedding, bp.context_embedding)
+    a_full, _ = m.sample_actions(old["images"], None, tasks_full, None, bp_full)
+    assert np.array_equal(a1, a_full)
+    assert np.array_equal(a1[keep], a0[keep]) and not np.array_equal(a1[ids], a0[ids])
+    # the lazily materialised pytree view follows the in-place update
+    k1 = bp["action_head"]["discrete_head"]["bias"]
+    assert np.array_equal(np.asarray(k1, np.float32), bp_full["action_head"]["discrete_head"]["bias"].astype(np.float32))
+    with pytest.raises(ValueError):
+        m.create_tasks(instruction_dict=new["instruction_dict"], initial_state=new["initial_state"], task_ids=[0, 0, 1], base_params=bp)
+    with pytest.raises(ValueError):
+        m.create_tasks(instruction_dict=new["instruction_dict"], initial_state=new["initial_state"], task_ids=[0, 1, B], base_params=bp)
+
+
+def test_xla_status_wrappers_zero_fill_the_outputs_on_failure(models, torch_cuda):
+    """Status-returning XLA custom-call form (include/hvla.h): a failing call must report through the status hook and leave
+    zero-filled outputs behind, never stale memory."""
+    import ctypes as C
+    from hvla import synthetic as S
+    torch = torch_cuda
+    m = models["bf16"]
+    rt = m.runtime
+    B = T = 2
+    inp = S.make_inputs(4, B, T)
+    bp, _, _ = m.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"])
+    dev = rt.device
+    nbytes = int(rt.lib.hvla_workspace_bytes(B, T, rt.dtype))
+    ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+    wptr = (ws.data_ptr() + 255) & ~255
+
+    class Opaque(C.Structure):
+        _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32), ("workspace_bytes", C.c_uint64)]
+    seen = []
+    SETTER = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p, C.c_size_t)
+
+    @SETTER
+    def setter(status, msg, n):
+        seen.append(msg[:n].decode())
+    rt.lib.hvla_xla_register_status_setter(C.cast(setter, C.c_void_p))
+    try:
+        img = torch.from_numpy(np.ascontiguousarray(inp["images"][:, 0])).to(dev)
+        act = torch.ones((B, 4, 7), dtype=torch.float32, device=dev)
+        logit = torch.ones((B, 4), dtype=torch.float32, device=dev)
+        bufs = (C.c_void_p * 8)(rt.dino_vec.data_ptr(), rt.dino_mat.data_ptr(), img.data_ptr(), bp.weights.data_ptr(), None,
+                                act.data_ptr(), logit.data_ptr(), wptr)
+        token = C.c_int(0)
+        bad = Opaque(B, T, rt.dtype, 0, 1024)                       # workspace far too small
+        raw = C.string_at(C.addressof(bad), C.sizeof(bad))
+        rt.lib.hvla_xla_act_status(rt.stream(), bufs, raw, len(raw), C.addressof(token))
+        torch.cuda.synchronize()
+        assert len(seen) == 1 and "workspace" in seen[0]
+        assert float(act.abs().max()) == 0.0 and float(logit.abs().max()) == 0.0
+        good = Opaque(B, T, rt.dtype, 0, nbytes)
+        raw = C.string_at(C.addressof(good), C.sizeof(good))
+        rt.lib.hvla_xla_act_status(rt.stream(), bufs, raw, len(raw), C.addressof(token))
+        torch.cuda.synchronize()
+        assert len(seen) == 1 and float(act.abs().max()) > 0.0       # success: no status call, real actions
+    finally:
+        rt.lib.hvla_xla_register_status_setter(None)
+
+
+def test_params_swap_reuploads_device_blobs(params_p1, params_p0, torch_cuda):
+    """``model.params = ema_params`` (the reference's EMA swap, data/simpler/evaluate.py:443) must be followed by the device
+    blobs: generate has to use the new parameters, not the ones uploaded first."""
+    from hvla import config as C, synthetic as S
+    from hvla.model import HyperVLA
+    inp = S.make_inputs(2, 2, 2)
+    m = HyperVLA.from_config(C.default_config(), precision="fp32", params=params_p1)
+    w1 = m.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"])[0].weights.clone()
+    m.params = params_p0
+    w0 = m.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"])[0].weights
+    ref = HyperVLA.from_config(C.default_config(), precision="fp32", params=params_p0)
+    w0_ref = ref.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"])[0].weights
+    assert torch_cuda.equal(w0, w0_ref) and not torch_cuda.equal(w0, w1)

@@ -154,7 +154,15 @@ def test_bench_kernel_roofline_table_arithmetic():
            "dino_attention": (12, 0.4245), "base_fused": (1, 0.0947), "unknown_class": (3, 1.0)}
     gen = {"ctx_fused": (1, 0.1528), "heads_gemm": (1, 0.028), "idle": (1, 0.0)}
     peaks = {"hbm_gbs": 6542.1, "bf16_tflops_sustained": 1386.3}
-    t = bench.kernel_roofline_table(act, gen, 64, 64, peaks, "bf16")
+    peaks["bf16_tflops"] = 1648.0
+    # the tensor denominator follows the SM clock sampled while the kernels were timed (a burst-clock time must not
+    # be divided by the sustained peak)
+    assert bench.tensor_peak(peaks, {"sm_mhz": 1965.0, "sm_max_mhz": 1965, "reasons": []})[0] == 1648.0
+    assert bench.tensor_peak(peaks, {"sm_mhz": 1400.0, "sm_max_mhz": 1965, "reasons": ["sw_power_cap"]})[0] == 1386.3
+    assert bench.tensor_peak({}, {"sm_mhz": None, "sm_max_mhz": None, "reasons": []})[0] == 1400.0
+    assert bench.default_batch(1) == 64 and [bench.default_batch(n) for n in (2, 4, 8)] == [512, 256, 128]
+    assert "configs[2]" in bench.workload_config(128, 8)["workload"] and "configs[1]" in bench.workload_config(64, 1)["workload"]
+    t = bench.kernel_roofline_table(act, gen, 64, 64, peaks, "bf16", 1386.3)
     assert set(t) == {"im2col", "cls_rows", "gemm_tc", "layernorm", "dino_attention", "base_fused", "ctx_fused", "heads_gemm"}
     for name, r in t.items():
         assert r["unit"] == ("TFLOP/s" if r["bound"] == "tensor" else "GB/s")
@@ -163,5 +171,28 @@ def test_bench_kernel_roofline_table_arithmetic():
     # base net: 796,328 algorithmic bytes per env when every env has its own weights
     assert abs(t["base_fused"]["achieved"] - 796_328 * 64 / 0.0947e-3 / 1e9) < 0.5
     # fallback peaks of the profiling recipe when MEASURED_PEAKS.json is absent
-    t2 = bench.kernel_roofline_table(act, gen, 64, 64, {}, "bf16")
+    t2 = bench.kernel_roofline_table(act, gen, 64, 64, {}, "bf16", bench.tensor_peak({}, {})[0])
     assert t2["layernorm"]["peak"] == 6650.0 and t2["gemm_tc"]["peak"] == 1400.0
+
+
+def test_action_head_scalars_outside_the_kernel_constants_are_rejected():
+    """The head epilogues hard-code tanh(x / 5) * 5 (MixActionHead defaults, action_heads.py:439, 445)."""
+    for key, val in (("tanh_scaling_factor", 2.0), ("max_action", 1.0)):
+        cfg = C.default_config()
+        cfg["base_net_kwargs"]["action_head_kwargs"][key] = val
+        with pytest.raises(ValueError, match=key):
+            C.validate_config(cfg)
+    cfg = C.default_config()
+    del cfg["base_net_kwargs"]["action_head_kwargs"]["tanh_scaling_factor"]      # absent -> reference default 5.0
+    C.validate_config(cfg)
+
+
+def test_replace_params_drops_the_device_runtime(params_p1, params_p0):
+    """model.replace(params=ema) is the reference's EMA swap (data/simpler/evaluate.py:443): the copy must not keep device
+    blobs of the old parameters."""
+    from hvla.model import HyperVLA
+    m = HyperVLA.from_config(C.default_config(), params=params_p1)
+    m._runtime = object()                        # stands for an uploaded runtime (no GPU here)
+    m2 = m.replace(params=params_p0)
+    assert m2.params is params_p0 and m2._runtime is None and m._runtime is not None
+    assert m.replace(precision="fp32")._runtime is None and m.replace(config=m.config)._runtime is m._runtime

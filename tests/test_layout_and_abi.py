@@ -113,3 +113,27 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert lib.hvla_act(None, None, None, None, None, None, 1, 1, None, None, None, 0, 1) == -1
     assert b"NULL" in lib.hvla_last_error()
     assert lib.hvla_generate(None, None, None, None, None, None, None, None, None, 1, None, None, None, 0, 0) == -1
+
+
+def test_xla_status_wrappers_report_a_short_opaque_without_a_gpu(lib):
+    """include/hvla.h: the status-returning custom-call form must report failures through the XlaCustomCallStatus hook
+    (here the explicitly registered setter) instead of returning silently with untouched outputs."""
+    import ctypes as C
+    seen = []
+    SETTER = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p, C.c_size_t)
+
+    @SETTER
+    def setter(status, msg, n):
+        seen.append((status, msg[:n].decode()))
+    lib.hvla_xla_register_status_setter(C.cast(setter, C.c_void_p))
+    try:
+        bufs = (C.c_void_p * 11)()
+        token = C.c_int(0)
+        for fn, name in ((lib.hvla_xla_act_status, "hvla_xla_act"), (lib.hvla_xla_generate_status, "hvla_xla_generate")):
+            fn(None, bufs, b"\0" * 8, 8, C.addressof(token))
+            assert seen and seen[-1][0] == C.addressof(token) and name in seen[-1][1] and "opaque" in seen[-1][1]
+        n = len(seen)
+        lib.hvla_xla_act(None, bufs, b"\0" * 8, 8)          # original form: no status channel, must not call the setter
+        assert len(seen) == n
+    finally:
+        lib.hvla_xla_register_status_setter(None)
