@@ -21,7 +21,17 @@ constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*epilogue bias/ls*/ +
                            1024 + 8 * 2048 /*TMA-store slabs*/;
 
-enum Epi { EPI_BIAS_BF16 = 0, EPI_BIAS_GELU_BF16 = 1, EPI_RESIDUAL_F32 = 2, EPI_PATCH_F32 = 3 };
+enum Epi {
+  EPI_BIAS_BF16 = 0, EPI_BIAS_GELU_BF16 = 1, EPI_RESIDUAL_F32 = 2, EPI_PATCH_F32 = 3,
+  // LayerNorm-free flow over the BLOCKED fp32 stream (see "stream LayerNorm without a LayerNorm kernel"):
+  EPI_BIAS_BF16_FOLD = 4, EPI_BIAS_GELU_BF16_FOLD = 5,   // consumers: A = un-normalised bf16 shadow, row statistics applied in the epilogue
+  EPI_RESIDUAL_BLK = 6,                                  // producer: x += ls*(acc+bias) in place + bf16 shadow + row statistics
+  EPI_PATCH_BLK = 7                                      // patch embedding: x += acc+bias at the shifted stream rows (no shadow)
+};
+constexpr bool epi_fold(int e) { return e == EPI_BIAS_BF16_FOLD || e == EPI_BIAS_GELU_BF16_FOLD; }
+constexpr bool epi_gelu(int e) { return e == EPI_BIAS_GELU_BF16 || e == EPI_BIAS_GELU_BF16_FOLD; }
+constexpr bool epi_bf16_out(int e) { return e == EPI_BIAS_BF16 || e == EPI_BIAS_GELU_BF16 || epi_fold(e); }
+constexpr bool epi_blk(int e) { return e == EPI_RESIDUAL_BLK || e == EPI_PATCH_BLK; }
 
 struct EpiP {
   const float* bias;   // [N]
@@ -37,12 +47,21 @@ struct EpiP {
   int* splits_used;    //        host out: number of K splits of this launch (1 = none)
   int patch_rows;      // EPI 2 used for the patch embedding: GEMM row b*256+p lands in stream row b*257+1+p; ls == null means 1
   // ---- LayerNorm fused away (see "stream LayerNorm without a LayerNorm kernel" below) ----
-  int rows;            // M (valid rows), for the per-row loads of the two modes below
-  const float* stats;  // EPI 0/1 consumer: [M][6][2] partial (sum, sum of squares) of the A rows; A is the UN-normalised bf16 shadow
+  int rows;            // valid rows: M (EPI 4/5/7: GEMM rows; EPI 6: stream rows = GEMM rows)
+  const float* stats;  // EPI 4/5 consumer: [M][6][2] partial (sum, sum of squares) of the A rows; A is the UN-normalised bf16 shadow
   const float* cs;     //                   [N] column sums of the (gamma-folded, bf16-rounded) weight; bias = folded bias
-  bf16* shadow;        // EPI 2 producer: bf16 copy of the updated stream [M,768] (null: classic reduce-add epilogue)
+  bf16* shadow;        // EPI 6 producer: bf16 copy of the updated stream [M,768]; `out` is the BLOCKED fp32 stream
   float* stats_out;    //                 [M][6][2] partial row statistics of the updated stream
 };
+
+// Blocked fp32 residual stream: element (row, col) of the logical [M,768] stream lives at float index
+//   ((row >> 5) * 192 + (col >> 2)) * 128 + (row & 31) * 4 + (col & 3)
+// i.e. 32-row blocks, inside a block one 512-byte run per group of 4 columns.  A tcgen05 epilogue thread owns one ROW
+// (TMEM lane) and a warp 32 consecutive rows, so the warp's 16-byte accesses to one column group are 512 contiguous bytes:
+// the residual epilogues read and write the stream in place, fully coalesced, without shared memory or TMA.
+__host__ __device__ __forceinline__ int64_t xblk_f4(int row, int col4) {      // float4 index of (row, columns 4*col4 .. 4*col4+3)
+  return ((int64_t)(row >> 5) * (DD / 4) + col4) * 32 + (row & 31);
+}
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,20 +116,16 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 
 // ---- stream LayerNorm without a LayerNorm kernel ------------------------------------------------------------------------
 // The 24 LayerNorms between the residual GEMMs and the q|k|v / fc1 GEMMs cost 13 % of a step as a separate HBM pass
-// (50 MB fp32 in, 25 MB bf16 out each).  Instead:
-//  * producer (proj / fc2 epilogue): x_new = x_old + ls*(acc+bias) is formed in registers (x_old read straight from the
-//    stream), stored as fp32 (plain TMA store instead of a reduce-add) AND as a bf16 shadow, and each thread -- it owns one
-//    row and 128 columns of the tile -- writes its partial (sum, sum of squares): 6 partials per row (3 n-tiles x 2 halves);
-//  * consumer (q|k|v / fc1 epilogue): A is the un-normalised shadow, gamma/beta are folded into W and the bias
+// (50 MB fp32 in, 25 MB bf16 out each).  In the large-batch flow (hvla_capi.cu: dino_bf16, "flow B") they do not exist:
+//  * producer (proj / fc2, EPI_RESIDUAL_BLK): x_new = x_old + ls*(acc+bias) is formed in registers; x_old is read from and x_new
+//    written to the BLOCKED stream in place (coalesced 16-byte accesses, see xblk_f4), a bf16 shadow of x_new goes out through
+//    the per-warp slab + TMA store, and each thread -- it owns one row and 128 columns of the tile -- writes its partial
+//    (sum, sum of squares): 6 partials per row (3 n-tiles x 2 halves);
+//  * consumer (q|k|v / fc1, EPI_*_FOLD): A is the un-normalised shadow, gamma/beta are folded into W and the bias
 //    (params.py), and the row statistics enter after the matrix product:  rstd*(x W' - mean*colsum(W')) + b_f.
-// Small batches (split-K) and the first layer produce shadow + statistics with stream_shadow_kernel instead.
-// Compiled in only with -DHVLA_WITH_FUSED_LN (HVLA_NVCC_EXTRA): it is slower today, and the extra epilogue
-// code costs every GEMM launch ~1 us of instruction fetch at batch 1 (49 launches per step) even when it is not taken.
-#ifdef HVLA_WITH_FUSED_LN
-constexpr bool kFusedLn = true;
-#else
-constexpr bool kFusedLn = false;
-#endif
+// Round 1 had the producer read the old values from a ROW-MAJOR stream (32 different lines per warp instruction) and store
+// the new ones through fp32 slabs: proj 27.7 -> 71.8 us.  The blocked layout is what makes the in-place update cheap.
+// Small batches (split-K) keep the classic flow: row-major stream, TMA reduce-add, LayerNorm kernels.
 //
 // ---- split-K partial products -------------------------------------------------------------------------------
 // At small batch the residual GEMMs (N = 768) have only a handful of output tiles; their K range is then split
@@ -307,7 +322,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
   float* sl = sb + 256;
   sb[te] = add_bias ? __ldg(ep.bias + n0 + te) : 0.f;      // split-K: only the first K split contributes the bias
   if (EPI == EPI_RESIDUAL_F32) sl[te] = ep.ls ? __ldg(ep.ls + n0 + te) : 1.0f;
-  const bool fold = kFusedLn && (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) && ep.stats != nullptr;
+  constexpr bool fold = epi_fold(EPI);
   if (fold) sl[te] = __ldg(ep.cs + n0 + te);
   const int row0 = m0 + quarter * 32 + (ep.patch_rows ? m0 / 256 + 1 : 0);
   const int myrow = row0 + lane;                              // the stream / A row this thread's TMEM lane holds
@@ -320,21 +335,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
     f_rstd = 1.0f / sqrtf(fmaxf(0.f, sq * (1.f / 768.f) - mean * mean) + 1e-6f);
     f_nmr = -mean * f_rstd;
   }
-  const bool produce = kFusedLn && EPI == EPI_RESIDUAL_F32 && ep.shadow != nullptr && split == 0;
-  float p_sum = 0.f, p_sq = 0.f;                              // producer: this thread's partial row statistics
   // NSLAB 2 KB slabs per warp: with two, the TMA store of one chunk reads its slab while the next chunk is written
   const uint32_t slab0 = sstage + (uint32_t)ew * (2048u * NSLAB);
   const uint32_t my0 = slab0 + (uint32_t)lane * 64u;
   const uint32_t sw = (uint32_t)((lane >> 1) & 3);          // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
-  // producer: the old stream values do not depend on the MMAs -- chunk 0 is requested while the mainloop is still running,
-  // chunk c+1 while chunk c is processed (row-per-thread 128-byte reads straight from the stream)
-  float4 xo[2][8];
-  const bool xok = produce && myrow < ep.rows;
-  const float4* xrow = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.out) + (int64_t)(xok ? myrow : 0) * ep.ldo + n0 + half * 128);
-  if (produce) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) xo[0][j] = xok ? __ldcg(xrow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
   epi_bar_sync();
   mbar_wait(tfull_bar_addr, aph);
   tc_fence_after();
@@ -371,8 +375,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
         v[j] = lo.x; v[j + 1] = lo.y; v[j + 2] = hi.x; v[j + 3] = hi.y;
       }
     }
-    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
-      if (EPI == EPI_BIAS_GELU_BF16) {
+    if (epi_bf16_out(EPI)) {
+      if (epi_gelu(EPI)) {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           const float2 g = gelu_erf_tanhfit2(make_float2(v[j], v[j + 1]));
@@ -399,60 +403,6 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
         tma_store_2d(tmO, slab, col, row0);
         bulk_commit();
       }
-    } else if (produce) {   // EPI_RESIDUAL_F32, LayerNorm-free flow: x_new = x_old + ls*v -> fp32 store, bf16 shadow, row statistics
-      float xn[32];
-      {
-        if (c < 3) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) xo[(c + 1) & 1][j] = xok ? __ldcg(xrow + (c + 1) * 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 x4 = xo[c & 1][j];
-          const float4 l4 = *reinterpret_cast<const float4*>(sl + cl + 4 * j);
-          xn[4 * j] = fmaf(v[4 * j], l4.x, x4.x); xn[4 * j + 1] = fmaf(v[4 * j + 1], l4.y, x4.y);
-          xn[4 * j + 2] = fmaf(v[4 * j + 2], l4.z, x4.z); xn[4 * j + 3] = fmaf(v[4 * j + 3], l4.w, x4.w);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { p_sum += xn[j]; p_sq = fmaf(xn[j], xn[j], p_sq); }
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const uint32_t slab = slab0, my = my0;
-        if (lane == 0) bulk_wait_read<0>();
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int e = u * 16 + j * 4;
-          const uint32_t a = my + ((((uint32_t)j) ^ sw) << 4);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(xn[e]), "f"(xn[e + 1]), "f"(xn[e + 2]), "f"(xn[e + 3]) : "memory");
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(tmO, slab, col + u * 16, row0);
-          bulk_commit();
-        }
-      }
-      {                                                       // the same 32 columns as bf16 into the shadow
-        const uint32_t slab = slab0, my = my0;
-        if (lane == 0) bulk_wait_read<0>();
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t a = my + ((((uint32_t)j) ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16(xn[8 * j], xn[8 * j + 1])),
-                       "r"(pack_bf16(xn[8 * j + 2], xn[8 * j + 3])), "r"(pack_bf16(xn[8 * j + 4], xn[8 * j + 5])),
-                       "r"(pack_bf16(xn[8 * j + 6], xn[8 * j + 7]))
-                       : "memory");
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(tmX, slab, col, row0);
-          bulk_commit();
-        }
-      }
     } else {   // EPI_RESIDUAL_F32: two units of 16 fp32 columns, reduce-added into the residual stream
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -478,8 +428,95 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
       }
     }
   }
-  if (produce && myrow < ep.rows)                              // partial (sum, sumsq) of this row over this tile's 128-column half
-    *reinterpret_cast<float2*>(ep.stats_out + (int64_t)myrow * 12 + ((n0 / BN) * 2 + half) * 2) = make_float2(p_sum, p_sq);
+  tc_fence_before();
+  __syncwarp();
+}
+
+// ---- epilogue over the BLOCKED fp32 stream (EPI_RESIDUAL_BLK, EPI_PATCH_BLK) ------------------------------------------------
+// x_new = x_old + ls * (acc + bias), in place.  The old values do not depend on the MMAs: chunk 0 is requested while the mainloop is
+// still running, chunk c+1 while chunk c is processed.  EPI_RESIDUAL_BLK also emits the bf16 shadow (slab + TMA store) and the
+// thread's partial row statistics; EPI_PATCH_BLK maps GEMM row b*256+p to stream row b*257+1+p (ls == 1).
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile_blk(const EpiP& ep, const CUtensorMap* tmS, float* sepi, uint32_t sstage, uint32_t tfull_bar_addr,
+                                                  uint32_t aph, int as, uint32_t tmem_base, int m0, int n0, int warp, int lane) {
+  constexpr bool PATCH = EPI == EPI_PATCH_BLK;
+  const int ew = warp - 2;
+  const int quarter = warp & 3;
+  const int half = ew >> 2;
+  const int te = threadIdx.x - 64;
+  float* sb = sepi + as * 512;
+  float* sl = sb + 256;
+  sb[te] = __ldg(ep.bias + n0 + te);
+  sl[te] = (!PATCH && ep.ls) ? __ldg(ep.ls + n0 + te) : 1.0f;
+  const int grow = m0 + quarter * 32 + lane;                   // GEMM row of this thread's TMEM lane
+  const int srow = PATCH ? grow + m0 / 256 + 1 : grow;         // its stream row
+  const bool ok = grow < ep.rows;
+  float4* xp = reinterpret_cast<float4*>(ep.out) + xblk_f4(ok ? srow : 0, (n0 + half * 128) >> 2);   // + 32 per group of 4 columns
+  // old values: prefetch distance of TWO 32-column chunks (an L2 / HBM round trip is longer than one chunk of epilogue work, and with
+  // two epilogue warps per scheduler nothing else hides it): chunks 0 and 1 are requested here, chunk c+2 as soon as chunk c is consumed
+  float4 xo[2][8];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xo[u][j] = ok ? __ldcg(xp + 32 * (u * 8 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint32_t slab = sstage + (uint32_t)ew * 2048u;
+  const uint32_t my = slab + (uint32_t)lane * 64u;
+  const uint32_t sw = (uint32_t)((lane >> 1) & 3);          // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+  float p_sum = 0.f, p_sq = 0.f;
+  epi_bar_sync();
+  mbar_wait(tfull_bar_addr, aph);
+  tc_fence_after();
+  const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * 128);
+  uint32_t r[2][32];
+  tmem_ld32(taddr, r[0]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    tmem_wait_ld();
+    if (c < 3) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+    const uint32_t(&rc)[32] = r[c & 1];
+    const int cl = half * 128 + c * 32;
+    float xn[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sb + cl + 4 * j);
+      const float4 l4 = *reinterpret_cast<const float4*>(sl + cl + 4 * j);
+      const float4 x4 = xo[c & 1][j];
+      xn[4 * j] = fmaf(__uint_as_float(rc[4 * j]) + b4.x, l4.x, x4.x);
+      xn[4 * j + 1] = fmaf(__uint_as_float(rc[4 * j + 1]) + b4.y, l4.y, x4.y);
+      xn[4 * j + 2] = fmaf(__uint_as_float(rc[4 * j + 2]) + b4.z, l4.z, x4.z);
+      xn[4 * j + 3] = fmaf(__uint_as_float(rc[4 * j + 3]) + b4.w, l4.w, x4.w);
+    }
+    if (c < 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xo[c & 1][j] = ok ? __ldcg(xp + 32 * ((c + 2) * 8 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (ok) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) __stcg(xp + 32 * (c * 8 + j), make_float4(xn[4 * j], xn[4 * j + 1], xn[4 * j + 2], xn[4 * j + 3]));
+    }
+    if (!PATCH) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { p_sum += xn[j]; p_sq = fmaf(xn[j], xn[j], p_sq); }
+      if (lane == 0) bulk_wait_read<0>();                      // the slab's previous TMA store has finished reading it
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t a = my + ((((uint32_t)j) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16(xn[8 * j], xn[8 * j + 1])),
+                     "r"(pack_bf16(xn[8 * j + 2], xn[8 * j + 3])), "r"(pack_bf16(xn[8 * j + 4], xn[8 * j + 5])),
+                     "r"(pack_bf16(xn[8 * j + 6], xn[8 * j + 7]))
+                     : "memory");
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmS, slab, n0 + cl, m0 + quarter * 32);
+        bulk_commit();
+      }
+    }
+  }
+  if (!PATCH && ok)                                            // partial (sum, sumsq) of this row over this tile's 128-column half
+    *reinterpret_cast<float2*>(ep.stats_out + (int64_t)grow * 12 + ((n0 / BN) * 2 + half) * 2) = make_float2(p_sum, p_sq);
   tc_fence_before();
   __syncwarp();
 }

@@ -102,9 +102,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmO);
+    if (EPI != EPI_PATCH_BLK) tma_prefetch_desc(&tmO);
     if (splits > 1) tma_prefetch_desc(&tmP);
-    if (EPI == EPI_RESIDUAL_F32 && ep.shadow != nullptr) tma_prefetch_desc(&tmX);
     for (int s = 0; s < STAGES2; ++s) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
@@ -175,7 +174,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t aph = (it >> 1) & 1;
       const int tile = unit / splits;
       const int m0 = (tile / n_tiles_n) * BM2 + (int)rank * 128, n0 = (tile % n_tiles_n) * BN;
-      if (EPI == EPI_PATCH_F32 && ep.patch_rows)      // patch embedding accumulated onto the pre-initialised stream rows (TMA reduce-add)
+      if (epi_blk(EPI))                               // blocked stream: in-place update (+ shadow through tmO, + row statistics)
+        epilogue_tile_blk<EPI>(ep, &tmO, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane);
+      else if (EPI == EPI_PATCH_F32 && ep.patch_rows)      // patch embedding accumulated onto the pre-initialised stream rows (TMA reduce-add)
         epilogue_tile_tma<EPI_RESIDUAL_F32, NSLAB2>(ep, &tmO, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane);
       else if (EPI == EPI_PATCH_F32) epilogue_tile_direct<EPI>(ep, sepi, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, M, warp, lane);
       else {
@@ -222,8 +223,6 @@ inline int launch_one2(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap
   EpiP ep2 = ep;
   ep2.rows = M;
   CUtensorMap mx = mo;
-  if (EPI == EPI_RESIDUAL_F32 && ep.shadow != nullptr && splits == 1) HVLA_TRY(make_map_out(&mx, ep.shadow, M, N, false));
-  else ep2.shadow = nullptr;                 // split K: classic reduce-add + partials, the caller rebuilds shadow / statistics
   const int tiles = tiles0 * splits;
   if (const char* e = getenv("HVLA_GEMM_MAX_PAIRS")) { const int v = atoi(e); if (v > 0 && v < pairs) pairs = v; }   // experiment knob
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
@@ -238,8 +237,21 @@ inline int gemm_tc2(cudaStream_t st, const void* A, const void* Wt, int M, int N
   CUtensorMap ma, mb, mo;
   HVLA_TRY(make_map_bf16(&ma, A, M, K, 128));
   HVLA_TRY(make_map_bf16(&mb, Wt, N, K, 128));
-  HVLA_TRY(make_out_map_for(&mo, epi, ep, M));
+  if (epi == EPI_RESIDUAL_BLK) {             // the only TMA output of this epilogue is the bf16 shadow of the stream
+    if (!ep.shadow || !ep.stats_out || N != DD) return fail(HVLA_ERR_ARG, "gemm_tc2: EPI_RESIDUAL_BLK needs shadow, stats_out and N == 768");
+    HVLA_TRY(make_map_out(&mo, ep.shadow, M, N, false));
+  } else if (epi == EPI_PATCH_BLK) {
+    if (N != DD || M % 256 != 0) return fail(HVLA_ERR_ARG, "gemm_tc2: EPI_PATCH_BLK needs N == 768 and whole images");
+    memset(&mo, 0, sizeof mo);
+  } else {
+    if (epi_fold(epi) && (!ep.stats || !ep.cs)) return fail(HVLA_ERR_ARG, "gemm_tc2: folded-LayerNorm epilogue needs stats and cs");
+    HVLA_TRY(make_out_map_for(&mo, epi, ep, M));
+  }
   switch (epi) {
+    case EPI_BIAS_BF16_FOLD: return launch_one2<EPI_BIAS_BF16_FOLD>(st, ma, mb, mo, ep, M, N, K);
+    case EPI_BIAS_GELU_BF16_FOLD: return launch_one2<EPI_BIAS_GELU_BF16_FOLD>(st, ma, mb, mo, ep, M, N, K);
+    case EPI_RESIDUAL_BLK: return launch_one2<EPI_RESIDUAL_BLK>(st, ma, mb, mo, ep, M, N, K);
+    case EPI_PATCH_BLK: return launch_one2<EPI_PATCH_BLK>(st, ma, mb, mo, ep, M, N, K);
     case EPI_BIAS_BF16: return launch_one2<EPI_BIAS_BF16>(st, ma, mb, mo, ep, M, N, K);
     case EPI_BIAS_GELU_BF16: return launch_one2<EPI_BIAS_GELU_BF16>(st, ma, mb, mo, ep, M, N, K);
     case EPI_RESIDUAL_F32: return launch_one2<EPI_RESIDUAL_F32>(st, ma, mb, mo, ep, M, N, K);

@@ -56,7 +56,7 @@ static Plan make_plan(int B, int T, int dtype) {
   p.hc = take(Tt * CTOK * CF * 4);
   p.e = take(Tt * CD * 4);
   const size_t M = Bb * DTOK;
-  p.x = take(M * DD * 4);
+  p.x = take((M + 31) / 32 * 32 * DD * 4);                 // fp32 residual stream (flow B: blocked layout, whole 32-row blocks)
   p.y = take(M * DD * es);
   p.qkv = take(M * 3 * DD * es);
   p.att = take(M * DD * es);
@@ -282,8 +282,101 @@ __global__ void __launch_bounds__(256) dino_init_rows_kernel(const float* __rest
   reinterpret_cast<float4*>(X)[i] = v;
 }
 
+// the same for the BLOCKED stream (gemm_tc.cuh: xblk_f4): one thread per (row, group of 4 columns), stores are 512-byte runs
+__global__ void __launch_bounds__(256) dino_init_rows_blk_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ X,
+                                                                 int rows, int64_t total4) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int r = (int)(i & 31), c4 = (int)((i >> 5) % (DD / 4));
+  const int row = (int)(i / (32 * (DD / 4))) * 32 + r;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < rows) {
+    const int tok = row % DTOK;
+    v = __ldg(reinterpret_cast<const float4*>(pos + (int64_t)tok * DD) + c4);
+    if (tok == 0) {
+      const float4 c = __ldg(reinterpret_cast<const float4*>(cls) + c4);
+      v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+    }
+  }
+  reinterpret_cast<float4*>(X)[i] = v;
+}
+
+// ---- large-batch flow ("flow B"): no LayerNorm kernels between the GEMMs (gemm_tc.cuh, "stream LayerNorm without a LayerNorm kernel")
+// The fp32 residual stream is kept in the BLOCKED layout; the residual GEMMs (proj, fc2) update it in place in their epilogue and
+// emit the un-normalised bf16 shadow (Y) + per-row statistics (ST) that q|k|v / fc1 fold into THEIR epilogue.  Per layer: 4 GEMMs
+// + attention, nothing else; two stream_blk_rows launches per forward (shadow of the embedded tokens, final LayerNorm).
+static int dino_bf16_blk(cudaStream_t st, const float* dv, const bf16* dm, const uint8_t* images, int B, bf16* out_emb,
+                         uint8_t* ws, const Plan& pl) {
+  typedef DvecLayout V;
+  typedef DmatLayout Mx;
+  const int M = B * DTOK;
+  float* X = reinterpret_cast<float*>(ws + pl.x);          // blocked, (M + 31) / 32 row blocks
+  bf16* Y = reinterpret_cast<bf16*>(ws + pl.y);
+  bf16* QKV = reinterpret_cast<bf16*>(ws + pl.qkv);
+  bf16* ATT = reinterpret_cast<bf16*>(ws + pl.att);
+  bf16* HID = reinterpret_cast<bf16*>(ws + pl.hid);
+  bf16* A0 = HID;
+  float* ST = reinterpret_cast<float*>(ws + pl.st);
+  {
+    ProfScope ps(st, "im2col");
+    launch_k(im2col_norm_bf16_kernel, dim3(B * GRID), dim3(256), 0, st, images, A0, B);
+    HVLA_LAUNCH_CHECK("im2col");
+  }
+  {
+    ProfScope ps(st, "cls_rows");
+    const int64_t total4 = (int64_t)((M + 31) / 32) * 32 * (DD / 4);
+    launch_k(dino_init_rows_blk_kernel, dim3(cdiv(total4, 256)), dim3(256), 0, st, dv + V::cls, dv + V::pos, X, M, total4);
+    HVLA_LAUNCH_CHECK("dino_init_rows_blk");
+  }
+  {
+    tc::EpiP ep; memset(&ep, 0, sizeof ep);
+    ep.bias = dv + V::patch_b; ep.out = X; ep.ldo = DD; ep.rows = B * NPATCH;
+    HVLA_TRY(tc2::gemm_tc2(st, A0, dm + Mx::patch_w, B * NPATCH, DD, PATCH_KP, tc::EPI_PATCH_BLK, ep));
+  }
+  HVLA_TRY(stream_blk_rows(st, X, Y, ST, nullptr, nullptr, M));     // shadow + statistics of the embedded tokens
+  for (int l = 0; l < DL; ++l) {
+    const float* v = dv + V::layers + (int64_t)l * V::layer_size;
+    const bf16* m = dm + Mx::layers + (int64_t)l * Mx::layer_size;
+    {
+      tc::EpiP ep; memset(&ep, 0, sizeof ep);
+      ep.bias = v + V::bqkv_f; ep.out = QKV; ep.ldo = 3 * DD; ep.stats = ST; ep.cs = v + V::cs_qkv;
+      HVLA_TRY(tc2::gemm_tc2(st, Y, m + Mx::wqkv, M, 3 * DD, DD, tc::EPI_BIAS_BF16_FOLD, ep));
+    }
+    HVLA_TRY(attn_tc::dino_attention_tc(st, QKV, ATT, B));
+    {
+      tc::EpiP ep; memset(&ep, 0, sizeof ep);
+      ep.bias = v + V::bo; ep.out = X; ep.ldo = DD; ep.ls = v + V::ls1; ep.shadow = Y; ep.stats_out = ST;
+      HVLA_TRY(tc2::gemm_tc2(st, ATT, m + Mx::wo, M, DD, DD, tc::EPI_RESIDUAL_BLK, ep));
+    }
+    {
+      tc::EpiP ep; memset(&ep, 0, sizeof ep);
+      ep.bias = v + V::b1_f; ep.out = HID; ep.ldo = DF; ep.stats = ST; ep.cs = v + V::cs_1;
+      HVLA_TRY(tc2::gemm_tc2(st, Y, m + Mx::w1, M, DF, DD, tc::EPI_BIAS_GELU_BF16_FOLD, ep));
+    }
+    {
+      tc::EpiP ep; memset(&ep, 0, sizeof ep);
+      ep.bias = v + V::b2; ep.out = X; ep.ldo = DD; ep.ls = v + V::ls2; ep.shadow = Y; ep.stats_out = ST;
+      HVLA_TRY(tc2::gemm_tc2(st, HID, m + Mx::w2, M, DD, DF, tc::EPI_RESIDUAL_BLK, ep));
+    }
+  }
+  return stream_blk_rows(st, X, out_emb, nullptr, dv + V::lnf_s, dv + V::lnf_b, M);
+}
+
+// Flow B is used from this many images on (HVLA_FUSED_LN=0 / =1 force either flow): below it the N = 768 GEMMs have fewer tiles
+// than CTA pairs, and the classic flow's split-K with partial products folded by the LayerNorm kernel is the faster one.
+static bool use_flow_blk(int B) {
+  const char* e = getenv("HVLA_FUSED_LN");
+  if (e && e[0]) return e[0] != '0';
+  return (int64_t)((B * DTOK + 255) / 256) * 3 >= num_sms() / 2;
+}
+
 static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uint8_t* images, int B, bf16* out_emb,
                      uint8_t* ws, const Plan& pl) {
+  if (use_flow_blk(B) && !env_flag("HVLA_DEBUG_SIMT_GEMM") && !env_flag("HVLA_DEBUG_SIMT_ATTN") && !env_flag("HVLA_ATTN_MMA") &&
+      !env_flag("HVLA_GEMM_1CTA"))
+    return dino_bf16_blk(st, dv, dm, images, B, out_emb, ws, pl);
   typedef DvecLayout V;
   typedef DmatLayout Mx;
   const int M = B * DTOK;
@@ -334,15 +427,6 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
     ep.patch_rows = one_cta ? 0 : 1;     // 2-CTA path: the stream already holds cls/pos, the GEMM reduce-adds onto it
     HVLA_TRY(gemm(A0, dm + Mx::patch_w, B * NPATCH, DD, PATCH_KP, tc::EPI_PATCH_F32, ep));
   }
-  // LayerNorm-free flow (gemm_tc.cuh), EXPERIMENTAL: compiled in with -DHVLA_WITH_FUSED_LN and then enabled by HVLA_FUSED_LN=1: the q|k|v / fc1 GEMMs read the
-  // un-normalised bf16 shadow of the stream (kept in Y) and apply the row statistics in their epilogue; shadow + statistics
-  // come from the preceding residual GEMM's epilogue, or from stream_shadow_kernel in front of layer 0 and after a split-K
-  // GEMM.  Correct (all parity tests pass with it on) but slower: the 25 LayerNorm launches disappear (0.41 -> 0.03 ms per
-  // 64-env step) while the residual GEMMs pay more than that for reading the old stream row-per-thread (TMEM lane = row):
-  // proj 27.7 -> 71.8 us, fc2 61.6 -> 90.6 us, step 3.24 -> 3.86 ms.  See DESIGN.md section 6c.
-  const bool fused_ln = tc::kFusedLn && !one_cta && !simt_gemm && env_flag("HVLA_FUSED_LN");
-  float* ST = reinterpret_cast<float*>(ws + pl.st);
-  bool shadow_ready = false;                 // Y / ST describe the current stream
   for (int l = 0; l < DL; ++l) {
     const float* v = dv + V::layers + (int64_t)l * V::layer_size;
     const bf16* m = dm + Mx::layers + (int64_t)l * Mx::layer_size;
@@ -350,12 +434,10 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
     // gamma / beta of both LayerNorms are folded into wqkv / w1 and their biases (params.py: pack_dino_tree): plain (x-mean)*rstd here
     ln.x = X; ln.ldx = DD; ln.y = Y; ln.ldy = DD; ln.scale = nullptr; ln.bias = nullptr; ln.rows = M; ln.rows_per_batch = 1;
     ln.part = PART; ln.part_stride = part_stride; ln.nsplit = splits - 1;   // partial products of the previous layer's fc2
-    if (!fused_ln) HVLA_TRY((layernorm<float, bf16>(st, ln, DD)));
-    else if (!shadow_ready) HVLA_TRY(stream_shadow(st, X, Y, ST, M, PART, splits - 1, part_stride));
+    HVLA_TRY((layernorm<float, bf16>(st, ln, DD)));
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
       ep.bias = v + V::bqkv_f; ep.out = QKV; ep.ldo = 3 * DD;   // q / sqrt(64) is folded into the packed weights and bias
-      if (fused_ln) { ep.stats = ST; ep.cs = v + V::cs_qkv; }
       HVLA_TRY(gemm(Y, m + Mx::wqkv, M, 3 * DD, DD, tc::EPI_BIAS_BF16, ep));
     }
     if (simt_attn) {
@@ -371,26 +453,21 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
       ep.bias = v + V::bo; ep.out = X; ep.ldo = DD; ep.ls = v + V::ls1;
       ep.part = PART; ep.part_bytes = PART_BYTES; ep.splits_used = &splits;
-      if (fused_ln) { ep.shadow = Y; ep.stats_out = ST; }
       HVLA_TRY(gemm(ATT, m + Mx::wo, M, DD, DD, tc::EPI_RESIDUAL_F32, ep));
     }
     ln.nsplit = splits - 1;      // this LayerNorm first folds the split-K partial products into the stream
-    if (!fused_ln) HVLA_TRY((layernorm<float, bf16>(st, ln, DD)));
-    else if (splits > 1) HVLA_TRY(stream_shadow(st, X, Y, ST, M, PART, splits - 1, part_stride));
+    HVLA_TRY((layernorm<float, bf16>(st, ln, DD)));
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
       ep.bias = v + V::b1_f; ep.out = HID; ep.ldo = DF;
-      if (fused_ln) { ep.stats = ST; ep.cs = v + V::cs_1; }
       HVLA_TRY(gemm(Y, m + Mx::w1, M, DF, DD, tc::EPI_BIAS_GELU_BF16, ep));
     }
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
       ep.bias = v + V::b2; ep.out = X; ep.ldo = DD; ep.ls = v + V::ls2;
       ep.part = PART; ep.part_bytes = PART_BYTES; ep.splits_used = &splits;
-      if (fused_ln) { ep.shadow = Y; ep.stats_out = ST; }
       HVLA_TRY(gemm(HID, m + Mx::w2, M, DD, DF, tc::EPI_RESIDUAL_F32, ep));
     }
-    shadow_ready = fused_ln && splits == 1;   // fc2's epilogue left shadow + statistics of the new stream
   }
   LnP ln; memset(&ln, 0, sizeof ln);
   ln.x = X; ln.ldx = DD; ln.y = out_emb; ln.ldy = DD; ln.scale = dv + V::lnf_s; ln.bias = dv + V::lnf_b; ln.rows = M; ln.rows_per_batch = 1;

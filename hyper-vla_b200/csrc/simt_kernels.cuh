@@ -318,6 +318,88 @@ inline int stream_shadow(cudaStream_t st, float* x, __nv_bfloat16* xb, float* st
   return HVLA_OK;
 }
 
+// ---- blocked fp32 stream (gemm_tc.cuh: xblk_f4) -> row-major bf16, one CTA per 32-row block ------------------------------------
+// NORMALIZE = false: the un-normalised bf16 shadow + row statistics the folded-LayerNorm GEMM epilogues consume (in front of the
+// first layer, where no residual epilogue has produced them yet); NORMALIZE = true: the final LayerNorm (scale / bias) -> embeddings.
+// Loads are the blocked layout's 512-byte runs (lane = row); the 32 x 768 tile is transposed through shared memory so that the
+// row-major stores are 16-byte, fully coalesced as well.
+constexpr int XB_LD = 776;                                 // bf16 row stride of the staged tile (1552 B: conflict-free 8-byte column writes)
+template <bool NORMALIZE>
+__global__ void __launch_bounds__(256) stream_blk_rows_kernel(const float* __restrict__ xb, __nv_bfloat16* __restrict__ y, float* __restrict__ stats,
+                                                              const float* __restrict__ scale, const float* __restrict__ bias, int rows) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) uint8_t xb_smem[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(xb_smem);                     // [32][XB_LD]
+  float* red = reinterpret_cast<float*>(xb_smem + 32 * XB_LD * 2);                     // [8 warps][32 rows][2]
+  float* fin = red + 8 * 32 * 2;                                                       // [32 rows][2]: mean, rstd
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rb = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(xb) + (int64_t)rb * 192 * 32 + lane;
+  float4 v[24];                                            // this warp's column groups cc = warp + 8 i of row `lane`
+#pragma unroll
+  for (int i = 0; i < 24; ++i) v[i] = __ldcg(src + (warp + 8 * i) * 32);
+  float s = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    s2 = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, fmaf(v[i].w, v[i].w, s2))));
+  }
+  red[(warp * 32 + lane) * 2] = s;
+  red[(warp * 32 + lane) * 2 + 1] = s2;
+  __syncthreads();
+  if (warp == 0) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a += red[(w * 32 + lane) * 2]; b += red[(w * 32 + lane) * 2 + 1]; }
+    const int row = rb * 32 + lane;
+    if (!NORMALIZE) {
+      if (row < rows) {
+        float4* sp = reinterpret_cast<float4*>(stats + (int64_t)row * 12);
+        sp[0] = make_float4(a, b, 0.f, 0.f); sp[1] = make_float4(0.f, 0.f, 0.f, 0.f); sp[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      const float mean = a / 768.f;
+      fin[lane * 2] = mean;
+      fin[lane * 2 + 1] = 1.0f / sqrtf(fmaxf(0.f, b / 768.f - mean * mean) + 1e-6f);
+    }
+  }
+  if (NORMALIZE) __syncthreads();
+  const float mean = NORMALIZE ? fin[lane * 2] : 0.f, rstd = NORMALIZE ? fin[lane * 2 + 1] : 1.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    const int c = (warp + 8 * i) * 4;
+    float o[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+    if (NORMALIZE) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(scale + c)), bb = __ldg(reinterpret_cast<const float4*>(bias + c));
+      o[0] = (o[0] - mean) * (rstd * g.x) + bb.x; o[1] = (o[1] - mean) * (rstd * g.y) + bb.y;
+      o[2] = (o[2] - mean) * (rstd * g.z) + bb.z; o[3] = (o[3] - mean) * (rstd * g.w) + bb.w;
+    }
+    Vec4<__nv_bfloat16>::store(tile + lane * XB_LD + c, o);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * 96; i += 256) {       // 96 16-byte pieces per row
+    const int r = i / 96, c8 = (i % 96) * 8;
+    if (rb * 32 + r < rows)
+      *reinterpret_cast<uint4*>(y + (int64_t)(rb * 32 + r) * 768 + c8) = *reinterpret_cast<const uint4*>(tile + r * XB_LD + c8);
+  }
+}
+constexpr int XB_SMEM = 32 * XB_LD * 2 + 8 * 32 * 2 * 4 + 32 * 2 * 4;
+
+inline int stream_blk_rows(cudaStream_t st, const float* xb, __nv_bfloat16* y, float* stats, const float* scale, const float* bias, int rows) {
+  static std::atomic<uint64_t> attr{0};   // per-device one-time setup
+  if (device_once(attr)) {
+    HVLA_CUDA(cudaFuncSetAttribute(stream_blk_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, XB_SMEM));
+    HVLA_CUDA(cudaFuncSetAttribute(stream_blk_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, XB_SMEM));
+  }
+  ProfScope ps(st, "layernorm");
+  const dim3 grid(cdiv(rows, 32)), block(256);
+  if (scale) launch_k(stream_blk_rows_kernel<true>, grid, block, (size_t)XB_SMEM, st, xb, y, stats, scale, bias, rows);
+  else launch_k(stream_blk_rows_kernel<false>, grid, block, (size_t)XB_SMEM, st, xb, y, stats, scale, bias, rows);
+  HVLA_LAUNCH_CHECK("stream_blk_rows");
+  return HVLA_OK;
+}
+
 template <typename TS, typename TO>
 inline int layernorm(cudaStream_t st, const LnP& p, int D) {
   if (p.nsplit > 0 && !(D == 768 && std::is_same<TS, float>::value && p.sS == 0 && p.ldx == 768 && p.ldy == 768 && p.post_div == 0.f))

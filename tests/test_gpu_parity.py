@@ -597,3 +597,43 @@ def test_params_swap_reuploads_device_blobs(params_p1, params_p0, torch_cuda):
     ref = HyperVLA.from_config(C.default_config(), precision="fp32", params=params_p0)
     w0_ref = ref.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"])[0].weights
     assert torch_cuda.equal(w0, w0_ref) and not torch_cuda.equal(w0, w1)
+
+
+@pytest.mark.parametrize("case", ["ref_c2_b3_t3", "ref_c5_b6_t2"])
+def test_layernorm_free_flow_matches_golden_and_the_classic_flow(models, golden, torch_cuda, case):
+    """Large batches run without LayerNorm kernels (blocked fp32 stream updated in place by the residual-GEMM epilogues, row
+    statistics folded into the q|k|v / fc1 epilogues; gemm_tc.cuh).  HVLA_FUSED_LN=1 forces that flow at fixture size: same bf16
+    bar against the reference-run fixtures, and close to the classic flow (LayerNorm kernels) on the same inputs."""
+    from hvla import synthetic as S
+    m = models["bf16"]
+    rt = m.runtime
+    ci, B, T = CASES[case]
+    g = golden[case]
+    out = {}
+    for flag in ("0", "1"):
+        os.environ["HVLA_FUSED_LN"] = flag
+        rt._graphs.clear()
+        try:
+            inp, bp, action, logit = run_case(m, ci, B, T)
+            hidden = rt.dino_forward(torch_cuda.from_numpy(inp["images"][:, 0]).to(rt.device)).float().cpu().numpy()
+        finally:
+            os.environ.pop("HVLA_FUSED_LN", None)
+            rt._graphs.clear()
+        out[flag] = (action, logit, hidden)
+        e_act = rel_err(action[..., :6], g["action"][..., :6])
+        print(f"[flow {'B' if flag == '1' else 'classic'} {case}] action {e_act:.2e} logit {rel_err(logit, g['logit']):.2e}")
+        assert e_act <= TOL["bf16"]
+    assert rel_err(out["1"][2], out["0"][2]) <= 2e-2                     # DINOv2 hidden states of the two flows
+    assert rel_err(out["1"][0][..., :6], out["0"][0][..., :6]) <= 2e-2
+    # a batch large enough to take flow B by itself (and with an M tail: 40 * 257 is not a multiple of 256)
+    img = torch_cuda.randint(0, 256, (40, 224, 224, 3), dtype=torch_cuda.uint8, device=rt.device)
+    h_auto = rt.dino_forward(img).float()
+    os.environ["HVLA_FUSED_LN"] = "0"
+    try:
+        h_classic = rt.dino_forward(img).float()
+    finally:
+        os.environ.pop("HVLA_FUSED_LN", None)
+    err = float((h_auto - h_classic).abs().max() / h_classic.abs().max())
+    print(f"[flow B vs classic, 40 images] hidden {err:.2e}")
+    assert err <= 2e-2 and not torch_cuda.equal(h_auto, h_classic)
+    assert torch_cuda.equal(h_auto, rt.dino_forward(img).float())           # run-to-run deterministic
