@@ -368,13 +368,16 @@ def run_ours(args):
     sampler.start()
 
     def timed_leg(step_fn, preheat_s: float):
-        """W warm-up steps, >= preheat_s seconds of back-to-back steps (reported as the sustained figure), then EXACTLY K
-        steps between a barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks.
+        """W warm-up steps, barrier + synchronize, then >= preheat_s seconds of back-to-back steps (reported as the `sustained`
+        figure) running STRAIGHT INTO the EXACTLY K timed steps -- no host synchronisation in between, so the timed steps see the
+        clocks of a long job (a sync gap of a millisecond lets the power controller step the clock back up: measured 3.00 vs 3.43 ms
+        per step) -- then barrier + synchronize.  CUDA events on the launching stream, max over ranks.
         -> (ms of the K steps, sustained dict, clocks during the K steps)"""
         for i in range(Wm):
             step_fn(i)
-        torch.cuda.synchronize()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        p0 = torch.cuda.Event(enable_timing=True)
+        marks = []                                             # (steps launched, event) every 8 steps: bounds the launch queue without draining it
         tp0 = time.perf_counter()
         n_pre = 0
         p0.record()
@@ -382,14 +385,13 @@ def run_ours(args):
             for i in range(8):
                 step_fn(n_pre + i)
             n_pre += 8
-            torch.cuda.current_stream().synchronize()          # bounds the launch queue; ~1 sync per 8 steps
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((n_pre, ev))
+            if len(marks) > 2:
+                marks[-3][1].synchronize()                     # at most ~16 steps in flight; the GPU never idles
             if time.perf_counter() - tp0 >= preheat_s:
                 break
-        p1.record()
-        torch.cuda.synchronize()
-        tp1 = time.perf_counter()
-        pre_ms = max_over_ranks(p0.elapsed_time(p1))
-        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
@@ -399,7 +401,8 @@ def run_ours(args):
         barrier()
         t1 = time.perf_counter()
         ms = max_over_ranks(e0.elapsed_time(e1))
-        sustained = {"seconds": pre_ms / 1e3, "steps": n_pre, "ms_per_step": pre_ms / n_pre, "clocks": sampler.window(tp0, tp1)}
+        pre_ms = max_over_ranks(p0.elapsed_time(marks[-1][1]))
+        sustained = {"seconds": pre_ms / 1e3, "steps": n_pre, "ms_per_step": pre_ms / n_pre, "clocks": sampler.window(tp0, t0)}
         return ms, sustained, sampler.window(t0, t1)
 
     # every rank owns its own shard of environments (different seeds per rank); one task per environment

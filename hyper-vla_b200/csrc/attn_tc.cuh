@@ -431,11 +431,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < 4; ++j) tmem_ld32(tm + 32 * j, r[j]);
       tmem_wait_ld();
-      float mx = -3.0e38f;
+      // four independent chains (the compiler emits 3-input FMNMX3): one chain of 64 dependent FMNMX3 is ~300 cycles of pure latency
+      float mq[4] = {-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[j][i]));
+        for (int i = 0; i < 32; i += 2) mq[(i >> 1) & 3] = fmaxf(mq[(i >> 1) & 3], fmaxf(__uint_as_float(r[j][i]), __uint_as_float(r[j][i + 1])));
+      float mx = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
       float sx = 0.f;
       if (hf == 1) {
         if (t == 0 || g == begin) mbar_wait(sx_full + 8 * s, (il >> 1) & 1);     // the helpers' key-256 column of this item

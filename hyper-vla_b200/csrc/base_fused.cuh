@@ -55,9 +55,20 @@ static_assert(2 * 256 * ELD * 2 <= OFF_K, "embedding chunks are double-buffered 
 static_assert(768 * PLD * 2 <= OFF_VEC - OFF_K, "projection kernel staging must fit in the K/V/W region");
 static_assert(SMEM <= 232448, "shared memory budget");
 
+// tanh-GELU of the patch rows (transformer.py:66) with tanh.approx.f32 (one MUFU op, 2^-11 relative: the result is rounded to bf16
+// right after): tanhf costs ~25 instructions, and this kernel is bound by instruction issue / dependent latency, not by any pipe.
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
   const float c = 0.7978845608028654f;
-  return 0.5f * x * (1.0f + tanhf(c * (x + 0.044715f * (x * x * x))));
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(c * fmaf(0.044715f * x, x * x, x)));
+  const float hx = 0.5f * x;
+  return fmaf(hx, th, hx);
+}
+// exp2 of a non-positive argument: one MUFU op (exp2f adds a range check and two scalings per call; 512 calls per thread and layer)
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // C[16 x NTL*8] += A[16 x KS*16] * W[k0.., n0..]   (W row-major bf16 in smem, row stride ld elements)
@@ -484,7 +495,7 @@ base_fused_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ weights
                 }
                 mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
                 mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-                const float c0 = exp2f((m0[u] - mx0) * LOG2E), c1 = exp2f((m1[u] - mx1) * LOG2E);
+                const float c0 = ex2_fast((m0[u] - mx0) * LOG2E), c1 = ex2_fast((m1[u] - mx1) * LOG2E);
                 m0[u] = mx0; m1[u] = mx1;
                 l0[u] *= c0; l1[u] *= c1;
                 oh[u][0][0] *= c0; oh[u][0][1] *= c0; oh[u][0][2] *= c1; oh[u][0][3] *= c1;
@@ -495,8 +506,8 @@ base_fused_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ weights
               for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                  s[u][nt][0] = exp2f(fmaf(s[u][nt][0], LOG2E, -ms0[u])); s[u][nt][1] = exp2f(fmaf(s[u][nt][1], LOG2E, -ms0[u]));
-                  s[u][nt][2] = exp2f(fmaf(s[u][nt][2], LOG2E, -ms1[u])); s[u][nt][3] = exp2f(fmaf(s[u][nt][3], LOG2E, -ms1[u]));
+                  s[u][nt][0] = ex2_fast(fmaf(s[u][nt][0], LOG2E, -ms0[u])); s[u][nt][1] = ex2_fast(fmaf(s[u][nt][1], LOG2E, -ms0[u]));
+                  s[u][nt][2] = ex2_fast(fmaf(s[u][nt][2], LOG2E, -ms1[u])); s[u][nt][3] = ex2_fast(fmaf(s[u][nt][3], LOG2E, -ms1[u]));
                   l0[u] += s[u][nt][0] + s[u][nt][1];
                   l1[u] += s[u][nt][2] + s[u][nt][3];
                 }

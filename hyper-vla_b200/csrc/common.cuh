@@ -71,7 +71,9 @@ struct DvecLayout {
                            // LayerNorm folded into the next linear (tensor-core path): folded biases and column sums of gamma*W
                            bqkv_f = ls2 + DD, cs_qkv = bqkv_f + 3 * DD, b1_f = cs_qkv + 3 * DD, cs_1 = b1_f + DF,
                            layer_size = cs_1 + DF;
-  static constexpr int64_t lnf_s = layers + DL * layer_size, lnf_b = lnf_s + DD, total = lnf_b + DD;
+  static constexpr int64_t lnf_s = layers + DL * layer_size, lnf_b = lnf_s + DD;
+  // position rows of the 256 patch tokens in the blocked stream layout, indexed by patch p: [p >> 5][col >> 2][p & 31][4]
+  static constexpr int64_t pos_blk = lnf_b + DD, total = pos_blk + (int64_t)NPATCH * DD;
 };
 
 // ---- DINO matrix blob (fp32 [K,N] or bf16 [N,K]; same element offsets) ------------------------

@@ -38,7 +38,7 @@ struct EpiP {
   void* out;           // bf16 [M,ldo] (EPI 0/1) | fp32 residual stream X (EPI 2/3)
   int ldo;
   const float* ls;     // [N] layer scale (EPI 2)
-  const float* pos;    // [257,768] position table (EPI 3)
+  const float* pos;    // [257,768] position table (EPI 3); EPI 7: the blocked table of the 256 patch rows (DvecLayout::pos_blk)
   float qscale;        // EPI 0: columns < qcols are multiplied by qscale (query pre-scaling)
   int qcols;
   int debug;           // experiment knob (hvla_gemm_bf16 only): 1 = handshake only, 2 = TMEM loads only, 4 = no global stores
@@ -452,13 +452,16 @@ __device__ __forceinline__ void epilogue_tile_blk(const EpiP& ep, const CUtensor
   const int srow = PATCH ? grow + m0 / 256 + 1 : grow;         // its stream row
   const bool ok = grow < ep.rows;
   float4* xp = reinterpret_cast<float4*>(ep.out) + xblk_f4(ok ? srow : 0, (n0 + half * 128) >> 2);   // + 32 per group of 4 columns
+  // what the update is added to: the stream itself, or (patch embedding) the position row of patch p = grow % 256 from a table in
+  // the same blocked layout -- the embedded tokens are WRITTEN, the stream needs no initialisation pass and no read
+  const float4* xin = PATCH ? reinterpret_cast<const float4*>(ep.pos) + xblk_f4(grow & 255, (n0 + half * 128) >> 2) : xp;
   // old values: prefetch distance of TWO 32-column chunks (an L2 / HBM round trip is longer than one chunk of epilogue work, and with
   // two epilogue warps per scheduler nothing else hides it): chunks 0 and 1 are requested here, chunk c+2 as soon as chunk c is consumed
   float4 xo[2][8];
 #pragma unroll
   for (int u = 0; u < 2; ++u)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) xo[u][j] = ok ? __ldcg(xp + 32 * (u * 8 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < 8; ++j) xo[u][j] = ok ? __ldcg(xin + 32 * (u * 8 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
   const uint32_t slab = sstage + (uint32_t)ew * 2048u;
   const uint32_t my = slab + (uint32_t)lane * 64u;
   const uint32_t sw = (uint32_t)((lane >> 1) & 3);          // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
@@ -488,7 +491,7 @@ __device__ __forceinline__ void epilogue_tile_blk(const EpiP& ep, const CUtensor
     }
     if (c < 2) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) xo[c & 1][j] = ok ? __ldcg(xp + 32 * ((c + 2) * 8 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < 8; ++j) xo[c & 1][j] = ok ? __ldcg(xin + 32 * ((c + 2) * 8 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (ok) {
 #pragma unroll

@@ -203,7 +203,7 @@ static int generate_impl(cudaStream_t st, const float* hn, const void* hn_lp, co
 
 // ---- DINOv2 (K4-K7) -----------------------------------------------------------------------------------
 static int dino_f32(cudaStream_t st, const float* dv, const float* dm, const uint8_t* images, int B, float* out_emb,
-                    uint8_t* ws, const Plan& pl) {
+                    uint8_t* ws, const Plan& pl, float* maps = nullptr) {
   typedef DvecLayout V;
   typedef DmatLayout Mx;
   const int M = B * DTOK;
@@ -234,6 +234,7 @@ static int dino_f32(cudaStream_t st, const float* dv, const float* dm, const uin
     ln.x = X; ln.ldx = DD; ln.y = Y; ln.ldy = DD; ln.scale = v + V::ln1_s; ln.bias = v + V::ln1_b; ln.rows = M; ln.rows_per_batch = 1;
     HVLA_TRY((layernorm<float, float>(st, ln, DD)));
     HVLA_TRY((gemm_simt<float, float, float, float>(st, gemm_params(Y, DD, m + Mx::wqkv, 3 * DD, v + V::bqkv, QKV, 3 * DD, M, 3 * DD, DD), 1)));
+    if (maps) HVLA_TRY((attn_probs<float, DHD>(st, QKV, maps + (int64_t)l * B * DH * DTOK * DTOK, DTOK, DH, B, 0, 0.125f)));
     AttnP ap; memset(&ap, 0, sizeof ap);
     ap.qkv = QKV; ap.out = ATT; ap.S = DTOK; ap.H = DH; ap.nbatch = B; ap.mask = 0;
     HVLA_TRY((attention_simt<float, float>(st, ap, DHD)));
@@ -282,25 +283,13 @@ __global__ void __launch_bounds__(256) dino_init_rows_kernel(const float* __rest
   reinterpret_cast<float4*>(X)[i] = v;
 }
 
-// the same for the BLOCKED stream (gemm_tc.cuh: xblk_f4): one thread per (row, group of 4 columns), stores are 512-byte runs
-__global__ void __launch_bounds__(256) dino_init_rows_blk_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ X,
-                                                                 int rows, int64_t total4) {
+// cls rows of the BLOCKED stream (gemm_tc.cuh: xblk_f4): X[b,0,:] = cls + pos[0]; the patch rows are written by the patch-embedding GEMM
+__global__ void __launch_bounds__(192) dino_cls_rows_blk_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ X) {
   pdl_trigger();
   pdl_wait();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total4) return;
-  const int r = (int)(i & 31), c4 = (int)((i >> 5) % (DD / 4));
-  const int row = (int)(i / (32 * (DD / 4))) * 32 + r;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (row < rows) {
-    const int tok = row % DTOK;
-    v = __ldg(reinterpret_cast<const float4*>(pos + (int64_t)tok * DD) + c4);
-    if (tok == 0) {
-      const float4 c = __ldg(reinterpret_cast<const float4*>(cls) + c4);
-      v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
-    }
-  }
-  reinterpret_cast<float4*>(X)[i] = v;
+  const int c4 = threadIdx.x;
+  const float4 c = __ldg(reinterpret_cast<const float4*>(cls) + c4), p = __ldg(reinterpret_cast<const float4*>(pos) + c4);
+  reinterpret_cast<float4*>(X)[tc::xblk_f4(blockIdx.x * DTOK, c4)] = make_float4(c.x + p.x, c.y + p.y, c.z + p.z, c.w + p.w);
 }
 
 // ---- large-batch flow ("flow B"): no LayerNorm kernels between the GEMMs (gemm_tc.cuh, "stream LayerNorm without a LayerNorm kernel")
@@ -326,13 +315,12 @@ static int dino_bf16_blk(cudaStream_t st, const float* dv, const bf16* dm, const
   }
   {
     ProfScope ps(st, "cls_rows");
-    const int64_t total4 = (int64_t)((M + 31) / 32) * 32 * (DD / 4);
-    launch_k(dino_init_rows_blk_kernel, dim3(cdiv(total4, 256)), dim3(256), 0, st, dv + V::cls, dv + V::pos, X, M, total4);
-    HVLA_LAUNCH_CHECK("dino_init_rows_blk");
+    launch_k(dino_cls_rows_blk_kernel, dim3(B), dim3(DD / 4), 0, st, dv + V::cls, dv + V::pos, X);
+    HVLA_LAUNCH_CHECK("dino_cls_rows_blk");
   }
   {
     tc::EpiP ep; memset(&ep, 0, sizeof ep);
-    ep.bias = dv + V::patch_b; ep.out = X; ep.ldo = DD; ep.rows = B * NPATCH;
+    ep.bias = dv + V::patch_b; ep.out = X; ep.ldo = DD; ep.rows = B * NPATCH; ep.pos = dv + V::pos_blk;
     HVLA_TRY(tc2::gemm_tc2(st, A0, dm + Mx::patch_w, B * NPATCH, DD, PATCH_KP, tc::EPI_PATCH_BLK, ep));
   }
   HVLA_TRY(stream_blk_rows(st, X, Y, ST, nullptr, nullptr, M));     // shadow + statistics of the embedded tokens
@@ -373,8 +361,8 @@ static bool use_flow_blk(int B) {
 }
 
 static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uint8_t* images, int B, bf16* out_emb,
-                     uint8_t* ws, const Plan& pl) {
-  if (use_flow_blk(B) && !env_flag("HVLA_DEBUG_SIMT_GEMM") && !env_flag("HVLA_DEBUG_SIMT_ATTN") && !env_flag("HVLA_ATTN_MMA") &&
+                     uint8_t* ws, const Plan& pl, float* maps = nullptr) {
+  if (!maps && use_flow_blk(B) && !env_flag("HVLA_DEBUG_SIMT_GEMM") && !env_flag("HVLA_DEBUG_SIMT_ATTN") && !env_flag("HVLA_ATTN_MMA") &&
       !env_flag("HVLA_GEMM_1CTA"))
     return dino_bf16_blk(st, dv, dm, images, B, out_emb, ws, pl);
   typedef DvecLayout V;
@@ -440,6 +428,7 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
       ep.bias = v + V::bqkv_f; ep.out = QKV; ep.ldo = 3 * DD;   // q / sqrt(64) is folded into the packed weights and bias
       HVLA_TRY(gemm(Y, m + Mx::wqkv, M, 3 * DD, DD, tc::EPI_BIAS_BF16, ep));
     }
+    if (maps) HVLA_TRY((attn_probs<bf16, DHD>(st, QKV, maps + (int64_t)l * B * DH * DTOK * DTOK, DTOK, DH, B, 0, 1.0f)));   // q is pre-scaled
     if (simt_attn) {
       AttnP ap; memset(&ap, 0, sizeof ap);
       ap.qkv = QKV; ap.out = ATT; ap.S = DTOK; ap.H = DH; ap.nbatch = B; ap.mask = 0; ap.prescaled = 1;
@@ -480,7 +469,7 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
 // TE: embedding storage type; TW: generated-weight storage type.  All math fp32.
 template <typename TE, typename TW>
 static int base_generic(cudaStream_t st, const TE* emb, const TW* weights, const int32_t* tidx, int B, int T,
-                        float* out_action, float* out_logit, uint8_t* ws, const Plan& pl) {
+                        float* out_action, float* out_logit, uint8_t* ws, const Plan& pl, float* maps = nullptr) {
   typedef GenLayout G;
   float* PT = reinterpret_cast<float*>(ws + pl.pt);
   float* X = reinterpret_cast<float*>(ws + pl.xb);
@@ -512,6 +501,7 @@ static int base_generic(cudaStream_t st, const TE* emb, const TW* weights, const
       g.sA = (int64_t)BTOK * BD; g.sW = sW; g.sBias = sW; g.sC = (int64_t)BTOK * 3 * BD; g.widx = tidx;
       HVLA_TRY((gemm_simt<float, TW, TW, float>(st, g, B)));
     }
+    if (maps) HVLA_TRY((attn_probs<float, BHD>(st, QKV, maps + (int64_t)l * B * BH * BTOK * BTOK, BTOK, BH, B, 1, 0.25f)));
     AttnP ap; memset(&ap, 0, sizeof ap);
     ap.qkv = QKV; ap.out = CB; ap.S = BTOK; ap.H = BH; ap.nbatch = B; ap.mask = 1;
     HVLA_TRY((attention_simt<float, float>(st, ap, BHD)));
@@ -557,7 +547,7 @@ static int check_common(int B, int T, int dtype, const void* ws, size_t ws_bytes
 }
 
 static int base_act_impl(cudaStream_t st, const void* emb, const void* weights, const int32_t* task_index, int B, int T,
-                         float* out_action, float* out_logit, uint8_t* ws, const Plan& pl, int dtype) {
+                         float* out_action, float* out_logit, uint8_t* ws, const Plan& pl, int dtype, float* maps = nullptr) {
   if (!task_index && !(T == B || T == 1)) return fail(HVLA_ERR_ARG, "task_index is NULL but T != B and T != 1");
   const int32_t* tidx = task_index;
   if (!tidx && T == 1 && B > 1) {   // shared weights: materialise an all-zero index (B == 1: identity already is)
@@ -568,10 +558,10 @@ static int base_act_impl(cudaStream_t st, const void* emb, const void* weights, 
   }
   if (dtype == HVLA_F32)
     return base_generic<float, float>(st, reinterpret_cast<const float*>(emb), reinterpret_cast<const float*>(weights), tidx, B,
-                                      T, out_action, out_logit, ws, pl);
-  if (env_flag("HVLA_DEBUG_GENERIC_BASE"))   // debugging aid: the same math through the generic CUDA-core kernels
+                                      T, out_action, out_logit, ws, pl, maps);
+  if (maps || env_flag("HVLA_DEBUG_GENERIC_BASE"))   // attention maps / debugging aid: the same math through the generic CUDA-core kernels
     return base_generic<bf16, bf16>(st, reinterpret_cast<const bf16*>(emb), reinterpret_cast<const bf16*>(weights), tidx, B, T,
-                                    out_action, out_logit, ws, pl);
+                                    out_action, out_logit, ws, pl, maps);
   return basefused::base_act_bf16(st, reinterpret_cast<const bf16*>(emb), reinterpret_cast<const bf16*>(weights), tidx, B,
                                   out_action, out_logit);
 }
@@ -644,7 +634,7 @@ int64_t hvla_layout_offset(const char* name) {
       FL(DvecLayout, bqkv_f) FL(DvecLayout, cs_qkv) FL(DvecLayout, b1_f) FL(DvecLayout, cs_1)
       return -1;
     }
-    F(DvecLayout, patch_b) F(DvecLayout, cls) F(DvecLayout, pos) F(DvecLayout, lnf_s) F(DvecLayout, lnf_b) F(DvecLayout, total)
+    F(DvecLayout, patch_b) F(DvecLayout, cls) F(DvecLayout, pos) F(DvecLayout, lnf_s) F(DvecLayout, lnf_b) F(DvecLayout, pos_blk) F(DvecLayout, total)
     return -1;
   }
   if (s.rfind("dmat.", 0) == 0) {
@@ -734,6 +724,24 @@ int hvla_act(hvla_stream_t stream, const float* dino_vec, const void* dino_mat, 
   void* emb = ws + pl.emb;
   HVLA_TRY(hvla_dino_forward(stream, dino_vec, dino_mat, images, B, emb, workspace, workspace_bytes, dtype));
   return base_act_impl(reinterpret_cast<cudaStream_t>(stream), emb, weights, task_index, B, T, out_action, out_logit, ws, pl, dtype);
+}
+
+int hvla_act_debug(hvla_stream_t stream, const float* dino_vec, const void* dino_mat, const uint8_t* images, const void* weights,
+                   const int32_t* task_index, int B, int T, float* out_action, float* out_logit, float* dino_maps, float* base_maps,
+                   void* workspace, size_t workspace_bytes, int dtype) {
+  if (!dino_vec || !dino_mat || !images || !weights || !out_action) return fail(HVLA_ERR_ARG, "hvla_act_debug: NULL argument");
+  if (T <= 0 && B > 0) return fail(HVLA_ERR_ARG, "hvla_act_debug: T must be >= 1");
+  HVLA_TRY(check_common(B, 0, dtype, workspace, workspace_bytes));
+  if (B == 0) return HVLA_OK;
+  const Plan pl = make_plan(B, 0, dtype);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  void* emb = ws + pl.emb;
+  if (dtype == HVLA_F32)
+    HVLA_TRY(dino_f32(st, dino_vec, reinterpret_cast<const float*>(dino_mat), images, B, reinterpret_cast<float*>(emb), ws, pl, dino_maps));
+  else
+    HVLA_TRY(dino_bf16(st, dino_vec, reinterpret_cast<const bf16*>(dino_mat), images, B, reinterpret_cast<bf16*>(emb), ws, pl, dino_maps));
+  return base_act_impl(st, emb, weights, task_index, B, T, out_action, out_logit, ws, pl, dtype, base_maps);
 }
 
 int hvla_act_host(hvla_stream_t stream, const float* dino_vec, const void* dino_mat, const uint8_t* images_host,

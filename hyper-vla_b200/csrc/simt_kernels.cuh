@@ -686,6 +686,61 @@ __global__ void __launch_bounds__(128) mix_head_kernel(const float* __restrict__
 // hypernetwork.py:205-217 as one skinny GEMM).  HBM-bound on W for small T.
 // Each thread owns 4 adjacent columns; tasks are processed 8 at a time from smem.
 // =============================================================================================
+// Debug aid (hvla_act_debug: the `intermediates` the reference sows, hypervla/model.py:135-137): attention probabilities of one layer,
+// softmax(q k^T * qscale) as fp32 [nbatch, H, S, S], from the layer's q|k|v buffer [nbatch*S, 3*H*HD].  One warp per (batch, head, query);
+// mask_mode 1 = base ViT (rows < S-1 do not see column S-1, base_vit.py:209-214).  Not on the hot path: no tuning.
+template <typename T, int HD>
+__global__ void __launch_bounds__(128) attn_probs_kernel(const T* __restrict__ qkv, float* __restrict__ probs, int S, int H, int nbatch,
+                                                         int mask_mode, float qscale) {
+  __shared__ float qs[4][HD];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 4 + w;              // (b * H + h) * S + i
+  if (row >= (int64_t)nbatch * H * S) return;
+  const int i = (int)(row % S), h = (int)((row / S) % H), b = (int)(row / ((int64_t)S * H));
+  const int ld = 3 * H * HD;
+  const T* q = qkv + ((int64_t)b * S + i) * ld + h * HD;
+  for (int d = lane; d < HD; d += 32) qs[w][d] = to_f(q[d]) * qscale;
+  __syncwarp();
+  float sc[9];                                                  // S <= 288
+  float mx = -3.4028234663852886e38f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int j = lane + 32 * t;
+    float a = -3.4028234663852886e38f;
+    if (j < S) {
+      const T* k = qkv + ((int64_t)b * S + j) * ld + H * HD + h * HD;
+      a = 0.f;
+      for (int d = 0; d < HD; ++d) a = fmaf(qs[w][d], to_f(k[d]), a);
+      if (mask_mode == 1 && i < S - 1 && j == S - 1) a = -3.4028234663852886e38f;      // where(mask, s, finfo.min)
+    }
+    sc[t] = a;
+    mx = fmaxf(mx, a);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    sc[t] = (lane + 32 * t < S) ? expf(sc[t] - mx) : 0.f;
+    sum += sc[t];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  float* out = probs + row * S;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+    if (lane + 32 * t < S) out[lane + 32 * t] = sc[t] * inv;
+}
+template <typename T, int HD>
+inline int attn_probs(cudaStream_t st, const T* qkv, float* probs, int S, int H, int nbatch, int mask_mode, float qscale) {
+  if (S > 288) return fail(HVLA_ERR_ARG, "attn_probs: S > 288");
+  const int64_t rows = (int64_t)nbatch * H * S;
+  attn_probs_kernel<T, HD><<<cdiv(rows, 4), 128, 0, st>>>(qkv, probs, S, H, nbatch, mask_mode, qscale);
+  HVLA_LAUNCH_CHECK("attn_probs");
+  return HVLA_OK;
+}
+
 constexpr int HEADS_TT = 8;
 template <typename TW, typename TO>
 __global__ void __launch_bounds__(256) heads_gemm_kernel(const float* __restrict__ E, const TW* __restrict__ W,

@@ -29,6 +29,7 @@ SIGNATURES = {
     "hvla_dino_forward": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_void_p, c_size_t, c_int]),
     "hvla_base_act": (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
     "hvla_act": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
+    "hvla_act_debug": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
     "hvla_act_host": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
     "hvla_gemm_bf16": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int]),
     "hvla_dino_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),

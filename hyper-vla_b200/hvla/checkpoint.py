@@ -8,9 +8,10 @@ Formats:
     ``jax._src.array._reconstruct_array(np_reconstruct, args, state, aval_state)``, which is resolved here to the
     underlying numpy array by a restricted unpickler (nothing else from the stream is ever imported).
   * ``<dir>/params_<step>.npz`` -- flat "a/b/c" keys; written by ``HyperVLA.save_pretrained`` and by
-    tools/convert_orbax_checkpoint.py, which must run where orbax/jax are installed (the reference's environment):
-    the orbax PyTree checkpoint (``CheckpointManager.restore``, hypervla/model.py:208-214) is a tensorstore/OCDBT
-    directory and is not parsed here.
+    tools/convert_orbax_checkpoint.py (runs where orbax/jax are installed: the reference's environment).
+  * ``<dir>/<step>/default/<leaf.path>/.zarray`` -- the orbax PyTree checkpoint itself (``CheckpointManager.restore``,
+    hypervla/model.py:208-214) in its zarr-per-leaf encoding, read without orbax by hvla/orbax_reader.py; the OCDBT encoding
+    (``manifest.ocdbt``) is detected and refused with a pointer to the converter.
 """
 from __future__ import annotations
 
@@ -101,6 +102,10 @@ def load_params(checkpoint_path: str, step: Optional[int] = None, ema=None) -> d
         npz = os.path.join(checkpoint_path, f"params_{step}.npz")
         if os.path.exists(npz):
             return load_flat_npz(npz)
+        from . import orbax_reader as OR
+        step_dir = os.path.join(checkpoint_path, str(step))
+        if OR.is_orbax_step(step_dir):             # the orbax checkpoint itself (zarr-per-leaf layout; OCDBT is refused with a hint)
+            return OR.read_orbax_pytree(step_dir)
     cand = sorted(n for n in os.listdir(checkpoint_path) if n.startswith("params") and n.endswith(".npz"))
     if cand and step is None:
         return load_flat_npz(os.path.join(checkpoint_path, cand[-1]))

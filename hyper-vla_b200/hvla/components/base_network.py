@@ -26,8 +26,9 @@ class BaseNetwork:
         return cls(**config["base_net_kwargs"], octo_kwargs=config.get("model", {}))
 
     def predict_action(self, variables, observation, task, timestep_pad_mask, rng=None, train=False,
-                       image_embeddings=None, *, model=None, task_index=None):
-        """base_network.py:170-183: squeeze the window axis, encode, head.  Returns (action, gripper_logits)."""
+                       image_embeddings=None, *, model=None, task_index=None, attention_maps=False):
+        """base_network.py:170-183: squeeze the window axis, encode, head.  Returns (action, gripper_logits), and with
+        ``attention_maps`` also the DINOv2 / base-encoder attention weights (the reference's sown intermediates)."""
         base_params = variables["params"]
         shape = tuple(observation.shape)
         if len(shape) == 5:
@@ -40,6 +41,11 @@ class BaseNetwork:
         except ImportError:  # pragma: no cover
             on_device = False
         rt = model.runtime
+        if attention_maps:
+            act, logit, dmaps, bmaps = rt.act_debug(observation, base_params.weights, task_index)
+            if on_device:
+                return act, logit, dmaps, bmaps
+            return act.cpu().numpy(), logit.cpu().numpy(), dmaps.cpu().numpy(), bmaps.cpu().numpy()
         if on_device:
             return rt.act_device(observation, base_params.weights, task_index)
         return rt.act_host(observation, base_params.weights, task_index)

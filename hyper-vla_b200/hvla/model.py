@@ -13,7 +13,8 @@ Differences a caller can see (all documented in INTEGRATION.md):
   * batching: the reference is batch-1 at inference (hypervla_interface.py:207, 249).  Here
     ``create_tasks`` accepts T tasks and ``sample_actions`` B images plus an optional
     ``task_index`` (B,) -- semantics of the vmapped validation path (scripts/train.py:546-583).
-  * ``intermediate_states`` holds ``{"gripper_logits": (B,4)}`` instead of sown attention maps.
+  * ``intermediate_states`` holds ``{"gripper_logits": (B,4)}``; the sown attention maps (38 MB per image) are produced only on
+    request: ``sample_actions(..., return_attention_maps=True)``.
 """
 from __future__ import annotations
 
@@ -212,18 +213,32 @@ class HyperVLA:
 
     # ---- act -------------------------------------------------------------------------------------------
     def sample_actions(self, images, instruction_dict=None, task=None, timestep_pad_mask=None, base_params=None,
-                       train: bool = False, rng=None, image_embeddings=None, *, task_index=None):
+                       train: bool = False, rng=None, image_embeddings=None, *, task_index=None, return_attention_maps: bool = False):
         """One control step (reference: model.py:85-137).  ``images`` (B, 1, 224, 224, 3) uint8 -- host
         array (numpy / pinned torch) or CUDA tensor.  Host in -> numpy out (includes the device->host read
         the caller performs at hypervla_interface.py:207); CUDA in -> CUDA tensors out, asynchronous.
-        Returns ``(action (B,4,7) float32, intermediate_states)``."""
+        Returns ``(action (B,4,7) float32, intermediate_states)``.
+
+        ``intermediate_states`` is ``{"gripper_logits": (B,4)}``; with ``return_attention_maps=True`` (a debugging call, off the
+        captured-graph path) it also carries the tree the reference sows (model.py:125-137, read by InferenceWrapper at
+        data/utils/hypervla_interface.py:208-217): ``["intermediates"]["encoder"]["DINO_attention_map"][0]`` = tuple of 12 arrays
+        (B,12,257,257) and ``[...]["Transformer_0"]["encoderblock_i"]["MultiHeadDotProductAttention_0"]["attention_weights"][0]``
+        = (B,4,257,257)."""
         if train:
             raise ValueError("hvla is an inference path: train=True is unsupported")
         if image_embeddings is not None:
             raise ValueError("image_embeddings are only used by the Siglip encoder, which is outside the supported config")
         if not isinstance(base_params, GeneratedBaseParams):
             raise TypeError("base_params must be the object returned by HyperVLA.create_tasks")
+        ti = task_index if task_index is not None else base_params.task_index
+        if return_attention_maps:
+            action, logits, dmaps, bmaps = self.base_net.apply({"params": base_params}, images, None, timestep_pad_mask, rng=rng, train=False,
+                                                               method=BaseNetwork.predict_action, model=self, task_index=ti,
+                                                               attention_maps=True)
+            enc = {"DINO_attention_map": (tuple(dmaps[l] for l in range(Cfg.DINO_LAYERS)),),
+                   "Transformer_0": {f"encoderblock_{i}": {"MultiHeadDotProductAttention_0": {"attention_weights": (bmaps[i],)}}
+                                     for i in range(Cfg.BASE_LAYERS)}}
+            return action, {"gripper_logits": logits, "intermediates": {"encoder": enc}}
         action, logits = self.base_net.apply({"params": base_params}, images, None, timestep_pad_mask, rng=rng, train=False,
-                                             method=BaseNetwork.predict_action, model=self,
-                                             task_index=task_index if task_index is not None else base_params.task_index)
+                                             method=BaseNetwork.predict_action, model=self, task_index=ti)
         return action, {"gripper_logits": logits}

@@ -287,6 +287,7 @@ def dino_vec_layout() -> Dict[str, Tuple[int, int]]:
             add(f"l{l}.{nm}", n)
     add("lnf_s", D)
     add("lnf_b", D)
+    add("pos_blk", C.N_PATCH * D)      # position rows of the patch tokens in the blocked stream layout (csrc/gemm_tc.cuh: xblk_f4)
     lay["__total__"] = (off, 0)
     return lay
 
@@ -353,7 +354,10 @@ def pack_dino_tree(t: dict, transposed: bool) -> Tuple[np.ndarray, np.ndarray]:
     emb = t["embeddings"]
     putv("patch_b", emb["patch_embeddings"]["projection"]["bias"])
     putv("cls", emb["cls_token"])
-    putv("pos", interpolate_pos_table(emb["position_embeddings"]))
+    pos = np.asarray(interpolate_pos_table(emb["position_embeddings"]), F32).reshape(C.DINO_TOKENS, D)
+    putv("pos", pos)
+    # rows 1..256 again, blocked like the fp32 residual stream of the large-batch flow: [p >> 5][col >> 2][p & 31][col & 3]
+    putv("pos_blk", pos[1:].reshape(C.N_PATCH // 32, 32, D // 4, 4).transpose(0, 2, 1, 3))
     wp = np.zeros((DINO_PATCH_K_PAD, D), F32)
     wp[:C.DINO_PATCH_K] = emb["patch_embeddings"]["projection"]["kernel"].reshape(C.DINO_PATCH_K, D)
     putm("patch_w", wp)

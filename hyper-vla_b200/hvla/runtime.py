@@ -258,6 +258,30 @@ class Runtime:
         torch.cuda.current_stream(self.device).synchronize()
         return act.numpy().copy(), logit.numpy().copy()
 
+    def act_debug(self, images, weights, task_index=None):
+        """One eager act step that also returns the attention weights the reference sows as ``intermediates``
+        (hvla_act_debug): -> (action (B,4,7), logit (B,4), dino_maps (12,B,12,257,257), base_maps (4,B,4,257,257)), CUDA
+        tensors.  Debugging call (38 MB of maps per image, base net on the generic kernels)."""
+        torch = _torch()
+        img = images if torch.is_tensor(images) else torch.from_numpy(np.ascontiguousarray(images))
+        img = img.to(self.device).contiguous()
+        B, T = int(img.shape[0]), int(weights.shape[0])
+        if tuple(img.shape[1:]) != (Cfg.IMAGE_SIZE, Cfg.IMAGE_SIZE, 3) or img.dtype != torch.uint8:
+            raise ValueError("Input image size must be 224x224 (uint8, NHWC)")
+        keep, tptr = self._tidx(task_index, B, T)
+        S = Cfg.DINO_TOKENS
+        act = torch.empty((B, Cfg.ACTION_HORIZON, Cfg.ACTION_DIM), dtype=torch.float32, device=self.device)
+        logit = torch.empty((B, Cfg.ACTION_HORIZON), dtype=torch.float32, device=self.device)
+        dmaps = torch.empty((Cfg.DINO_LAYERS, B, Cfg.DINO_HEADS, S, S), dtype=torch.float32, device=self.device)
+        bmaps = torch.empty((Cfg.BASE_LAYERS, B, Cfg.BASE_HEADS, S, S), dtype=torch.float32, device=self.device)
+        if B:
+            with self._on_device():
+                ws, ws_bytes = self.workspace(B, 0)
+                N.check(self.lib.hvla_act_debug(self.stream(), self.dino_vec.data_ptr(), self.dino_mat.data_ptr(), img.data_ptr(),
+                                                weights.data_ptr(), tptr, B, T, act.data_ptr(), logit.data_ptr(), dmaps.data_ptr(),
+                                                bmaps.data_ptr(), ws, ws_bytes, self.dtype), "hvla_act_debug")
+        return act, logit, dmaps, bmaps
+
     def profile(self, fn, repeats: int = 1) -> dict:
         """Run ``fn`` with per-kernel-class event timing on; -> {class: (launches, total_ms)} per repeat."""
         self.lib.hvla_profile_enable(1)

@@ -112,6 +112,15 @@ int hvla_act(hvla_stream_t stream, const float* dino_vec, const void* dino_mat, 
              const void* weights, const int32_t* task_index, int B, int T,
              float* out_action, float* out_logit, void* workspace, size_t workspace_bytes, int dtype);
 
+/* ---- act with the `intermediates` the reference sows (hypervla/model.py:125-137 mutable=['intermediates']; read by
+ * InferenceWrapper.save_attention_map, data/utils/hypervla_interface.py:208-217): the softmax attention weights of
+ * every DINOv2 layer, dino_maps [12,B,12,257,257] f32 (FlaxDinov2 `outputs.attentions`, base_vit.py:118), and of every base
+ * encoder block, base_maps [4,B,4,257,257] f32 (transformer.py:172-191); either may be NULL.  A debugging call: the base net
+ * runs on the generic CUDA-core kernels and every map is an extra pass over q|k|v (38 MB + 1 MB of maps per image). */
+int hvla_act_debug(hvla_stream_t stream, const float* dino_vec, const void* dino_mat, const uint8_t* images,
+                   const void* weights, const int32_t* task_index, int B, int T, float* out_action, float* out_logit,
+                   float* dino_maps, float* base_maps, void* workspace, size_t workspace_bytes, int dtype);
+
 /* ---- same, HOST image/action buffers (pinned or pageable): H2D copy, act, D2H copy on
  * `stream`, then ONE cudaStreamSynchronize.  The call InferenceWrapper.step makes
  * (data/utils/hypervla_interface.py:197-207: model call followed by the host read). */

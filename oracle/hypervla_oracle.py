@@ -79,6 +79,25 @@ def softmax(x):
     return e / e.sum(axis=-1, keepdims=True)
 
 
+_ATTENTION_SINK = None      # list collecting every attention-weight tensor (N,H,S,S) in call order, see capture_attention()
+
+
+class capture_attention:
+    """``with capture_attention() as maps: sample_actions(...)`` -> maps = the softmax attention weights of every attention call
+    in order: the 12 DINOv2 layers (what FlaxDinov2 returns as ``outputs.attentions``, sown at base_vit.py:118), then the 4 base
+    encoder blocks (``sow_weights`` / ``attention_map``, transformer.py:172-191) -- the reference's ``intermediates``."""
+
+    def __enter__(self):
+        global _ATTENTION_SINK
+        _ATTENTION_SINK = []
+        return _ATTENTION_SINK
+
+    def __exit__(self, *exc):
+        global _ATTENTION_SINK
+        _ATTENTION_SINK = None
+        return False
+
+
 def _attend(q, k, v, mask):
     """q,k,v (N,S,H,e) -> (N,S,H*e): q/sqrt(e), masked softmax(qk^T) v (batched matmuls, BLAS)."""
     dt = q.dtype
@@ -87,6 +106,8 @@ def _attend(q, k, v, mask):
     if mask is not None:
         s = np.where(mask, s, np.finfo(dt).min)
     w = softmax(s)
+    if _ATTENTION_SINK is not None:
+        _ATTENTION_SINK.append(w.copy())
     o = np.matmul(w, v.transpose(0, 2, 1, 3))                                 # (N,H,S,e)
     N, H, S, e = o.shape
     return o.transpose(0, 2, 1, 3).reshape(N, S, H * e)

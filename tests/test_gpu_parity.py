@@ -225,8 +225,9 @@ def test_fused_base_kernel_matches_generic_path_and_oracle(models, params_p1, to
 def test_grouped_equals_per_sample_and_is_deterministic(models, torch_cuda):
     """Full-size property test (B=64): a batch with mixed task weights gives the same actions as evaluating envs with
     their own task's weights in other batch compositions, and the step is deterministic.  Bit-identical among batches
-    that use the same GEMM K-split configuration (sub-batches of 16 here); a batch of ONE env splits K of the residual
-    GEMMs over more CTAs (ordered, deterministic), so it agrees to fp32 summation-order noise instead."""
+    that take the same DINOv2 flow (sub-batches of 32 here: like 64 envs they run the LayerNorm-free large-batch flow).  Smaller
+    batches take the classic flow (LayerNorm kernels; a batch of ONE env also splits K of the residual GEMMs over more CTAs,
+    ordered and deterministic): the two flows round at different points, so those agree to bf16 noise, not bit for bit."""
     from hvla import synthetic as S
     m = models["bf16"]
     rt = m.runtime
@@ -237,14 +238,19 @@ def test_grouped_equals_per_sample_and_is_deterministic(models, torch_cuda):
     a1, i1 = m.sample_actions(inp["images"], None, tasks, None, bp, task_index=ti)
     a2, i2 = m.sample_actions(inp["images"], None, tasks, None, bp, task_index=ti)
     assert np.array_equal(a1, a2) and np.array_equal(i1["gripper_logits"], i2["gripper_logits"])
+    for b0 in (0, 32):
+        ab, _ = m.sample_actions(inp["images"][b0:b0 + 32], None, tasks, None, bp, task_index=ti[b0:b0 + 32])
+        assert np.array_equal(ab, a1[b0:b0 + 32]), b0
     for b0 in (0, 48):
         ab, _ = m.sample_actions(inp["images"][b0:b0 + 16], None, tasks, None, bp, task_index=ti[b0:b0 + 16])
-        assert np.array_equal(ab, a1[b0:b0 + 16]), b0
+        ab2, _ = m.sample_actions(inp["images"][b0:b0 + 16], None, tasks, None, bp, task_index=ti[b0:b0 + 16])
+        assert np.array_equal(ab, ab2), b0
+        assert rel_err(ab[..., :6], a1[b0:b0 + 16][..., :6]) < 2e-2, b0
     for b in (0, 17, 63):
         ab, ib = m.sample_actions(inp["images"][b:b + 1], None, tasks, None, bp, task_index=ti[b:b + 1])
         ab2, _ = m.sample_actions(inp["images"][b:b + 1], None, tasks, None, bp, task_index=ti[b:b + 1])
         assert np.array_equal(ab, ab2), b                                    # deterministic at batch 1 too
-        assert rel_err(ab[0][:, :6], a1[b][:, :6]) < 5e-3, b
+        assert rel_err(ab[0][:, :6], a1[b][:, :6]) < 2e-2, b
         sure = np.abs(i1["gripper_logits"][b]) > 2e-2 * np.abs(i1["gripper_logits"]).max()
         assert np.array_equal(ab[0][:, 6][sure], a1[b][:, 6][sure]), b
     assert np.isfinite(a1).all() and np.abs(a1[..., :6]).max() <= 5.0
@@ -637,3 +643,114 @@ def test_layernorm_free_flow_matches_golden_and_the_classic_flow(models, golden,
     print(f"[flow B vs classic, 40 images] hidden {err:.2e}")
     assert err <= 2e-2 and not torch_cuda.equal(h_auto, h_classic)
     assert torch_cuda.equal(h_auto, rt.dino_forward(img).float())           # run-to-run deterministic
+
+
+def test_bf16_gripper_bits_measured_at_the_north_star_margin(models, torch_cuda):
+    """north_star: gripper bits identical wherever the reference logit margin exceeds 1e-3.  The fp32 path is asserted at exactly
+    that margin (here on 80 (image, task) pairs, and on every golden case above).  The bf16 path cannot promise it: its logits
+    carry the bf16 error of twelve DINOv2 blocks (about 1e-2 of max|logit|), so a reference logit closer to zero than that may
+    land on the other side.  This test MEASURES it -- flips at the 1e-3 margin out of all compared bits, printed -- and asserts
+    what does hold: the logit error stays inside the stated bf16 bar (2e-2 of max|logit|) and no bit flips outside that band."""
+    from hvla import synthetic as S
+    small = S.make_inputs(5, 8, 10)
+    small["initial_state"] = {"patch_embeddings": small["initial_state"]["patch_embeddings"][:, :1]}
+    img_id, task_id = np.repeat(np.arange(8), 10), np.tile(np.arange(10), 8).astype(np.int32)
+    out = {}
+    for prec in ("fp32", "bf16"):
+        m = models[prec]
+        bp, tasks, _ = m.create_tasks(instruction_dict=small["instruction_dict"], initial_state=small["initial_state"])
+        act, inter = m.sample_actions(small["images"][img_id], None, tasks, None, bp, task_index=task_id)
+        out[prec] = (act[..., 6], inter["gripper_logits"])
+    bits32, ref = out["fp32"]
+    bits16, lg = out["bf16"]
+    assert np.array_equal(bits32, (ref >= 0).astype(np.float32))
+    err = np.abs(lg - ref)
+    scale = np.abs(ref).max()
+    sure = np.abs(ref) > 1e-3
+    flipped = sure & (bits16 != bits32)
+    worst = float(np.abs(ref[flipped]).max()) if flipped.any() else 0.0
+    print(f"[bf16 gripper bits] {int(flipped.sum())} of {int(sure.sum())} bits with |ref logit| > 1e-3 flipped; max|ref logit| among the flipped "
+          f"{worst:.3e}; bf16 logit error max {err.max():.3e} = {err.max() / scale:.2e} of max|logit| {scale:.3f}; "
+          f"{int((np.abs(ref) <= err.max()).sum())} reference logits lie inside the error band")
+    assert err.max() <= 2e-2 * scale
+    assert not (flipped & (np.abs(ref) > 2e-2 * scale)).any()
+
+
+def test_config4_regenerate_every_task_switch_at_256_envs(models, params_p1, torch_cuda):
+    """BASELINE.json configs[3]: 256 envs with shared (fine-tuned) DINOv2 leaves and hypernet regeneration at every task switch, at
+    full size: generate 256 weight sets, act, switch EVERY env to another task in place (task-switch scheduler), act again.
+    Size-independent properties (copies of an (image, task) pair are bit-identical; the in-place regeneration equals a fresh
+    generate) plus oracle spot checks before and after the switch."""
+    from hvla import metadata as M, params as P, synthetic as S
+    from oracle import hypervla_oracle as O
+    m = models["bf16"]
+    rt = m.runtime
+    small = S.make_inputs(4, 8, 10)
+    lang = small["instruction_dict"]["language_instruction"]
+    cls = small["initial_state"]["patch_embeddings"][:, :1]
+    B = 256
+    i_of = np.arange(B) % 8
+    gen, _ = O.generate(params_p1, lang["token_embedding"], lang["attention_mask"], cls[:, 0], generated_paths=M.generated_leaves_canonical())
+    dino = P.dino_tree_from_params(params_p1)
+    bp = None
+    for rnd, shift in enumerate((0, 3)):
+        t_of = (np.arange(B) + shift) % 10
+        instr = {"language_instruction": {k: np.ascontiguousarray(v[t_of]) for k, v in lang.items()}}
+        state = {"patch_embeddings": np.ascontiguousarray(cls[t_of])}
+        if bp is None:
+            bp, tasks, _ = m.create_tasks(instruction_dict=instr, initial_state=state)
+            m.sample_actions(small["images"][i_of], None, tasks, None, bp)
+            caps = rt.graph_captures
+        else:
+            bp, tasks, _ = m.create_tasks(instruction_dict=instr, initial_state=state, task_ids=np.arange(B), base_params=bp)
+        act, inter = m.sample_actions(small["images"][i_of], None, tasks, None, bp)
+        assert rt.graph_captures == caps
+        fresh, _, _ = m.create_tasks(instruction_dict=instr, initial_state=state)
+        assert torch_cuda.equal(fresh.weights[:, :M.N_GENERATED], bp.weights[:, :M.N_GENERATED])
+        idx40 = np.arange(B) % 40
+        assert np.array_equal(act, act[idx40]) and np.array_equal(inter["gripper_logits"], inter["gripper_logits"][idx40])
+        sel = np.array([0, 101, 255])
+        ref_act, ref_logit = O.sample_actions(dino, O.to_tree({p: v[t_of[sel]] for p, v in gen.items()}), small["images"][i_of[sel], 0])
+        e = rel_err(act[sel][..., :6], ref_act[..., :6])
+        print(f"[config 4, round {rnd}] action error vs oracle on envs {sel.tolist()}: {e:.2e}")
+        assert e <= TOL["bf16"]
+        sure = np.abs(ref_logit) > 2e-2 * np.abs(ref_logit).max()
+        assert np.array_equal(act[sel][..., 6][sure], ref_act[..., 6][sure])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_attention_map_intermediates_on_request(models, params_p1, torch_cuda, prec):
+    """The reference sows 12 DINOv2 + 4 base attention maps per step (hypervla/model.py:125-137) that only save_attention_map reads
+    (data/utils/hypervla_interface.py:208-217).  Here they cost nothing unless asked for; with return_attention_maps=True the
+    same tree comes back and matches the oracle's attention weights, and the actions equal the normal path's."""
+    from hvla import metadata as M, params as P, synthetic as S
+    from oracle import hypervla_oracle as O
+    m = models[prec]
+    inp = S.make_inputs(6, 2, 2)
+    lang = inp["instruction_dict"]["language_instruction"]
+    bp, tasks, _ = m.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"])
+    act0, inter0 = m.sample_actions(inp["images"], None, tasks, None, bp)
+    assert set(inter0) == {"gripper_logits"}
+    act, inter = m.sample_actions(inp["images"], None, tasks, None, bp, return_attention_maps=True)
+    assert rel_err(act[..., :6], act0[..., :6]) <= (1e-5 if prec == "fp32" else 2e-2)
+    gen, _ = O.generate(params_p1, lang["token_embedding"], lang["attention_mask"], inp["initial_state"]["patch_embeddings"][:, 0],
+                        generated_paths=M.generated_leaves_canonical())
+    with O.capture_attention() as maps:
+        O.sample_actions(P.dino_tree_from_params(params_p1), O.to_tree(gen), inp["images"][:, 0])
+    assert len(maps) == 16
+    enc = inter["intermediates"]["encoder"]
+    dino = enc["DINO_attention_map"][0]
+    assert len(dino) == 12 and dino[0].shape == (2, 12, 257, 257)
+    # probabilities in [0, 1], absolute error: fp32 at the fp32 bar; bf16 q/k logits carry ~1e-2 relative error which a peaked
+    # softmax turns into up to a few 1e-2 of probability mass in the last DINOv2 layers (measured 2.2e-2)
+    tol = 1e-5 if prec == "fp32" else 5e-2
+    e_d = max(float(np.abs(dino[l] - maps[l]).max()) for l in range(12))
+    base = [enc["Transformer_0"][f"encoderblock_{i}"]["MultiHeadDotProductAttention_0"]["attention_weights"][0] for i in range(4)]
+    e_b = max(float(np.abs(base[i] - maps[12 + i]).max()) for i in range(4))
+    print(f"[{prec}] attention maps: DINOv2 max abs err {e_d:.2e}, base {e_b:.2e}")
+    assert e_d <= tol and e_b <= tol
+    assert np.allclose(dino[3].sum(-1), 1.0, atol=1e-4) and float(np.abs(base[2][:, :, :-1, -1]).max()) == 0.0     # patches never see the action token
+    # what InferenceWrapper.save_attention_map slices out of it (hypervla_interface.py:210-217)
+    dmap = np.stack([x[0, :, 0, 1:] for x in dino])
+    hmap = np.stack([base[i][0, :, -1, :-1] for i in range(4)])
+    assert dmap.shape == (12, 12, 256) and hmap.shape == (4, 4, 256)

@@ -5,7 +5,9 @@
 
 Restores the orbax PyTree checkpoint the way HyperVLA.load_pretrained does (hypervla/model.py:208-214, without the
 shape template) and writes <checkpoint_dir>/params_<step>.npz with flat "a/b/c" keys, which
-hvla.model.HyperVLA.load_pretrained reads.  UNTESTED here: orbax is not installable in the build container."""
+hvla.model.HyperVLA.load_pretrained reads.  Needed only for OCDBT checkpoints (manifest.ocdbt): the zarr-per-leaf layout is read
+directly by hvla/orbax_reader.py.  orbax is not installable in the build container; tests/test_checkpoint_ingest.py runs this
+script against stand-ins for the two library calls it makes."""
 import sys
 
 import numpy as np
