@@ -183,7 +183,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=None,
                     help="environments per GPU (default: 64 on one GPU = configs[1]; 1024/N on N GPUs = configs[2])")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp32x3"],
+                    help="bf16 = tensor-core path (headline); fp32 = exact CUDA-core path; fp32x3 = fp32-class accuracy on the tensor cores")
     ap.add_argument("--preheat-s", type=float, default=2.0, help="seconds of back-to-back steps before every timed leg (sustained regime)")
     ap.add_argument("--base-envs", type=int, default=None, help="environments per GPU of the base-net-only leg (default 1024/N)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="images in the bounded CPU-baseline sample")
@@ -622,7 +623,7 @@ def run_ours(args):
             "metric": "actions_per_sec", "value": value, "unit": "actions/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak" if (world == 1 or B * world != TARGET_ENVS) else "strong", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "dtype": {"bf16": "bf16", "fp32": "f32", "fp32x3": "bf16x3 (split operands, fp32-class)"}[args.precision], "data": "synthetic",
             "config": dict(workload_config(B, world),
                            regime=f"K timed steps directly after {sustained['seconds']:.1f} s of back-to-back steps (sustained clocks); see sustained / clocks",
                            l2=f"inputs+activations exceed L2: rotating {n_sets} input sets ({n_sets * B * 150528 / 1e6:.0f} MB) and "

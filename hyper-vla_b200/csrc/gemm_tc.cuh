@@ -26,11 +26,16 @@ enum Epi {
   // LayerNorm-free flow over the BLOCKED fp32 stream (see "stream LayerNorm without a LayerNorm kernel"):
   EPI_BIAS_BF16_FOLD = 4, EPI_BIAS_GELU_BF16_FOLD = 5,   // consumers: A = un-normalised bf16 shadow, row statistics applied in the epilogue
   EPI_RESIDUAL_BLK = 6,                                  // producer: x += ls*(acc+bias) in place + bf16 shadow + row statistics
-  EPI_PATCH_BLK = 7                                      // patch embedding: x += acc+bias at the shifted stream rows (no shadow)
+  EPI_PATCH_BLK = 7,                                     // patch embedding: x += acc+bias at the shifted stream rows (no shadow)
+  // split-operand ("bf16x3") flow, fp32-class accuracy on the tensor cores (dino_x3.cuh): the fp32 result v = acc + bias
+  // (EPI_SPLIT_GELU_BF16: exact erf-GELU of it) leaves as TWO bf16 numbers, hi = bf16(v) and lo = bf16(v - hi), written as the
+  // planes [hi | lo] or [hi | lo | hi] of the next GEMM's K-concatenated A operand (plane p at column p * plane_stride)
+  EPI_SPLIT_BF16 = 8, EPI_SPLIT_GELU_BF16 = 9
 };
+constexpr bool epi_split(int e) { return e == EPI_SPLIT_BF16 || e == EPI_SPLIT_GELU_BF16; }
 constexpr bool epi_fold(int e) { return e == EPI_BIAS_BF16_FOLD || e == EPI_BIAS_GELU_BF16_FOLD; }
 constexpr bool epi_gelu(int e) { return e == EPI_BIAS_GELU_BF16 || e == EPI_BIAS_GELU_BF16_FOLD; }
-constexpr bool epi_bf16_out(int e) { return e == EPI_BIAS_BF16 || e == EPI_BIAS_GELU_BF16 || epi_fold(e); }
+constexpr bool epi_bf16_out(int e) { return e == EPI_BIAS_BF16 || e == EPI_BIAS_GELU_BF16 || epi_fold(e) || epi_split(e); }
 constexpr bool epi_blk(int e) { return e == EPI_RESIDUAL_BLK || e == EPI_PATCH_BLK; }
 
 struct EpiP {
@@ -52,6 +57,8 @@ struct EpiP {
   const float* cs;     //                   [N] column sums of the (gamma-folded, bf16-rounded) weight; bias = folded bias
   bf16* shadow;        // EPI 6 producer: bf16 copy of the updated stream [M,768]; `out` is the BLOCKED fp32 stream
   float* stats_out;    //                 [M][6][2] partial row statistics of the updated stream
+  int plane_stride;    // EPI 8/9: columns between the hi / lo / hi planes of the output row (the next GEMM's K)
+  int nplanes;         //          2 = [hi | lo], 3 = [hi | lo | hi]
 };
 
 // Blocked fp32 residual stream: element (row, col) of the logical [M,768] stream lives at float index
@@ -382,9 +389,51 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
           const float2 g = gelu_erf_tanhfit2(make_float2(v[j], v[j + 1]));
           v[j] = g.x; v[j + 1] = g.y;
         }
-      } else if (col < ep.qcols) {
+      } else if (!epi_split(EPI) && col < ep.qcols) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= ep.qscale;
+      }
+      if (EPI == EPI_SPLIT_GELU_BF16) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);         // exact erf-GELU: this flow is the fp32-class one
+      }
+      if (epi_split(EPI)) {                                         // hi plane(s), then the lo plane through the same slab
+        float lo[32];
+        uint32_t hp[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j], v[j + 1]);
+          hp[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+          lo[j] = v[j] - __low2float(h2);
+          lo[j + 1] = v[j + 1] - __high2float(h2);
+        }
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my0 + ((((uint32_t)j) ^ sw) << 4)), "r"(hp[4 * j]), "r"(hp[4 * j + 1]),
+                       "r"(hp[4 * j + 2]), "r"(hp[4 * j + 3]) : "memory");
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tmO, slab0, col, row0);
+          if (ep.nplanes == 3) tma_store_2d(tmO, slab0, col + 2 * ep.plane_stride, row0);
+          bulk_commit();
+          bulk_wait_read<0>();
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my0 + ((((uint32_t)j) ^ sw) << 4)), "r"(pack_bf16(lo[8 * j], lo[8 * j + 1])),
+                       "r"(pack_bf16(lo[8 * j + 2], lo[8 * j + 3])), "r"(pack_bf16(lo[8 * j + 4], lo[8 * j + 5])),
+                       "r"(pack_bf16(lo[8 * j + 6], lo[8 * j + 7])) : "memory");
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tmO, slab0, col + ep.plane_stride, row0);
+          bulk_commit();
+        }
+        continue;
       }
       const uint32_t slab = slab0 + (uint32_t)((c % NSLAB) * 2048), my = my0 + (uint32_t)((c % NSLAB) * 2048);
       if (lane == 0) bulk_wait_read<NSLAB - 1>();       // the slab's previous TMA store has finished reading it

@@ -245,6 +245,8 @@ inline int gemm_tc2(cudaStream_t st, const void* A, const void* Wt, int M, int N
     memset(&mo, 0, sizeof mo);
   } else {
     if (epi_fold(epi) && (!ep.stats || !ep.cs)) return fail(HVLA_ERR_ARG, "gemm_tc2: folded-LayerNorm epilogue needs stats and cs");
+    if (epi_split(epi) && !((ep.nplanes == 2 || ep.nplanes == 3) && ep.plane_stride >= N && ep.ldo >= ep.nplanes * ep.plane_stride))
+      return fail(HVLA_ERR_ARG, "gemm_tc2: split epilogue needs nplanes in {2,3}, plane_stride >= N and ldo >= nplanes * plane_stride");
     HVLA_TRY(make_out_map_for(&mo, epi, ep, M));
   }
   switch (epi) {
@@ -252,6 +254,8 @@ inline int gemm_tc2(cudaStream_t st, const void* A, const void* Wt, int M, int N
     case EPI_BIAS_GELU_BF16_FOLD: return launch_one2<EPI_BIAS_GELU_BF16_FOLD>(st, ma, mb, mo, ep, M, N, K);
     case EPI_RESIDUAL_BLK: return launch_one2<EPI_RESIDUAL_BLK>(st, ma, mb, mo, ep, M, N, K);
     case EPI_PATCH_BLK: return launch_one2<EPI_PATCH_BLK>(st, ma, mb, mo, ep, M, N, K);
+    case EPI_SPLIT_BF16: return launch_one2<EPI_SPLIT_BF16>(st, ma, mb, mo, ep, M, N, K);
+    case EPI_SPLIT_GELU_BF16: return launch_one2<EPI_SPLIT_GELU_BF16>(st, ma, mb, mo, ep, M, N, K);
     case EPI_BIAS_BF16: return launch_one2<EPI_BIAS_BF16>(st, ma, mb, mo, ep, M, N, K);
     case EPI_BIAS_GELU_BF16: return launch_one2<EPI_BIAS_GELU_BF16>(st, ma, mb, mo, ep, M, N, K);
     case EPI_RESIDUAL_F32: return launch_one2<EPI_RESIDUAL_F32>(st, ma, mb, mo, ep, M, N, K);

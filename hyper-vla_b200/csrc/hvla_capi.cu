@@ -12,6 +12,7 @@
 #include "postprocess.cuh"
 #include "preprocess.cuh"
 #include "t5_embed.cuh"
+#include "dino_x3.cuh"
 
 #include <stdlib.h>
 #include <type_traits>
@@ -35,6 +36,8 @@ struct Plan {
   size_t pt, xb, yb, qkvb, cb, hb;
   // host staging (hvla_act_host)
   size_t img, act, logit, tidx;
+  // split-operand flow (HVLA_BF16X3, dino_x3.cuh): A' of the 768-wide inputs, [hi | lo] of q|k|v, A' of the MLP hidden layer
+  size_t a3, qkv2, a3l;
   size_t total;
 };
 
@@ -74,6 +77,10 @@ static Plan make_plan(int B, int T, int dtype) {
   p.act = take(Bb * AH * AD * 4);
   p.logit = take(Bb * AH * 4);
   p.tidx = take(Bb * 4);
+  const bool x3f = dtype == HVLA_BF16X3;
+  p.a3 = take(x3f ? M * 3 * DD * 2 : 0);
+  p.qkv2 = take(x3f ? M * 2 * 3 * DD * 2 : 0);
+  p.a3l = take(x3f ? M * 3 * DF * 2 : 0);
   p.total = off;
   return p;
 }
@@ -538,7 +545,7 @@ __global__ void fill_index_kernel(int* idx, int B, int identity) {
 }
 
 static int check_common(int B, int T, int dtype, const void* ws, size_t ws_bytes) {
-  if (dtype != HVLA_F32 && dtype != HVLA_BF16) return fail(HVLA_ERR_ARG, "dtype must be HVLA_F32 or HVLA_BF16");
+  if (dtype != HVLA_F32 && dtype != HVLA_BF16 && dtype != HVLA_BF16X3) return fail(HVLA_ERR_ARG, "dtype must be HVLA_F32, HVLA_BF16 or HVLA_BF16X3");
   if (B < 0 || T < 0) return fail(HVLA_ERR_ARG, "negative batch");
   if (!ws) return fail(HVLA_ERR_WORKSPACE, "workspace is NULL");
   if (ws_bytes < make_plan(B, T, dtype).total) return fail(HVLA_ERR_WORKSPACE, "workspace too small (see hvla_workspace_bytes)");
@@ -556,7 +563,7 @@ static int base_act_impl(cudaStream_t st, const void* emb, const void* weights, 
     HVLA_LAUNCH_CHECK("fill_index");
     tidx = z;
   }
-  if (dtype == HVLA_F32)
+  if (dtype == HVLA_F32 || dtype == HVLA_BF16X3)        // fp32 embeddings and generated weights: the exact CUDA-core base net
     return base_generic<float, float>(st, reinterpret_cast<const float*>(emb), reinterpret_cast<const float*>(weights), tidx, B,
                                       T, out_action, out_logit, ws, pl, maps);
   if (maps || env_flag("HVLA_DEBUG_GENERIC_BASE"))   // attention maps / debugging aid: the same math through the generic CUDA-core kernels
@@ -664,7 +671,7 @@ int hvla_generate(hvla_stream_t stream, const float* hn_blob, const void* hn_blo
   const Plan pl = make_plan(0, T, dtype);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  if (dtype == HVLA_F32)
+  if (dtype != HVLA_BF16)      // HVLA_F32 and HVLA_BF16X3: fp32 generated weights from the fp32 path
     return generate_impl<float>(st, hn_blob, nullptr, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, out_weights, out_ctx, ws, pl);
   return generate_impl<bf16>(st, hn_blob, hn_blob_f16, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, out_weights, out_ctx, ws, pl);
 }
@@ -681,7 +688,7 @@ int hvla_generate_rows(hvla_stream_t stream, const float* hn_blob, const void* h
   const Plan pl = make_plan(0, T, dtype);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  if (dtype == HVLA_F32)
+  if (dtype != HVLA_BF16)
     return generate_impl<float>(st, hn_blob, nullptr, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, weights, ctx, ws, pl,
                                 row_index, T_max);
   return generate_impl<bf16>(st, hn_blob, hn_blob_f16, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, weights, ctx, ws, pl,
@@ -698,6 +705,12 @@ int hvla_dino_forward(hvla_stream_t stream, const float* dino_vec, const void* d
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   if (dtype == HVLA_F32)
     return dino_f32(st, dino_vec, reinterpret_cast<const float*>(dino_mat), images, B, reinterpret_cast<float*>(out_emb), ws, pl);
+  if (dtype == HVLA_BF16X3) {
+    x3::Ws w;
+    w.X = reinterpret_cast<float*>(ws + pl.x); w.A3 = reinterpret_cast<bf16*>(ws + pl.a3); w.QKV2 = reinterpret_cast<bf16*>(ws + pl.qkv2);
+    w.A3L = reinterpret_cast<bf16*>(ws + pl.a3l); w.A0 = reinterpret_cast<float*>(ws + pl.qkv2);      // im2col matrix aliases the q|k|v planes
+    return x3::dino_forward(st, dino_vec, reinterpret_cast<const bf16*>(dino_mat), images, B, reinterpret_cast<float*>(out_emb), w);
+  }
   return dino_bf16(st, dino_vec, reinterpret_cast<const bf16*>(dino_mat), images, B, reinterpret_cast<bf16*>(out_emb), ws, pl);
 }
 
@@ -737,6 +750,7 @@ int hvla_act_debug(hvla_stream_t stream, const float* dino_vec, const void* dino
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   void* emb = ws + pl.emb;
+  if (dtype == HVLA_BF16X3) return fail(HVLA_ERR_UNSUPPORTED, "hvla_act_debug: attention maps come from the HVLA_F32 or HVLA_BF16 paths");
   if (dtype == HVLA_F32)
     HVLA_TRY(dino_f32(st, dino_vec, reinterpret_cast<const float*>(dino_mat), images, B, reinterpret_cast<float*>(emb), ws, pl, dino_maps));
   else

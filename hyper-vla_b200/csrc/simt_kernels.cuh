@@ -514,11 +514,77 @@ __global__ void __launch_bounds__(128) attention_simt_kernel(AttnP p) {
   }
 }
 
+// Base-ViT attention of the fp32 paths (HVLA_F32 and HVLA_BF16X3): 257 tokens, 4 heads x 16, per-env q|k|v in fp32 [B*257, 192].
+// One CTA per (head, env): K (rows padded to 17 floats) and V of the head live in shared memory, a warp owns every 8th query; lane = key
+// for the scores, lane = (key parity, d) for P V.  Same operation order as attention_simt_kernel (q / sqrt(16) first, masked scores =
+// finfo.min, d ascending, keys ascending within a parity class); the generic kernel read every K / V row from global memory per
+// query and took 4.4 ms for 64 envs x 4 blocks -- more than the twelve DINOv2 blocks of the split-operand flow together.
+__global__ void __launch_bounds__(256) base_attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out) {
+  constexpr int S = BTOK, HD = BHD, D = BH * BHD, LD = 3 * D;
+  __shared__ float sk[S][HD + 1];
+  __shared__ __align__(16) float sv[S][HD];
+  __shared__ float ps[8][S + 7];
+  const int h = blockIdx.x, b = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* base = qkv + (int64_t)b * S * LD + h * HD;
+  for (int e = threadIdx.x; e < S * (HD / 4); e += 256) {
+    const int r = e >> 2, c4 = e & 3;
+    const float4 k4 = __ldg(reinterpret_cast<const float4*>(base + (int64_t)r * LD + D) + c4);
+    const float4 v4 = __ldg(reinterpret_cast<const float4*>(base + (int64_t)r * LD + 2 * D) + c4);
+    sk[r][c4 * 4] = k4.x; sk[r][c4 * 4 + 1] = k4.y; sk[r][c4 * 4 + 2] = k4.z; sk[r][c4 * 4 + 3] = k4.w;
+    *reinterpret_cast<float4*>(&sv[r][c4 * 4]) = v4;
+  }
+  __syncthreads();
+  for (int q = w; q < S; q += 8) {
+    float qv[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) qv[d] = __ldg(base + (int64_t)q * LD + d) / 4.0f;      // q / sqrt(16): flax scales the query first
+    float sc[9];
+    float m = -FLT_MAX;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const int key = lane + 32 * i;
+      float s = -FLT_MAX;
+      if (key < S) {
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) a = fmaf(qv[d], sk[key][d], a);
+        s = ((key != S - 1) || (q == S - 1)) ? a : -FLT_MAX;                             // patches never see the action token (base_vit.py:209-214)
+        m = fmaxf(m, s);
+      }
+      sc[i] = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      if (lane + 32 * i < S) { sc[i] = expf(sc[i] - m); sum += sc[i]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+      if (lane + 32 * i < S) ps[w][lane + 32 * i] = sc[i] / sum;
+    __syncwarp();
+    const int d = lane & 15, par = lane >> 4;                       // even keys on lanes 0..15, odd keys on lanes 16..31: conflict-free V reads
+    float a = 0.f;
+    for (int key = par; key < S; key += 2) a = fmaf(ps[w][key], sv[key][d], a);
+    a += __shfl_xor_sync(0xffffffffu, a, 16);
+    if (par == 0) out[((int64_t)b * S + q) * D + h * HD + d] = a;
+    __syncwarp();
+  }
+}
+
 template <typename T, typename TO>
 inline int attention_simt(cudaStream_t st, const AttnP& p, int dh) {
   if (p.S > 288) return fail(HVLA_ERR_ARG, "attention_simt: S too large");
-  dim3 grid(cdiv(p.S, 4), p.H, p.nbatch);
   ProfScope ps(st, "attention_simt");
+  if (std::is_same<T, float>::value && std::is_same<TO, float>::value && dh == BHD && p.S == BTOK && p.H == BH && p.mask == 1 && !p.prescaled) {
+    base_attention_f32_kernel<<<dim3(BH, p.nbatch), 256, 0, st>>>(reinterpret_cast<const float*>(p.qkv), reinterpret_cast<float*>(p.out));
+    HVLA_LAUNCH_CHECK("base_attention_f32");
+    return HVLA_OK;
+  }
+  dim3 grid(cdiv(p.S, 4), p.H, p.nbatch);
   if (dh == 16) attention_simt_kernel<T, TO, 16><<<grid, 128, 0, st>>>(p);
   else if (dh == 32) attention_simt_kernel<T, TO, 32><<<grid, 128, 0, st>>>(p);
   else if (dh == 64) attention_simt_kernel<T, TO, 64><<<grid, 128, 0, st>>>(p);

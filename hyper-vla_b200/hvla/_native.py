@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-HVLA_F32, HVLA_BF16 = 0, 1
+HVLA_F32, HVLA_BF16, HVLA_BF16X3 = 0, 1, 2
 _LIB = None
 
 c_void_p, c_int, c_i64, c_size_t = C.c_void_p, C.c_int, C.c_int64, C.c_size_t

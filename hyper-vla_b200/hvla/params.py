@@ -321,6 +321,24 @@ def pack_dino(params: dict, transposed: bool) -> Tuple[np.ndarray, np.ndarray]:
     return pack_dino_tree(dino_tree_from_params(params), transposed)
 
 
+def split_matrices_x3(mat_kn: np.ndarray) -> np.ndarray:
+    """DINOv2 matrix blob of the split-operand flow (csrc/dino_x3.cuh, dtype HVLA_BF16X3) from the fp32 Flax [K,N] blob: every matrix
+    becomes [N, 3K] = [hi | hi | lo] of its transpose, hi = bf16(w), lo = bf16(w - hi), at 3x its element offset.  Returned as the
+    uint16 bit patterns of the bf16 values (view as torch.bfloat16)."""
+    lay = dino_mat_layout(False)
+    out = np.empty(3 * lay["__total__"][0], np.uint16)
+    for name, (off, shape) in lay.items():
+        if name == "__total__":
+            continue
+        k, n = shape
+        wt = np.ascontiguousarray(mat_kn[off:off + k * n].reshape(k, n).T, F32)       # [N, K]
+        hi = bf16_round(wt)
+        lo = bf16_round(wt - hi)
+        hb, lb = (hi.view(np.uint32) >> 16).astype(np.uint16), (lo.view(np.uint32) >> 16).astype(np.uint16)
+        out[3 * off:3 * off + 3 * k * n] = np.concatenate([hb, hb, lb], axis=1).ravel()
+    return out
+
+
 def bf16_round(x: np.ndarray) -> np.ndarray:
     """float32 -> nearest bfloat16 (ties to even), returned as float32: what the tensor cores will multiply."""
     u = np.ascontiguousarray(x, F32).view(np.uint32).astype(np.uint64)

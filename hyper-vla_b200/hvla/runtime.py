@@ -23,13 +23,13 @@ def _torch():
 class Runtime:
     def __init__(self, params: dict, precision: str = "bf16", device: Optional[object] = None):
         torch = _torch()
-        if precision not in ("bf16", "fp32"):
-            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if precision not in ("bf16", "fp32", "fp32x3"):
+            raise ValueError("precision must be 'bf16', 'fp32' or 'fp32x3' (fp32-class accuracy on the tensor cores, split bf16 operands)")
         if not torch.cuda.is_available():
             raise N.HvlaError("no CUDA device: the hvla hot path is CUDA-only (there is no CPU fallback)")
         self.lib = N.lib()
         self.precision = precision
-        self.dtype = N.HVLA_BF16 if precision == "bf16" else N.HVLA_F32
+        self.dtype = {"bf16": N.HVLA_BF16, "fp32": N.HVLA_F32, "fp32x3": N.HVLA_BF16X3}[precision]
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.tdtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self._ws = None
@@ -58,13 +58,19 @@ class Runtime:
         self.heads_w = torch.from_numpy(W).to(self.tdtype).to(dev)
         self.heads_b = torch.from_numpy(b).to(dev)
         del W
-        vec, mat = P.pack_dino(params, transposed=(self.precision == "bf16"))
-        assert vec.size == self.lib.hvla_dino_vec_elems() and mat.size == self.lib.hvla_dino_mat_elems()
-        self.dino_vec = torch.from_numpy(vec).to(dev)
-        self.dino_mat = torch.from_numpy(mat).to(self.tdtype).to(dev)
-        del mat
+        self.dino_vec, self.dino_mat = self._dino_blobs(*P.pack_dino(params, transposed=(self.precision == "bf16")))
         self._params_id = id(params)
         self._graphs.clear()            # captured graphs hold pointers into the previous blobs
+
+    def _dino_blobs(self, vec, mat):
+        """(vec, matrix) host blobs of P.pack_dino* -> device tensors in this runtime's matrix format."""
+        torch = _torch()
+        assert vec.size == self.lib.hvla_dino_vec_elems() and mat.size == self.lib.hvla_dino_mat_elems()
+        if self.precision == "fp32x3":          # [hi | hi | lo] bf16 planes of every transposed matrix
+            m = torch.from_numpy(P.split_matrices_x3(mat).view(np.int16)).view(torch.bfloat16).to(self.device)
+        else:
+            m = torch.from_numpy(mat).to(self.tdtype).to(self.device)
+        return torch.from_numpy(vec).to(self.device), m
 
     # ---- scratch ------------------------------------------------------------------------------------
     def workspace(self, B: int, T: int):
@@ -304,8 +310,7 @@ class Runtime:
         """Upload another DINOv2-base param tree (e.g. the frozen pretrained encoder of the initial image,
         data/simpler/evaluate.py:146-163) -> (vec, mat) device blobs for ``dino_forward(..., blobs=...)``."""
         torch = _torch()
-        vec, mat = P.pack_dino_tree(tree, transposed=(self.precision == "bf16"))
-        return torch.from_numpy(vec).to(self.device), torch.from_numpy(mat).to(self.tdtype).to(self.device)
+        return self._dino_blobs(*P.pack_dino_tree(tree, transposed=(self.precision == "bf16")))
 
     def dino_forward(self, images, blobs=None):
         """images uint8 CUDA (B,224,224,3) -> last_hidden_state (B,257,768) in the runtime dtype."""

@@ -15,7 +15,9 @@
  *     (except the *_host entry points, which say so);
  *   - `dtype` selects the arithmetic: HVLA_F32 = exact fp32 CUDA-core path (parity
  *     <= 1e-5 against the fp32 oracle); HVLA_BF16 = tensor-core path (bf16 operands,
- *     fp32 accumulation; parity <= 2e-2);
+ *     fp32 accumulation; parity <= 2e-2); HVLA_BF16X3 = fp32-class accuracy ON the tensor cores: every DINOv2 matrix
+ *     product runs with operands split into two bf16 numbers (hi + lo, three products, fp32 accumulation; csrc/dino_x3.cuh),
+ *     generate and the base net on the fp32 path; all buffers as for HVLA_F32 except dino_mat (below);
  *   - there is no CPU fallback: without a CUDA device every compute entry point
  *     returns HVLA_ERR_CUDA.
  *
@@ -34,6 +36,7 @@
  *                     12 x { ln1_s ln1_b bqkv[2304] bo ls1 ln2_s ln2_b b1[3072] b2 ls2 } lnf_s lnf_b
  *   DINO mat:         patch_w, 12 x { wqkv wo w1 w2 }.  HVLA_F32: fp32, Flax [K,N] layout,
  *                     patch K padded 588->640.  HVLA_BF16: bf16, transposed [N,K] (K contiguous).
+ *                     HVLA_BF16X3: bf16, every matrix [N, 3K] = [hi | hi | lo] of the transposed fp32 matrix, at 3x the offsets.
  */
 #ifndef HVLA_H_
 #define HVLA_H_
@@ -48,7 +51,7 @@ extern "C" {
 typedef void* hvla_stream_t; /* cudaStream_t */
 
 enum { HVLA_OK = 0, HVLA_ERR_ARG = -1, HVLA_ERR_CUDA = -2, HVLA_ERR_UNSUPPORTED = -3, HVLA_ERR_WORKSPACE = -4 };
-enum { HVLA_F32 = 0, HVLA_BF16 = 1 };
+enum { HVLA_F32 = 0, HVLA_BF16 = 1, HVLA_BF16X3 = 2 };
 
 /* ---- host-only queries (usable without a GPU) -------------------------------------- */
 int hvla_version(void);

@@ -14,7 +14,10 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-5, "bf16": 2e-2}
+TOL = {"fp32": 1e-5, "bf16": 2e-2,
+       # fp32-class accuracy on the tensor cores (split bf16 operands, csrc/dino_x3.cuh): every product carries 2^-17..2^-18 relative
+       # error per operand pair instead of fp32's 2^-24; measured 1-2e-5 after twelve DINOv2 blocks (printed by the tests)
+       "fp32x3": 3e-5}
 CASES = {"c1_b1_t1": (1, 1, 1), "c2_b3_t3": (2, 3, 3), "c5_b6_t2": (5, 6, 2)}
 # the same cases against fixtures produced by executing the reference's own code (tests/golden/make_ref_golden.py)
 CASES.update({"ref_" + k: v for k, v in list(CASES.items())})
@@ -38,7 +41,7 @@ def models(params_p1, torch_cuda):
     from hvla import config as C
     from hvla.model import HyperVLA
     out = {}
-    for prec in ("fp32", "bf16"):
+    for prec in ("fp32", "bf16", "fp32x3"):
         out[prec] = HyperVLA.from_config(C.default_config(), precision=prec, params=params_p1)
         out[prec].runtime  # upload now
     return out
@@ -54,7 +57,7 @@ def run_case(model, ci, B, T):
     return inp, base_params, action, inter["gripper_logits"]
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp32x3"])
 @pytest.mark.parametrize("case", list(CASES))
 def test_generate_and_act_match_golden(models, golden, prec, case):
     ci, B, T = CASES[case]
@@ -73,12 +76,12 @@ def test_generate_and_act_match_golden(models, golden, prec, case):
     assert e_rows <= tol
     assert e_sum <= tol
     assert e_act <= tol
-    sure = np.abs(g["logit"]) > (1e-3 if prec == "fp32" else 2e-2 * np.abs(g["logit"]).max())
+    sure = np.abs(g["logit"]) > (1e-3 if prec != "bf16" else 2e-2 * np.abs(g["logit"]).max())
     assert np.array_equal(action[..., 6][sure], g["action"][..., 6][sure])
     assert set(np.unique(action[..., 6])) <= {0.0, 1.0}
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp32x3"])
 def test_dino_hidden_matches_golden(models, golden, torch_cuda, prec):
     from hvla import synthetic as S
     g = golden["c2_b3_t3"]

@@ -196,3 +196,21 @@ def test_replace_params_drops_the_device_runtime(params_p1, params_p0):
     m2 = m.replace(params=params_p0)
     assert m2.params is params_p0 and m2._runtime is None and m._runtime is not None
     assert m.replace(precision="fp32")._runtime is None and m.replace(config=m.config)._runtime is m._runtime
+
+
+def test_split_operand_matrix_packing():
+    """hvla.params.split_matrices_x3 (dtype HVLA_BF16X3, csrc/dino_x3.cuh): every matrix [N, 3K] = [hi | hi | lo] of its transpose at 3x its
+    offset, hi + lo reproducing the fp32 weight to 2^-17."""
+    rng = np.random.default_rng(3)
+    lay = P.dino_mat_layout(False)
+    mat = (rng.standard_normal(lay["__total__"][0]) * 0.02).astype(np.float32)
+    x3 = P.split_matrices_x3(mat)
+    assert x3.dtype == np.uint16 and x3.size == 3 * mat.size
+    f = lambda u: (u.astype(np.uint32) << 16).view(np.float32)
+    for name in ("patch_w", "l0.wqkv", "l11.w2"):
+        off, (k, n) = lay[name]
+        blk = x3[3 * off:3 * off + 3 * k * n].reshape(n, 3 * k)
+        w = mat[off:off + k * n].reshape(k, n).T
+        hi, hi2, lo = f(blk[:, :k]), f(blk[:, k:2 * k]), f(blk[:, 2 * k:])
+        assert np.array_equal(hi, hi2) and np.array_equal(hi, P.bf16_round(w))
+        assert np.abs(hi + lo - w).max() <= 2.0 ** -17 * np.abs(w).max()
