@@ -482,12 +482,37 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
 }
 
 // ---- epilogue over the BLOCKED fp32 stream (EPI_RESIDUAL_BLK, EPI_PATCH_BLK) ------------------------------------------------
-// x_new = x_old + ls * (acc + bias), in place.  The old values do not depend on the MMAs: chunk 0 is requested while the mainloop is
-// still running, chunk c+1 while chunk c is processed.  EPI_RESIDUAL_BLK also emits the bf16 shadow (slab + TMA store) and the
-// thread's partial row statistics; EPI_PATCH_BLK maps GEMM row b*256+p to stream row b*257+1+p (ls == 1).
+// x_new = x_old + ls * (acc + bias), in place.  The old values do not depend on the MMAs, and an L2 / HBM round trip is longer than one
+// 32-column chunk of epilogue work (two epilogue warps per scheduler hide nothing), so they are prefetched TWO chunks ahead and ACROSS
+// tiles: chunks 0 and 1 of the next tile of this CTA are requested while chunks 2 and 3 of the current one are processed (`xo` and
+// `primed` live in the caller's tile loop).  EPI_RESIDUAL_BLK also emits the bf16 shadow -- transposed through the warp's 2 KB slab and
+// written with plain 16-byte stores (8 rows x 64 contiguous bytes per warp instruction; a TMA store per chunk made the warp wait for
+// the TMA engine to drain the slab four times per tile) -- and the thread's partial row statistics; EPI_PATCH_BLK maps GEMM row
+// b*256+p to stream row b*257+1+p (ls == 1) and adds to the position row of the patch instead of the stream.
 template <int EPI>
-__device__ __forceinline__ void epilogue_tile_blk(const EpiP& ep, const CUtensorMap* tmS, float* sepi, uint32_t sstage, uint32_t tfull_bar_addr,
-                                                  uint32_t aph, int as, uint32_t tmem_base, int m0, int n0, int warp, int lane) {
+struct BlkTile {
+  float4* xp;            // this thread's row in the blocked stream, first column group of its 128-column half (+32 per group)
+  const float4* xin;     // what the update is added to (the stream, or the blocked position table for the patch embedding)
+  int grow;              // GEMM row of this thread's TMEM lane
+  bool ok;
+  __device__ __forceinline__ BlkTile(const EpiP& ep, int m0, int n0, int quarter, int half, int lane) {
+    constexpr bool PATCH = EPI == EPI_PATCH_BLK;
+    grow = m0 + quarter * 32 + lane;
+    const int srow = PATCH ? grow + m0 / 256 + 1 : grow;         // stream row
+    ok = grow < ep.rows;
+    xp = reinterpret_cast<float4*>(ep.out) + xblk_f4(ok ? srow : 0, (n0 + half * 128) >> 2);
+    xin = PATCH ? reinterpret_cast<const float4*>(ep.pos) + xblk_f4(grow & 255, (n0 + half * 128) >> 2) : xp;
+  }
+  __device__ __forceinline__ void load(float4 (&dst)[8], int chunk) const {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = ok ? __ldcg(xin + 32 * (chunk * 8 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+};
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile_blk(const EpiP& ep, float* sepi, uint32_t sstage, uint32_t tfull_bar_addr, uint32_t aph, int as,
+                                                  uint32_t tmem_base, int m0, int n0, int warp, int lane, float4 (&xo)[2][8], bool primed,
+                                                  bool has_next, int m0_next, int n0_next) {
   constexpr bool PATCH = EPI == EPI_PATCH_BLK;
   const int ew = warp - 2;
   const int quarter = warp & 3;
@@ -497,23 +522,12 @@ __device__ __forceinline__ void epilogue_tile_blk(const EpiP& ep, const CUtensor
   float* sl = sb + 256;
   sb[te] = __ldg(ep.bias + n0 + te);
   sl[te] = (!PATCH && ep.ls) ? __ldg(ep.ls + n0 + te) : 1.0f;
-  const int grow = m0 + quarter * 32 + lane;                   // GEMM row of this thread's TMEM lane
-  const int srow = PATCH ? grow + m0 / 256 + 1 : grow;         // its stream row
-  const bool ok = grow < ep.rows;
-  float4* xp = reinterpret_cast<float4*>(ep.out) + xblk_f4(ok ? srow : 0, (n0 + half * 128) >> 2);   // + 32 per group of 4 columns
-  // what the update is added to: the stream itself, or (patch embedding) the position row of patch p = grow % 256 from a table in
-  // the same blocked layout -- the embedded tokens are WRITTEN, the stream needs no initialisation pass and no read
-  const float4* xin = PATCH ? reinterpret_cast<const float4*>(ep.pos) + xblk_f4(grow & 255, (n0 + half * 128) >> 2) : xp;
-  // old values: prefetch distance of TWO 32-column chunks (an L2 / HBM round trip is longer than one chunk of epilogue work, and with
-  // two epilogue warps per scheduler nothing else hides it): chunks 0 and 1 are requested here, chunk c+2 as soon as chunk c is consumed
-  float4 xo[2][8];
-#pragma unroll
-  for (int u = 0; u < 2; ++u)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) xo[u][j] = ok ? __ldcg(xin + 32 * (u * 8 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const BlkTile<EPI> t(ep, m0, n0, quarter, half, lane);
+  const BlkTile<EPI> tn(ep, has_next ? m0_next : m0, has_next ? n0_next : n0, quarter, half, lane);
+  if (!primed) { t.load(xo[0], 0); t.load(xo[1], 1); }
   const uint32_t slab = sstage + (uint32_t)ew * 2048u;
   const uint32_t my = slab + (uint32_t)lane * 64u;
-  const uint32_t sw = (uint32_t)((lane >> 1) & 3);          // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+  const uint32_t sw = (uint32_t)((lane >> 1) & 3);          // 16-byte piece index ^= (row >> 1) & 3: conflict-free 16-byte column writes
   float p_sum = 0.f, p_sq = 0.f;
   epi_bar_sync();
   mbar_wait(tfull_bar_addr, aph);
@@ -538,19 +552,16 @@ __device__ __forceinline__ void epilogue_tile_blk(const EpiP& ep, const CUtensor
       xn[4 * j + 2] = fmaf(__uint_as_float(rc[4 * j + 2]) + b4.z, l4.z, x4.z);
       xn[4 * j + 3] = fmaf(__uint_as_float(rc[4 * j + 3]) + b4.w, l4.w, x4.w);
     }
-    if (c < 2) {
+    if (c < 2) t.load(xo[c & 1], c + 2);                      // two chunks ahead ...
+    else if (has_next) tn.load(xo[c & 1], c - 2);             // ... also across the tile boundary
+    if (t.ok) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) xo[c & 1][j] = ok ? __ldcg(xin + 32 * ((c + 2) * 8 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (ok) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) __stcg(xp + 32 * (c * 8 + j), make_float4(xn[4 * j], xn[4 * j + 1], xn[4 * j + 2], xn[4 * j + 3]));
+      for (int j = 0; j < 8; ++j) __stcg(t.xp + 32 * (c * 8 + j), make_float4(xn[4 * j], xn[4 * j + 1], xn[4 * j + 2], xn[4 * j + 3]));
     }
     if (!PATCH) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) { p_sum += xn[j]; p_sq = fmaf(xn[j], xn[j], p_sq); }
-      if (lane == 0) bulk_wait_read<0>();                      // the slab's previous TMA store has finished reading it
-      __syncwarp();
+      __syncwarp();                                            // the previous chunk's read-back of the slab is complete
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t a = my + ((((uint32_t)j) ^ sw) << 4);
@@ -559,16 +570,21 @@ __device__ __forceinline__ void epilogue_tile_blk(const EpiP& ep, const CUtensor
                      "r"(pack_bf16(xn[8 * j + 6], xn[8 * j + 7]))
                      : "memory");
       }
-      fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
-        tma_store_2d(tmS, slab, n0 + cl, m0 + quarter * 32);
-        bulk_commit();
+      const int rbase = m0 + quarter * 32;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {                            // 8 rows x 64 bytes per warp instruction
+        const int row = 8 * i + (lane >> 2), pc = lane & 3;
+        uint32_t v0, v1, v2, v3;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                     : "r"(slab + (uint32_t)(row * 64) + ((((uint32_t)pc) ^ (uint32_t)((row >> 1) & 3)) << 4)) : "memory");
+        if (rbase + row < ep.rows)
+          __stcg(reinterpret_cast<uint4*>(ep.shadow + (int64_t)(rbase + row) * DD + n0 + cl + pc * 8), make_uint4(v0, v1, v2, v3));
       }
     }
   }
-  if (!PATCH && ok)                                            // partial (sum, sumsq) of this row over this tile's 128-column half
-    *reinterpret_cast<float2*>(ep.stats_out + (int64_t)grow * 12 + ((n0 / BN) * 2 + half) * 2) = make_float2(p_sum, p_sq);
+  if (!PATCH && t.ok)                                          // partial (sum, sumsq) of this row over this tile's 128-column half
+    *reinterpret_cast<float2*>(ep.stats_out + (int64_t)t.grow * 12 + ((n0 / BN) * 2 + half) * 2) = make_float2(p_sum, p_sq);
   tc_fence_before();
   __syncwarp();
 }

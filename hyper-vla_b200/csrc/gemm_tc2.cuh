@@ -169,14 +169,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     // ===================== epilogue warps (both CTAs, own 128 TMEM lanes) =====================
     int it = 0;
+    float4 xo[epi_blk(EPI) ? 2 : 1][8];               // blocked-stream epilogue: old values prefetched across tiles
+    bool primed = false;
     for (int unit = pair; unit < n_tiles; unit += n_pairs, ++it) {
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int tile = unit / splits;
       const int m0 = (tile / n_tiles_n) * BM2 + (int)rank * 128, n0 = (tile % n_tiles_n) * BN;
-      if (epi_blk(EPI))                               // blocked stream: in-place update (+ shadow through tmO, + row statistics)
-        epilogue_tile_blk<EPI>(ep, &tmO, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane);
-      else if (EPI == EPI_PATCH_F32 && ep.patch_rows)      // patch embedding accumulated onto the pre-initialised stream rows (TMA reduce-add)
+      if constexpr (epi_blk(EPI)) {                   // blocked stream: in-place update (+ bf16 shadow, + row statistics); splits == 1
+        const int nxt = unit + n_pairs;
+        const bool has_next = nxt < n_tiles;
+        epilogue_tile_blk<EPI>(ep, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane, xo, primed, has_next,
+                               (nxt / n_tiles_n) * BM2 + (int)rank * 128, (nxt % n_tiles_n) * BN);
+        primed = has_next;
+      } else if (EPI == EPI_PATCH_F32 && ep.patch_rows)      // patch embedding accumulated onto the pre-initialised stream rows (TMA reduce-add)
         epilogue_tile_tma<EPI_RESIDUAL_F32, NSLAB2>(ep, &tmO, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane);
       else if (EPI == EPI_PATCH_F32) epilogue_tile_direct<EPI>(ep, sepi, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, M, warp, lane);
       else {
