@@ -102,10 +102,17 @@ def kernel_roofline_table(act_prof: dict, gen_prof: dict, B: int, T: int, peaks:
     }
     notes = {
         "cls_rows": "write-only, absorbed by the 126 MB L2 at this batch: can exceed the HBM copy peak",
-        "dino_attention": "bound by MUFU.EX2 (16/clk/SM) and instruction issue before the tensor pipe (DESIGN.md section 3)",
-        "base_fused": "latency-bound (dependent mma.sync chains per env), not bandwidth-bound at this batch (DESIGN.md section 3)",
+        "dino_attention": "bound by MUFU.EX2 (16/clk/SM) and instruction issue before the tensor pipe: see the mufu entry (DESIGN.md section 3)",
+        "base_fused": "bound by instruction issue and MUFU.EX2, not by HBM: 0.79 M exponentials per env put its floor at 0.18 ms per 1024 envs, above "
+                      "the 0.12 ms its HBM bytes take (mufu entry; DESIGN.md section 3)",
         "ctx_fused": "latency-bound: one CTA per task, weights streamed from L2 (DESIGN.md section 3)",
     }
+    # The attention and the base net are bound by the exponential unit, not by the roofline SURVEY 8(d) names for them: MUFU.EX2 retires
+    # 16 results per clock per SM (measured, tools/micro/mufu_bench.cu).  Exponentials per step: DINOv2 attention B x 12 layers x 12 heads x
+    # 257^2; base net per env 3 blocks x 4 heads x 256 x 256 (patch rows; the last block only feeds the action token) + 4 x 4 x 257.
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    mufu_peak = 16.0 * 148 * sm_max * 1e6 / 1e9                                # Gexp/s at the maximum SM clock
+    mufu_work = {"dino_attention": B * 12 * 12 * 257 * 257, "base_fused": B * (3 * 4 * 256 * 256 + 4 * 4 * 257)}
     out = {}
     for src in (act_prof, gen_prof):
         for name, (n, ms) in src.items():
@@ -118,6 +125,9 @@ def kernel_roofline_table(act_prof: dict, gen_prof: dict, B: int, T: int, peaks:
                 a, pk, unit = w / (ms / 1e3) / 1e9, hbm, "GB/s"
             out[name] = {"bound": bound, "launches": n, "ms": round(ms, 4), "achieved": round(a, 2), "peak": pk, "unit": unit,
                          "frac": round(a / pk, 4)}
+            if name in mufu_work:
+                g = mufu_work[name] / (ms / 1e3) / 1e9
+                out[name]["mufu"] = {"bound": "mufu", "achieved": round(g, 1), "peak": round(mufu_peak, 1), "unit": "Gexp/s", "frac": round(g / mufu_peak, 4)}
             if name in notes:
                 out[name]["note"] = notes[name]
     return out
@@ -684,11 +694,16 @@ def time_base_only(model, Bb: int, K: int, Wm: int, world: int, rank: int, peaks
     bytes_step = Bb * (256 * 768 * e + 112) + Bb * 201_500 * e
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     gbs = bytes_step / (ms / K / 1e3) / 1e9
+    gexp = Bb * (3 * 4 * 256 * 256 + 4 * 4 * 257) / (ms / K / 1e3) / 1e9
+    mufu_peak = 16.0 * 148 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e9
     return {"value": world * Bb * K / (ms / 1e3), "unit": "actions/s", "envs_per_gpu": Bb, "ms_per_step": ms / K,
             "kernel": "base_fused_kernel (hvla_base_act; embeddings + per-env generated weights resident in HBM, 817 MB per step at 1024 envs > L2)",
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                          "algorithmic_bytes_per_step": bytes_step,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"},
+            "mufu_roofline": {"bound": "mufu", "achieved": gexp, "peak": mufu_peak, "unit": "Gexp/s", "frac": gexp / mufu_peak,
+                              "note": "the base net's real bound: 0.79 M softmax exponentials per env at 16 MUFU.EX2 results per clock per SM put the floor of 1024 envs "
+                                      "at 0.18 ms, above the 0.12 ms its HBM bytes take"},
             "clocks": clk}
 
 
