@@ -28,7 +28,7 @@ using attn::cp_async_wait;
 // embeddings in shared memory across slabs when they fit one pass (T <= 64).
 __global__ void __launch_bounds__(256, 2)
 heads_mma_kernel(const float* __restrict__ E, const bf16* __restrict__ W, const float* __restrict__ bias, bf16* __restrict__ out, int T,
-                 int nslabs, const int32_t* __restrict__ rows, int T_max) {
+                 int nslabs, const int32_t* __restrict__ rows, int T_max, int64_t ngp) {
   extern __shared__ __align__(16) uint8_t smem[];
   bf16* Es = reinterpret_cast<bf16*>(smem + 2 * WSLAB);
   bf16* Os = Es + TM * LDS_;
@@ -40,10 +40,10 @@ heads_mma_kernel(const float* __restrict__ E, const bf16* __restrict__ W, const 
   auto stage_w = [&](int slab, int buf) {
     if (slab < nslabs) {
       const int64_t col0 = (int64_t)slab * NC;
-      const int ncols = (int)((NGP - col0) < NC ? (NGP - col0) : NC);   // NGP % 32 == 0: the last slab is 32 wide
+      const int ncols = (int)((ngp - col0) < NC ? (ngp - col0) : NC);   // ngp % 32 == 0: the last slab may be narrower
       for (int i = threadIdx.x; i < 128 * 16; i += 256) {
         const int r = i >> 4, c = (i & 15) * 8;
-        if (c < ncols) cp_async16(sbase + (uint32_t)(buf * WSLAB + (r * LDS_ + c) * 2), W + (int64_t)r * NGP + col0 + c);
+        if (c < ncols) cp_async16(sbase + (uint32_t)(buf * WSLAB + (r * LDS_ + c) * 2), W + (int64_t)r * ngp + col0 + c);
       }
       if (threadIdx.x < ncols / 4) cp_async16(sB + (uint32_t)((buf * NC + threadIdx.x * 4) * 4), bias + col0 + threadIdx.x * 4);
     }
@@ -63,7 +63,7 @@ heads_mma_kernel(const float* __restrict__ E, const bf16* __restrict__ W, const 
   for (int slab = blockIdx.x; slab < nslabs; slab += gridDim.x, ++it) {
     const int buf = it & 1;
     const int64_t col0 = (int64_t)slab * NC;
-    const int ncols = (int)((NGP - col0) < NC ? (NGP - col0) : NC);
+    const int ncols = (int)((ngp - col0) < NC ? (ngp - col0) : NC);
     stage_w(slab + gridDim.x, buf ^ 1);                         // the other buffer was released by the barrier that ended the previous slab
     cp_async_wait<1>();
     __syncthreads();                                            // this slab (and E on the first one) is visible to every warp
@@ -107,7 +107,7 @@ heads_mma_kernel(const float* __restrict__ E, const bf16* __restrict__ W, const 
         if (t0 + r < T && c < ncols) {
           const int orow = rows ? __ldg(rows + t0 + r) : t0 + r;          // task-switch scheduler: scattered rows of a persistent buffer
           if (orow >= 0 && orow < T_max)
-            *reinterpret_cast<uint4*>(out + (int64_t)orow * NGP + col0 + c) = *reinterpret_cast<const uint4*>(Os + r * LDS_ + c);
+            *reinterpret_cast<uint4*>(out + (int64_t)orow * ngp + col0 + c) = *reinterpret_cast<const uint4*>(Os + r * LDS_ + c);
         }
       }
       __syncthreads();                                          // Os (and this W buffer, after the last pass) may be overwritten
@@ -117,16 +117,17 @@ heads_mma_kernel(const float* __restrict__ E, const bf16* __restrict__ W, const 
 }
 
 inline int heads_gemm_bf16(cudaStream_t st, const float* E, const bf16* W, const float* bias, bf16* out, int T,
-                           const int32_t* rows = nullptr, int T_max = 0) {
+                           const int32_t* rows = nullptr, int T_max = 0, int64_t ngp = NGP) {
+  if (ngp % 32 != 0) return fail(HVLA_ERR_ARG, "heads_gemm_bf16: the row stride must be a multiple of 32 elements");
   static std::atomic<uint64_t> attr{0};   // per-device one-time setup
   if (device_once(attr)) {
     HVLA_CUDA(cudaFuncSetAttribute(heads_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     HVLA_CUDA(cudaFuncSetAttribute(heads_mma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   }
   const int grid = 2 * num_sms();                               // two resident CTAs per SM
-  const int nslabs = cdiv(NGP, NC);
+  const int nslabs = cdiv(ngp, NC);
   ProfScope ps(st, "heads_gemm");
-  heads_mma_kernel<<<grid < nslabs ? grid : nslabs, 256, SMEM, st>>>(E, W, bias, out, T, nslabs, rows, rows ? T_max : T);
+  heads_mma_kernel<<<grid < nslabs ? grid : nslabs, 256, SMEM, st>>>(E, W, bias, out, T, nslabs, rows, rows ? T_max : T, ngp);
   HVLA_LAUNCH_CHECK("heads_mma");
   return HVLA_OK;
 }

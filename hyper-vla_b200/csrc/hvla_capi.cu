@@ -13,6 +13,7 @@
 #include "preprocess.cuh"
 #include "t5_embed.cuh"
 #include "dino_x3.cuh"
+#include "discrete_head.cuh"
 
 #include <stdlib.h>
 #include <type_traits>
@@ -68,11 +69,12 @@ static Plan make_plan(int B, int T, int dtype) {
   p.part = take(dtype == HVLA_BF16 ? PART_BYTES : 0);   // split-K partial products (small batches)
   p.st = take(dtype == HVLA_BF16 ? M * 12 * 4 : 0);      // partial row statistics of the stream (LayerNorm-free flow)
   p.pt = take(Bb * NPATCH * BD * 4);
-  p.xb = take(Bb * BTOK * BD * 4);
-  p.yb = take(Bb * BTOK * BD * 4);
-  p.qkvb = take(Bb * BTOK * 3 * BD * 4);
-  p.cb = take(Bb * BTOK * BD * 4);
-  p.hb = take(Bb * BTOK * BF * 4);
+  constexpr size_t BTOKMAX = NPATCH + AH * AD;     // discrete head: up to 28 readout tokens (discrete_head.cuh)
+  p.xb = take(Bb * BTOKMAX * BD * 4);
+  p.yb = take(Bb * BTOKMAX * BD * 4);
+  p.qkvb = take(Bb * BTOKMAX * 3 * BD * 4);
+  p.cb = take(Bb * BTOKMAX * BD * 4);
+  p.hb = take(Bb * BTOKMAX * BF * 4);
   p.img = take(Bb * IMG * IMG * 3);
   p.act = take(Bb * AH * AD * 4);
   p.logit = take(Bb * AH * 4);
@@ -132,7 +134,7 @@ __global__ void scatter_rows_kernel(const float* __restrict__ src, float* __rest
 template <typename TW>
 static int generate_impl(cudaStream_t st, const float* hn, const void* hn_lp, const void* heads_w, const float* heads_b, const float* tok_emb,
                          const int32_t* tok_mask, const uint8_t* lang_pad, const float* init_cls, int T, void* out_w,
-                         float* out_ctx, uint8_t* ws, const Plan& pl, const int32_t* rows = nullptr, int T_max = 0) {
+                         float* out_ctx, uint8_t* ws, const Plan& pl, const int32_t* rows = nullptr, int T_max = 0, int64_t ngp = NGP) {
   float* TPj = reinterpret_cast<float*>(ws + pl.tp);
   float* IPj = reinterpret_cast<float*>(ws + pl.ip);
   float* X = reinterpret_cast<float*>(ws + pl.xc);
@@ -155,7 +157,7 @@ static int generate_impl(cudaStream_t st, const float* hn, const void* hn_lp, co
     // bf16 tensor-core path: the whole context encoder is one kernel, the 73 heads another
     HVLA_TRY(ctxf::ctx_encode_lp(st, hn, reinterpret_cast<const ctxf::lp*>(hn_lp), tok_emb, tok_mask, lang_pad, init_cls, T, E));
     HVLA_TRY(scatter_ctx());
-    return heads::heads_gemm_bf16(st, E, reinterpret_cast<const bf16*>(heads_w), heads_b, reinterpret_cast<bf16*>(out_w), T, rows, T_max);
+    return heads::heads_gemm_bf16(st, E, reinterpret_cast<const bf16*>(heads_w), heads_b, reinterpret_cast<bf16*>(out_w), T, rows, T_max, ngp);
   }
   // K1: projections (hypernetwork.py:112, 126)
   HVLA_TRY((gemm_simt<float, float, float, float>(
@@ -200,10 +202,10 @@ static int generate_impl(cudaStream_t st, const float* hn, const void* hn_lp, co
   // K3: all 73 output heads as one skinny GEMM (hypernetwork.py:205-217, 227)
   HVLA_TRY(scatter_ctx());
   if (std::is_same<TW, bf16>::value && !env_flag("HVLA_DEBUG_SIMT_HEADS"))
-    return heads::heads_gemm_bf16(st, E, reinterpret_cast<const bf16*>(heads_w), heads_b, reinterpret_cast<bf16*>(out_w), T, rows, T_max);
+    return heads::heads_gemm_bf16(st, E, reinterpret_cast<const bf16*>(heads_w), heads_b, reinterpret_cast<bf16*>(out_w), T, rows, T_max, ngp);
   ProfScope ps(st, "heads_gemm");
-  heads_gemm_kernel<TW, TW><<<cdiv(NGP, 1024), 256, 0, st>>>(E, reinterpret_cast<const TW*>(heads_w), heads_b,
-                                                             reinterpret_cast<TW*>(out_w), T, rows, T_max);
+  heads_gemm_kernel<TW, TW><<<cdiv(ngp, 1024), 256, 0, st>>>(E, reinterpret_cast<const TW*>(heads_w), heads_b,
+                                                             reinterpret_cast<TW*>(out_w), T, rows, T_max, ngp);
   HVLA_LAUNCH_CHECK("heads_gemm");
   return HVLA_OK;
 }
@@ -476,15 +478,18 @@ static int dino_bf16(cudaStream_t st, const float* dv, const bf16* dm, const uin
 // TE: embedding storage type; TW: generated-weight storage type.  All math fp32.
 template <typename TE, typename TW>
 static int base_generic(cudaStream_t st, const TE* emb, const TW* weights, const int32_t* tidx, int B, int T,
-                        float* out_action, float* out_logit, uint8_t* ws, const Plan& pl, float* maps = nullptr) {
+                        float* out_action, float* out_logit, uint8_t* ws, const Plan& pl, float* maps = nullptr,
+                        const BaseShape* shape = nullptr, int32_t* out_tokens = nullptr, float* out_top2 = nullptr) {
   typedef GenLayout G;
+  const BaseShape sh = shape ? *shape : mix_shape();     // mix head: one readout token; discrete head: 4 or 28 (discrete_head.cuh)
+  const int S = sh.S;
   float* PT = reinterpret_cast<float*>(ws + pl.pt);
   float* X = reinterpret_cast<float*>(ws + pl.xb);
   float* Y = reinterpret_cast<float*>(ws + pl.yb);
   float* QKV = reinterpret_cast<float*>(ws + pl.qkvb);
   float* CB = reinterpret_cast<float*>(ws + pl.cb);
   float* HB = reinterpret_cast<float*>(ws + pl.hb);
-  const int64_t sW = NGP;                  // weight-batch stride; T==1 is handled by an all-zero index below
+  const int64_t sW = sh.ngp;               // weight-batch stride; T==1 is handled by an all-zero index below
   // image_embedding_projection on patch tokens (skip CLS row): base_vit.py:122, 130-133
   {
     GemmP g = gemm_params(emb + DD, DD, weights + G::proj_w, BD, weights + G::proj_b, PT, BD, NPATCH, BD, DD);
@@ -492,45 +497,51 @@ static int base_generic(cudaStream_t st, const TE* emb, const TW* weights, const
     HVLA_TRY((gemm_simt<TE, TW, TW, float>(st, g, B)));
   }
   {
-    const int64_t total = (int64_t)B * BTOK * BD;
-    base_assemble_kernel<TW><<<cdiv(total, 256), 256, 0, st>>>(PT, weights, tidx, X, B);
+    const int64_t total = (int64_t)B * S * BD;
+    base_assemble_kernel<TW><<<cdiv(total, 256), 256, 0, st>>>(PT, weights, tidx, X, B, S, sh.ngp);
     HVLA_LAUNCH_CHECK("base_assemble");
   }
   for (int l = 0; l < BL; ++l) {
-    const TW* lw = weights + G::layers + (int64_t)l * G::layer_size;
+    const TW* lw = weights + sh.layers + (int64_t)l * G::layer_size;
     LnP ln; memset(&ln, 0, sizeof ln);
     ln.x = X; ln.ldx = BD; ln.y = Y; ln.ldy = BD; ln.scale = lw + G::ln0_s; ln.bias = lw + G::ln0_b; ln.sS = sW; ln.widx = tidx;
-    ln.rows = B * BTOK; ln.rows_per_batch = BTOK;
+    ln.rows = B * S; ln.rows_per_batch = S;
     HVLA_TRY((layernorm<TW, float>(st, ln, BD)));
     const int64_t wofs[3] = {G::wq, G::wk, G::wv}, bofs[3] = {G::bq, G::bk, G::bv};
     for (int j = 0; j < 3; ++j) {
-      GemmP g = gemm_params(Y, BD, lw + wofs[j], BD, lw + bofs[j], QKV + j * BD, 3 * BD, BTOK, BD, BD);
-      g.sA = (int64_t)BTOK * BD; g.sW = sW; g.sBias = sW; g.sC = (int64_t)BTOK * 3 * BD; g.widx = tidx;
+      GemmP g = gemm_params(Y, BD, lw + wofs[j], BD, lw + bofs[j], QKV + j * BD, 3 * BD, S, BD, BD);
+      g.sA = (int64_t)S * BD; g.sW = sW; g.sBias = sW; g.sC = (int64_t)S * 3 * BD; g.widx = tidx;
       HVLA_TRY((gemm_simt<float, TW, TW, float>(st, g, B)));
     }
     if (maps) HVLA_TRY((attn_probs<float, BHD>(st, QKV, maps + (int64_t)l * B * BH * BTOK * BTOK, BTOK, BH, B, 1, 0.25f)));
     AttnP ap; memset(&ap, 0, sizeof ap);
-    ap.qkv = QKV; ap.out = CB; ap.S = BTOK; ap.H = BH; ap.nbatch = B; ap.mask = 1;
+    ap.qkv = QKV; ap.out = CB; ap.S = S; ap.H = BH; ap.nbatch = B; ap.mask = 1; ap.n_act = sh.A;
     HVLA_TRY((attention_simt<float, float>(st, ap, BHD)));
     {
-      GemmP g = gemm_params(CB, BD, lw + G::wo, BD, lw + G::bo, X, BD, BTOK, BD, BD);
-      g.sA = (int64_t)BTOK * BD; g.sW = sW; g.sBias = sW; g.sC = (int64_t)BTOK * BD; g.widx = tidx;
-      g.R = X; g.ldr = BD; g.sR = (int64_t)BTOK * BD;
+      GemmP g = gemm_params(CB, BD, lw + G::wo, BD, lw + G::bo, X, BD, S, BD, BD);
+      g.sA = (int64_t)S * BD; g.sW = sW; g.sBias = sW; g.sC = (int64_t)S * BD; g.widx = tidx;
+      g.R = X; g.ldr = BD; g.sR = (int64_t)S * BD;
       HVLA_TRY((gemm_simt<float, TW, TW, float>(st, g, B)));
     }
     ln.scale = lw + G::ln1_s; ln.bias = lw + G::ln1_b;
     HVLA_TRY((layernorm<TW, float>(st, ln, BD)));
     {
-      GemmP g = gemm_params(Y, BD, lw + G::w0, BF, lw + G::b0, HB, BF, BTOK, BF, BD);
-      g.sA = (int64_t)BTOK * BD; g.sW = sW; g.sBias = sW; g.sC = (int64_t)BTOK * BF; g.widx = tidx; g.act = 1;
+      GemmP g = gemm_params(Y, BD, lw + G::w0, BF, lw + G::b0, HB, BF, S, BF, BD);
+      g.sA = (int64_t)S * BD; g.sW = sW; g.sBias = sW; g.sC = (int64_t)S * BF; g.widx = tidx; g.act = 1;
       HVLA_TRY((gemm_simt<float, TW, TW, float>(st, g, B)));
     }
     {
-      GemmP g = gemm_params(HB, BF, lw + G::w1, BD, lw + G::b1, X, BD, BTOK, BD, BF);
-      g.sA = (int64_t)BTOK * BF; g.sW = sW; g.sBias = sW; g.sC = (int64_t)BTOK * BD; g.widx = tidx;
-      g.R = X; g.ldr = BD; g.sR = (int64_t)BTOK * BD;
+      GemmP g = gemm_params(HB, BF, lw + G::w1, BD, lw + G::b1, X, BD, S, BD, BF);
+      g.sA = (int64_t)S * BF; g.sW = sW; g.sBias = sW; g.sC = (int64_t)S * BD; g.widx = tidx;
+      g.R = X; g.ldr = BD; g.sR = (int64_t)S * BD;
       HVLA_TRY((gemm_simt<float, TW, TW, float>(st, g, B)));
     }
+  }
+  if (sh.V > 0) {                          // DiscreteActionHead + BinTokenizer.decode
+    ProfScope ps(st, "discrete_head");
+    discrete_head_kernel<TW><<<B, 256, 0, st>>>(X, weights, tidx, sh, out_tokens, out_action, out_top2);
+    HVLA_LAUNCH_CHECK("discrete_head");
+    return HVLA_OK;
   }
   ProfScope ps(st, "mix_head");
   mix_head_kernel<TW><<<cdiv(B, 4), 128, 0, st>>>(X, weights, tidx, out_action, out_logit, B);
@@ -554,7 +565,8 @@ static int check_common(int B, int T, int dtype, const void* ws, size_t ws_bytes
 }
 
 static int base_act_impl(cudaStream_t st, const void* emb, const void* weights, const int32_t* task_index, int B, int T,
-                         float* out_action, float* out_logit, uint8_t* ws, const Plan& pl, int dtype, float* maps = nullptr) {
+                         float* out_action, float* out_logit, uint8_t* ws, const Plan& pl, int dtype, float* maps = nullptr,
+                         const BaseShape* shape = nullptr, int32_t* out_tokens = nullptr, float* out_top2 = nullptr) {
   if (!task_index && !(T == B || T == 1)) return fail(HVLA_ERR_ARG, "task_index is NULL but T != B and T != 1");
   const int32_t* tidx = task_index;
   if (!tidx && T == 1 && B > 1) {   // shared weights: materialise an all-zero index (B == 1: identity already is)
@@ -565,10 +577,11 @@ static int base_act_impl(cudaStream_t st, const void* emb, const void* weights, 
   }
   if (dtype == HVLA_F32 || dtype == HVLA_BF16X3)        // fp32 embeddings and generated weights: the exact CUDA-core base net
     return base_generic<float, float>(st, reinterpret_cast<const float*>(emb), reinterpret_cast<const float*>(weights), tidx, B,
-                                      T, out_action, out_logit, ws, pl, maps);
-  if (maps || env_flag("HVLA_DEBUG_GENERIC_BASE"))   // attention maps / debugging aid: the same math through the generic CUDA-core kernels
+                                      T, out_action, out_logit, ws, pl, maps, shape, out_tokens, out_top2);
+  // attention maps / discrete head (several readout tokens) / debugging aid: the same math through the generic CUDA-core kernels
+  if (maps || shape || env_flag("HVLA_DEBUG_GENERIC_BASE"))
     return base_generic<bf16, bf16>(st, reinterpret_cast<const bf16*>(emb), reinterpret_cast<const bf16*>(weights), tidx, B, T,
-                                    out_action, out_logit, ws, pl, maps);
+                                    out_action, out_logit, ws, pl, maps, shape, out_tokens, out_top2);
   return basefused::base_act_bf16(st, reinterpret_cast<const bf16*>(emb), reinterpret_cast<const bf16*>(weights), tidx, B,
                                   out_action, out_logit);
 }
@@ -693,6 +706,51 @@ int hvla_generate_rows(hvla_stream_t stream, const float* hn_blob, const void* h
                                 row_index, T_max);
   return generate_impl<bf16>(st, hn_blob, hn_blob_f16, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, weights, ctx, ws, pl,
                              row_index, T_max);
+}
+
+int64_t hvla_discrete_generated_elems(int n_action_tokens) {
+  BaseShape sh;
+  return discrete_shape(n_action_tokens, &sh) ? sh.total : -1;
+}
+int64_t hvla_discrete_row_stride(int n_action_tokens) {
+  BaseShape sh;
+  return discrete_shape(n_action_tokens, &sh) ? sh.ngp : -1;
+}
+
+int hvla_generate_n(hvla_stream_t stream, const float* hn_blob, const void* hn_blob_f16, const void* heads_w, const float* heads_b,
+                    const float* tok_emb, const int32_t* tok_mask, const uint8_t* lang_pad, const float* init_cls, int T,
+                    int64_t row_stride, void* out_weights, float* out_ctx, void* workspace, size_t workspace_bytes, int dtype) {
+  if (!hn_blob || !heads_w || !heads_b || !tok_emb || !tok_mask || !init_cls || !out_weights)
+    return fail(HVLA_ERR_ARG, "hvla_generate_n: NULL argument");
+  if (row_stride <= 0 || row_stride % 32 != 0) return fail(HVLA_ERR_ARG, "hvla_generate_n: row_stride must be a positive multiple of 32");
+  HVLA_TRY(check_common(0, T, dtype, workspace, workspace_bytes));
+  if (T == 0) return HVLA_OK;
+  const Plan pl = make_plan(0, T, dtype);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  if (dtype != HVLA_BF16)
+    return generate_impl<float>(st, hn_blob, nullptr, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, out_weights, out_ctx, ws, pl,
+                                nullptr, 0, row_stride);
+  return generate_impl<bf16>(st, hn_blob, hn_blob_f16, heads_w, heads_b, tok_emb, tok_mask, lang_pad, init_cls, T, out_weights, out_ctx, ws, pl,
+                             nullptr, 0, row_stride);
+}
+
+int hvla_act_discrete(hvla_stream_t stream, const float* dino_vec, const void* dino_mat, const uint8_t* images, const void* weights,
+                      const int32_t* task_index, int B, int T, int n_action_tokens, float* out_action, int32_t* out_tokens, float* out_top2,
+                      void* workspace, size_t workspace_bytes, int dtype) {
+  if (!dino_vec || !dino_mat || !images || !weights || !out_action || !out_tokens) return fail(HVLA_ERR_ARG, "hvla_act_discrete: NULL argument");
+  BaseShape sh;
+  if (!discrete_shape(n_action_tokens, &sh))
+    return fail(HVLA_ERR_UNSUPPORTED, "hvla_act_discrete: n_action_tokens must be 4 (action_horizon) or 28 (action_dim_and_action_horizon)");
+  if (T <= 0 && B > 0) return fail(HVLA_ERR_ARG, "hvla_act_discrete: T must be >= 1");
+  HVLA_TRY(check_common(B, 0, dtype, workspace, workspace_bytes));
+  if (B == 0) return HVLA_OK;
+  const Plan pl = make_plan(B, 0, dtype);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  void* emb = ws + pl.emb;
+  HVLA_TRY(hvla_dino_forward(stream, dino_vec, dino_mat, images, B, emb, workspace, workspace_bytes, dtype));
+  return base_act_impl(reinterpret_cast<cudaStream_t>(stream), emb, weights, task_index, B, T, out_action, nullptr, ws, pl, dtype, nullptr, &sh,
+                       out_tokens, out_top2);
 }
 
 int hvla_dino_forward(hvla_stream_t stream, const float* dino_vec, const void* dino_mat, const uint8_t* images, int B,

@@ -446,6 +446,7 @@ struct AttnP {
   const int32_t* tok_mask;         // [nbatch, 32] (mask 2)
   const uint8_t* lang_pad;         // [nbatch] or null
   int prescaled;                   // q already divided by sqrt(DH)
+  int n_act;                       // mask 1: number of trailing action tokens the other tokens cannot see (0 means 1)
 };
 
 template <typename T, typename TO, int DH_>
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(128) attention_simt_kernel(AttnP p) {
 #pragma unroll 8
       for (int d = 0; d < DH_; ++d) a = fmaf(qs[w][d], to_f(kp[d]), a);
       bool ok = true;
-      if (p.mask == 1) ok = (key != p.S - 1) || (q == p.S - 1);
+      if (p.mask == 1) { const int na = p.n_act > 0 ? p.n_act : 1; ok = (key < p.S - na) || (q >= p.S - na); }
       else if (p.mask == 2) {
         if (key < 32) ok = (p.tok_mask[b * 32 + key] != 0) && (p.lang_pad ? p.lang_pad[b] != 0 : true);
         else if (key == 33) ok = (q == 33);
@@ -579,7 +580,7 @@ template <typename T, typename TO>
 inline int attention_simt(cudaStream_t st, const AttnP& p, int dh) {
   if (p.S > 288) return fail(HVLA_ERR_ARG, "attention_simt: S too large");
   ProfScope ps(st, "attention_simt");
-  if (std::is_same<T, float>::value && std::is_same<TO, float>::value && dh == BHD && p.S == BTOK && p.H == BH && p.mask == 1 && !p.prescaled) {
+  if (std::is_same<T, float>::value && std::is_same<TO, float>::value && dh == BHD && p.S == BTOK && p.H == BH && p.mask == 1 && !p.prescaled && p.n_act <= 1) {
     base_attention_f32_kernel<<<dim3(BH, p.nbatch), 256, 0, st>>>(reinterpret_cast<const float*>(p.qkv), reinterpret_cast<float*>(p.out));
     HVLA_LAUNCH_CHECK("base_attention_f32");
     return HVLA_OK;
@@ -693,14 +694,14 @@ __global__ void ctx_assemble_kernel(const float* __restrict__ TPj, const float* 
 // base-ViT tokens (base_vit.py:182-204): X[b,p,:] = patches + pos;  X[b,256,:] = 0 + pos[256]
 template <typename TW>
 __global__ void base_assemble_kernel(const float* __restrict__ Pt, const TW* __restrict__ weights,
-                                     const int* __restrict__ tidx, float* __restrict__ X, int B) {
+                                     const int* __restrict__ tidx, float* __restrict__ X, int B, int S, int64_t ngp) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)B * BTOK * BD;
+  const int64_t total = (int64_t)B * S * BD;
   if (idx >= total) return;
   const int c = (int)(idx % BD);
   const int64_t row = idx / BD;
-  const int t = (int)(row % BTOK), b = (int)(row / BTOK);
-  const TW* pos = weights + (int64_t)(tidx ? tidx[b] : b) * NGP + GenLayout::pos;
+  const int t = (int)(row % S), b = (int)(row / S);
+  const TW* pos = weights + (int64_t)(tidx ? tidx[b] : b) * ngp + GenLayout::pos;
   const float base = t < NPATCH ? Pt[((int64_t)b * NPATCH + t) * BD + c] : 0.f;
   X[idx] = base + to_f(pos[t * BD + c]);
 }
@@ -811,10 +812,10 @@ constexpr int HEADS_TT = 8;
 template <typename TW, typename TO>
 __global__ void __launch_bounds__(256) heads_gemm_kernel(const float* __restrict__ E, const TW* __restrict__ W,
                                                          const float* __restrict__ bias, TO* __restrict__ out, int T,
-                                                         const int32_t* __restrict__ rows, int T_max) {
+                                                         const int32_t* __restrict__ rows, int T_max, int64_t ngp) {
   __shared__ float es[HEADS_TT][CD];
   const int64_t col = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
-  const bool active = col < NGP;
+  const bool active = col < ngp;
   float bv[4] = {0.f, 0.f, 0.f, 0.f};
   if (active) Vec4<float>::load(bias + col, bv);
   for (int t0 = 0; t0 < T; t0 += HEADS_TT) {
@@ -833,7 +834,7 @@ __global__ void __launch_bounds__(256) heads_gemm_kernel(const float* __restrict
 #pragma unroll 4
     for (int k = 0; k < CD; ++k) {
       float w[4];
-      Vec4<TW>::load(W + (int64_t)k * NGP + col, w);
+      Vec4<TW>::load(W + (int64_t)k * ngp + col, w);
 #pragma unroll
       for (int tt = 0; tt < HEADS_TT; ++tt) {
         const float e = es[tt][k];
@@ -848,7 +849,7 @@ __global__ void __launch_bounds__(256) heads_gemm_kernel(const float* __restrict
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[j] = acc[tt][j] + bv[j];
         const int orow = rows ? __ldg(rows + t0 + tt) : t0 + tt;      // task-switch scheduler: scattered rows of a persistent buffer
-        if (orow >= 0 && orow < T_max) Vec4<TO>::store(out + (int64_t)orow * NGP + col, o);
+        if (orow >= 0 && orow < T_max) Vec4<TO>::store(out + (int64_t)orow * ngp + col, o);
       }
     }
   }

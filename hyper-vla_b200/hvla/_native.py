@@ -30,6 +30,10 @@ SIGNATURES = {
     "hvla_base_act": (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
     "hvla_act": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
     "hvla_act_debug": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
+    "hvla_discrete_generated_elems": (c_i64, [c_int]),
+    "hvla_discrete_row_stride": (c_i64, [c_int]),
+    "hvla_generate_n": (c_int, [c_void_p] * 9 + [c_int, c_i64, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
+    "hvla_act_discrete": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
     "hvla_act_host": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
     "hvla_gemm_bf16": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int]),
     "hvla_dino_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),

@@ -41,6 +41,11 @@ class BaseNetwork:
         except ImportError:  # pragma: no cover
             on_device = False
         rt = model.runtime
+        if self.action_head_type == "discrete":       # DiscreteActionHead.predict_action(argmax=True) + BinTokenizer.decode (action_heads.py:372-396)
+            act, tok = rt.act_discrete(observation, base_params.weights, task_index)
+            if on_device:
+                return act, tok
+            return act.cpu().numpy(), tok.cpu().numpy()
         if attention_maps:
             act, logit, dmaps, bmaps = rt.act_debug(observation, base_params.weights, task_index)
             if on_device:

@@ -150,7 +150,7 @@ def validate_config(config: dict) -> dict:
     _require(not hk.get("share_all_params", False), "share_all_params")
     _require(hk.get("output_head_bias", True), "output_head_bias=False")
     _require(bk.get("model_type") == "vit", "model_type != 'vit'")
-    _require(bk.get("action_head_type") == "mix", "action_head_type != 'mix'")
+    _require(bk.get("action_head_type") in ("mix", "discrete"), "action_head_type not in ('mix', 'discrete')")
     _require(bk.get("action_horizon") == ACTION_HORIZON and bk.get("action_dim") == ACTION_DIM,
              "action_horizon/action_dim != 4/7")
     _require(vk.get("encoder_type") == "DINOv2", "encoder_type != 'DINOv2'")
@@ -163,6 +163,11 @@ def validate_config(config: dict) -> dict:
     _require(not vk.get("use_differential_transformer", False), "use_differential_transformer")
     _require(not vk.get("return_attention_map", False), "return_attention_map")
     _require(float(vk.get("image_embedding_noise", 0.0)) == 0.0, "image_embedding_noise > 0")
+    if bk.get("action_head_type") == "discrete":
+        # DiscreteActionHead (action_heads.py:252-396) on 4 or 28 readout tokens, 256 uniform bins over [-1, 1] (its defaults)
+        _require(ak.get("discrete_token_type") in ("action_horizon", "action_dim_and_action_horizon"),
+                 "discrete_token_type not in ('action_horizon', 'action_dim_and_action_horizon')")
+        return cfg
     _require(not ak.get("token_per_horizon", False), "token_per_horizon")
     _require(ak.get("squash_continuous_action", True), "squash_continuous_action=False")
     _require(len(tuple(ak.get("hidden_dims", ()))) == 0, "action head hidden_dims")

@@ -86,21 +86,72 @@ def _copy_tree(t):
     return {k: _copy_tree(v) if isinstance(v, dict) else v for k, v in t.items()}
 
 
-def base_net_shapes() -> dict:
-    """``BaseNetwork`` param tree for the README config."""
+class HeadSpec:
+    """Which action head the base network carries and how many readout (action) tokens its ViT appends
+    (hypervla/components/base_network.py:22-33): the README ``mix`` head reads ONE token; ``DiscreteActionHead`` reads
+    ``action_horizon`` (4) tokens, each projected to action_dim * 256 logits, or ``action_horizon * action_dim`` (28) tokens, each
+    projected to 256 logits (components/action_heads.py:252-300)."""
+
+    def __init__(self, kind: str = "mix", n_action_tokens: int = 1):
+        if kind == "mix" and n_action_tokens != 1:
+            raise ValueError("the mix head reads one action token (token_per_horizon=False)")
+        if kind == "discrete" and n_action_tokens not in (C.ACTION_HORIZON, C.ACTION_HORIZON * C.ACTION_DIM):
+            raise ValueError("discrete head: 4 (action_horizon) or 28 (action_dim_and_action_horizon) action tokens")
+        if kind not in ("mix", "discrete"):
+            raise ValueError(f"unsupported action head {kind!r}")
+        self.kind, self.n_action_tokens = kind, n_action_tokens
+
+    @property
+    def vocab_out(self) -> int:          # outputs of vocab_proj per token
+        return 0 if self.kind == "mix" else (C.ACTION_DIM * 256 if self.n_action_tokens == C.ACTION_HORIZON else 256)
+
+    @property
+    def tokens(self) -> int:             # base-ViT sequence length
+        return C.N_PATCH + self.n_action_tokens
+
+    def __eq__(self, other):
+        return isinstance(other, HeadSpec) and (self.kind, self.n_action_tokens) == (other.kind, other.n_action_tokens)
+
+    def __hash__(self):
+        return hash((self.kind, self.n_action_tokens))
+
+    def __repr__(self):
+        return f"HeadSpec({self.kind!r}, {self.n_action_tokens})"
+
+    @classmethod
+    def from_config(cls, config: dict) -> "HeadSpec":
+        bk = config["base_net_kwargs"]
+        if bk.get("action_head_type") == "discrete":
+            tok = bk.get("action_head_kwargs", {}).get("discrete_token_type")
+            n = {"action_horizon": C.ACTION_HORIZON, "action_dim_and_action_horizon": C.ACTION_HORIZON * C.ACTION_DIM}.get(tok)
+            if n is None:
+                raise ValueError(f"discrete_token_type {tok!r} is not supported")
+            return cls("discrete", n)
+        return cls("mix", 1)
+
+
+MIX = HeadSpec("mix", 1)
+
+
+def base_net_shapes(spec: HeadSpec = MIX) -> dict:
+    """``BaseNetwork`` param tree (SURVEY.md Appendix A.2 for the README ``mix`` config)."""
     d = C.BASE_DIM
+    if spec.kind == "mix":
+        head = {
+            "continuous_head": {"kernel": (d, C.ACTION_HORIZON * (C.ACTION_DIM - 1)),
+                                "bias": (C.ACTION_HORIZON * (C.ACTION_DIM - 1),)},
+            "discrete_head": {"kernel": (d, C.ACTION_HORIZON), "bias": (C.ACTION_HORIZON,)},
+        }
+    else:       # DiscreteActionHead.setup: self.vocab_proj = nn.Dense(final_layer_size)  (action_heads.py:281-300)
+        head = {"vocab_proj": {"kernel": (d, spec.vocab_out), "bias": (spec.vocab_out,)}}
     return {
         "encoder": {
             "image_encoder": dinov2_shapes(),
             "image_embedding_projection": {"kernel": (C.DINO_DIM, d), "bias": (d,)},
-            "pos_embedding": (1, C.BASE_TOKENS, d),
+            "pos_embedding": (1, spec.tokens, d),
             "Transformer_0": transformer_shapes(d, C.BASE_LAYERS, C.BASE_HEADS, C.BASE_MLP),
         },
-        "action_head": {
-            "continuous_head": {"kernel": (d, C.ACTION_HORIZON * (C.ACTION_DIM - 1)),
-                                "bias": (C.ACTION_HORIZON * (C.ACTION_DIM - 1),)},
-            "discrete_head": {"kernel": (d, C.ACTION_HORIZON), "bias": (C.ACTION_HORIZON,)},
-        },
+        "action_head": head,
     }
 
 
@@ -147,7 +198,7 @@ def head_name(path: Path) -> str:
 def build_base_net_metadata(config: dict) -> dict:
     """The ``base_net_metadata`` dict of model.py:460-513 for the supported config."""
     shared = tuple(config["hypernet_kwargs"].get("shared_modules", ()))
-    shapes = base_net_shapes()
+    shapes = base_net_shapes(HeadSpec.from_config(config))
     param_shape, param_dim, token_index, generation_flag = {}, {}, {}, {}
     output_head_info = OrderedDict()
     total = 0
@@ -176,20 +227,20 @@ def build_base_net_metadata(config: dict) -> dict:
 # ----------------------------------------------------------------------------------
 # generated leaves: canonical (jax) order and the packed kernel order
 # ----------------------------------------------------------------------------------
-def generated_leaves_canonical() -> List[Tuple[Path, Tuple[int, ...]]]:
-    """The 73 generated leaves in jax sorted-key order."""
-    return [(p, s) for p, s in iter_leaves(base_net_shapes()) if is_generated(p)]
+def generated_leaves_canonical(spec: HeadSpec = MIX) -> List[Tuple[Path, Tuple[int, ...]]]:
+    """The generated leaves (73 for the mix head) in jax sorted-key order."""
+    return [(p, s) for p, s in iter_leaves(base_net_shapes(spec)) if is_generated(p)]
 
 
 def _blk(l: int, *rest: str) -> Path:
     return ("encoder", "Transformer_0", f"encoderblock_{l}") + rest
 
 
-def generated_leaves_packed() -> List[Tuple[Path, Tuple[int, ...]]]:
+def generated_leaves_packed(spec: HeadSpec = MIX) -> List[Tuple[Path, Tuple[int, ...]]]:
     """Leaf order of the packed per-task weight row the kernels consume
     (layer-streaming order: what the base-net kernel touches first comes first).
     Every leaf is stored flat in its Flax row-major shape."""
-    shapes = base_net_shapes()
+    shapes = base_net_shapes(spec)
     order: List[Path] = [
         ("encoder", "image_embedding_projection", "kernel"),
         ("encoder", "image_embedding_projection", "bias"),
@@ -210,13 +261,18 @@ def generated_leaves_packed() -> List[Tuple[Path, Tuple[int, ...]]]:
     order += [
         ("encoder", "Transformer_0", "encoder_norm", "scale"),
         ("encoder", "Transformer_0", "encoder_norm", "bias"),
-        ("action_head", "continuous_head", "kernel"),
-        ("action_head", "continuous_head", "bias"),
-        ("action_head", "discrete_head", "kernel"),
-        ("action_head", "discrete_head", "bias"),
     ]
+    if spec.kind == "mix":
+        order += [
+            ("action_head", "continuous_head", "kernel"),
+            ("action_head", "continuous_head", "bias"),
+            ("action_head", "discrete_head", "kernel"),
+            ("action_head", "discrete_head", "bias"),
+        ]
+    else:
+        order += [("action_head", "vocab_proj", "kernel"), ("action_head", "vocab_proj", "bias")]
     out = [(p, tuple(get_path(shapes, p))) for p in order]
-    assert sorted(p for p, _ in out) == sorted(p for p, _ in generated_leaves_canonical())
+    assert sorted(p for p, _ in out) == sorted(p for p, _ in generated_leaves_canonical(spec))
     return out
 
 
@@ -224,14 +280,24 @@ N_GENERATED = 201_500
 N_GENERATED_PADDED = 201_504      # row stride of the packed blob (multiple of 32 elements)
 
 
-def packed_offsets() -> "OrderedDict[Path, Tuple[int, Tuple[int, ...]]]":
+def n_generated(spec: HeadSpec = MIX) -> int:
+    """Generated parameters per task: 201,500 (mix), 316,352 (discrete, 4 tokens), 218,048 (discrete, 28 tokens)."""
+    return sum(int(np.prod(s)) for _, s in generated_leaves_packed(spec))
+
+
+def n_generated_padded(spec: HeadSpec = MIX) -> int:
+    """Row stride of the packed blob: the next multiple of 32 elements (hvla_generated_row_stride / hvla_discrete_row_stride)."""
+    return (n_generated(spec) + 31) // 32 * 32
+
+
+def packed_offsets(spec: HeadSpec = MIX) -> "OrderedDict[Path, Tuple[int, Tuple[int, ...]]]":
     """path -> (element offset in the packed row, shape)."""
     table: "OrderedDict[Path, Tuple[int, Tuple[int, ...]]]" = OrderedDict()
     off = 0
-    for path, shape in generated_leaves_packed():
+    for path, shape in generated_leaves_packed(spec):
         table[path] = (off, shape)
         off += int(np.prod(shape))
-    assert off == N_GENERATED, off
+    assert off == n_generated(spec) and (spec != MIX or off == N_GENERATED), off
     return table
 
 

@@ -47,14 +47,14 @@ class GeneratedBaseParams(Mapping):
         self.generation = 0             # bumped by every in-place row regeneration (task-switch scheduler)
 
     def packed_numpy(self) -> np.ndarray:
-        return self.weights.float().cpu().numpy()[:, :M.N_GENERATED]
+        return self.weights.float().cpu().numpy()[:, :M.n_generated(self._model.head_spec)]
 
     def tree(self) -> dict:
         """The pytree ``create_tasks`` returns in the reference: generated leaves (leading T unless
         T == 1, model.py:81) plus the shared DINOv2 leaves under encoder/image_encoder."""
         if self._tree is None:
             rows = self.packed_numpy()
-            gen = P.unpack_generated(rows[0] if self._squeeze else rows)
+            gen = P.unpack_generated(rows[0] if self._squeeze else rows, self._model.head_spec)
             gen.setdefault("encoder", {})["image_encoder"] = P.dino_tree_from_params(self._model.params)
             self._tree = gen
         return self._tree
@@ -99,7 +99,7 @@ class HyperVLA:
         cfg = Cfg.validate_config(config)
         meta = M.build_base_net_metadata(cfg)
         if params is None:
-            params = P.init_params(_seed_from_rng(rng, int(cfg.get("seed", 2025))), params_variant)
+            params = P.init_params(_seed_from_rng(rng, int(cfg.get("seed", 2025))), params_variant, M.HeadSpec.from_config(cfg))
         return cls(hypernet=HyperNetwork(meta, cfg["hypernet_kwargs"]), base_net=BaseNetwork.from_config(cfg),
                    config=cfg, params=params, base_net_metadata=meta, example_batch=example_batch,
                    dataset_statistics=dataset_statistics, precision=precision, device=device)
@@ -138,10 +138,15 @@ class HyperVLA:
                 json.dump(self.dataset_statistics, f, default=lambda x: np.asarray(x).tolist())
 
     @property
+    def head_spec(self) -> "M.HeadSpec":
+        """README mix head (one readout token) or DiscreteActionHead on 4 / 28 readout tokens (base_network.py:22-33)."""
+        return M.HeadSpec.from_config(self.config)
+
+    @property
     def runtime(self):
         if self._runtime is None:
             from .runtime import Runtime
-            self._runtime = Runtime(self.params, self.precision, self.device)
+            self._runtime = Runtime(self.params, self.precision, self.device, self.head_spec)
         elif self._runtime._params_id != id(self.params):
             # ``model.params = ema_params`` (the reference's EMA swap is base_model.replace(params=...), data/simpler/
             # evaluate.py:443): re-upload the device blobs and drop the captured graphs that point into the old ones
@@ -231,6 +236,12 @@ class HyperVLA:
         if not isinstance(base_params, GeneratedBaseParams):
             raise TypeError("base_params must be the object returned by HyperVLA.create_tasks")
         ti = task_index if task_index is not None else base_params.task_index
+        if self.head_spec.kind == "discrete":
+            if return_attention_maps:
+                raise ValueError("attention maps are produced for the mix-head configuration")
+            action, tokens = self.base_net.apply({"params": base_params}, images, None, timestep_pad_mask, rng=rng, train=False,
+                                                 method=BaseNetwork.predict_action, model=self, task_index=ti)
+            return action, {"action_tokens": tokens}
         if return_attention_maps:
             action, logits, dmaps, bmaps = self.base_net.apply({"params": base_params}, images, None, timestep_pad_mask, rng=rng, train=False,
                                                                method=BaseNetwork.predict_action, model=self, task_index=ti,

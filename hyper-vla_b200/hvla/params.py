@@ -117,27 +117,31 @@ def _init_dinov2(rng, variant):
     }
 
 
-def init_base_params(rng, variant="P0") -> dict:
-    """One ``BaseNetwork.init`` draw (the values BIAS_INIT copies into head biases)."""
+def init_base_params(rng, variant="P0", spec: "M.HeadSpec" = M.MIX) -> dict:
+    """One ``BaseNetwork.init`` draw (the values BIAS_INIT copies into head biases).  The draw order of the mix head is frozen
+    (the committed golden fixtures depend on it)."""
     d = C.BASE_DIM
     n_cont = C.ACTION_HORIZON * (C.ACTION_DIM - 1)
-    return {
-        "encoder": {
-            "image_encoder": _init_dinov2(rng, variant),
-            "image_embedding_projection": {"kernel": _xavier(rng, (C.DINO_DIM, d), C.DINO_DIM, d),
-                                           "bias": np.zeros((d,), F32)},
-            "pos_embedding": _normal(rng, (1, C.BASE_TOKENS, d), 0.02),
-            "Transformer_0": _init_transformer(rng, d, C.BASE_LAYERS, C.BASE_HEADS, C.BASE_MLP, "P0"),
-        },
-        "action_head": {
+    enc = {
+        "image_encoder": _init_dinov2(rng, variant),
+        "image_embedding_projection": {"kernel": _xavier(rng, (C.DINO_DIM, d), C.DINO_DIM, d),
+                                       "bias": np.zeros((d,), F32)},
+        "pos_embedding": _normal(rng, (1, spec.tokens, d), 0.02),
+        "Transformer_0": _init_transformer(rng, d, C.BASE_LAYERS, C.BASE_HEADS, C.BASE_MLP, "P0"),
+    }
+    if spec.kind == "mix":
+        head = {
             "continuous_head": {"kernel": _xavier(rng, (d, n_cont), d, n_cont), "bias": np.zeros((n_cont,), F32)},
             "discrete_head": {"kernel": _xavier(rng, (d, C.ACTION_HORIZON), d, C.ACTION_HORIZON),
                               "bias": np.zeros((C.ACTION_HORIZON,), F32)},
-        },
-    }
+        }
+    else:
+        v = spec.vocab_out
+        head = {"vocab_proj": {"kernel": _xavier(rng, (d, v), d, v), "bias": np.zeros((v,), F32)}}
+    return {"encoder": enc, "action_head": head}
 
 
-def init_params(seed: int = 2025, variant: str = "P1") -> dict:
+def init_params(seed: int = 2025, variant: str = "P1", spec: "M.HeadSpec" = M.MIX) -> dict:
     """Hypernetwork param pytree (what ``HyperVLA.params`` holds)."""
     if variant not in ("P0", "P1"):
         raise ValueError(f"unknown params variant {variant!r}")
@@ -153,7 +157,7 @@ def init_params(seed: int = 2025, variant: str = "P1") -> dict:
         "layer_pos_embedding": _normal(rng, (1, 1, d), 0.02),
         "context_encoder": _init_transformer(rng, d, C.CTX_LAYERS, C.CTX_HEADS, C.CTX_MLP, variant),
     }
-    base = init_base_params(rng, variant)
+    base = init_base_params(rng, variant, spec)
     for path, value in M.iter_leaves(base):
         name = M.head_name(path)
         if M.is_generated(path):
@@ -252,13 +256,13 @@ def hn_blob_size() -> int:
     return 2 * (C.LANG_DIM * d + d) + (C.LANG_TOKENS + 2) * d + C.CTX_LAYERS * per_layer + 2 * d
 
 
-def pack_heads(params: dict) -> Tuple[np.ndarray, np.ndarray]:
+def pack_heads(params: dict, spec: "M.HeadSpec" = M.MIX) -> Tuple[np.ndarray, np.ndarray]:
     """Output heads as ONE matrix: W [128, NGP] and b [NGP] in packed column order
     (the 73 ``Dense(128->leaf)`` heads of hypernetwork.py:65-67 side by side)."""
-    NGP = M.N_GENERATED_PADDED
+    NGP = M.n_generated_padded(spec)
     W = np.zeros((C.CTX_DIM, NGP), F32)
     b = np.zeros((NGP,), F32)
-    for path, (off, shape) in M.packed_offsets().items():
+    for path, (off, shape) in M.packed_offsets(spec).items():
         n = int(np.prod(shape))
         head = params[f"output_head_{M.head_name(path)}"]
         W[:, off:off + n] = head["kernel"]
@@ -410,11 +414,11 @@ def pack_dino_tree(t: dict, transposed: bool) -> Tuple[np.ndarray, np.ndarray]:
     return vec, mat
 
 
-def unpack_generated(row: np.ndarray) -> dict:
+def unpack_generated(row: np.ndarray, spec: "M.HeadSpec" = M.MIX) -> dict:
     """Packed per-task weight row -> base-net pytree (generated leaves only, Flax names)."""
     tree: dict = {}
     row = np.asarray(row)
-    for path, (off, shape) in M.packed_offsets().items():
+    for path, (off, shape) in M.packed_offsets(spec).items():
         n = int(np.prod(shape))
         M.set_path(tree, path, row[..., off:off + n].reshape(row.shape[:-1] + tuple(shape)))
     return tree

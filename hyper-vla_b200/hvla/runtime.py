@@ -21,8 +21,10 @@ def _torch():
 
 
 class Runtime:
-    def __init__(self, params: dict, precision: str = "bf16", device: Optional[object] = None):
+    def __init__(self, params: dict, precision: str = "bf16", device: Optional[object] = None, spec: "M.HeadSpec" = M.MIX):
         torch = _torch()
+        self.spec = spec                # action head variant: README mix head, or DiscreteActionHead on 4 / 28 readout tokens
+        self.ngp = M.n_generated_padded(spec)
         if precision not in ("bf16", "fp32", "fp32x3"):
             raise ValueError("precision must be 'bf16', 'fp32' or 'fp32x3' (fp32-class accuracy on the tensor cores, split bf16 operands)")
         if not torch.cuda.is_available():
@@ -54,7 +56,7 @@ class Runtime:
         assert hn.size == self.lib.hvla_hn_blob_elems()
         self.hn_blob = torch.from_numpy(hn).to(dev)
         self.hn_blob_f16 = self.hn_blob.to(torch.float16) if self.precision == "bf16" else None
-        W, b = P.pack_heads(params)
+        W, b = P.pack_heads(params, self.spec)
         self.heads_w = torch.from_numpy(W).to(self.tdtype).to(dev)
         self.heads_b = torch.from_numpy(b).to(dev)
         del W
@@ -124,15 +126,22 @@ class Runtime:
             pad_ptr = pad.data_ptr()
         f16 = self.hn_blob_f16.data_ptr() if self.hn_blob_f16 is not None else None
         if rows is None:
-            out = torch.empty((T, M.N_GENERATED_PADDED), dtype=self.tdtype, device=dev)
+            out = torch.empty((T, self.ngp), dtype=self.tdtype, device=dev)
             ctx = torch.empty((T, Cfg.CTX_DIM), dtype=torch.float32, device=dev)
             with self._on_device():
                 ws, ws_bytes = self.workspace(0, T)
-                st = self.lib.hvla_generate(self.stream(), self.hn_blob.data_ptr(), f16, self.heads_w.data_ptr(), self.heads_b.data_ptr(),
-                                            tok.data_ptr(), am.data_ptr(), pad_ptr, cls.data_ptr(), T, out.data_ptr(), ctx.data_ptr(),
-                                            ws, ws_bytes, self.dtype)
+                if self.spec == M.MIX:
+                    st = self.lib.hvla_generate(self.stream(), self.hn_blob.data_ptr(), f16, self.heads_w.data_ptr(), self.heads_b.data_ptr(),
+                                                tok.data_ptr(), am.data_ptr(), pad_ptr, cls.data_ptr(), T, out.data_ptr(), ctx.data_ptr(),
+                                                ws, ws_bytes, self.dtype)
+                else:       # another generated-row layout (discrete head): same kernels, explicit row stride
+                    st = self.lib.hvla_generate_n(self.stream(), self.hn_blob.data_ptr(), f16, self.heads_w.data_ptr(), self.heads_b.data_ptr(),
+                                                  tok.data_ptr(), am.data_ptr(), pad_ptr, cls.data_ptr(), T, self.ngp, out.data_ptr(),
+                                                  ctx.data_ptr(), ws, ws_bytes, self.dtype)
             N.check(st, "hvla_generate")
             return out, ctx
+        if self.spec != M.MIX:
+            raise ValueError("in-place row regeneration is implemented for the mix-head layout")
         # task-switch scheduler: regenerate rows `rows` of the persistent (weights, ctx) buffers in place
         out, ctx = into
         T_max = int(out.shape[0])
@@ -263,6 +272,29 @@ class Runtime:
         logit.copy_(st["logit_dev"], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return act.numpy().copy(), logit.numpy().copy()
+
+    def act_discrete(self, images, weights, task_index=None, want_top2: bool = False):
+        """DiscreteActionHead variant of the act step (hvla_act_discrete): DINOv2 -> base ViT with 4 / 28 readout tokens ->
+        vocab_proj -> argmax -> BinTokenizer.decode.  -> (action (B,4,7) f32 bin centres, tokens (B,4,7) i32[, top2 (B,4,7,2)]), CUDA tensors."""
+        torch = _torch()
+        img = images if torch.is_tensor(images) else torch.from_numpy(np.ascontiguousarray(images))
+        img = img.to(self.device).contiguous()
+        B, T = int(img.shape[0]), int(weights.shape[0])
+        if tuple(img.shape[1:]) != (Cfg.IMAGE_SIZE, Cfg.IMAGE_SIZE, 3) or img.dtype != torch.uint8:
+            raise ValueError("Input image size must be 224x224 (uint8, NHWC)")
+        if self.spec.kind != "discrete" or int(weights.shape[1]) != self.ngp:
+            raise ValueError("act_discrete needs a model configured with action_head_type='discrete' and its generated weights")
+        keep, tptr = self._tidx(task_index, B, T)
+        act = torch.empty((B, Cfg.ACTION_HORIZON, Cfg.ACTION_DIM), dtype=torch.float32, device=self.device)
+        tok = torch.empty((B, Cfg.ACTION_HORIZON, Cfg.ACTION_DIM), dtype=torch.int32, device=self.device)
+        top2 = torch.empty((B, Cfg.ACTION_HORIZON, Cfg.ACTION_DIM, 2), dtype=torch.float32, device=self.device) if want_top2 else None
+        if B:
+            with self._on_device():
+                ws, ws_bytes = self.workspace(B, 0)
+                N.check(self.lib.hvla_act_discrete(self.stream(), self.dino_vec.data_ptr(), self.dino_mat.data_ptr(), img.data_ptr(),
+                                                   weights.data_ptr(), tptr, B, T, self.spec.n_action_tokens, act.data_ptr(), tok.data_ptr(),
+                                                   top2.data_ptr() if top2 is not None else None, ws, ws_bytes, self.dtype), "hvla_act_discrete")
+        return (act, tok, top2) if want_top2 else (act, tok)
 
     def act_debug(self, images, weights, task_index=None):
         """One eager act step that also returns the attention weights the reference sows as ``intermediates``

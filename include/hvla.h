@@ -124,6 +124,24 @@ int hvla_act_debug(hvla_stream_t stream, const float* dino_vec, const void* dino
                    const void* weights, const int32_t* task_index, int B, int T, float* out_action, float* out_logit,
                    float* dino_maps, float* base_maps, void* workspace, size_t workspace_bytes, int dtype);
 
+/* ---- DiscreteActionHead variant: replaces the same predict_action call when the config says
+ * base_net_kwargs.action_head_type = "discrete" (hypervla/components/base_network.py:22-33, 92-99; action_heads.py:252-396;
+ * BinTokenizer.decode, octo/model/components/tokenizers.py:235-275).  The base ViT carries n_action_tokens readout tokens
+ * (4 = discrete_token_type "action_horizon", 28 = "action_dim_and_action_horizon") and the generated row has its own layout:
+ *   proj_w[768,64] proj_b[64] pos[256+A,64] 4 x block (as above) encn_s encn_b vocab_w[64,V] vocab_b[V],  V = 1792 (A=4) | 256 (A=28)
+ * hvla_discrete_generated_elems / hvla_discrete_row_stride give its size / padded stride; hvla_generate_n is hvla_generate with an
+ * explicit row stride (heads_w [128,row_stride], heads_b [row_stride], out_weights [T,row_stride]).
+ *   out_action [B,4,7] f32 = bin centres of the argmax tokens; out_tokens [B,4,7] i32; out_top2 [B,4,7,2] f32 (largest and second
+ *   largest logit of every slot, for margin-aware parity checks) or NULL.  Runs the base net on the generic CUDA-core kernels. */
+int64_t hvla_discrete_generated_elems(int n_action_tokens);
+int64_t hvla_discrete_row_stride(int n_action_tokens);
+int hvla_generate_n(hvla_stream_t stream, const float* hn_blob, const void* hn_blob_f16, const void* heads_w, const float* heads_b,
+                    const float* tok_emb, const int32_t* tok_mask, const uint8_t* lang_pad, const float* init_cls, int T,
+                    int64_t row_stride, void* out_weights, float* out_ctx, void* workspace, size_t workspace_bytes, int dtype);
+int hvla_act_discrete(hvla_stream_t stream, const float* dino_vec, const void* dino_mat, const uint8_t* images, const void* weights,
+                      const int32_t* task_index, int B, int T, int n_action_tokens, float* out_action, int32_t* out_tokens,
+                      float* out_top2, void* workspace, size_t workspace_bytes, int dtype);
+
 /* ---- same, HOST image/action buffers (pinned or pageable): H2D copy, act, D2H copy on
  * `stream`, then ONE cudaStreamSynchronize.  The call InferenceWrapper.step makes
  * (data/utils/hypervla_interface.py:197-207: model call followed by the host read). */

@@ -338,27 +338,51 @@ def dinov2_forward(dino, images_u8, dtype=np.float32, pos_table=None):
 # =====================================================================================
 # hypervla/components/base_vit.py + base_network.py + action_heads.py (per-sample weights)
 # =====================================================================================
-def base_mask(n, S):
-    """base_vit.py:209-214: all ones, except patches (rows :-1) cannot see the action token."""
+def base_mask(n, S, n_act=1):
+    """base_vit.py:209-214: all ones, except patches (rows :-n_act) cannot see the action token(s)."""
     m = np.ones((n, 1, S, S), bool)
-    m[:, :, :-1, -1:] = False
+    m[:, :, :-n_act, -n_act:] = False
     return m
 
 
-def base_vit_forward(gen, image_embeddings, dtype=np.float32):
+def base_vit_forward(gen, image_embeddings, dtype=np.float32, n_act=1):
     """ViT.__call__ after DINOv2 (base_vit.py:130-133, 157, 182-226) with per-sample weights.
     gen: base-net pytree whose generated leaves carry a leading B; image_embeddings (B,256,768)
-    = last_hidden_state[:, 1:].  Returns action embedding (B,64)."""
+    = last_hidden_state[:, 1:].  Returns the action embedding (B,64) (mix head: one readout token) or, with ``n_act`` > 1
+    (DiscreteActionHead: base_network.py:22-33), the readout-token embeddings (B,n_act,64)."""
     dt = np.dtype(dtype)
     enc = gen["encoder"]
     x = image_embeddings.astype(dt)
     B = x.shape[0]
     pk = enc["image_embedding_projection"]
     patches = np.matmul(x, pk["kernel"].astype(dt)) + pk["bias"].astype(dt)[:, None, :]                  # :130-133
-    tok = np.concatenate([patches, np.zeros((B, 1, BASE_DIM), dt)], axis=1)           # :182-183
-    tok = tok + enc["pos_embedding"].astype(dt).reshape(B, N_PATCH + 1, BASE_DIM)      # :204
-    out = transformer(tok, enc["Transformer_0"], base_mask(B, N_PATCH + 1), BASE_LAYERS, per_sample=True)
-    return out[:, -1]                                                                  # :226
+    tok = np.concatenate([patches, np.zeros((B, n_act, BASE_DIM), dt)], axis=1)       # :182-183
+    tok = tok + enc["pos_embedding"].astype(dt).reshape(B, N_PATCH + n_act, BASE_DIM)  # :204
+    out = transformer(tok, enc["Transformer_0"], base_mask(B, N_PATCH + n_act, n_act), BASE_LAYERS, per_sample=True)
+    return out[:, -1] if n_act == 1 else out[:, -n_act:]                               # :226
+
+
+def discrete_head(gen, h):
+    """DiscreteActionHead.__call__ / predict_action(argmax=True) (action_heads.py:300-333, 372-396) + BinTokenizer.decode with
+    256 uniform bins over [-1, 1] (octo/model/components/tokenizers.py:235-275).  h: readout tokens (B,n_tok,64), n_tok = 4
+    (one token per horizon step, 7*256 logits each) or 28 (one per (horizon, dim), 256 logits each).
+    Returns (action (B,4,7) f32 = bin centres, tokens (B,4,7) i32, logits (B,4,7,256))."""
+    dt = h.dtype
+    vp = gen["action_head"]["vocab_proj"]
+    logits = np.einsum("btd,bdn->btn", h, vp["kernel"].astype(dt)) + vp["bias"].astype(dt)[:, None, :]
+    logits = logits.reshape(h.shape[0], ACTION_HORIZON, ACTION_DIM, 256)             # :323-329
+    tokens = logits.argmax(-1).astype(np.int32)                                        # :386 (first maximum, like jnp.argmax)
+    thresholds = np.linspace(-1.0, 1.0, 257, dtype=np.float32)                         # tokenizers.py:251
+    centres = (thresholds[1:] + thresholds[:-1]) / np.float32(2)                       # :273
+    return centres[tokens].astype(np.float32), tokens, logits
+
+
+def sample_actions_discrete(dino, gen_tree, images_u8, n_act, dtype=np.float32, pos_table=None):
+    """sample_actions for the DiscreteActionHead configuration: -> (action, tokens, logits, readout tokens)."""
+    hidden = dinov2_forward(dino, images_u8, dtype, pos_table)
+    h = base_vit_forward(gen_tree, hidden[:, 1:], dtype, n_act=n_act)
+    act, tokens, logits = discrete_head(gen_tree, h)
+    return act, tokens, logits, h
 
 
 def mix_head(gen, h):

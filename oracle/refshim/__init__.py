@@ -108,7 +108,11 @@ def install(reference_root: str = "/root/reference") -> None:
                         DictKey=J.DictKey, SequenceKey=J.SequenceKey)
     lax = _module("jax.lax", stop_gradient=lambda x: x, rsqrt=lambda x: J.wrap(1.0 / np.sqrt(np.asarray(x))))
     jtyping = _module("jax.typing", ArrayLike=typing.Any, DTypeLike=typing.Any)
-    jnn = _module("jax.nn", gelu=F.gelu, softmax=F.softmax, swish=F.swish, silu=F.swish, relu=F.relu)
+    def _one_hot(x, num_classes, dtype=None):          # jax.nn.one_hot (BinTokenizer.decode, octo/model/components/tokenizers.py:272)
+        x = np.asarray(x)
+        return jaxlite.wrap((x[..., None] == np.arange(num_classes)).astype(dtype or np.float64)) if hasattr(jaxlite, "wrap") \
+            else (x[..., None] == np.arange(num_classes)).astype(dtype or np.float64)
+    jnn = _module("jax.nn", gelu=F.gelu, softmax=F.softmax, swish=F.swish, silu=F.swish, relu=F.relu, one_hot=_one_hot)
     mh = _module("jax.experimental.multihost_utils", process_allgather=lambda x, *a, **k: x)
     experimental = _module("jax.experimental", multihost_utils=mh)
     _module("jax", numpy=jnp, random=random, tree_util=tree_util, lax=lax, typing=jtyping, nn=jnn,

@@ -757,3 +757,44 @@ def test_attention_map_intermediates_on_request(models, params_p1, torch_cuda, p
     dmap = np.stack([x[0, :, 0, 1:] for x in dino])
     hmap = np.stack([base[i][0, :, -1, :-1] for i in range(4)])
     assert dmap.shape == (12, 12, 256) and hmap.shape == (4, 4, 256)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["ref_disc4_b2_t2", "ref_disc28_b2_t2"])
+def test_discrete_action_head_matches_the_reference_run_fixture(golden, torch_cuda, name, prec):
+    """SURVEY 8(f) row 5, second half: DiscreteActionHead + BinTokenizer.decode behind the same generate-then-act API
+    (base_network.py:22-33: 4 or 28 readout tokens in the base ViT).  Tokens must equal the reference's wherever its top-2 logit
+    margin exceeds the path's logit error; decoded actions are the bin centres of those tokens, bit for bit."""
+    from hvla import config as C, metadata as M, params as P, synthetic as S
+    from hvla.model import HyperVLA
+    g = golden[name]
+    A = int(g["n_action_tokens"])
+    cfg = C.default_config()
+    cfg["base_net_kwargs"]["action_head_type"] = "discrete"
+    cfg["base_net_kwargs"]["action_head_kwargs"] = {"discrete_token_type": {4: "action_horizon", 28: "action_dim_and_action_horizon"}[A]}
+    spec = M.HeadSpec("discrete", A)
+    m = HyperVLA.from_config(cfg, precision=prec, params=P.init_params(2025, "P1", spec))
+    inp = S.make_inputs(int(g["config_index"]), int(g["B"]), int(g["T"]))
+    bp, tasks, _ = m.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"])
+    rows = bp.packed_numpy()
+    assert rows.shape == (int(g["T"]), M.n_generated(spec))
+    assert rel_err(rows[:, ::97], g["rows_sample"]) <= TOL[prec]
+    action, inter = m.sample_actions(inp["images"], None, tasks, None, bp)
+    tokens = inter["action_tokens"]
+    assert action.shape == (2, 4, 7) and tokens.shape == (2, 4, 7) and tokens.dtype == np.int32
+    assert np.array_equal(action, (-1.0 + (2.0 * tokens + 1.0) / 256.0).astype(np.float32))
+    # the two largest logits of every slot, straight from the kernel
+    rt = m.runtime
+    _, tok2, top2 = rt.act_discrete(inp["images"][:, 0], bp.weights, None, want_top2=True)
+    assert np.array_equal(tok2.cpu().numpy(), tokens)
+    top2 = top2.cpu().numpy()
+    ref_sorted = np.sort(g["logits"], axis=-1)
+    scale = np.abs(g["logits"]).max()
+    e_top = float(np.abs(top2[..., 0] - ref_sorted[..., -1]).max() / scale)
+    margin = ref_sorted[..., -1] - ref_sorted[..., -2]
+    sure = margin > 2 * TOL[prec] * scale * (3 if prec == "fp32" else 1)
+    print(f"[{prec} {name}] max-logit err {e_top:.2e}; {int((tokens != g['tokens']).sum())} of {tokens.size} tokens differ, "
+          f"{int(sure.sum())} slots have a reference top-2 margin above the error band")
+    assert e_top <= TOL[prec] * (3 if prec == "fp32" else 1)
+    assert np.array_equal(tokens[sure], g["tokens"][sure])
+    assert np.array_equal(action[sure], g["action"][sure].astype(np.float32))

@@ -214,3 +214,28 @@ def test_split_operand_matrix_packing():
         hi, hi2, lo = f(blk[:, :k]), f(blk[:, k:2 * k]), f(blk[:, 2 * k:])
         assert np.array_equal(hi, hi2) and np.array_equal(hi, P.bf16_round(w))
         assert np.abs(hi + lo - w).max() <= 2.0 ** -17 * np.abs(w).max()
+
+
+def test_discrete_head_configuration_and_layout():
+    """action_head_type='discrete' (base_network.py:22-33): 4 or 28 readout tokens, 71 generated leaves, row sizes agree with the C library."""
+    from hvla import _native as N
+    for tok, A, V, total in (("action_horizon", 4, 1792, 316352), ("action_dim_and_action_horizon", 28, 256, 218048)):
+        cfg = C.default_config()
+        cfg["base_net_kwargs"]["action_head_type"] = "discrete"
+        cfg["base_net_kwargs"]["action_head_kwargs"] = {"discrete_token_type": tok}
+        cfg = C.validate_config(cfg)
+        spec = M.HeadSpec.from_config(cfg)
+        assert (spec.kind, spec.n_action_tokens, spec.vocab_out, spec.tokens) == ("discrete", A, V, 256 + A)
+        assert M.n_generated(spec) == total == N.lib().hvla_discrete_generated_elems(A)
+        assert M.n_generated_padded(spec) == N.lib().hvla_discrete_row_stride(A)
+        tbl = M.packed_offsets(spec)
+        assert tbl[("encoder", "pos_embedding")] == (49216, (1, 256 + A, 64))
+        assert tbl[("action_head", "vocab_proj", "kernel")][0] == 49216 + (256 + A) * 64 + 4 * 33472 + 128
+        meta = M.build_base_net_metadata(cfg)
+        assert meta["output_head_info"]["action_head_vocab_proj_kernel"]["output_dim"] == 64 * V
+    bad = C.default_config()
+    bad["base_net_kwargs"]["action_head_type"] = "discrete"
+    bad["base_net_kwargs"]["action_head_kwargs"] = {"discrete_token_type": ""}
+    with pytest.raises(ValueError):
+        C.validate_config(bad)
+    assert N.lib().hvla_discrete_row_stride(5) == -1

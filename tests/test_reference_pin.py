@@ -165,3 +165,29 @@ def test_reference_initialised_params_degenerate_case(reference_model):
         bias = np.asarray(model_init.params["output_head_" + "_".join(path)]["bias"], np.float64).reshape(shape)
         assert np.array_equal(np.asarray(leaf), bias), path                 # reference: generated leaf == head bias, exactly
         assert np.abs(gen[path][0] - bias).max() < 1e-15, path              # oracle on the same parameters
+
+
+@pytest.mark.parametrize("name", ["ref_disc4_b2_t2", "ref_disc28_b2_t2"])
+def test_discrete_head_oracle_matches_the_reference_run_fixture(golden, name):
+    """DiscreteActionHead configuration: the oracle's multi-readout-token base ViT, vocab projection, argmax and
+    BinTokenizer.decode against fixtures produced by the reference's own code (tests/golden/make_ref_discrete_golden.py)."""
+    from hvla import metadata as M, params as P, synthetic as S
+    from oracle import hypervla_oracle as O
+    g = golden[name]
+    A = int(g["n_action_tokens"])
+    spec = M.HeadSpec("discrete", A)
+    assert M.n_generated(spec) == {4: 316352, 28: 218048}[A]
+    params = P.init_params(2025, "P1", spec)
+    inp = S.make_inputs(int(g["config_index"]), int(g["B"]), int(g["T"]))
+    lang = inp["instruction_dict"]["language_instruction"]
+    gen, ctx = O.generate(params, lang["token_embedding"], lang["attention_mask"], inp["initial_state"]["patch_embeddings"][:, 0],
+                          generated_paths=M.generated_leaves_canonical(spec), dtype=np.float64)
+    rows = np.concatenate([np.asarray(gen[p]).reshape(int(g["T"]), -1) for p, _ in M.generated_leaves_packed(spec)], axis=1)
+    assert np.abs(rows[:, ::97] - g["rows_sample"]).max() <= 1e-12 * np.abs(g["rows_sample"]).max()
+    tree = O.to_tree(O.take_tasks(gen, inp["task_index"]))
+    act, tokens, logits, h = O.sample_actions_discrete(P.dino_tree_from_params(params), tree, inp["images"][:, 0], A, dtype=np.float64)
+    assert np.abs(h - g["h"]).max() <= 1e-8 * np.abs(g["h"]).max()
+    assert np.abs(logits - g["logits"]).max() <= 1e-8 * np.abs(g["logits"]).max()
+    assert np.array_equal(tokens, g["tokens"]) and np.array_equal(act.astype(np.float64), g["action"])
+    # bin centres of 256 uniform bins over [-1, 1]
+    assert np.allclose(g["action"], -1.0 + (2.0 * g["tokens"] + 1.0) / 256.0, atol=0)
