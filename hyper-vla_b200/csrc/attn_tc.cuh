@@ -127,7 +127,7 @@ __device__ __forceinline__ void pv_chain(uint32_t tmem_d, uint32_t tmem_a, uint3
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmTail, const __grid_constant__ CUtensorMap tmOut,
-               int n_tiles, long long* __restrict__ tstamp, bf16* __restrict__ out) {
+               int n_tiles, long long* __restrict__ tstamp, bf16* __restrict__ out, int rev) {
   pdl_trigger();
   long long ts_c0 = 0, ts_g0 = 0;
   if (tstamp && threadIdx.x == 0) {
@@ -149,6 +149,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int begin = (int)((long long)blockIdx.x * n_tiles / gridDim.x), end = (int)((long long)(blockIdx.x + 1) * n_tiles / gridDim.x);
   const int item0 = begin >> 1;
+  const int last_item = (n_tiles >> 1) - 1;      // rev: the (image, head) items are walked from the last to the first (gemm_tc.cuh, "serpentine tile order")
 
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -179,7 +180,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       const int item1 = (end + 1) >> 1;
       for (int item = item0; item < item1; ++item) {
         const int il = item - item0, s = il & 1;
-        const int b = item / DH, h = item % DH;
+        const int ir = rev ? last_item - item : item;
+        const int b = ir / DH, h = ir % DH;
         const uint32_t st = smem_base + s * STAGE_BYTES;
         mbar_wait(in_empty + 8 * s, ((il >> 1) & 1) ^ 1);
         mbar_expect_tx(in_full + 8 * s, STAGE_BYTES);
@@ -242,7 +244,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     for (int item = item0; item < item1; ++item) {
       const int il = item - item0, s = il & 1;
       const bool own256 = 2 * item + 1 >= begin && 2 * item + 1 < end;     // the CTA holding tile 1 also produces query row 256
-      const int b = item / DH, h = item % DH;
+      const int ir = rev ? last_item - item : item;
+      const int b = ir / DH, h = ir % DH;
       const uint8_t* st = sm + s * STAGE_BYTES;
       const uint32_t st_u = smem_base + s * STAGE_BYTES;
       mbar_wait(in_full + 8 * s, (il >> 1) & 1);
@@ -365,7 +368,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     for (int g = begin; g < end; ++g) {
       const int n = g - begin, slot = n & 1, t = g & 1, item = g >> 1, il = item - item0, s = il & 1;
       const uint32_t ph = (n >> 1) & 1;
-      const int b = item / DH, h = item % DH;
+      const int ir = rev ? last_item - item : item;
+      const int b = ir / DH, h = ir % DH;
       uint8_t* st = sm + s * STAGE_BYTES;
       const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + 256 * slot + 192;
       if (t == 0 || g == begin) mbar_wait(sx_full + 8 * s, (il >> 1) & 1);     // the helpers' fp32 copy of V row 256 (and, through them, the stage)
@@ -505,7 +509,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   }
 }
 
-inline int dino_attention_tc(cudaStream_t st, const bf16* qkv, bf16* out, int B) {
+inline int dino_attention_tc(cudaStream_t st, const bf16* qkv, bf16* out, int B, int rev = 0) {
   static std::atomic<uint64_t> attr{0};   // per-device one-time setup
   if (device_once(attr)) {
     HVLA_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -520,7 +524,7 @@ inline int dino_attention_tc(cudaStream_t st, const bf16* qkv, bf16* out, int B)
   static long long* d_ts = nullptr;
   const bool ts = getenv("HVLA_ATTN_TS") != nullptr;            // experiments: phase timestamps of CTA 0, cycle counts of every CTA
   if (ts && !d_ts) { cudaMalloc(&d_ts, 1024 * sizeof(long long)); cudaMemset(d_ts, 0, 1024 * sizeof(long long)); }
-  launch_k(attn_tc_kernel, dim3(grid), dim3(NTHREADS), (size_t)SMEM_BYTES, st, map, tail, omap, n_tiles, ts ? d_ts : (long long*)nullptr, out);
+  launch_k(attn_tc_kernel, dim3(grid), dim3(NTHREADS), (size_t)SMEM_BYTES, st, map, tail, omap, n_tiles, ts ? d_ts : (long long*)nullptr, out, rev);
   if (ts) {
     long long h[1024];
     cudaMemcpy(h, d_ts, sizeof h, cudaMemcpyDeviceToHost);

@@ -59,7 +59,33 @@ struct EpiP {
   float* stats_out;    //                 [M][6][2] partial row statistics of the updated stream
   int plane_stride;    // EPI 8/9: columns between the hi / lo / hi planes of the output row (the next GEMM's K)
   int nplanes;         //          2 = [hi | lo], 3 = [hi | lo | hi]
+  // ---- L2 locality between consecutive kernels (see "serpentine tile order" below) ----
+  int rev;             // 1: the m-tiles are walked from the last row block to the first
+  int xhint;           // EPI 6/7: 1 = the blocked fp32 stream is read and written with an L2 evict_last policy
 };
+
+// ---- serpentine tile order -----------------------------------------------------------------------------------------------
+// Every activation of a DINOv2 layer (25 - 101 MB at 64 images) is written by one kernel and read by the next.  If both walk the
+// rows in the same direction the consumer starts with the OLDEST rows of a stream that is as large as the 126 MB L2 -- the rows
+// that have just been evicted -- and its own writes keep evicting the rows it is about to read: every read is an HBM read.
+// Consecutive kernels therefore walk the row blocks in OPPOSITE directions (ep.rev alternates along the launch chain, the
+// attention kernel takes the same flag): the consumer begins with the rows the producer wrote last, which are still in L2.
+// The fp32 residual stream is the one long-lived tensor (read by proj and fc2, two kernels apart): its accesses carry an
+// evict_last policy (ep.xhint) when it is small enough to stay resident beside the streaming operands.
+__device__ __forceinline__ uint64_t l2_policy(bool evict_last) {
+  uint64_t p;
+  if (evict_last) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldcg_hint(const float4* ptr, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stcg_hint(float4* ptr, const float4& v, uint64_t pol) {
+  asm volatile("st.global.cg.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
 
 // Blocked fp32 residual stream: element (row, col) of the logical [M,768] stream lives at float index
 //   ((row >> 5) * 192 + (col >> 2)) * 128 + (row & 31) * 4 + (col & 3)
@@ -495,7 +521,8 @@ struct BlkTile {
   const float4* xin;     // what the update is added to (the stream, or the blocked position table for the patch embedding)
   int grow;              // GEMM row of this thread's TMEM lane
   bool ok;
-  __device__ __forceinline__ BlkTile(const EpiP& ep, int m0, int n0, int quarter, int half, int lane) {
+  uint64_t pol;          // L2 policy of the stream accesses
+  __device__ __forceinline__ BlkTile(const EpiP& ep, int m0, int n0, int quarter, int half, int lane, uint64_t pol_) : pol(pol_) {
     constexpr bool PATCH = EPI == EPI_PATCH_BLK;
     grow = m0 + quarter * 32 + lane;
     const int srow = PATCH ? grow + m0 / 256 + 1 : grow;         // stream row
@@ -505,7 +532,7 @@ struct BlkTile {
   }
   __device__ __forceinline__ void load(float4 (&dst)[8], int chunk) const {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dst[j] = ok ? __ldcg(xin + 32 * (chunk * 8 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < 8; ++j) dst[j] = ok ? ldcg_hint(xin + 32 * (chunk * 8 + j), pol) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 };
 
@@ -522,8 +549,9 @@ __device__ __forceinline__ void epilogue_tile_blk(const EpiP& ep, float* sepi, u
   float* sl = sb + 256;
   sb[te] = __ldg(ep.bias + n0 + te);
   sl[te] = (!PATCH && ep.ls) ? __ldg(ep.ls + n0 + te) : 1.0f;
-  const BlkTile<EPI> t(ep, m0, n0, quarter, half, lane);
-  const BlkTile<EPI> tn(ep, has_next ? m0_next : m0, has_next ? n0_next : n0, quarter, half, lane);
+  const uint64_t pol = l2_policy(ep.xhint != 0);
+  const BlkTile<EPI> t(ep, m0, n0, quarter, half, lane, pol);
+  const BlkTile<EPI> tn(ep, has_next ? m0_next : m0, has_next ? n0_next : n0, quarter, half, lane, pol);
   if (!primed) { t.load(xo[0], 0); t.load(xo[1], 1); }
   const uint32_t slab = sstage + (uint32_t)ew * 2048u;
   const uint32_t my = slab + (uint32_t)lane * 64u;
@@ -556,7 +584,7 @@ __device__ __forceinline__ void epilogue_tile_blk(const EpiP& ep, float* sepi, u
     else if (has_next) tn.load(xo[c & 1], c - 2);             // ... also across the tile boundary
     if (t.ok) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) __stcg(t.xp + 32 * (c * 8 + j), make_float4(xn[4 * j], xn[4 * j + 1], xn[4 * j + 2], xn[4 * j + 3]));
+      for (int j = 0; j < 8; ++j) stcg_hint(t.xp + 32 * (c * 8 + j), make_float4(xn[4 * j], xn[4 * j + 1], xn[4 * j + 2], xn[4 * j + 3]), pol);
     }
     if (!PATCH) {
 #pragma unroll

@@ -98,6 +98,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int n_tiles_m = (M + BM2 - 1) / BM2;
   const int n_tiles = n_tiles_m * n_tiles_n * splits;   // work units: (tile, K split); splits > 1 only with the reduce-add epilogue
   const int n_kb = K / BK / splits;                     // K blocks per unit
+  const bool rev = ep.rev != 0;                         // serpentine tile order (gemm_tc.cuh): last row block first
+  auto tile_m = [&](int tile) { const int tm = tile / n_tiles_n; return rev ? n_tiles_m - 1 - tm : tm; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -129,7 +131,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t ph = 0;
       for (int unit = pair; unit < n_tiles; unit += n_pairs) {
         const int tile = unit / splits, kb0 = (unit % splits) * n_kb;
-        const int m0 = (tile / n_tiles_n) * BM2 + (int)rank * 128;
+        const int m0 = tile_m(tile) * BM2 + (int)rank * 128;
         const int n0 = (tile % n_tiles_n) * BN + (int)rank * 128;
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(empty_bar + 8 * s, ph ^ 1);
@@ -175,12 +177,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int tile = unit / splits;
-      const int m0 = (tile / n_tiles_n) * BM2 + (int)rank * 128, n0 = (tile % n_tiles_n) * BN;
+      const int m0 = tile_m(tile) * BM2 + (int)rank * 128, n0 = (tile % n_tiles_n) * BN;
       if constexpr (epi_blk(EPI)) {                   // blocked stream: in-place update (+ bf16 shadow, + row statistics); splits == 1
         const int nxt = unit + n_pairs;
         const bool has_next = nxt < n_tiles;
         epilogue_tile_blk<EPI>(ep, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane, xo, primed, has_next,
-                               (nxt / n_tiles_n) * BM2 + (int)rank * 128, (nxt % n_tiles_n) * BN);
+                               tile_m(nxt) * BM2 + (int)rank * 128, (nxt % n_tiles_n) * BN);
         primed = has_next;
       } else if (EPI == EPI_PATCH_F32 && ep.patch_rows)      // patch embedding accumulated onto the pre-initialised stream rows (TMA reduce-add)
         epilogue_tile_tma<EPI_RESIDUAL_F32, NSLAB2>(ep, &tmO, sepi, sstage, tfull_bar + 8 * as, aph, as, tmem_base, m0, n0, warp, lane);

@@ -317,6 +317,14 @@ static int dino_bf16_blk(cudaStream_t st, const float* dv, const bf16* dm, const
   bf16* HID = reinterpret_cast<bf16*>(ws + pl.hid);
   bf16* A0 = HID;
   float* ST = reinterpret_cast<float*>(ws + pl.st);
+  // L2 locality along the launch chain (gemm_tc.cuh, "serpentine tile order"): kernel k walks the row blocks forwards for even k and
+  // backwards for odd k, so every consumer starts with the rows its producer wrote last; the residual stream, when it is small enough to
+  // stay in L2 beside the streaming operands, is accessed with an evict_last policy.  HVLA_SERPENTINE=0 / HVLA_XHINT=0|1 are A/B switches.
+  static const bool serp = !(getenv("HVLA_SERPENTINE") && getenv("HVLA_SERPENTINE")[0] == '0');
+  static const int xh_env = getenv("HVLA_XHINT") ? atoi(getenv("HVLA_XHINT")) : -1;
+  const int xhint = xh_env >= 0 ? xh_env : ((int64_t)M * DD * 4 <= (int64_t)56 << 20 ? 1 : 0);
+  int chain = 0;
+  auto next_rev = [&]() { return serp ? (chain++ & 1) : 0; };
   {
     ProfScope ps(st, "im2col");
     launch_k(im2col_norm_bf16_kernel, dim3(B * GRID), dim3(256), 0, st, images, A0, B);
@@ -329,7 +337,7 @@ static int dino_bf16_blk(cudaStream_t st, const float* dv, const bf16* dm, const
   }
   {
     tc::EpiP ep; memset(&ep, 0, sizeof ep);
-    ep.bias = dv + V::patch_b; ep.out = X; ep.ldo = DD; ep.rows = B * NPATCH; ep.pos = dv + V::pos_blk;
+    ep.bias = dv + V::patch_b; ep.out = X; ep.ldo = DD; ep.rows = B * NPATCH; ep.pos = dv + V::pos_blk; ep.xhint = xhint;
     HVLA_TRY(tc2::gemm_tc2(st, A0, dm + Mx::patch_w, B * NPATCH, DD, PATCH_KP, tc::EPI_PATCH_BLK, ep));
   }
   HVLA_TRY(stream_blk_rows(st, X, Y, ST, nullptr, nullptr, M));     // shadow + statistics of the embedded tokens
@@ -338,23 +346,23 @@ static int dino_bf16_blk(cudaStream_t st, const float* dv, const bf16* dm, const
     const bf16* m = dm + Mx::layers + (int64_t)l * Mx::layer_size;
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
-      ep.bias = v + V::bqkv_f; ep.out = QKV; ep.ldo = 3 * DD; ep.stats = ST; ep.cs = v + V::cs_qkv;
+      ep.bias = v + V::bqkv_f; ep.out = QKV; ep.ldo = 3 * DD; ep.stats = ST; ep.cs = v + V::cs_qkv; ep.rev = next_rev();
       HVLA_TRY(tc2::gemm_tc2(st, Y, m + Mx::wqkv, M, 3 * DD, DD, tc::EPI_BIAS_BF16_FOLD, ep));
     }
-    HVLA_TRY(attn_tc::dino_attention_tc(st, QKV, ATT, B));
+    HVLA_TRY(attn_tc::dino_attention_tc(st, QKV, ATT, B, next_rev()));
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
-      ep.bias = v + V::bo; ep.out = X; ep.ldo = DD; ep.ls = v + V::ls1; ep.shadow = Y; ep.stats_out = ST;
+      ep.bias = v + V::bo; ep.out = X; ep.ldo = DD; ep.ls = v + V::ls1; ep.shadow = Y; ep.stats_out = ST; ep.rev = next_rev(); ep.xhint = xhint;
       HVLA_TRY(tc2::gemm_tc2(st, ATT, m + Mx::wo, M, DD, DD, tc::EPI_RESIDUAL_BLK, ep));
     }
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
-      ep.bias = v + V::b1_f; ep.out = HID; ep.ldo = DF; ep.stats = ST; ep.cs = v + V::cs_1;
+      ep.bias = v + V::b1_f; ep.out = HID; ep.ldo = DF; ep.stats = ST; ep.cs = v + V::cs_1; ep.rev = next_rev();
       HVLA_TRY(tc2::gemm_tc2(st, Y, m + Mx::w1, M, DF, DD, tc::EPI_BIAS_GELU_BF16_FOLD, ep));
     }
     {
       tc::EpiP ep; memset(&ep, 0, sizeof ep);
-      ep.bias = v + V::b2; ep.out = X; ep.ldo = DD; ep.ls = v + V::ls2; ep.shadow = Y; ep.stats_out = ST;
+      ep.bias = v + V::b2; ep.out = X; ep.ldo = DD; ep.ls = v + V::ls2; ep.shadow = Y; ep.stats_out = ST; ep.rev = next_rev(); ep.xhint = xhint;
       HVLA_TRY(tc2::gemm_tc2(st, HID, m + Mx::w2, M, DD, DF, tc::EPI_RESIDUAL_BLK, ep));
     }
   }
