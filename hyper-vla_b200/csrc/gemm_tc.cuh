@@ -340,12 +340,15 @@ __device__ __forceinline__ void epilogue_tile_direct(const EpiP& ep, float* sepi
 // the slab to the TMA engine: a plain tensor store for bf16 outputs, a tensor REDUCE-ADD (fp32) for the
 // residual stream, so x += ls * (acc + bias) needs no read of x through the SM at all.
 constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 2048;
+// called by every epilogue thread once the tile's accumulator is complete and before the tile's first global store
+// (gemm_chain.cuh publishes the PREVIOUS tile there: its stores are a whole tile old by then, so the fences cost nothing)
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
 
-template <int EPI, int NSLAB = 1>
+template <int EPI, int NSLAB = 1, class Hook = NoHook>
 __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensorMap* tmO, float* sepi, uint32_t sstage,
                                                   uint32_t tfull_bar_addr, uint32_t aph, int as, uint32_t tmem_base, int m0,
                                                   int n0, int warp, int lane, int split = 0, const CUtensorMap* tmP = nullptr,
-                                                  int part_row0 = 0, const CUtensorMap* tmX = nullptr) {
+                                                  int part_row0 = 0, const CUtensorMap* tmX = nullptr, Hook hook = Hook()) {
   const bool add_bias = split == 0;
   const int ew = warp - 2;
   const int quarter = warp & 3;
@@ -362,7 +365,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
   float f_rstd = 1.f, f_nmr = 0.f;                            // consumer: rstd and -mean*rstd of this row
   if (fold && myrow < ep.rows) {
     const float4* sp = reinterpret_cast<const float4*>(ep.stats + (int64_t)myrow * 12);
-    const float4 p0 = __ldg(sp), p1 = __ldg(sp + 1), p2 = __ldg(sp + 2);
+    const float4 p0 = __ldcg(sp), p1 = __ldcg(sp + 1), p2 = __ldcg(sp + 2);   // L2, not the read-only path: a GEMM chain rewrites the statistics inside one launch
     const float sum = ((p0.x + p0.z) + (p1.x + p1.z)) + (p2.x + p2.z), sq = ((p0.y + p0.w) + (p1.y + p1.w)) + (p2.y + p2.w);
     const float mean = sum * (1.f / 768.f);
     f_rstd = 1.0f / sqrtf(fmaxf(0.f, sq * (1.f / 768.f) - mean * mean) + 1e-6f);
@@ -375,6 +378,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiP& ep, const CUtensor
   epi_bar_sync();
   mbar_wait(tfull_bar_addr, aph);
   tc_fence_after();
+  hook();
   if (ep.debug & 1) { tc_fence_before(); __syncwarp(); return; }
   const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * 128);
   uint32_t r[2][32];
@@ -536,10 +540,10 @@ struct BlkTile {
   }
 };
 
-template <int EPI>
+template <int EPI, class Hook = NoHook>
 __device__ __forceinline__ void epilogue_tile_blk(const EpiP& ep, float* sepi, uint32_t sstage, uint32_t tfull_bar_addr, uint32_t aph, int as,
                                                   uint32_t tmem_base, int m0, int n0, int warp, int lane, float4 (&xo)[2][8], bool primed,
-                                                  bool has_next, int m0_next, int n0_next) {
+                                                  bool has_next, int m0_next, int n0_next, Hook hook = Hook()) {
   constexpr bool PATCH = EPI == EPI_PATCH_BLK;
   const int ew = warp - 2;
   const int quarter = warp & 3;
@@ -560,6 +564,7 @@ __device__ __forceinline__ void epilogue_tile_blk(const EpiP& ep, float* sepi, u
   epi_bar_sync();
   mbar_wait(tfull_bar_addr, aph);
   tc_fence_after();
+  hook();
   const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * 128);
   uint32_t r[2][32];
   tmem_ld32(taddr, r[0]);

@@ -4,6 +4,7 @@
 #include "simt_kernels.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
+#include "gemm_chain.cuh"
 #include "attn_mma.cuh"
 #include "attn_tc.cuh"
 #include "base_fused.cuh"
@@ -32,7 +33,7 @@ struct Plan {
   // generate region (fp32)
   size_t tp, ip, xc, yc, qkvc, cc, hc, e;
   // DINO region
-  size_t x, y, qkv, att, hid, emb, part, st;
+  size_t x, y, qkv, att, hid, emb, part, st, chain;
   // base region (fp32)
   size_t pt, xb, yb, qkvb, cb, hb;
   // host staging (hvla_act_host)
@@ -68,6 +69,7 @@ static Plan make_plan(int B, int T, int dtype) {
   p.emb = take(M * DD * es);
   p.part = take(dtype == HVLA_BF16 ? PART_BYTES : 0);   // split-K partial products (small batches)
   p.st = take(dtype == HVLA_BF16 ? M * 12 * 4 : 0);      // partial row statistics of the stream (LayerNorm-free flow)
+  p.chain = take(dtype == HVLA_BF16 ? (size_t)DL * chain::chain_ws_ints((int64_t)M) * 4 : 0);   // scheduler state of the GEMM chains (gemm_chain.cuh)
   p.pt = take(Bb * NPATCH * BD * 4);
   constexpr size_t BTOKMAX = NPATCH + AH * AD;     // discrete head: up to 28 readout tokens (discrete_head.cuh)
   p.xb = take(Bb * BTOKMAX * BD * 4);
@@ -341,30 +343,68 @@ static int dino_bf16_blk(cudaStream_t st, const float* dv, const bf16* dm, const
     HVLA_TRY(tc2::gemm_tc2(st, A0, dm + Mx::patch_w, B * NPATCH, DD, PATCH_KP, tc::EPI_PATCH_BLK, ep));
   }
   HVLA_TRY(stream_blk_rows(st, X, Y, ST, nullptr, nullptr, M));     // shadow + statistics of the embedded tokens
+  auto ep_qkv = [&](const float* v, int rev) {
+    tc::EpiP ep; memset(&ep, 0, sizeof ep);
+    ep.bias = v + V::bqkv_f; ep.out = QKV; ep.ldo = 3 * DD; ep.stats = ST; ep.cs = v + V::cs_qkv; ep.rev = rev;
+    return ep;
+  };
+  auto ep_res = [&](const float* bias, const float* ls, int rev) {
+    tc::EpiP ep; memset(&ep, 0, sizeof ep);
+    ep.bias = bias; ep.out = X; ep.ldo = DD; ep.ls = ls; ep.shadow = Y; ep.stats_out = ST; ep.rev = rev; ep.xhint = xhint;
+    return ep;
+  };
+  auto ep_fc1 = [&](const float* v, int rev) {
+    tc::EpiP ep; memset(&ep, 0, sizeof ep);
+    ep.bias = v + V::b1_f; ep.out = HID; ep.ldo = DF; ep.stats = ST; ep.cs = v + V::cs_1; ep.rev = rev;
+    return ep;
+  };
+  // One launch per layer for proj -> fc1 -> fc2 -> q|k|v of the next layer (gemm_chain.cuh); HVLA_CHAIN=0 keeps one launch per GEMM.
+  static const bool use_chain = !(getenv("HVLA_CHAIN") && getenv("HVLA_CHAIN")[0] == '0');
+  // wavefront lags in row blocks (proj -> fc1, fc1 -> fc2, fc2 -> q|k|v): HVLA_CHAIN_LAG="a,b,c" or one number for all three
+  static int chain_lags[3] = {1 << 20, 1 << 20, 1 << 20};     // >= row blocks: each GEMM's tiles follow the previous GEMM's (measured: interleaving them is slower)
+  static const bool lags_parsed = [&]() {
+    if (const char* e = getenv("HVLA_CHAIN_LAG")) {
+      int a = 0, b = 0, c = 0;
+      const int n = sscanf(e, "%d,%d,%d", &a, &b, &c);
+      if (n == 1) chain_lags[0] = chain_lags[1] = chain_lags[2] = a;
+      else if (n == 3) { chain_lags[0] = a; chain_lags[1] = b; chain_lags[2] = c; }
+    }
+    return true;
+  }();
+  (void)lags_parsed;
+  if (use_chain) {
+    int* cws = reinterpret_cast<int*>(ws + pl.chain);
+    const size_t cints = chain::chain_ws_ints(M);
+    HVLA_CUDA(cudaMemsetAsync(cws, 0, (size_t)DL * cints * 4, st));
+    const float* v0 = dv + V::layers;
+    HVLA_TRY(tc2::gemm_tc2(st, Y, dm + Mx::layers + Mx::wqkv, M, 3 * DD, DD, tc::EPI_BIAS_BF16_FOLD, ep_qkv(v0, 0)));
+    for (int l = 0; l < DL; ++l) {
+      const float* v = dv + V::layers + (int64_t)l * V::layer_size;
+      const bf16* m = dm + Mx::layers + (int64_t)l * Mx::layer_size;
+      // the chain walks the row blocks upwards: q|k|v rows of the last images are the freshest in L2, so attention starts there,
+      // and the attention rows of the first images are the freshest when the next chain starts
+      HVLA_TRY(attn_tc::dino_attention_tc(st, QKV, ATT, B, serp ? 1 : 0));
+      chain::ChainDesc d[4];
+      d[0] = {ATT, m + Mx::wo, DD, DD, tc::EPI_RESIDUAL_BLK, ep_res(v + V::bo, v + V::ls1, 0)};
+      d[1] = {Y, m + Mx::w1, DF, DD, tc::EPI_BIAS_GELU_BF16_FOLD, ep_fc1(v, 0)};
+      d[2] = {HID, m + Mx::w2, DD, DF, tc::EPI_RESIDUAL_BLK, ep_res(v + V::b2, v + V::ls2, 0)};
+      int n = 3;
+      if (l + 1 < DL) {
+        d[3] = {Y, m + Mx::layer_size + Mx::wqkv, 3 * DD, DD, tc::EPI_BIAS_BF16_FOLD, ep_qkv(v + V::layer_size, 0)};
+        n = 4;
+      }
+      HVLA_TRY(chain::gemm_chain(st, d, n, M, cws + (size_t)l * cints, chain_lags));
+    }
+    return stream_blk_rows(st, X, out_emb, nullptr, dv + V::lnf_s, dv + V::lnf_b, M);
+  }
   for (int l = 0; l < DL; ++l) {
     const float* v = dv + V::layers + (int64_t)l * V::layer_size;
     const bf16* m = dm + Mx::layers + (int64_t)l * Mx::layer_size;
-    {
-      tc::EpiP ep; memset(&ep, 0, sizeof ep);
-      ep.bias = v + V::bqkv_f; ep.out = QKV; ep.ldo = 3 * DD; ep.stats = ST; ep.cs = v + V::cs_qkv; ep.rev = next_rev();
-      HVLA_TRY(tc2::gemm_tc2(st, Y, m + Mx::wqkv, M, 3 * DD, DD, tc::EPI_BIAS_BF16_FOLD, ep));
-    }
+    HVLA_TRY(tc2::gemm_tc2(st, Y, m + Mx::wqkv, M, 3 * DD, DD, tc::EPI_BIAS_BF16_FOLD, ep_qkv(v, next_rev())));
     HVLA_TRY(attn_tc::dino_attention_tc(st, QKV, ATT, B, next_rev()));
-    {
-      tc::EpiP ep; memset(&ep, 0, sizeof ep);
-      ep.bias = v + V::bo; ep.out = X; ep.ldo = DD; ep.ls = v + V::ls1; ep.shadow = Y; ep.stats_out = ST; ep.rev = next_rev(); ep.xhint = xhint;
-      HVLA_TRY(tc2::gemm_tc2(st, ATT, m + Mx::wo, M, DD, DD, tc::EPI_RESIDUAL_BLK, ep));
-    }
-    {
-      tc::EpiP ep; memset(&ep, 0, sizeof ep);
-      ep.bias = v + V::b1_f; ep.out = HID; ep.ldo = DF; ep.stats = ST; ep.cs = v + V::cs_1; ep.rev = next_rev();
-      HVLA_TRY(tc2::gemm_tc2(st, Y, m + Mx::w1, M, DF, DD, tc::EPI_BIAS_GELU_BF16_FOLD, ep));
-    }
-    {
-      tc::EpiP ep; memset(&ep, 0, sizeof ep);
-      ep.bias = v + V::b2; ep.out = X; ep.ldo = DD; ep.ls = v + V::ls2; ep.shadow = Y; ep.stats_out = ST; ep.rev = next_rev(); ep.xhint = xhint;
-      HVLA_TRY(tc2::gemm_tc2(st, HID, m + Mx::w2, M, DD, DF, tc::EPI_RESIDUAL_BLK, ep));
-    }
+    HVLA_TRY(tc2::gemm_tc2(st, ATT, m + Mx::wo, M, DD, DD, tc::EPI_RESIDUAL_BLK, ep_res(v + V::bo, v + V::ls1, next_rev())));
+    HVLA_TRY(tc2::gemm_tc2(st, Y, m + Mx::w1, M, DF, DD, tc::EPI_BIAS_GELU_BF16_FOLD, ep_fc1(v, next_rev())));
+    HVLA_TRY(tc2::gemm_tc2(st, HID, m + Mx::w2, M, DD, DF, tc::EPI_RESIDUAL_BLK, ep_res(v + V::b2, v + V::ls2, next_rev())));
   }
   return stream_blk_rows(st, X, out_emb, nullptr, dv + V::lnf_s, dv + V::lnf_b, M);
 }
@@ -602,6 +642,9 @@ static int base_act_impl(cudaStream_t st, const void* emb, const void* weights, 
 using namespace hvla;
 
 extern "C" {
+#ifdef HVLA_CHAIN_STATS
+int hvla_debug_chain_stats(unsigned long long* out) { return cudaMemcpyFromSymbol(out, chain::g_chain_stats, 64) == cudaSuccess ? 0 : 1; }
+#endif
 
 int hvla_version(void) { return 1; }
 const char* hvla_last_error(void) { return g_last_error.c_str(); }
