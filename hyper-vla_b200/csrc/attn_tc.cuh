@@ -82,16 +82,21 @@ __device__ __forceinline__ void umma_ts2(uint32_t tmem_d, uint32_t tmem_a, uint3
 // ====================================================================================================================
 // One CTA per SM, 20 warps, both TMEM halves in flight, softmax warps that never wait.
 //   warps 0-7   softmax: TWO threads per query row (warp w: TMEM lane quarter w & 3, key half w >> 2).  A thread pulls its 128
-//               scores out of TMEM ONCE, keeps them in registers for both the max and the exp pass, and swaps the row max with
-//               its partner through shared memory (64-thread named barrier).  All eight warps work on the same tile, so a tile's
-//               softmax takes half as long and the MUFU pipes are fed back to back: while tile n is in softmax, S(n+1) = Q K^T
-//               is already sitting in the other TMEM half, and P(n-1) V, its epilogue and the loads of the next item run under it.
+//               scores out of TMEM ONCE, keeps them in registers for both the max and the exp pass; its key half is a softmax unit of
+//               its own (own maximum and sum, merged by the epilogue).  All eight warps work on the same tile: while tile n is in
+//               softmax, S(n+1) = Q K^T is already sitting in the other TMEM half, and P(n-1) V, its epilogue and the loads of the
+//               next item run under it.
 //   warps 8-11  epilogue: O out of TMEM, + p_256 v_256, / row sum, bf16, staged (128B-swizzled) in the dead Q tile, one TMA
 //               store per warp.
 //   warps 12-15 helpers: the key-256 score of all 256 rows and the whole of query row 256 (mma.sync matrix-vector products), one
 //               item ahead of the softmax warps.
 //   warp 16 TMA producer (two 102 KB stages), warp 17 MMA issuer, warps 18-19 register donors (setmaxnreg: 168 / 72 / 40 / 32).
-// TMEM half s (256 columns): S fp32 [0,256) -> P bf16 of keys 0..127 in [0,64), of keys 128..255 in [128,192), O in [192,256).
+// TMEM half s (256 columns): S fp32 [0,256) -> P bf16 of keys 0..127 in [0,64), of keys 128..255 in [128,192); the two key halves are
+// INDEPENDENT softmax units (own row maximum, own row sum): O0 = P0 V[0:128] accumulates in [64,128), O1 = P1 V[128:256] in [192,256), and
+// the epilogue merges them, (O0 w0 + (O1 + p_256 v_256) w1) / (l0 w0 + l1 w1) with w = exp(m_half - max(m0, m1)).  Nothing couples the
+// two softmax groups (warps 0-3 / 4-7) inside a tile: no row-maximum exchange, no 64-thread barrier, and P0 V0 is issued while the second
+// group is still in its exponential pass (softmax phase of a tile 3.3 k -> 2.45 k cycles; the tile period is now set by the hand-off of
+// the 102 KB input stage at item boundaries and by the O read-out -> Q K^T -> S chain of the two TMEM halves).
 // Work is split by TILE: CTA c owns tiles [c T / grid, (c+1) T / grid) (tile = item * 2 + half), so SMs differ by at most one
 // tile; an item cut by a range boundary is staged by both neighbours.
 // ====================================================================================================================
@@ -115,13 +120,13 @@ __device__ __forceinline__ void tmem_st8_nc(uint32_t taddr, const uint32_t (&r)[
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]));
 }
-__device__ __forceinline__ void pair_sync(int q) { asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory"); }
 __device__ __forceinline__ void helper_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-template <int K>
+// O_half = P_half V_half: eight K16 steps over keys [16 K0, 16 K0 + 128)
+template <int K, int K0>
 __device__ __forceinline__ void pv_chain(uint32_t tmem_d, uint32_t tmem_a, uint32_t vlo, uint32_t vhi, uint32_t idesc) {
-  if constexpr (K < 16) {
-    umma_ts2<K != 0, 8 * K + (K >= 8 ? 64 : 0), K * (2048 >> 4)>(tmem_d, tmem_a, vlo, vhi, idesc);
-    pv_chain<K + 1>(tmem_d, tmem_a, vlo, vhi, idesc);
+  if constexpr (K < K0 + 8) {
+    umma_ts2<K != K0, 8 * K + (K >= 8 ? 64 : 0), K * (2048 >> 4)>(tmem_d, tmem_a, vlo, vhi, idesc);
+    pv_chain<K + 1, K0>(tmem_d, tmem_a, vlo, vhi, idesc);
   }
 }
 
@@ -139,7 +144,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   const uint32_t bars = smem_base + OFF_BAR;
   // [2] each: in_full, in_empty (per stage); s_full, p_full, o_full, o_free (per TMEM half); sx_full (per stage)
   const uint32_t in_full = bars, in_empty = bars + 16, s_full = bars + 32, p_full = bars + 48, o_full = bars + 64, o_free = bars + 80;
-  const uint32_t sx_full = bars + 96, tmem_slot = bars + 112;
+  const uint32_t sx_full = bars + 96, tmem_slot = bars + 112, p_full1 = bars + 128;      // p_full: key half 0, p_full1: key half 1
   uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t* tmem_slot_ptr = reinterpret_cast<const uint32_t*>(sm + OFF_BAR + 112);
   float* sxs = reinterpret_cast<float*>(sm + OFF_SX);
@@ -159,7 +164,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       mbar_init(in_full + 8 * s, 1);
       mbar_init(in_empty + 8 * s, 9);     // MMA commit + 4 helper warps + 4 epilogue warps
       mbar_init(s_full + 8 * s, 1);
-      mbar_init(p_full + 8 * s, 8);
+      mbar_init(p_full + 8 * s, 4);
+      mbar_init(p_full1 + 8 * s, 4);
       mbar_init(o_full + 8 * s, 1);
       mbar_init(o_free + 8 * s, 4);
       mbar_init(sx_full + 8 * s, 4);
@@ -221,10 +227,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       for (int g = begin; g < end; ++g) {
         if (g + 1 < end) issue_qk(g + 1);
         const int n = g - begin, slot = n & 1, t = g & 1, il = (g >> 1) - item0, s = il & 1;
+        const uint32_t d = tmem_base + 256 * slot;
         mbar_wait(p_full + 8 * slot, (n >> 1) & 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + 256 * slot;
-        pv_chain<0>(d + 192, d, vlo + s * (STAGE_BYTES >> 4), vhi, idesc_o);
+        pv_chain<0, 0>(d + 64, d, vlo + s * (STAGE_BYTES >> 4), vhi, idesc_o);
+        mbar_wait(p_full1 + 8 * slot, (n >> 1) & 1);
+        tc_fence_after();
+        pv_chain<8, 8>(d + 192, d, vlo + s * (STAGE_BYTES >> 4), vhi, idesc_o);
         umma_commit(o_full + 8 * slot);
         if (t == 1 || g == end - 1) umma_commit(in_empty + 8 * s);    // every MMA reading this stage has been issued
       }
@@ -371,38 +380,47 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       const int ir = rev ? last_item - item : item;
       const int b = ir / DH, h = ir % DH;
       uint8_t* st = sm + s * STAGE_BYTES;
-      const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + 256 * slot + 192;
+      const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + 256 * slot;
       if (t == 0 || g == begin) mbar_wait(sx_full + 8 * s, (il >> 1) & 1);     // the helpers' fp32 copy of V row 256 (and, through them, the stage)
-      mbar_wait(p_full + 8 * slot, ph);                                         // ... and the softmax warps' row statistics
-      const float inv = 1.0f / (sums[(slot * 2 + 0) * 128 + rl] + sums[(slot * 2 + 1) * 128 + rl]);
-      const float px = pxs[slot * 128 + rl];
-      const float2 inv2 = make_float2(inv, inv), px2 = make_float2(px, px);
+      mbar_wait(p_full + 8 * slot, ph);                                         // ... and both softmax groups' row statistics
+      mbar_wait(p_full1 + 8 * slot, ph);
+      // merge of the two independent key halves: weights exp(m_half - m), common denominator
+      const float m0 = mxs[(slot * 2 + 0) * 128 + rl], m1 = mxs[(slot * 2 + 1) * 128 + rl];
+      const float mm = fmaxf(m0, m1);
+      const float e0 = ex2a((m0 - mm) * LOG2E), e1 = ex2a((m1 - mm) * LOG2E);
+      const float inv = 1.0f / fmaf(sums[(slot * 2 + 0) * 128 + rl], e0, sums[(slot * 2 + 1) * 128 + rl] * e1);
+      const float w0 = e0 * inv, w1 = e1 * inv, px = pxs[slot * 128 + rl] * w1;
+      const float2 w02 = make_float2(w0, w0), w12 = make_float2(w1, w1), px2 = make_float2(px, px);
       mbar_wait(o_full + 8 * slot, ph);
       tc_fence_after();
       uint8_t* stg = st + t * TILE_BYTES + q * 4096 + lane * 128;     // this warp's 32 x 128 B slice of the dead Q tile
       const float4* vf = reinterpret_cast<const float4*>(sm + OFF_VF + s * 256);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tm + 32 * c, r);
+      for (int c = 0; c < 4; ++c) {                           // 16 output columns at a time: O0 in [64,128), O1 in [192,256)
+        uint32_t r0[16], r1[16];
+        tmem_ld16(tm + 64 + 16 * c, r0);
+        tmem_ld16(tm + 192 + 16 * c, r1);
         tmem_wait_ld();
-        if (c == 1) {
+        if (c == 3) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(o_free + 8 * slot);      // O is in registers now: the next S may overwrite this TMEM half
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {                         // (O + p_256 v_256) / sum on the packed fp32x2 pipe
+        for (int i = 0; i < 2; ++i) {                         // O0 w0 + O1 w1 + p_256 v_256 (w = weight / denominator) on the packed fp32x2 pipe
           uint32_t w[4];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const float4 v4 = vf[c * 8 + i * 2 + e];
-            const float2 lo = __fmul2_rn(__ffma2_rn(px2, make_float2(v4.x, v4.y), make_float2(__uint_as_float(r[i * 8 + 4 * e]), __uint_as_float(r[i * 8 + 4 * e + 1]))), inv2);
-            const float2 hi = __fmul2_rn(__ffma2_rn(px2, make_float2(v4.z, v4.w), make_float2(__uint_as_float(r[i * 8 + 4 * e + 2]), __uint_as_float(r[i * 8 + 4 * e + 3]))), inv2);
+            const float4 v4 = vf[c * 4 + i * 2 + e];
+            const int k = i * 8 + 4 * e;
+            const float2 lo = __ffma2_rn(w02, make_float2(__uint_as_float(r0[k]), __uint_as_float(r0[k + 1])),
+                                         __ffma2_rn(w12, make_float2(__uint_as_float(r1[k]), __uint_as_float(r1[k + 1])), __fmul2_rn(px2, make_float2(v4.x, v4.y))));
+            const float2 hi = __ffma2_rn(w02, make_float2(__uint_as_float(r0[k + 2]), __uint_as_float(r0[k + 3])),
+                                         __ffma2_rn(w12, make_float2(__uint_as_float(r1[k + 2]), __uint_as_float(r1[k + 3])), __fmul2_rn(px2, make_float2(v4.z, v4.w))));
             w[2 * e] = pack_bf16(lo.x, lo.y);
             w[2 * e + 1] = pack_bf16(hi.x, hi.y);
           }
-          *reinterpret_cast<uint4*>(stg + (((c * 4 + i) ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(stg + (((c * 2 + i) ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
       fence_proxy_async();
@@ -448,9 +466,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         sx = sxs[s * 256 + t * 128 + rl];
         mx = fmaxf(mx, sx);
       }
-      mxs[(slot * 2 + hf) * 128 + rl] = mx;
-      pair_sync(q);
-      mx = fmaxf(mx, mxs[(slot * 2 + (hf ^ 1)) * 128 + rl]);
+      mxs[(slot * 2 + hf) * 128 + rl] = mx;                   // this key half's own maximum: the epilogue merges the halves
       const float nm = -mx * LOG2E;
       TS(2);
       // P = exp2((s - max) log2e) as bf16 into this thread's own (already consumed) half: columns [128 hf, 128 hf + 64).
@@ -489,7 +505,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full + 8 * slot);
+      if (lane == 0) mbar_arrive((hf ? p_full1 : p_full) + 8 * slot);
       TS(3);
     }
 #undef TS10
