@@ -510,13 +510,13 @@ def run_ours(args):
     if gemm_ms > 0:
         achieved = FLOP_DINO_GEMM_IMG * B / (gemm_ms / 1e3) / 1e12
         roofline = {
-            "bound": "tensor", "kernel": "gemm_tc2_kernel (tcgen05 cta_group::2; the 49 DINOv2 GEMMs of one step)",
+            "bound": "tensor", "kernel": "gemm_chain_kernel + gemm_tc2_kernel (tcgen05 cta_group::2; the 49 DINOv2 GEMMs of one step: 12 chained launches of proj -> fc1 -> fc2 -> q|k|v, the patch embedding and the first q|k|v)",
             "achieved": achieved, "peak": tens_peak, "unit": "TFLOP/s", "frac": achieved / tens_peak, "peak_source": tens_src,
             "frac_of_burst_peak": achieved / float(peaks.get("bf16_tflops", 1590.0)),
             "frac_of_sustained_peak": achieved / float(peaks.get("bf16_tflops_sustained", 1400.0)),
             "clocks_while_profiled": prof_clocks,
             "launches_per_step": gemm_n, "ms_per_step": gemm_ms, "share_of_step": gemm_ms / sum(v[1] for v in prof.values()),
-            "traffic": traffic, "traffic_note": "dram read+write bytes per GEMM launch, ncu --set full capture of this config (profiles/)",
+            "traffic": traffic, "traffic_note": "mean dram read+write bytes per GEMM-class launch, ncu --set full capture of this config (profiles/ncu_traffic.json)",
         }
     kernel_ms = {k: round(v[1], 4) for k, v in prof.items()}
     gen_prof = rt.profile(lambda: model.create_tasks(instruction_dict=inp["instruction_dict"], initial_state=inp["initial_state"]), repeats=2)
