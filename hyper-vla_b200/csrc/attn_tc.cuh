@@ -90,7 +90,8 @@ __device__ __forceinline__ void umma_ts2(uint32_t tmem_d, uint32_t tmem_a, uint3
 //               store per warp.
 //   warps 12-15 helpers: the key-256 score of all 256 rows and the whole of query row 256 (mma.sync matrix-vector products), one
 //               item ahead of the softmax warps.
-//   warp 16 TMA producer (two 102 KB stages), warp 17 MMA issuer, warps 18-19 register donors (setmaxnreg: 168 / 72 / 40 / 32).
+//   warp 16 TMA producer (two 102 KB stages), warp 17 MMA issuer, warps 18-19 register donors (setmaxnreg: 168 / 72 / 40 / 32: exactly the 96 x 640 registers
+//   the CTA is launched with -- the pool setmaxnreg redistributes is the launch allocation, not the 64 K file: asking for more hangs).
 // TMEM half s (256 columns): S fp32 [0,256) -> P bf16 of keys 0..127 in [0,64), of keys 128..255 in [128,192); the two key halves are
 // INDEPENDENT softmax units (own row maximum, own row sum): O0 = P0 V[0:128] accumulates in [64,128), O1 = P1 V[128:256] in [192,256), and
 // the epilogue merges them, (O0 w0 + (O1 + p_256 v_256) w1) / (l0 w0 + l1 w1) with w = exp(m_half - max(m0, m1)).  Nothing couples the
@@ -142,9 +143,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + OFF_BAR;
-  // [2] each: in_full, in_empty (per stage); s_full, p_full, o_full, o_free (per TMEM half); sx_full (per stage)
+  // [2] each: in_full, in_empty (per stage, part A = Q0 | K | Qtail); s_full, p_full, o_full, o_free (per TMEM half); sx_full (per stage);
+  // p_full1 (key half 1); in_fullB, in_emptyB (per stage, part B = Q1 | V).  The stage is handed back in two parts: K and Q0 -- all that
+  // S of the next item's first tile needs -- are free as soon as both Q K^T of the item are done and tile 0's output has left its
+  // staging area, a whole softmax phase before Q1 and V are.
   const uint32_t in_full = bars, in_empty = bars + 16, s_full = bars + 32, p_full = bars + 48, o_full = bars + 64, o_free = bars + 80;
   const uint32_t sx_full = bars + 96, tmem_slot = bars + 112, p_full1 = bars + 128;      // p_full: key half 0, p_full1: key half 1
+  const uint32_t in_fullB = bars + 144, in_emptyB = bars + 160;
   uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t* tmem_slot_ptr = reinterpret_cast<const uint32_t*>(sm + OFF_BAR + 112);
   float* sxs = reinterpret_cast<float*>(sm + OFF_SX);
@@ -163,6 +168,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       mbar_init(in_full + 8 * s, 1);
       mbar_init(in_empty + 8 * s, 9);     // MMA commit + 4 helper warps + 4 epilogue warps
+      mbar_init(in_fullB + 8 * s, 1);
+      mbar_init(in_emptyB + 8 * s, 9);
       mbar_init(s_full + 8 * s, 1);
       mbar_init(p_full + 8 * s, 4);
       mbar_init(p_full1 + 8 * s, 4);
@@ -189,17 +196,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         const int ir = rev ? last_item - item : item;
         const int b = ir / DH, h = ir % DH;
         const uint32_t st = smem_base + s * STAGE_BYTES;
-        mbar_wait(in_empty + 8 * s, ((il >> 1) & 1) ^ 1);
-        mbar_expect_tx(in_full + 8 * s, STAGE_BYTES);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          tma_load_2d(st + j * TILE_BYTES, &tmQKV, in_full + 8 * s, h * DHD, b * S_ + 128 * j);
-          tma_load_2d(st + OFF_K + j * TILE_BYTES, &tmQKV, in_full + 8 * s, DD + h * DHD, b * S_ + 128 * j);
-          tma_load_2d(st + OFF_V + j * TILE_BYTES, &tmQKV, in_full + 8 * s, 2 * DD + h * DHD, b * S_ + 128 * j);
-        }
+        const uint32_t par = ((il >> 1) & 1) ^ 1;
+        mbar_wait(in_empty + 8 * s, par);                            // part A: Q0 | K (272 rows) | Qtail
+        mbar_expect_tx(in_full + 8 * s, TILE_BYTES + KV_BYTES + 16 * 128);
+        tma_load_2d(st, &tmQKV, in_full + 8 * s, h * DHD, b * S_);
+        tma_load_2d(st + OFF_K, &tmQKV, in_full + 8 * s, DD + h * DHD, b * S_);
+        tma_load_2d(st + OFF_K + TILE_BYTES, &tmQKV, in_full + 8 * s, DD + h * DHD, b * S_ + 128);
         tma_load_2d(st + OFF_K + 2 * TILE_BYTES, &tmTail, in_full + 8 * s, DD + h * DHD, b * S_ + 256);
-        tma_load_2d(st + OFF_V + 2 * TILE_BYTES, &tmTail, in_full + 8 * s, 2 * DD + h * DHD, b * S_ + 256);
         tma_load_2d(st + OFF_QT, &tmTail, in_full + 8 * s, h * DHD, b * S_ + 256);
+        mbar_wait(in_emptyB + 8 * s, par);                           // part B: Q1 | V (272 rows)
+        mbar_expect_tx(in_fullB + 8 * s, TILE_BYTES + KV_BYTES);
+        tma_load_2d(st + TILE_BYTES, &tmQKV, in_fullB + 8 * s, h * DHD, b * S_ + 128);
+        tma_load_2d(st + OFF_V, &tmQKV, in_fullB + 8 * s, 2 * DD + h * DHD, b * S_);
+        tma_load_2d(st + OFF_V + TILE_BYTES, &tmQKV, in_fullB + 8 * s, 2 * DD + h * DHD, b * S_ + 128);
+        tma_load_2d(st + OFF_V + 2 * TILE_BYTES, &tmTail, in_fullB + 8 * s, 2 * DD + h * DHD, b * S_ + 256);
       }
     } else if (warp == W_MMA && lane == 0) {
       // ============================ MMA issuer ============================
@@ -212,6 +222,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       auto issue_qk = [&](int g) {
         const int n = g - begin, slot = n & 1, t = g & 1, il = (g >> 1) - item0, s = il & 1;
         if (t == 0 || g == begin) mbar_wait(in_full + 8 * s, (il >> 1) & 1);
+        if (t == 1) mbar_wait(in_fullB + 8 * s, (il >> 1) & 1);        // Q1
         mbar_wait(o_free + 8 * slot, ((n >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t ks = klo + s * (STAGE_BYTES >> 4);
@@ -222,12 +233,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         umma_ss2<true, 4>(d, qs, ks, khi, idesc_s);
         umma_ss2<true, 6>(d, qs, ks, khi, idesc_s);
         umma_commit(s_full + 8 * slot);
+        if (t == 1 || g == end - 1) umma_commit(in_empty + 8 * s);     // the last Q K^T of the item here: K and Q0 are free when it retires
       };
       if (begin < end) issue_qk(begin);
       for (int g = begin; g < end; ++g) {
         if (g + 1 < end) issue_qk(g + 1);
         const int n = g - begin, slot = n & 1, t = g & 1, il = (g >> 1) - item0, s = il & 1;
         const uint32_t d = tmem_base + 256 * slot;
+        mbar_wait(in_fullB + 8 * s, (il >> 1) & 1);                    // V
         mbar_wait(p_full + 8 * slot, (n >> 1) & 1);
         tc_fence_after();
         pv_chain<0, 0>(d + 64, d, vlo + s * (STAGE_BYTES >> 4), vhi, idesc_o);
@@ -235,7 +248,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         tc_fence_after();
         pv_chain<8, 8>(d + 192, d, vlo + s * (STAGE_BYTES >> 4), vhi, idesc_o);
         umma_commit(o_full + 8 * slot);
-        if (t == 1 || g == end - 1) umma_commit(in_empty + 8 * s);    // every MMA reading this stage has been issued
+        if (t == 1 || g == end - 1) umma_commit(in_emptyB + 8 * s);   // every MMA reading this stage has been issued
       }
     }
   } else if (warp >= W_HELP) {
@@ -258,6 +271,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       const uint8_t* st = sm + s * STAGE_BYTES;
       const uint32_t st_u = smem_base + s * STAGE_BYTES;
       mbar_wait(in_full + 8 * s, (il >> 1) & 1);
+      mbar_wait(in_fullB + 8 * s, (il >> 1) & 1);
       // ---- key-256 column: rows [64 hw, 64 hw + 64) of Q times k_256 (B fragment column 0 = lanes 0..3) ----
       {
         uint32_t vb[8];
@@ -356,7 +370,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(in_empty + 8 * s);        // this warp is done reading the stage
+        if (lane == 0) { mbar_arrive(in_empty + 8 * s); mbar_arrive(in_emptyB + 8 * s); }        // this warp is done reading the stage
         helper_sync();
         if (hw == 0) {
           const float il2 = 1.0f / l;
@@ -367,7 +381,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
         }
       } else {
         __syncwarp();
-        if (lane == 0) mbar_arrive(in_empty + 8 * s);
+        if (lane == 0) { mbar_arrive(in_empty + 8 * s); mbar_arrive(in_emptyB + 8 * s); }
       }
     }
   } else if (warp >= W_EPI) {
@@ -396,7 +410,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       uint8_t* stg = st + t * TILE_BYTES + q * 4096 + lane * 128;     // this warp's 32 x 128 B slice of the dead Q tile
       const float4* vf = reinterpret_cast<const float4*>(sm + OFF_VF + s * 256);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {                           // 16 output columns at a time: O0 in [64,128), O1 in [192,256)
+      for (int c = 0; c < 4; ++c) {                           // 16 output columns at a time (72 registers): O0 in [64,128), O1 in [192,256)
         uint32_t r0[16], r1[16];
         tmem_ld16(tm + 64 + 16 * c, r0);
         tmem_ld16(tm + 192 + 16 * c, r1);
@@ -428,9 +442,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       if (lane == 0) {
         tma_store_2d(&tmOut, smem_base + s * STAGE_BYTES + t * TILE_BYTES + q * 4096, h * DHD, b * S_ + t * 128 + q * 32);
         bulk_commit();
-        if (t == 1 || g == end - 1) {                        // last tile of the item here: hand the stage back once TMA has read the staging
+        const bool first = t == 0 || g == begin, last = t == 1 || g == end - 1;   // of this item's tiles in this CTA
+        if (first || last) {                                 // hand the stage back once TMA has read the staging: Q0 | K after the first tile, Q1 | V after the last
           bulk_wait_read0();
-          mbar_arrive(in_empty + 8 * s);
+          if (first) mbar_arrive(in_empty + 8 * s);
+          if (last) mbar_arrive(in_emptyB + 8 * s);
         }
       }
       __syncwarp();
