@@ -26,6 +26,12 @@ constexpr int OFF_QT = OFF_V + KV_BYTES;        // query rows 256..271 (only row
 constexpr int STAGE_BYTES = OFF_QT + 16 * 128; // Q0 Q1 | K[272] | V[272] | Qtail[16] = 102 KB
 static_assert(STAGE_BYTES % 1024 == 0 && OFF_V % 1024 == 0, "UMMA / TMA 128B-swizzle tiles need 1024-byte alignment");
 constexpr float LOG2E = 1.4426950408889634f;
+#ifndef HVLA_ATTN_NPOLY
+#define HVLA_ATTN_NPOLY 0
+#endif
+constexpr int NPOLY = HVLA_ATTN_NPOLY;            // of every 8 key pairs, this many take the polynomial exp2 (0 = all MUFU, the default:
+                                                 // measured with 2 and 3 of 8, the kernel got 10-14 % SLOWER -- the extra 10 instructions per pair
+                                                 // cost more issue slots and registers than the freed MUFU slots return; A/B switch only)
 
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2a(float x) {
@@ -44,6 +50,26 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
   return d;
 }
 constexpr uint32_t make_idesc_bmn(int M, int N) { return make_idesc(M, N) | (1u << 16); }   // B is MN-major
+
+// 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): x = n + f with n = rint(x) (magic-number add), f in [-0.5, 0.5], 2^f by a degree-3
+// minimax polynomial (relative error 7.6e-5, far below the bf16 rounding of P), 2^n by adding n to the exponent field.  Two elements at
+// a time on the packed fp32 pipe: 3 FADD2 + 3 FFMA2 + 2 FMNMX + 2 IMAD per pair.  The exponential pass is MUFU-bound (89 % of the
+// 16 results / clk / SM while both softmax groups are in it); a share of the keys can go this way instead (HVLA_ATTN_NPOLY).
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
+  const float2 t = __fadd2_rn(x, magic);                      // low mantissa bits of t = rint(x) (two's complement)
+  const float2 n = __fadd2_rn(t, nmagic);
+  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+  float2 p = __ffma2_rn(make_float2(0.05520550534129143f, 0.05520550534129143f), f, make_float2(0.24261397123336792f, 0.24261397123336792f));
+  p = __ffma2_rn(p, f, make_float2(0.6932547688484192f, 0.6932547688484192f));
+  p = __ffma2_rn(p, f, make_float2(0.9999276995658875f, 0.9999276995658875f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
 
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -496,7 +522,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float2 x = __ffma2_rn(make_float2(__uint_as_float(r[blk >> 1][16 * (blk & 1) + 2 * i]), __uint_as_float(r[blk >> 1][16 * (blk & 1) + 2 * i + 1])), l2, nm2);
-          o[i] = make_float2(ex2a(x.x), ex2a(x.y));
+          if (i < NPOLY) o[i] = ex2_poly2(x);                   // this pair on the FMA pipe ...
+          else o[i] = make_float2(ex2a(x.x), ex2a(x.y));        // ... the others on the MUFU pipe
         }
       };
       exp_block(0, e[0]);
