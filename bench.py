@@ -119,6 +119,8 @@ def kernel_roofline_table(act_prof: dict, gen_prof: dict, B: int, T: int, peaks:
             if name not in work or ms <= 0:
                 continue
             bound, w = work[name]
+            if name == "layernorm":
+                w = w * n / 25.0           # flow B (>= 25 images) has two stream passes per forward instead of 25 LayerNorm launches
             if bound == "tensor":
                 a, pk, unit = w / (ms / 1e3) / 1e12, tens, "TFLOP/s"
             else:
