@@ -137,12 +137,13 @@ gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
   float* sepi = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
   const uint32_t sstage = (tmem_slot + 16 + 4096 + 1023u) & ~1023u;
   // control block in the alignment gap below the slabs (880 bytes): the ring of posted units (entry + "posted" barrier each), the
-  // "taken" barrier (producer -> scheduler) and the publisher mailbox (two barrier pairs + the done[] index of the tile in each slot)
+  // "taken" counter (producer -> scheduler) and the publisher mailbox (two barrier pairs + the done[] index of the tile in each slot)
   const uint32_t ctl = sstage - 256;
   const uint32_t ring_bar = ctl, ring_val = ctl + 8 * RING, taken_bar = ring_val + 4 * RING;
   const uint32_t pub_full = taken_bar + 8, pub_empty = pub_full + 16, pub_idx_a = pub_empty + 16;
   volatile int* ring = reinterpret_cast<volatile int*>(smem_raw + (ring_val - smem_u32(smem_raw)));
   volatile int* pub_idx = reinterpret_cast<volatile int*>(smem_raw + (pub_idx_a - smem_u32(smem_raw)));
+  volatile int* taken_cnt = reinterpret_cast<volatile int*>(smem_raw + (taken_bar - smem_u32(smem_raw)));   // units the leader's producer has taken
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -164,7 +165,7 @@ gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
       mbar_init(pub_empty + 8 * s, 1);
     }
     for (int s = 0; s < RING; ++s) mbar_init(ring_bar + 8 * s, 1);
-    mbar_init(taken_bar, 1);
+    *taken_cnt = 0;
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
@@ -189,7 +190,7 @@ gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
     if (rank == 0 && lane == 0) {
       int slot = 0;
       for (int j = 0;; ++j) {
-        if (j >= 1) mbar_wait(taken_bar, (j - 1) & 1);          // the producer has taken unit j - 1
+        if (j >= 1) { while (*taken_cnt < j) { } }               // the producer has taken unit j - 1
         const int u = atomicAdd(p.next, 1);
         int v = -1;
         if (u < p.n_units) {
@@ -225,8 +226,8 @@ gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
       uint32_t ph = 0;
       for (int j = 0;; ++j) {
         const int v = posted(j);
-        if (rank == 0) mbar_arrive(taken_bar);
         if (v < 0) break;
+        if (rank == 0) *taken_cnt = j + 1;          // flow control only (no data behind it): the scheduler may pull the next unit
         const Unit un = unpack_unit(v);
 #ifndef HVLA_CHAIN_NO_RFENCE
         fence_proxy_async_all();      // generic-proxy writes of other SMs (shadow rows), acquired by the scheduler, before this thread's TMA reads
