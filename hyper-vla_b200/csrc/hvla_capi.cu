@@ -358,8 +358,12 @@ static int dino_bf16_blk(cudaStream_t st, const float* dv, const bf16* dm, const
     ep.bias = v + V::b1_f; ep.out = HID; ep.ldo = DF; ep.stats = ST; ep.cs = v + V::cs_1; ep.rev = rev;
     return ep;
   };
-  // One launch per layer for proj -> fc1 -> fc2 -> q|k|v of the next layer (gemm_chain.cuh); HVLA_CHAIN=0 keeps one launch per GEMM.
-  static const bool use_chain = !(getenv("HVLA_CHAIN") && getenv("HVLA_CHAIN")[0] == '0');
+  // One launch per layer for proj -> fc1 -> fc2 -> q|k|v of the next layer (gemm_chain.cuh).
+  // Default: while the N = 768 GEMMs have at most 12 waves of tiles (<= ~290 images) -- the chain buys back their tails and the launch
+  // boundaries (64 / 128 images: +1.5 % sustained); from 20 waves on (512 images) the tails are noise and one launch per GEMM, with its
+  // static tile order and cross-tile stream prefetch, is 2-5 % faster.  HVLA_CHAIN=0 / 1 force either.
+  static const int chain_env = getenv("HVLA_CHAIN") ? atoi(getenv("HVLA_CHAIN")) : -1;
+  const bool use_chain = chain_env >= 0 ? chain_env != 0 : (int64_t)((M + 255) / 256) * 3 <= (int64_t)12 * (num_sms() / 2);
   // wavefront lags in row blocks (proj -> fc1, fc1 -> fc2, fc2 -> q|k|v): HVLA_CHAIN_LAG="a,b,c" or one number for all three
   static int chain_lags[3] = {1 << 20, 1 << 20, 1 << 20};     // >= row blocks: each GEMM's tiles follow the previous GEMM's (measured: interleaving them is slower)
   static const bool lags_parsed = [&]() {
