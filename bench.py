@@ -525,6 +525,14 @@ def run_ours(args):
     gen_kernel_ms = {k: [v[0], round(v[1], 4)] for k, v in gen_prof.items()}
     kernel_rooflines = kernel_roofline_table(prof, gen_prof, B, B, peaks, args.precision, tens_peak)
 
+    # ---- the GEMM class against cuBLAS on the same shapes (context for roofline.frac) ----
+    gemm_vs_cublas = None
+    if not args.no_extras and rank == 0 and args.precision == "bf16":
+        try:
+            gemm_vs_cublas = time_gemm_vs_cublas(B)
+        except Exception as exc:
+            gemm_vs_cublas = {"error": repr(exc)}
+
     # ---- base net only on cached weights + cached embeddings (BASELINE configs[2]: "per-step base net only (cached weights)") ----
     base_only = None
     if not args.no_extras:
@@ -650,6 +658,7 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "base_only": base_only,
+            "gemm_vs_cublas_same_shape": gemm_vs_cublas,
             "weak_64_per_gpu": weak64,
             "gather_actions": gather,
             "kernel_ms_per_step": kernel_ms,
@@ -666,6 +675,49 @@ def run_ours(args):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_gemm_vs_cublas(B: int, secs: float = 0.7) -> dict:
+    """Context for `roofline.frac`: the tcgen05 GEMM of this repo (hvla_gemm_bf16: bias / GELU epilogue) and cuBLAS (torch.matmul, no
+    epilogue) on the SAME four shapes of one DINOv2 layer at this batch, each looped alone for `secs` (sustained clocks), TFLOP/s.
+    cuBLAS is called here as a yardstick only; nothing on the product path uses it."""
+    import torch
+    from hvla import _native as N
+    lib = N.lib()
+    st = int(torch.cuda.current_stream().cuda_stream)
+    M = B * 257
+    out = {}
+
+    def loop(fn):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0, n = time.perf_counter(), 0
+        a.record()
+        while time.perf_counter() - t0 < secs:
+            for _ in range(20):
+                fn()
+            n += 20
+            if n % 200 == 0:
+                torch.cuda.current_stream().synchronize()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n          # ms per launch
+
+    for name, n, k, act in (("qkv", 2304, 768, 0), ("proj", 768, 768, 0), ("fc1_gelu", 3072, 768, 2), ("fc2", 768, 3072, 0)):
+        A = torch.randn(M, k, device="cuda").to(torch.bfloat16)
+        Wt = (torch.randn(n, k, device="cuda") * 0.05).to(torch.bfloat16)
+        W = Wt.t().contiguous()
+        bias = torch.randn(n, device="cuda")
+        Cc = torch.empty(M, n, device="cuda", dtype=torch.bfloat16)
+        flop = 2.0 * M * n * k
+        ours = loop(lambda: lib.hvla_gemm_bf16(st, A.data_ptr(), Wt.data_ptr(), bias.data_ptr(), Cc.data_ptr(), M, n, k, act))
+        cub = loop(lambda: torch.matmul(A, W, out=Cc))
+        out[name] = {"M": M, "N": n, "K": k, "ours_tflops": round(flop / ours / 1e9, 1), "cublas_tflops": round(flop / cub / 1e9, 1),
+                     "ratio": round(cub / ours, 3)}
+    out["note"] = ("each kernel looped alone under the power cap; ours includes the bias (+ erf-GELU for fc1) epilogue, cuBLAS has no epilogue; "
+                   "MEASURED_PEAKS bf16_tflops_sustained is cuBLAS at 8192^3, a figure K = 768 GEMMs do not reach in either implementation")
+    return out
 
 
 def time_base_only(model, Bb: int, K: int, Wm: int, world: int, rank: int, peaks: dict, timed_leg, args) -> dict:
