@@ -526,12 +526,16 @@ def run_ours(args):
     kernel_rooflines = kernel_roofline_table(prof, gen_prof, B, B, peaks, args.precision, tens_peak)
 
     # ---- the GEMM class against cuBLAS on the same shapes (context for roofline.frac) ----
-    gemm_vs_cublas = None
+    gemm_vs_cublas, attn_vs_lib = None, None
     if not args.no_extras and rank == 0 and args.precision == "bf16":
         try:
             gemm_vs_cublas = time_gemm_vs_cublas(B)
         except Exception as exc:
             gemm_vs_cublas = {"error": repr(exc)}
+        try:
+            attn_vs_lib = time_attention_vs_library(B)
+        except Exception as exc:
+            attn_vs_lib = {"error": repr(exc)}
 
     # ---- base net only on cached weights + cached embeddings (BASELINE configs[2]: "per-step base net only (cached weights)") ----
     base_only = None
@@ -659,6 +663,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "base_only": base_only,
             "gemm_vs_cublas_same_shape": gemm_vs_cublas,
+            "attention_vs_library": attn_vs_lib,
             "weak_64_per_gpu": weak64,
             "gather_actions": gather,
             "kernel_ms_per_step": kernel_ms,
@@ -675,6 +680,52 @@ def run_ours(args):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_attention_vs_library(B: int, secs: float = 0.7) -> dict:
+    """Context for the attention kernel's roofline fractions: hvla_dino_attention and the library attentions torch ships (SDPA cuDNN /
+    flash backends) on the same problem -- B images x 12 heads x 257 tokens x 64 -- each looped alone for `secs`.  Yardstick only."""
+    import torch
+    import torch.nn.functional as F
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    from hvla import _native as N
+    lib = N.lib()
+    st = int(torch.cuda.current_stream().cuda_stream)
+    H, S, D = 12, 257, 64
+    qkv = torch.randn(B * S, 3 * H * D, device="cuda")
+    qkv[:, :H * D] *= 0.35
+    qkv = qkv.to(torch.bfloat16)
+    o = torch.empty(B * S, H * D, device="cuda", dtype=torch.bfloat16)
+    q4 = qkv.view(B, S, 3, H, D)
+    q, k, v = (q4[:, :, i].transpose(1, 2).contiguous() for i in range(3))
+
+    def loop(fn):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0, n = time.perf_counter(), 0
+        a.record()
+        while time.perf_counter() - t0 < secs:
+            for _ in range(20):
+                fn()
+            n += 20
+            if n % 200 == 0:
+                torch.cuda.current_stream().synchronize()
+        b.record()
+        torch.cuda.synchronize()
+        return round(a.elapsed_time(b) * 1e3 / n, 1)
+
+    out = {"problem": f"{B} x 12 heads x 257 x 64, bf16", "ours_us": loop(lambda: lib.hvla_dino_attention(st, qkv.data_ptr(), o.data_ptr(), B, 1))}
+    for nm, be in (("cudnn_sdpa_us", SDPBackend.CUDNN_ATTENTION), ("flash_sdpa_us", SDPBackend.FLASH_ATTENTION)):
+        def run(be=be):
+            with sdpa_kernel(be):
+                return F.scaled_dot_product_attention(q, k, v, scale=1.0)
+        try:
+            out[nm] = loop(run)
+        except Exception as exc:
+            out[nm] = f"unavailable: {type(exc).__name__}"
+    out["note"] = "library kernels get [B,H,S,D]-contiguous q, k, v; ours reads the packed q|k|v rows of the GEMM before it"
+    return out
 
 
 def time_gemm_vs_cublas(B: int, secs: float = 0.7) -> dict:
