@@ -1,4 +1,4 @@
-// A CHAIN of dependent tcgen05 GEMMs in ONE persistent launch (flow B of dino_bf16, >= 24 images):
+// A CHAIN of dependent tcgen05 GEMMs in ONE persistent launch (flow B of dino_bf16, 25 to ~290 images):
 //     proj (+ residual)  ->  fc1 (+ GELU)  ->  fc2 (+ residual)  ->  q|k|v of the next layer
 // instead of four launches.  Same CTA-pair tiles, TMA ring, TMEM double buffering and epilogues as gemm_tc2_kernel; what changes
 // is WHO computes WHAT and WHEN:
@@ -6,14 +6,15 @@
 //     atomic counter, so there is no tail (195 tiles on 74 pairs = 2.6 waves cost 3) and no launch / drain / pipeline-fill gap
 //     between the GEMMs of a layer;
 //   * a unit of GEMM g > 0 needs row block m of GEMM g-1 complete: every CTA bumps done[g][m] when its half tile is in global
-//     memory (stores complete, fence, release), the TMA producer and the epilogue warps of a consumer unit acquire
-//     done[g-1][m] == 2 * n_tiles_n(g-1) before they touch the rows;
-//   * the list is a WAVEFRONT over row blocks: slot s holds the tiles of proj(s), fc1(s - lag), fc2(s - 2 lag), qkv(s - 3 lag), so
-//     a row block's shadow, hidden activations and residual rows are consumed a few dozen microseconds after they were written --
-//     out of the 126 MB L2 instead of HBM -- while HBM-bound units (proj) and tensor-bound units (fc1, fc2) run side by side
-//     on different SMs.  lag is large enough (>= 2 * pairs units) that a dependency is long complete when its consumer is pulled.
-// No deadlock: every pair takes units in increasing list order, dependencies point to earlier list positions, and all 148 CTAs are
-// co-resident (one per SM), so the pair holding the smallest unfinished unit never waits.
+//     memory (a PUBLISHER warp does the release, fed lazily by the epilogue warps), and a SCHEDULER warp acquires
+//     done[g-1][m] == 2 * n_tiles_n(g-1) BEFORE it posts the unit to the pair: producer, MMA thread and epilogue warps never see an
+//     atomic or a counter;
+//   * the list is parametrised as a wavefront over row blocks (slot s holds the tiles of proj(s), fc1(s - lag1), fc2(s - lag1 - lag2),
+//     qkv(s - lag1 - lag2 - lag3)); the default lags are >= the number of row blocks, i.e. GEMM after GEMM: interleaving the GEMMs so
+//     that a row block's activations are re-read out of L2 measured 3-15 % slower.
+// No deadlock: every pair takes units in increasing list order, dependencies point to earlier list positions, only running pairs own
+// units, and an epilogue warp hands its finished tile over before it blocks on a unit that is not posted yet.
+// Bit-identical to one launch per GEMM for every schedule (tools/chain_check.py, tests/test_gpu_chain.py).
 #pragma once
 #include "gemm_tc2.cuh"
 
