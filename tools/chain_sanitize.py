@@ -8,6 +8,7 @@ import sys
 import numpy as np
 
 os.environ.setdefault("HVLA_FUSED_LN", "1")          # flow B (blocked stream + chain) also below 25 images
+os.environ.setdefault("HVLA_CHAIN", "1")             # ... and above ~290
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "hyper-vla_b200"))
 import torch  # noqa: E402
