@@ -568,6 +568,10 @@ __device__ __forceinline__ void epilogue_tile_blk(const EpiP& ep, float* sepi, u
   const uint32_t my = slab + (uint32_t)lane * 64u;
   const uint32_t sw = (uint32_t)((lane >> 1) & 3);          // 16-byte piece index ^= (row >> 1) & 3: conflict-free 16-byte column writes
   float p_sum = 0.f, p_sq = 0.f;
+  // the patch embedding emits shadow + statistics too when it is given the buffers (no separate pass in front of the first q|k|v);
+  // its GEMM row b*256+p is stream row b*257+1+p
+  const bool emit = !PATCH || ep.shadow != nullptr;
+  const int roff = PATCH ? m0 / 256 + 1 : 0;
   epi_bar_sync();
   mbar_wait(tfull_bar_addr, aph);
   tc_fence_after();
@@ -598,7 +602,7 @@ __device__ __forceinline__ void epilogue_tile_blk(const EpiP& ep, float* sepi, u
 #pragma unroll
       for (int j = 0; j < 8; ++j) stcg_hint(t.xp + 32 * (c * 8 + j), make_float4(xn[4 * j], xn[4 * j + 1], xn[4 * j + 2], xn[4 * j + 3]), pol);
     }
-    if (!PATCH) {
+    if (emit) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) { p_sum += xn[j]; p_sq = fmaf(xn[j], xn[j], p_sq); }
       __syncwarp();                                            // the previous chunk's read-back of the slab is complete
@@ -619,12 +623,12 @@ __device__ __forceinline__ void epilogue_tile_blk(const EpiP& ep, float* sepi, u
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
                      : "r"(slab + (uint32_t)(row * 64) + ((((uint32_t)pc) ^ (uint32_t)((row >> 1) & 3)) << 4)) : "memory");
         if (rbase + row < ep.rows)
-          __stcg(reinterpret_cast<uint4*>(ep.shadow + (int64_t)(rbase + row) * DD + n0 + cl + pc * 8), make_uint4(v0, v1, v2, v3));
+          __stcg(reinterpret_cast<uint4*>(ep.shadow + (int64_t)(rbase + row + roff) * DD + n0 + cl + pc * 8), make_uint4(v0, v1, v2, v3));
       }
     }
   }
-  if (!PATCH && t.ok)                                          // partial (sum, sumsq) of this row over this tile's 128-column half
-    *reinterpret_cast<float2*>(ep.stats_out + (int64_t)t.grow * 12 + ((n0 / BN) * 2 + half) * 2) = make_float2(p_sum, p_sq);
+  if (emit && t.ok)                                            // partial (sum, sumsq) of this row over this tile's 128-column half
+    *reinterpret_cast<float2*>(ep.stats_out + (int64_t)(t.grow + roff) * 12 + ((n0 / BN) * 2 + half) * 2) = make_float2(p_sum, p_sq);
   tc_fence_before();
   __syncwarp();
 }

@@ -295,12 +295,32 @@ __global__ void __launch_bounds__(256) dino_init_rows_kernel(const float* __rest
 }
 
 // cls rows of the BLOCKED stream (gemm_tc.cuh: xblk_f4): X[b,0,:] = cls + pos[0]; the patch rows are written by the patch-embedding GEMM
-__global__ void __launch_bounds__(192) dino_cls_rows_blk_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ X) {
+__global__ void __launch_bounds__(192) dino_cls_rows_blk_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ X,
+                                                                bf16* __restrict__ Y, float* __restrict__ ST) {
   pdl_trigger();
   pdl_wait();
   const int c4 = threadIdx.x;
   const float4 c = __ldg(reinterpret_cast<const float4*>(cls) + c4), p = __ldg(reinterpret_cast<const float4*>(pos) + c4);
-  reinterpret_cast<float4*>(X)[tc::xblk_f4(blockIdx.x * DTOK, c4)] = make_float4(c.x + p.x, c.y + p.y, c.z + p.z, c.w + p.w);
+  const float4 v = make_float4(c.x + p.x, c.y + p.y, c.z + p.z, c.w + p.w);
+  const int64_t row = (int64_t)blockIdx.x * DTOK;
+  reinterpret_cast<float4*>(X)[tc::xblk_f4((int)row, c4)] = v;
+  // bf16 shadow + row statistics of the CLS row for the first q|k|v (the patch rows get theirs from the patch-embedding epilogue)
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(Y + row * DD + 4 * c4) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  float s = (v.x + v.y) + (v.z + v.w), q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  __shared__ float red[6][2];
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = s; red[threadIdx.x >> 5][1] = q; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0) {
+      o.x = ((red[0][0] + red[1][0]) + (red[2][0] + red[3][0])) + (red[4][0] + red[5][0]);
+      o.y = ((red[0][1] + red[1][1]) + (red[2][1] + red[3][1])) + (red[4][1] + red[5][1]);
+    }
+    reinterpret_cast<float4*>(ST + row * 12)[threadIdx.x] = o;
+  }
 }
 
 // ---- large-batch flow ("flow B"): no LayerNorm kernels between the GEMMs (gemm_tc.cuh, "stream LayerNorm without a LayerNorm kernel")
@@ -334,15 +354,15 @@ static int dino_bf16_blk(cudaStream_t st, const float* dv, const bf16* dm, const
   }
   {
     ProfScope ps(st, "cls_rows");
-    launch_k(dino_cls_rows_blk_kernel, dim3(B), dim3(DD / 4), 0, st, dv + V::cls, dv + V::pos, X);
+    launch_k(dino_cls_rows_blk_kernel, dim3(B), dim3(DD / 4), 0, st, dv + V::cls, dv + V::pos, X, Y, ST);
     HVLA_LAUNCH_CHECK("dino_cls_rows_blk");
   }
   {
     tc::EpiP ep; memset(&ep, 0, sizeof ep);
     ep.bias = dv + V::patch_b; ep.out = X; ep.ldo = DD; ep.rows = B * NPATCH; ep.pos = dv + V::pos_blk; ep.xhint = xhint;
+    ep.shadow = Y; ep.stats_out = ST;        // shadow + statistics of the embedded tokens for the first q|k|v: no separate stream pass
     HVLA_TRY(tc2::gemm_tc2(st, A0, dm + Mx::patch_w, B * NPATCH, DD, PATCH_KP, tc::EPI_PATCH_BLK, ep));
   }
-  HVLA_TRY(stream_blk_rows(st, X, Y, ST, nullptr, nullptr, M));     // shadow + statistics of the embedded tokens
   auto ep_qkv = [&](const float* v, int rev) {
     tc::EpiP ep; memset(&ep, 0, sizeof ep);
     ep.bias = v + V::bqkv_f; ep.out = QKV; ep.ldo = 3 * DD; ep.stats = ST; ep.cs = v + V::cs_qkv; ep.rev = rev;
