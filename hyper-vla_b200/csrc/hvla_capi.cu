@@ -326,7 +326,8 @@ __global__ void __launch_bounds__(192) dino_cls_rows_blk_kernel(const float* __r
 // ---- large-batch flow ("flow B"): no LayerNorm kernels between the GEMMs (gemm_tc.cuh, "stream LayerNorm without a LayerNorm kernel")
 // The fp32 residual stream is kept in the BLOCKED layout; the residual GEMMs (proj, fc2) update it in place in their epilogue and
 // emit the un-normalised bf16 shadow (Y) + per-row statistics (ST) that q|k|v / fc1 fold into THEIR epilogue.  Per layer: 4 GEMMs
-// + attention, nothing else; two stream_blk_rows launches per forward (shadow of the embedded tokens, final LayerNorm).
+// + attention (or one GEMM chain + attention), nothing else; the shadow of the embedded tokens comes out of the patch-embedding epilogue
+// and the CLS-row kernel, one stream_blk_rows launch per forward is the final LayerNorm.
 static int dino_bf16_blk(cudaStream_t st, const float* dv, const bf16* dm, const uint8_t* images, int B, bf16* out_emb,
                          uint8_t* ws, const Plan& pl) {
   typedef DvecLayout V;
