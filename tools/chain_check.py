@@ -40,7 +40,7 @@ def child(B, out):
         n = 14
         print(f"   chain stats per forward: units with a dependency {buf[0] / n:.0f}, had to wait {buf[1] / n:.0f}, spins {buf[2] / n:.0f}, "
               f"cycles waited {buf[3] / n:.0f} (sum over pairs; {buf[3] / n / 74 / 1.9e3:.1f} us per pair at 1.9 GHz)")
-    print(f"B={B} {os.environ.get('HVLA_CHAIN', '1')=} lag={os.environ.get('HVLA_CHAIN_LAG', 'default')}: dino forward median {ts[len(ts) // 2]:.3f} ms, min {ts[0]:.3f} ms, "
+    print(f"B={B} chain={os.environ.get('HVLA_CHAIN', 'default')} lag={os.environ.get('HVLA_CHAIN_LAG', 'default')}: dino forward median {ts[len(ts) // 2]:.3f} ms, min {ts[0]:.3f} ms, "
           f"repeatable {rep}, finite {bool(torch.isfinite(emb.float()).all())}", flush=True)
 
 
