@@ -64,7 +64,10 @@ int64_t hvla_dino_mat_elems(void);
 /* element offset of a named field: "hn.<field>", "gen.<field>", "dvec.<field>", "dmat.<field>";
  * per-layer fields are "l<k>.<field>".  Returns -1 for an unknown name. */
 int64_t hvla_layout_offset(const char* name);
-/* bytes of scratch the compute entry points need for B environments and T tasks */
+/* bytes of scratch the compute entry points need for B environments and T tasks.  The scratch is owned by ONE call at a time: two calls
+ * that may run concurrently (different streams) need different buffers -- besides the activations it holds scheduler state of the
+ * persistent GEMM kernels (unit counter, per-row-block completion counters), which every call zeroes itself on its stream.  Its contents
+ * need not be preserved or initialised between calls. */
 size_t hvla_workspace_bytes(int B, int T, int dtype);
 
 /* ---- generate: replaces HyperNetwork.apply inside HyperVLA.create_tasks -----------------
