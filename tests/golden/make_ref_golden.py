@@ -3,7 +3,7 @@ hypervla/components/*.py, unmodified) in float64 through oracle/refshim (NumPy s
 primitives, HF torch DINOv2 for the un-vendored FlaxDinov2Model).  Needs /root/reference, so it runs in the build
 container only; the fixtures it writes are committed and travel to the GPU box.
 
-    python tests/golden/make_ref_golden.py            # writes ref_c1_b1_t1.npz, ref_c2_b3_t3.npz, ref_c5_b6_t2.npz
+    python tests/golden/make_ref_golden.py [case ...]   # writes ref_c1_b1_t1.npz, ref_c2_b3_t3.npz, ref_c5_b6_t2.npz, ref_c2_b64_t64.npz
 
 Call shapes used (all reference code):
   * model = HyperVLA.from_config(config, example_batch)                    hypervla/model.py:286-368
@@ -29,7 +29,9 @@ sys.path.insert(0, os.path.join(ROOT, "hyper-vla_b200"))
 
 from hvla import config as C, metadata as M, params as P, synthetic as S   # noqa: E402
 
-CASES = {"ref_c1_b1_t1": (1, 1, 1), "ref_c2_b3_t3": (2, 3, 3), "ref_c5_b6_t2": (5, 6, 2)}
+CASES = {"ref_c1_b1_t1": (1, 1, 1), "ref_c2_b3_t3": (2, 3, 3), "ref_c5_b6_t2": (5, 6, 2),
+         # BASELINE configs[1] at its full size: 64 envs, one task each -- the batch the headline bench line runs (LayerNorm-free flow, GEMM chain)
+         "ref_c2_b64_t64": (2, 64, 64)}
 WEIGHT_STRIDE = 97
 
 
@@ -132,6 +134,8 @@ def main():
     model, RM = build_reference_model(params)
     out_dir = os.path.dirname(os.path.abspath(__file__))
     for name, (ci, B, T) in CASES.items():
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         r = run_reference(model, RM, ci, B, T)
         save_case(os.path.join(out_dir, name + ".npz"), ci, B, T, r)
         print(name, "action[0,0]=", r["action"][0, 0], "logit[0]=", r["logit"][0])

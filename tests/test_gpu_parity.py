@@ -82,6 +82,33 @@ def test_generate_and_act_match_golden(models, golden, prec, case):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16", "fp32x3"])
+def test_headline_config_at_full_size_matches_the_reference_run_fixture(models, golden, prec):
+    """BASELINE configs[1] AT ITS FULL SIZE -- 64 environments, one generated weight set each, the batch the bench line is quoted on --
+    against a fixture produced by executing the reference's own code for all 64 environments (tests/golden/make_ref_golden.py
+    ref_c2_b64_t64).  In bf16 this is the large-batch flow: LayerNorm-free blocked stream, GEMM chain, tcgen05 attention, cluster base kernel."""
+    case = "ref_c2_b64_t64"
+    if case not in golden:
+        pytest.skip("fixture not generated")
+    g = golden[case]
+    ci, B, T = int(g["config_index"]), int(g["B"]), int(g["T"])
+    assert (B, T) == (64, 64)
+    inp, bp, action, logit = run_case(models[prec], ci, B, T)
+    rows = bp.packed_numpy()
+    tol = TOL[prec]
+    e_ctx = rel_err(bp.context_embedding.cpu().numpy(), g["ctx"])
+    e_rows = rel_err(rows[:, ::97], g["rows_sample"])
+    e_act = rel_err(action[..., :6], g["action"][..., :6])
+    e_logit = rel_err(logit, g["logit"])
+    margin = 1e-3 if prec != "bf16" else 2e-2 * np.abs(g["logit"]).max()
+    sure = np.abs(g["logit"]) > margin
+    flips = int((action[..., 6][sure] != g["action"][..., 6][sure]).sum())
+    print(f"[{prec} {case}] ctx {e_ctx:.2e} rows {e_rows:.2e} action {e_act:.2e} logit {e_logit:.2e}; gripper bits: {flips} of {int(sure.sum())} "
+          f"with |reference logit| > {margin:.1e} differ")
+    assert e_ctx <= tol and e_rows <= tol and e_act <= tol
+    assert flips == 0
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp32x3"])
 def test_dino_hidden_matches_golden(models, golden, torch_cuda, prec):
     from hvla import synthetic as S
     g = golden["c2_b3_t3"]

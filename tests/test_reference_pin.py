@@ -59,6 +59,33 @@ def test_fp64_oracle_matches_reference_run(params_p1, golden, case):
     assert np.array_equal(np.asarray(r["action"])[..., 6][sure], g["action"][..., 6][sure])
 
 
+def test_fp64_oracle_matches_the_full_size_reference_run_on_sampled_envs(params_p1, golden):
+    """BASELINE configs[1] at its full size (64 envs, one task each): the reference's own code was run for all 64 environments
+    (ref_c2_b64_t64); the restatement is checked on all 64 generated weight sets and on a spread of environments."""
+    from hvla import metadata as M, params as P, synthetic as S
+    from oracle import hypervla_oracle as O
+    g = golden["ref_c2_b64_t64"]
+    ci, B, T = int(g["config_index"]), int(g["B"]), int(g["T"])
+    assert (B, T) == (64, 64) and "reference code executed" in str(g["source"])
+    inp = S.make_inputs(ci, B, T)
+    lang = inp["instruction_dict"]["language_instruction"]
+    gen, emb = O.generate(params_p1, lang["token_embedding"], lang["attention_mask"], inp["initial_state"]["patch_embeddings"][:, 0],
+                          dtype=np.float64, generated_paths=M.generated_leaves_canonical())
+    rows = np.zeros((T, M.N_GENERATED), np.float64)
+    for path, (off, shape) in M.packed_offsets().items():
+        n = int(np.prod(shape))
+        rows[:, off:off + n] = gen[path].reshape(T, n)
+    assert rel(emb[:, 0], g["ctx"]) < 1e-12
+    assert rel(rows[:, ::97], g["rows_sample"]) < 1e-12
+    assert rel(np.abs(rows).sum(1), g["rows_abs"]) < 1e-12
+    envs = np.array([0, 21, 42, 63])
+    per_env = O.to_tree(O.take_tasks(gen, inp["task_index"][envs]))
+    act, logit, _, h = O.sample_actions(P.dino_tree_from_params(params_p1), per_env, inp["images"][envs, 0], dtype=np.float64, return_all=True)
+    assert rel(h.reshape(len(envs), -1), g["h"][envs]) < 1e-9
+    assert rel(logit.reshape(len(envs), -1), g["logit"][envs]) < 1e-9
+    assert rel(act[..., :6], g["action"][envs][..., :6]) < 2e-7
+
+
 def test_fp32_oracle_within_north_star_tolerance_of_reference_run(params_p1, golden):
     """The fp32 restatement (the JAX-CPU stand-in timed by bench.py) is within 1e-5 of the reference run."""
     case = "ref_c2_b3_t3"
