@@ -239,3 +239,38 @@ def test_discrete_head_configuration_and_layout():
     with pytest.raises(ValueError):
         C.validate_config(bad)
     assert N.lib().hvla_discrete_row_stride(5) == -1
+
+
+# ---- GEMM chain unit list (csrc/gemm_chain.cuh: units_before / decode_unit), restated: the invariants the kernel's liveness rests on ----
+def _chain_units(ntm, ntn, lags):
+    """The ordered unit list of a chain of len(ntn) GEMMs over ntm row blocks: slot s holds the column tiles of row block s - lag_g of GEMM g."""
+    lag = [0]
+    for l in lags[:len(ntn) - 1]:
+        lag.append(lag[-1] + min(l, ntm))
+    n_slots = ntm + lag[-1]
+
+    def before(s):
+        return sum(min(max(s - lag[g], 0), ntm) * ntn[g] for g in range(len(ntn)))
+    units = []
+    for s in range(n_slots):
+        assert before(s) == len(units)
+        for g in range(len(ntn)):
+            m = s - lag[g]
+            if 0 <= m < ntm:
+                units += [(g, m, n) for n in range(ntn[g])]
+    assert before(n_slots) == len(units)
+    return units
+
+
+@pytest.mark.parametrize("ntm", [1, 3, 26, 65, 514])
+@pytest.mark.parametrize("lags", [(0, 0, 0), (3, 3, 3), (12, 10, 24), (1 << 20, 1 << 20, 1 << 20)])
+@pytest.mark.parametrize("ntn", [(3, 12, 3, 9), (3, 12, 3)])
+def test_gemm_chain_unit_list_is_a_permutation_with_dependencies_first(ntm, lags, ntn):
+    units = _chain_units(ntm, ntn, lags)
+    assert len(units) == len(set(units)) == ntm * sum(ntn)                     # every (GEMM, row block, column tile) exactly once
+    pos = {u: i for i, u in enumerate(units)}
+    for (g, m, n), i in pos.items():
+        if g > 0:                                                              # a unit reads row block m of GEMM g - 1: all of its tiles come earlier
+            assert all(pos[(g - 1, m, k)] < i for k in range(ntn[g - 1]))
+    if min(lags) >= ntm:                                                       # default lags: GEMM after GEMM
+        assert [u[0] for u in units] == sorted(u[0] for u in units)
