@@ -208,7 +208,14 @@ gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
             atomicAdd(&g_chain_stats[0], 1ull);
             if (spins) { atomicAdd(&g_chain_stats[1], 1ull); atomicAdd(&g_chain_stats[2], spins); atomicAdd(&g_chain_stats[3], (unsigned long long)(clock64() - t0)); }
 #else
-            while (ld_acquire(c) < target) { }
+            // the only unbounded wait of the protocol that is not an mbarrier: fail loudly (sticky launch error) instead of hanging if the
+            // rows never complete -- which the list order rules out, so this only fires on a broken build or a corrupted workspace
+            if (ld_acquire(c) < target) {
+              const long long t0 = clock64();
+              while (ld_acquire(c) < target) {
+                if (clock64() - t0 > (1ll << 33)) __trap();             // ~5 s at 1.7 GHz
+              }
+            }
 #endif
           }
           v = pack_unit(un);
